@@ -1,0 +1,98 @@
+"""ORACLE -- test infrastructure only.  Generates tests/golden/*.npz.
+
+Run in the build container (the only place /root/reference exists):
+    python -m oracle.make_golden
+Each fixture is produced by executing the reference's OWN model files
+(/root/reference/network/SNN_models.py + blocks.py, unmodified, via oracle/run_reference.py)
+on top of the restated neuron (oracle/sj_compat.py), on CPU in fp32.
+
+Weights (72 MB) are not stored: they are regenerated from ``torch.manual_seed(seed)`` +
+PyTorch default Conv2d init by constructing the model, and guarded by a checksum so that an
+RNG/initialiser drift between torch builds is detected (the test then skips with a message
+instead of reporting a false parity failure).  Inputs are stored (uint8 event counts).
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import ref_model as rm
+from . import run_reference as rr
+from . import sj_compat as sj
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+# name -> (variant, monocular, multiply_factor, tau, T, weight seed)
+CASES = {
+    'stereospike_if_T2': ('if', False, 5.0, 3.0, 2, 2021),
+    'bino_lif_T2': ('lif', False, 15.0, 3.0, 2, 2022),
+    'mono_plif_T2': ('plif', True, 15.0, 3.0, 2, 2023),
+}
+
+
+def weight_checksum(model):
+    sd = model.state_dict()
+    tot = 0.0
+    for k in sorted(sd):
+        tot += float(sd[k].double().abs().sum())
+    probe = sd['conv1.0.weight'].flatten()[:8].double().numpy()
+    return np.array([tot] + list(probe))
+
+
+def simple_loss(depths, label):
+    """Sum over the 4 scales of the NaN-masked mean absolute error (metrics.py:83-95 per scale).
+    Used instead of network/loss.py::Total_Loss, whose Sobel filters are moved to CUDA whenever
+    CUDA exists (loss.py:60-65) and therefore cannot run on CPU tensors on a GPU box."""
+    mask = ~torch.isnan(label)
+    n = mask.count_nonzero()
+    tot = 0.0
+    for d in depths:
+        tot = tot + (d - torch.nan_to_num(label))[mask].abs().sum() / n
+    return tot
+
+
+def run_case(name, build=None):
+    variant, mono, gain, tau, T, seed = CASES[name]
+    torch.manual_seed(seed)
+    net = (build or rr.build_reference)(variant, mono, multiply_factor=gain, tau=tau)
+    x = rm.synthetic_inputs(1, T, 2 if mono else 4, lam=0.05, seed=seed + 100)
+    label = rm.synthetic_label(1, seed=seed + 200)
+    sj.reset_net(net)
+    out = None
+    for t in range(T):
+        out = net(x[:, t:t + 1])
+    depths = out if mono else out[0]
+    loss = simple_loss(depths, label)
+    loss.backward()
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    res = dict(
+        x=x.numpy().astype(np.uint8),
+        label=label.numpy(),
+        depth1=depths[0].detach().numpy(),
+        depth_sums=np.array([float(d.detach().double().sum()) for d in depths]),
+        depth_abs_sums=np.array([float(d.detach().double().abs().sum()) for d in depths]),
+        mde=np.array(float(rm.mean_depth_error(depths[0].detach(), label))),
+        loss=np.array(float(loss.detach())),
+        weight_checksum=weight_checksum(net),
+        grad_names=np.array(sorted(grads)),
+        grad_l2=np.array([float(grads[k].double().norm()) for k in sorted(grads)]),
+        grad_sum=np.array([float(grads[k].double().sum()) for k in sorted(grads)]),
+    )
+    if not mono:
+        spks = out[1]
+        res['spk_counts'] = np.array([float(s.detach().double().sum()) for s in spks])
+        res['spk_nonzero'] = np.array([int(s.count_nonzero()) for s in spks])
+    return res
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name in CASES:
+        res = run_case(name)
+        path = os.path.join(GOLDEN_DIR, name + '.npz')
+        np.savez_compressed(path, **res)
+        print(name, 'mde', float(res['mde']), 'loss', float(res['loss']), os.path.getsize(path), 'bytes')
+
+
+if __name__ == '__main__':
+    main()

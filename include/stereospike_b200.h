@@ -1,0 +1,164 @@
+/* stereospike_b200 -- C ABI of the B200-native StereoSpike hot path.
+ *
+ * The reference (urancon/StereoSpike) is pure Python and has no FFI: its "operator interface" for this
+ * path is the nn.Module surface of network/blocks.py and network/SNN_models.py plus the SpikingJelly
+ * neuron modules they call.  Each entry point below names the reference code it replaces; the Python
+ * host side (stereospike_b200/*.py) mirrors the reference classes and reaches these symbols through
+ * ctypes.
+ *
+ * Conventions: plain pointers and sizes only.  Every pointer is a DEVICE pointer owned by the caller
+ * (the library never allocates or frees device memory and never synchronises the host); `stream` is a
+ * cudaStream_t passed as void*.  Functions return 0 on success or a negative SS_E* code, and
+ * ss_last_error() returns a thread-local description of the last failure.
+ *
+ * Data layout in HBM
+ *   spikes / activations : bf16, [T][B][H][W][C]  (timestep-major NHWC; values are small integers
+ *                          {0..3} -- exact in bf16)
+ *   first-layer input    : fp32, [B][T][C][H][W]  (the reference's own NCHW event-count frames,
+ *                          train.py:201-218), read directly by the first block
+ *   membrane potentials  : fp32, [B][H][W][C]
+ *   pre-reset potentials : fp32, [T][B][H][W][C]  (optional, saved for the surrogate backward)
+ *   depth (I-neurons)    : fp32, [B][H][W]
+ */
+#ifndef STEREOSPIKE_B200_H
+#define STEREOSPIKE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_ABI_VERSION 1
+
+/* error codes */
+#define SS_OK 0
+#define SS_EINVAL (-1)      /* bad argument / unsupported geometry */
+#define SS_ECUDA (-2)       /* a CUDA runtime / driver call failed (launch errors included) */
+#define SS_EUNSUPPORTED (-3)
+
+/* neuron kinds -- spikingjelly.clock_driven.neuron.{IFNode,LIFNode,ParametricLIFNode}
+ * (call sites network/SNN_models.py:78,266 and network/blocks.py:150,157) */
+#define SS_NEURON_IF 0
+#define SS_NEURON_LIF 1     /* h = v + (x - (v - v_reset)) / tau                */
+#define SS_NEURON_PLIF 2    /* h = v + (x - (v - v_reset)) * (*decay)  (decay = sigmoid(w), device scalar) */
+
+/* surrogate kinds -- spikingjelly.clock_driven.surrogate.{ATan(alpha=2),Sigmoid(alpha=4)}
+ * (train.py:118, network/blocks.py:142) */
+#define SS_SURR_ATAN 0
+#define SS_SURR_SIGMOID 1
+
+/* input layouts of ss_conv_neuron_fwd */
+#define SS_IN_BF16_TBHWC 0
+#define SS_IN_F32_BTCHW 1
+
+/* implementations */
+#define SS_IMPL_AUTO 0
+#define SS_IMPL_SIMT 1      /* fp32 CUDA-core implicit GEMM (exact fp32 weights) */
+#define SS_IMPL_UMMA 2      /* tcgen05 tensor-core implicit GEMM, bf16 weight planes, fp32 TMEM accumulate */
+
+typedef struct ss_conv_geom {
+    int32_t T, B;
+    int32_t Hin, Win, Cin;       /* source activation */
+    int32_t Hout, Wout, Cout;    /* block output */
+    int32_t ks;                  /* taps per axis; GEMM K = ks*ks*Cin, k = (ky*ks+kx)*Cin + c */
+    int32_t in_layout;           /* SS_IN_* */
+    int32_t neuron;              /* SS_NEURON_* */
+    int32_t impl;                /* SS_IMPL_* */
+    float gain;                  /* MultiplyBy scalar, applied to the conv result (blocks.py:106-107) */
+    float v_th, v_reset, tau;
+    int32_t weight_planes;       /* UMMA: number of bf16 planes per weight (1 = bf16, 2, 3 = fp32-exact split) */
+    int32_t reserved;
+} ss_conv_geom;
+
+/* Fused spiking block, forward, all T timesteps in one launch.
+ * Replaces  nn.Sequential(Conv2d(bias=False) | NNConvUpsampling, MultiplyBy, neuron)  called once per
+ * timestep (network/SNN_models.py:75-129, network/blocks.py:110-132,145-157) and, through `resid`, the
+ * skip additions (SNN_models.py:171,176,181,186) and the SEW 'ADD' connect (blocks.py:170-171).
+ *
+ *   ymap [Hout*ks], xmap [Wout*ks] : source row / column read by output row oy at tap ky (resp. ox, kx),
+ *                                    or -1 for a zero-padded tap.  One table pair expresses strided
+ *                                    zero-padded convs and the nearest-neighbour-upsampled valid convs.
+ *   w_kn   : fp32 [K][Cout]                      (SIMT)      k ordered (ky,kx,c)
+ *   w_umma : bf16 [planes][Cout][Kpad]           (UMMA)      Kpad = K rounded up to 64, zero padded
+ *   decay  : device scalar, PLIF only
+ *   v_in   : initial membrane potential or NULL (= v_reset); v_out: final potential or NULL
+ *   resid  : bf16 [T][B][Hout][Wout][Cout] added to the spikes before they are written, or NULL
+ *   out    : bf16 [T][B][Hout][Wout][Cout]
+ *   h_seq  : fp32 pre-reset potential h_t (for the backward), or NULL
+ */
+int ss_conv_neuron_fwd(const ss_conv_geom* g, const void* x, const int32_t* ymap, const int32_t* xmap,
+                       const float* w_kn, const void* w_umma, const float* decay,
+                       const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,
+                       void* stream);
+
+/* Prediction heads + I-neuron readout, forward, all T timesteps.
+ * Replaces  Ineurons(predict_depthK(out_addK))  for K = 4,3,2,1 (SNN_models.py:133-150,172-188):
+ * v += gain * (conv3x3(NNupsample(out_addK)) + bias_K), in that order, every timestep.
+ *   acts[i], C[i], Hs[i], Ws[i], w[i] (fp32 [9][C]), bias[i] (device scalar), ymap[i] [H*3], xmap[i] [W*3]
+ *   for i = 0..3 in execution order (head 4 first).
+ *   v_io   : fp32 [B][H][W] I-neuron potential, updated in place (caller zero-fills / sets the prior)
+ *   depths : fp32 [4][B][H][W]; depths[i] = potential right after head i of the LAST timestep
+ */
+typedef struct ss_heads_args {
+    int32_t T, B, H, W;
+    float gain;
+    int32_t C[4], Hs[4], Ws[4];
+    const void* acts[4];
+    const float* w[4];
+    const float* bias[4];
+    const int32_t* ymap[4];
+    const int32_t* xmap[4];
+} ss_heads_args;
+int ss_heads_fwd(const ss_heads_args* a, float* v_io, float* depths, void* stream);
+
+/* Stand-alone neuron layer over T steps (spikingjelly neuron.*Node.forward on an arbitrary tensor, e.g. the
+ * I-neuron pool of SNN_models.py:150).  x, s_out fp32 [T][N]; v_io fp32 [N] in/out; h_seq fp32 [T][N] or NULL. */
+int ss_neuron_fwd(int32_t T, int64_t N, int32_t neuron, float v_th, float v_reset, float tau, const float* decay,
+                  const float* x, float* v_io, float* s_out, float* h_seq, void* stream);
+
+/* Surrogate-gradient scan (BPTT through the neuron), reverse time.  Replaces autograd through
+ * BaseNode.forward with surrogate.{ATan,Sigmoid}.backward and detach_reset=True:
+ *   g_h(t) = g_s(t) * ds/du(h_t - v_th) + g_v(t) * (1 - s_t);  g_x(t) = g_h(t) * r;  g_v(t-1) = g_h(t) * (1 - r)
+ * with r = 1 (IF: g_v(t-1) = g_h(t)), 1/tau (LIF), *decay (PLIF).
+ *   h_seq fp32 [T][N], g_s fp32 [T][N] (gradient w.r.t. the block's spikes), g_v_last fp32 [N] or NULL
+ *   g_acc  fp32 [T][N]: gradient w.r.t. the conv result (gain folded in)
+ *   g_decay: device scalar accumulated with atomicAdd (PLIF; gradient w.r.t. *decay), may be NULL
+ */
+int ss_neuron_bwd(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain,
+                  float v_th, float v_reset, float tau, const float* decay, const float* h_seq,
+                  const float* v_init, const float* g_s, const float* g_v_last, float* g_acc,
+                  float* g_v_init, float* g_decay, void* stream);
+
+/* Convolution gradients of the fused block (replaces cuDNN dgrad / wgrad and upsample_nearest2d_backward
+ * reached through autograd; the (ymap, xmap) tables fold the upsampling into the gather / scatter).
+ *   g_acc fp32 [T][B][Hout][Wout][Cout] (output of ss_neuron_bwd)
+ *   g_x   fp32 [T][B][Hin][Win][Cin], ACCUMULATED into (caller zero-fills or passes the skip-path gradient)
+ *   g_w   fp32 [K][Cout], ACCUMULATED into
+ */
+int ss_conv_dgrad(const ss_conv_geom* g, const int32_t* ymap, const int32_t* xmap, const float* w_kn,
+                  const float* g_acc, float* g_x, void* stream);
+int ss_conv_wgrad(const ss_conv_geom* g, const void* x, const int32_t* ymap, const int32_t* xmap,
+                  const float* g_acc, float* g_w, void* stream);
+
+/* Backward of ss_heads_fwd (autograd through predict_depthK + the I-neuron running sum).
+ *   g_depths fp32 [4][B][H][W]: gradient w.r.t. the four returned depth maps (execution order)
+ *   g_acts[i] fp32 [T][B][Hs][Ws][C] accumulated; g_w[i] fp32 [9][C] accumulated; g_bias[i] scalar accumulated
+ *   bins[i]   fp32 [2][B][Hs][Ws][9] zero-filled workspace
+ */
+int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float* const* g_acts, float* const* g_w,
+                 float* const* g_bias, float* const* bins, void* stream);
+
+/* Repack weights for the UMMA path: fp32 [K][Cout] -> bf16 [planes][Cout][Kpad] (residual split). */
+int ss_pack_weights_umma(const float* w_kn, int32_t K, int32_t Cout, int32_t planes, void* w_umma, void* stream);
+
+int ss_abi_version(void);
+const char* ss_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t ss_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,91 @@
+"""ctypes binding of the C-ABI library (include/stereospike_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a symbol is absent, importing the
+ops raises.  Build it with ``python -m stereospike_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libstereospike_b200.so')
+
+SS_NEURON_IF, SS_NEURON_LIF, SS_NEURON_PLIF = 0, 1, 2
+SS_SURR_ATAN, SS_SURR_SIGMOID = 0, 1
+SS_IN_BF16_TBHWC, SS_IN_F32_BTCHW = 0, 1
+SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
+
+# every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
+SYMBOLS = ('ss_conv_neuron_fwd', 'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_conv_dgrad', 'ss_conv_wgrad',
+           'ss_heads_bwd', 'ss_pack_weights_umma', 'ss_abi_version', 'ss_last_error', 'ss_launch_count')
+
+
+class ConvGeom(ctypes.Structure):
+    _fields_ = [('T', ctypes.c_int32), ('B', ctypes.c_int32),
+                ('Hin', ctypes.c_int32), ('Win', ctypes.c_int32), ('Cin', ctypes.c_int32),
+                ('Hout', ctypes.c_int32), ('Wout', ctypes.c_int32), ('Cout', ctypes.c_int32),
+                ('ks', ctypes.c_int32), ('in_layout', ctypes.c_int32), ('neuron', ctypes.c_int32),
+                ('impl', ctypes.c_int32),
+                ('gain', ctypes.c_float), ('v_th', ctypes.c_float), ('v_reset', ctypes.c_float),
+                ('tau', ctypes.c_float),
+                ('weight_planes', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class HeadsArgs(ctypes.Structure):
+    _fields_ = [('T', ctypes.c_int32), ('B', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32),
+                ('gain', ctypes.c_float),
+                ('C', ctypes.c_int32 * 4), ('Hs', ctypes.c_int32 * 4), ('Ws', ctypes.c_int32 * 4),
+                ('acts', ctypes.c_void_p * 4), ('w', ctypes.c_void_p * 4), ('bias', ctypes.c_void_p * 4),
+                ('ymap', ctypes.c_void_p * 4), ('xmap', ctypes.c_void_p * 4)]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises LibraryMissing (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise LibraryMissing(
+            f'{LIB_PATH} not found: the CUDA extension is not built. Run `python -m stereospike_b200.build`. '
+            'There is no CPU or PyTorch fallback for the stereospike_b200 hot path.')
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    L.ss_conv_neuron_fwd.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 12
+    L.ss_conv_neuron_fwd.restype = ctypes.c_int
+    L.ss_heads_fwd.argtypes = [ctypes.POINTER(HeadsArgs), vp, vp, vp]
+    L.ss_heads_fwd.restype = ctypes.c_int
+    L.ss_heads_bwd.argtypes = [ctypes.POINTER(HeadsArgs), vp, vp * 4, vp * 4, vp * 4, vp * 4, vp]
+    L.ss_heads_bwd.restype = ctypes.c_int
+    L.ss_neuron_fwd.argtypes = [i32, i64, i32, f32, f32, f32] + [vp] * 6
+    L.ss_neuron_fwd.restype = ctypes.c_int
+    L.ss_neuron_bwd.argtypes = [i32, i64, i32, i32, f32, f32, f32, f32, f32] + [vp] * 9
+    L.ss_neuron_bwd.restype = ctypes.c_int
+    L.ss_conv_dgrad.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 6
+    L.ss_conv_dgrad.restype = ctypes.c_int
+    L.ss_conv_wgrad.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 6
+    L.ss_conv_wgrad.restype = ctypes.c_int
+    L.ss_pack_weights_umma.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.ss_pack_weights_umma.restype = ctypes.c_int
+    L.ss_abi_version.restype = ctypes.c_int
+    L.ss_last_error.restype = ctypes.c_char_p
+    L.ss_launch_count.restype = ctypes.c_int64
+    for s in SYMBOLS:
+        getattr(L, s)          # AttributeError here = header / library mismatch
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ss_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'{what} failed (code {rc}): {msg}')
+
+
+def launch_count():
+    return int(lib().ss_launch_count())

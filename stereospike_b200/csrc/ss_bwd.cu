@@ -1,0 +1,474 @@
+// Backward of the fused spiking block and of the prediction heads (fp32 CUDA-core kernels).
+//
+// Replaces PyTorch autograd through the reference path: the SpikingJelly surrogate
+// autograd.Function.backward (ATan / Sigmoid evaluated at h - v_th, detach_reset=True), cuDNN dgrad / wgrad of
+// every Conv2d, and upsample_nearest2d_backward -- the (ymap, xmap) tables fold the upsampling into the conv
+// gradient, so no upsampled gradient tensor is ever materialised.
+#include "ss_common.cuh"
+
+namespace ss {
+namespace {
+
+// ------------------------------------------------------------------------------------------ neuron BPTT scan
+__device__ __forceinline__ float surrogate_grad(int kind, float alpha, float u) {
+    if (kind == SS_SURR_ATAN) {
+        const float q = 1.5707963267948966f * alpha * u;
+        return alpha * 0.5f / (1.0f + q * q);
+    }
+    const float sg = 1.0f / (1.0f + __expf(-alpha * u));
+    return alpha * sg * (1.0f - sg);
+}
+
+__global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int neuron, int surrogate, float alpha,
+                                                         float gain, float v_th, float v_reset, float tau,
+                                                         const float* __restrict__ decay_p, const float* __restrict__ h_seq,
+                                                         const float* __restrict__ v_init, const float* g_s,
+                                                         const float* __restrict__ g_v_last, float* g_acc,
+                                                         float* __restrict__ g_v_init, float* __restrict__ g_decay) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float gd_local = 0.0f;
+    if (n < N) {
+        float r = 1.0f;
+        if (neuron == SS_NEURON_LIF) r = 1.0f / tau;
+        if (neuron == SS_NEURON_PLIF) r = __ldg(decay_p);
+        const float keep = (neuron == SS_NEURON_IF) ? 1.0f : 1.0f - r;
+        float g_v = (g_v_last != nullptr) ? g_v_last[n] : 0.0f;
+        float h = h_seq[(size_t)(T - 1) * N + n];
+        for (int t = T - 1; t >= 0; --t) {
+            // potential before this step: reset(h_{t-1}) or the initial state
+            float h_prev = 0.0f, v_prev;
+            if (t > 0) {
+                h_prev = h_seq[(size_t)(t - 1) * N + n];
+                v_prev = (h_prev - v_th >= 0.0f) ? v_reset : h_prev;
+            } else {
+                v_prev = (v_init != nullptr) ? v_init[n] : v_reset;
+            }
+            const float u = h - v_th;
+            const float s = (u >= 0.0f) ? 1.0f : 0.0f;
+            const float g_h = g_s[(size_t)t * N + n] * surrogate_grad(surrogate, alpha, u) + g_v * (1.0f - s);
+            const float g_x = (neuron == SS_NEURON_IF) ? g_h : g_h * r;
+            g_acc[(size_t)t * N + n] = g_x * gain;
+            if (neuron == SS_NEURON_PLIF) gd_local += g_h * ((h - v_prev) / r);  // d h / d r = x - (v - v_reset)
+            g_v = g_h * keep;
+            h = h_prev;
+        }
+        if (g_v_init != nullptr) g_v_init[n] = g_v;
+    }
+    if (neuron == SS_NEURON_PLIF && g_decay != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gd_local += __shfl_xor_sync(0xffffffffu, gd_local, o);
+        __shared__ float red[8];
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gd_local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.0f;
+            for (int i = 0; i < 8; ++i) tot += red[i];
+            atomicAdd(g_decay, tot);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ conv dgrad
+// G[m][k] = sum_n g_acc[m][n] * W[k][n], scattered to g_x[t][src(m, tap)][c] with atomics (k = tap*Cin + c).
+constexpr int DG_BM = 64, DG_BK = 64, DG_BN = 32;
+
+__global__ void __launch_bounds__(256) conv_dgrad_kernel(const ConvParams p, const float* __restrict__ g_acc, float* g_x) {
+    __shared__ __align__(16) float Gs[DG_BN][DG_BM + 4];  // [n][m]
+    __shared__ __align__(16) float Ws[DG_BN][DG_BK + 4];  // [n][k]
+    __shared__ int row_b[DG_BM], row_oy[DG_BM], row_ox[DG_BM];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * DG_BM;
+    const int k0 = blockIdx.y * DG_BK;
+    const int t = blockIdx.z;
+    const int HW = p.Hout * p.Wout;
+    if (tid < DG_BM) {
+        const int m = m0 + tid;
+        if (m < p.M) {
+            const int b = m / HW, q = m - b * HW;
+            row_b[tid] = b;
+            row_oy[tid] = q / p.Wout;
+            row_ox[tid] = q - (q / p.Wout) * p.Wout;
+        } else {
+            row_b[tid] = -1;
+            row_oy[tid] = row_ox[tid] = 0;
+        }
+    }
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int nb = 0; nb < p.Cout; nb += DG_BN) {
+        __syncthreads();
+        for (int idx = tid; idx < DG_BM * DG_BN; idx += 256) {
+            const int mm = idx / DG_BN, nn = idx - mm * DG_BN;
+            const int m = m0 + mm;
+            Gs[nn][mm] = (m < p.M) ? __ldg(g_acc + ((size_t)t * p.M + m) * p.Cout + nb + nn) : 0.0f;
+        }
+        for (int idx = tid; idx < DG_BK * DG_BN; idx += 256) {
+            const int kk = idx / DG_BN, nn = idx - kk * DG_BN;
+            const int k = k0 + kk;
+            Ws[nn][kk] = (k < p.K) ? __ldg(p.w_kn + (size_t)k * p.Cout + nb + nn) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int nn = 0; nn < DG_BN; ++nn) {
+            const float4 g4 = *reinterpret_cast<const float4*>(&Gs[nn][ty * 4]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&Ws[nn][tx * 4]);
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], wv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int mm = ty * 4 + i;
+        const int b = row_b[mm];
+        if (b < 0) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k >= p.K) continue;
+            const int tap = k / p.Cin, c = k - tap * p.Cin;
+            const int ky = tap / p.ks, kx = tap - ky * p.ks;
+            const int sy = __ldg(p.ymap + row_oy[mm] * p.ks + ky);
+            const int sx = __ldg(p.xmap + row_ox[mm] * p.ks + kx);
+            if (sy < 0 || sx < 0) continue;
+            atomicAdd(g_x + ((((size_t)t * p.B + b) * p.Hin + sy) * p.Win + sx) * p.Cin + c, acc[i][j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ conv wgrad
+// g_w[k][n] += sum over (t, m) of A[t][m][k] * g_acc[t][m][n]; the (t, m) range is split across blockIdx.z.
+constexpr int WG_BK = 64, WG_BN = 64, WG_BM = 32;
+
+template <int IN_LAYOUT>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvParams p, const float* __restrict__ g_acc, float* g_w,
+                                                         int rows_per_split) {
+    __shared__ __align__(16) float As[WG_BM][WG_BK + 4];  // [m][k]
+    __shared__ __align__(16) float Gs[WG_BM][WG_BN + 4];  // [m][n]
+    const int tid = threadIdx.x;
+    const int k0 = blockIdx.x * WG_BK;
+    const int n0 = blockIdx.y * WG_BN;
+    const long long TM = (long long)p.T * p.M;
+    const long long r_begin = (long long)blockIdx.z * rows_per_split;
+    long long r_end = r_begin + rows_per_split;
+    if (r_end > TM) r_end = TM;
+    const int HW = p.Hout * p.Wout;
+    const int tx = tid & 15, ty = tid >> 4;  // thread owns k = ty*4.., n = tx*4..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (long long r0 = r_begin; r0 < r_end; r0 += WG_BM) {
+        __syncthreads();
+        // gather A: 32 rows x 64 k
+        for (int idx = tid; idx < WG_BM * WG_BK; idx += 256) {
+            const int mm = idx / WG_BK, kk = idx - mm * WG_BK;
+            const long long r = r0 + mm;
+            const int k = k0 + kk;
+            float a = 0.0f;
+            if (r < r_end && k < p.K) {
+                const int t = (int)(r / p.M);
+                const int m = (int)(r - (long long)t * p.M);
+                const int b = m / HW, q = m - b * HW;
+                const int oy = q / p.Wout, ox = q - oy * p.Wout;
+                const int tap = k / p.Cin, c = k - tap * p.Cin;
+                const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                const int sy = __ldg(p.ymap + oy * p.ks + ky);
+                const int sx = __ldg(p.xmap + ox * p.ks + kx);
+                if (sy >= 0 && sx >= 0) {
+                    if (IN_LAYOUT == SS_IN_BF16_TBHWC)
+                        a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                            p.x)[((((size_t)t * p.B + b) * p.Hin + sy) * p.Win + sx) * p.Cin + c]);
+                    else
+                        a = __ldg(reinterpret_cast<const float*>(p.x) +
+                                  ((((size_t)b * p.T + t) * p.Cin + c) * p.Hin + sy) * p.Win + sx);
+                }
+            }
+            As[mm][kk] = a;
+        }
+        for (int idx = tid; idx < WG_BM * WG_BN; idx += 256) {
+            const int mm = idx / WG_BN, nn = idx - mm * WG_BN;
+            const long long r = r0 + mm;
+            Gs[mm][nn] = (r < r_end && n0 + nn < p.Cout) ? __ldg(g_acc + (size_t)r * p.Cout + n0 + nn) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int mm = 0; mm < WG_BM; ++mm) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
+            const float4 g4 = *reinterpret_cast<const float4*>(&Gs[mm][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty * 4 + i;
+        if (k >= p.K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < p.Cout && acc[i][j] != 0.0f) atomicAdd(g_w + (size_t)k * p.Cout + n, acc[i][j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ heads backward
+struct HeadsBwdParams {
+    int T, B, H, W;
+    float gain;
+    int C[4], Hs[4], Ws[4];
+    const __nv_bfloat16* acts[4];
+    const float* w[4];
+    const int* ymap[4];
+    const int* xmap[4];
+    const float* g_depths;
+    float* g_acts[4];
+    float* g_w[4];
+    float* g_bias[4];
+    float* bins[4];
+};
+
+// step 1: bin the per-pixel head gradients onto (source pixel, tap).  Class 0 = timesteps before the last
+// (every head sees the sum of all four depth gradients), class 1 = last timestep (suffix sums).
+__global__ void __launch_bounds__(256) heads_bin_kernel(const HeadsBwdParams p) {
+    const int HW = p.H * p.W;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float bsum[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    if (pix < (long long)p.B * HW) {
+        const int b = (int)(pix / HW);
+        const int q = (int)(pix - (long long)b * HW);
+        const int y = q / p.W, x = q - (q / p.W) * p.W;
+        float gd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gd[i] = p.g_depths[(size_t)i * p.B * HW + pix];
+        const float g_all = ((gd[0] + gd[1]) + gd[2]) + gd[3];
+        float suffix = 0.0f;
+        float g_last[4];
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            suffix += gd[i];
+            g_last[i] = suffix;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t plane = (size_t)p.B * p.Hs[i] * p.Ws[i] * 9;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int sy = __ldg(p.ymap[i] + y * 3 + ky);
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int sx = __ldg(p.xmap[i] + x * 3 + kx);
+                    if (sy < 0 || sx < 0) continue;
+                    const size_t o = (((size_t)b * p.Hs[i] + sy) * p.Ws[i] + sx) * 9 + ky * 3 + kx;
+                    if (p.T > 1) atomicAdd(p.bins[i] + o, g_all);
+                    atomicAdd(p.bins[i] + plane + o, g_last[i]);
+                }
+            }
+            bsum[i][0] = g_all;
+            bsum[i][1] = g_last[i];
+        }
+    }
+    // bias gradient: gain * sum over pixels and timesteps of the head gradient
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float vsum = bsum[i][0] * (float)(p.T - 1) + bsum[i][1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        if ((threadIdx.x & 31) == 0 && vsum != 0.0f) atomicAdd(p.g_bias[i], vsum * p.gain);
+    }
+}
+
+// step 2: per (t, source pixel): g_act[c] += gain * sum_tap bin[tap] * w[tap][c];  g_w[tap][c] += gain * bin[tap] * act[c]
+__global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, int head) {
+    extern __shared__ float sh[];  // w [9][C] then g_w accumulators [9][C]
+    const int C = p.C[head];
+    float* wsm = sh;
+    float* gws = sh + 9 * C;
+    for (int j = threadIdx.x; j < 9 * C; j += blockDim.x) {
+        wsm[j] = __ldg(p.w[head] + j);
+        gws[j] = 0.0f;
+    }
+    __syncthreads();
+    const int S = p.B * p.Hs[head] * p.Ws[head];
+    const size_t plane = (size_t)S * 9;
+    const int c8n = C / 8;
+    // one thread handles one (source pixel, 8-channel group); the timestep is blockIdx.y
+    const int t = blockIdx.y;
+    const float* bins = p.bins[head] + ((t == p.T - 1) ? plane : 0);
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < (long long)S * c8n) {
+        const int s = (int)(item / c8n);
+        const int c0 = (int)(item - (long long)s * c8n) * 8;
+        float bn[9];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            bn[k] = __ldg(bins + (size_t)s * 9 + k) * p.gain;
+            any |= bn[k] != 0.0f;
+        }
+        const size_t eo = ((size_t)t * S + s) * C + c0;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.acts[head] + eo));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float a[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h2[e]);
+            a[2 * e] = f.x;
+            a[2 * e + 1] = f.y;
+        }
+        float ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (any) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    ga[e] = fmaf(bn[k], wsm[k * C + c0 + e], ga[e]);
+                    if (a[e] != 0.0f && bn[k] != 0.0f) atomicAdd(&gws[k * C + c0 + e], bn[k] * a[e]);
+                }
+            }
+            float* gp = p.g_acts[head] + eo;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gp[e] += ga[e];
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 9 * C; j += blockDim.x)
+        if (gws[j] != 0.0f) atomicAdd(p.g_w[head] + j, gws[j]);
+}
+
+int fill_params(const ss_conv_geom* g, ConvParams& p) {
+    if (g == nullptr || g->Cin <= 0 || g->Cout <= 0 || g->ks <= 0) {
+        set_error("bad geometry");
+        return SS_EINVAL;
+    }
+    p = ConvParams();
+    p.T = g->T; p.B = g->B; p.Hin = g->Hin; p.Win = g->Win; p.Cin = g->Cin;
+    p.Hout = g->Hout; p.Wout = g->Wout; p.Cout = g->Cout; p.ks = g->ks;
+    p.K = g->ks * g->ks * g->Cin;
+    p.M = g->B * g->Hout * g->Wout;
+    p.neuron = g->neuron; p.gain = g->gain; p.v_th = g->v_th; p.v_reset = g->v_reset; p.tau = g->tau;
+    return SS_OK;
+}
+
+}  // namespace
+}  // namespace ss
+
+using namespace ss;
+
+extern "C" int ss_neuron_bwd(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,
+                             float v_reset, float tau, const float* decay, const float* h_seq, const float* v_init,
+                             const float* g_s, const float* g_v_last, float* g_acc, float* g_v_init, float* g_decay,
+                             void* stream) {
+    if (h_seq == nullptr || g_s == nullptr || g_acc == nullptr || T < 0 || N < 0) {
+        set_error("ss_neuron_bwd: bad argument");
+        return SS_EINVAL;
+    }
+    if (neuron == SS_NEURON_PLIF && decay == nullptr) {
+        set_error("ss_neuron_bwd: PLIF needs decay");
+        return SS_EINVAL;
+    }
+    if (T == 0 || N == 0) return SS_OK;
+    neuron_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc, g_v_init,
+        g_decay);
+    count_launch();
+    return check_launch("neuron_bwd");
+}
+
+extern "C" int ss_conv_dgrad(const ss_conv_geom* g, const int32_t* ymap, const int32_t* xmap, const float* w_kn,
+                             const float* g_acc, float* g_x, void* stream) {
+    ConvParams p;
+    if (fill_params(g, p) != SS_OK) return SS_EINVAL;
+    if (ymap == nullptr || xmap == nullptr || w_kn == nullptr || g_acc == nullptr || g_x == nullptr) {
+        set_error("ss_conv_dgrad: null argument");
+        return SS_EINVAL;
+    }
+    if (p.Cout % DG_BN != 0) {
+        set_error("ss_conv_dgrad: Cout %% 32 != 0");
+        return SS_EINVAL;
+    }
+    if (p.T == 0 || p.M == 0) return SS_OK;
+    p.ymap = ymap; p.xmap = xmap; p.w_kn = w_kn;
+    dim3 grid((p.M + DG_BM - 1) / DG_BM, (p.K + DG_BK - 1) / DG_BK, p.T);
+    conv_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g_acc, g_x);
+    count_launch();
+    return check_launch("conv_dgrad");
+}
+
+extern "C" int ss_conv_wgrad(const ss_conv_geom* g, const void* x, const int32_t* ymap, const int32_t* xmap,
+                             const float* g_acc, float* g_w, void* stream) {
+    ConvParams p;
+    if (fill_params(g, p) != SS_OK) return SS_EINVAL;
+    if (x == nullptr || ymap == nullptr || xmap == nullptr || g_acc == nullptr || g_w == nullptr) {
+        set_error("ss_conv_wgrad: null argument");
+        return SS_EINVAL;
+    }
+    if (p.T == 0 || p.M == 0) return SS_OK;
+    p.x = x; p.ymap = ymap; p.xmap = xmap;
+    const long long TM = (long long)p.T * p.M;
+    const int tiles = ((p.K + WG_BK - 1) / WG_BK) * ((p.Cout + WG_BN - 1) / WG_BN);
+    // enough splits to fill the machine ~4x, each at least 256 rows
+    long long splits = (148LL * 4 + tiles - 1) / tiles;
+    if (splits < 1) splits = 1;
+    long long rows = (TM + splits - 1) / splits;
+    if (rows < 256) rows = 256;
+    rows = (rows + WG_BM - 1) / WG_BM * WG_BM;
+    splits = (TM + rows - 1) / rows;
+    if (splits > 65535) {
+        set_error("ss_conv_wgrad: too many splits");
+        return SS_EINVAL;
+    }
+    dim3 grid((p.K + WG_BK - 1) / WG_BK, (p.Cout + WG_BN - 1) / WG_BN, (unsigned)splits);
+    if (g->in_layout == SS_IN_BF16_TBHWC)
+        conv_wgrad_kernel<SS_IN_BF16_TBHWC><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g_acc, g_w, (int)rows);
+    else
+        conv_wgrad_kernel<SS_IN_F32_BTCHW><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g_acc, g_w, (int)rows);
+    count_launch();
+    return check_launch("conv_wgrad");
+}
+
+extern "C" int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float* const* g_acts, float* const* g_w,
+                            float* const* g_bias, float* const* bins, void* stream) {
+    if (a == nullptr || g_depths == nullptr || g_acts == nullptr || g_w == nullptr || g_bias == nullptr || bins == nullptr) {
+        set_error("ss_heads_bwd: null argument");
+        return SS_EINVAL;
+    }
+    HeadsBwdParams p;
+    p.T = a->T; p.B = a->B; p.H = a->H; p.W = a->W; p.gain = a->gain;
+    for (int i = 0; i < 4; ++i) {
+        if (a->C[i] % 8 != 0) {
+            set_error("ss_heads_bwd: channels not a multiple of 8");
+            return SS_EINVAL;
+        }
+        p.C[i] = a->C[i]; p.Hs[i] = a->Hs[i]; p.Ws[i] = a->Ws[i];
+        p.acts[i] = reinterpret_cast<const __nv_bfloat16*>(a->acts[i]);
+        p.w[i] = a->w[i]; p.ymap[i] = a->ymap[i]; p.xmap[i] = a->xmap[i];
+        p.g_acts[i] = g_acts[i]; p.g_w[i] = g_w[i]; p.g_bias[i] = g_bias[i]; p.bins[i] = bins[i];
+    }
+    p.g_depths = g_depths;
+    const long long npix = (long long)p.B * p.H * p.W;
+    if (npix == 0 || p.T == 0) return SS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    heads_bin_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(p);
+    count_launch();
+    if (check_launch("heads_bin") != SS_OK) return SS_ECUDA;
+    for (int i = 0; i < 4; ++i) {
+        const long long items = (long long)p.B * p.Hs[i] * p.Ws[i] * (p.C[i] / 8);
+        const size_t smem = (size_t)18 * p.C[i] * sizeof(float);
+        dim3 grid((unsigned)((items + 255) / 256), p.T);
+        heads_src_kernel<<<grid, 256, smem, st>>>(p, i);
+        count_launch();
+        if (check_launch("heads_src") != SS_OK) return SS_ECUDA;
+    }
+    return SS_OK;
+}

@@ -1,0 +1,246 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through the C ABI
+(libstereospike_b200.so via ctypes); the oracle (oracle/) is the checker only.
+
+Protocol (DESIGN.md "Parity"): the spike function is a hard threshold, so two correct
+fp32 implementations that sum in a different order disagree on the O(1e-6) fraction of neurons whose potential
+lands within rounding of v_th, and each flip perturbs every downstream neuron it feeds.  Hence:
+  (i)  teacher-forced per block: same input spikes -> pre-reset potential h within TOL_H, spikes equal wherever
+       |h - v_th| > BAND;
+  (ii) end to end: |MDE_cuda - MDE_oracle| <= 1e-3 on a fixed synthetic label, early-layer spike mismatch tiny;
+  (iii) gradients: per-parameter cosine >= 0.999 against oracle autograd;
+  (iv) size-independent properties at the full benchmark size (determinism, batch independence, T-splitting).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_H = 2e-5      # abs+rel tolerance on the fp32 pre-reset potential (|h| up to ~10)
+BAND = 1e-4       # spikes must agree outside this band around the threshold
+TOL_MDE = 1e-3    # north_star: MDE within 1e-3 of the reference on identical inputs
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from stereospike_b200 import _lib
+    _lib.lib()        # the extension must be present: no fallback
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+BLOCKS = {
+    # strided 5x5 conv, Cin=32 (two taps per 64-wide K block, K tail zero-filled), M not a multiple of 128
+    'conv5_s2_c32': dict(kind='conv', Cin=32, Cout=64, ks=5, Hin=20, Win=27, stride=2, pad=2, up=None, neuron=0, T=3, B=2, resid=False),
+    # NN-upsampled decoder conv, Cout=32 tile, LIF, skip add
+    'upconv5_lif_skip': dict(kind='upconv', Cin=64, Cout=32, ks=5, Hin=9, Win=11, stride=1, pad=0, up=(19, 23), neuron=1, T=3, B=2, resid=True),
+    # SEW-style 3x3, PLIF, residual
+    'conv3_plif_res': dict(kind='conv', Cin=64, Cout=128, ks=3, Hin=12, Win=13, stride=1, pad=1, up=None, neuron=2, T=4, B=1, resid=True),
+    # bottleneck geometry at full size: 512 -> 512 @ 17x22 (4 N tiles)
+    'bottleneck_512': dict(kind='conv', Cin=512, Cout=512, ks=3, Hin=17, Win=22, stride=1, pad=1, up=None, neuron=0, T=2, B=1, resid=True),
+    # deconv3 geometry at full size: 33x44 -> 65x87
+    'deconv3_full': dict(kind='upconv', Cin=256, Cout=128, ks=5, Hin=33, Win=44, stride=1, pad=0, up=(65, 87), neuron=1, T=2, B=1, resid=True),
+    # single pixel row / single timestep / ragged tiny M
+    'tiny': dict(kind='conv', Cin=8, Cout=32, ks=3, Hin=3, Win=5, stride=1, pad=1, up=None, neuron=0, T=1, B=1, resid=False),
+}
+
+
+@pytest.mark.parametrize('impl,planes', [('simt', 0), ('umma', 3)])
+@pytest.mark.parametrize('name', sorted(BLOCKS))
+def test_block_teacher_forced(name, impl, planes):
+    from tests._cases import block_case
+    r = block_case(impl=impl, planes=planes, **BLOCKS[name])
+    if r['n'] > 5000:
+        assert 0.02 < r['rate'] < 0.9, r                  # a live block, not a dead one
+    assert r['max_dh_t0'] <= TOL_H * max(1.0, r['h_absmax']), r
+    assert r['spike_mismatch_outside_band'] == 0, r
+    assert r['spike_mismatch_all'] <= max(2, 2e-5 * r['n']), r
+
+
+@pytest.mark.parametrize('planes,tol', [(1, 2e-2), (2, 2e-4)])
+def test_block_reduced_weight_planes(planes, tol):
+    """1 plane = plain bf16 weights (the bf16 training configuration), 2 planes = 16-bit weight mantissa."""
+    from tests._cases import block_case
+    r = block_case(impl='umma', planes=planes, **BLOCKS['conv3_plif_res'])
+    assert r['max_dh_t0'] <= tol * max(1.0, r['h_absmax']), r
+
+
+def _mk_block(T, B, seed=0, Cin=64, Cout=64, H=10, W=13, neuron=1):
+    from stereospike_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    geom = ops.BlockGeom('conv', Cin, Cout, 3, H, W, H, W, 1, 1)
+    x = ((torch.rand(T, B, H, W, Cin, generator=g) < 0.2).float()).to('cuda', torch.bfloat16)
+    w = ((torch.rand(Cout, Cin, 3, 3, generator=g) * 2 - 1) / 8).cuda()
+    w_kn = ops.weight_to_kn(w)
+    return geom, x, w_kn, ops.pack_weights_umma(w_kn, 3)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'umma'])
+def test_state_carry_equals_one_long_sequence(impl):
+    """Running T=4 in one launch is bit-identical to 2 + 2 with v_out -> v_in (the register-resident membrane
+    potential is the same state the reference keeps in ``node.v`` between calls)."""
+    from stereospike_b200 import ops, _lib
+    geom, x, w_kn, w_um = _mk_block(4, 2)
+    kw = dict(in_layout=0, neuron=_lib.SS_NEURON_LIF, gain=4.0, v_th=1.0, v_reset=0.0, tau=3.0,
+              impl=_lib.SS_IMPL_UMMA if impl == 'umma' else _lib.SS_IMPL_SIMT, planes=3)
+    full, v_full, _ = ops.conv_neuron_fwd(x, geom, w_kn, w_um, T=4, B=2, want_v_out=True, **kw)
+    a, v_a, _ = ops.conv_neuron_fwd(x[:2].contiguous(), geom, w_kn, w_um, T=2, B=2, want_v_out=True, **kw)
+    b, v_b, _ = ops.conv_neuron_fwd(x[2:].contiguous(), geom, w_kn, w_um, T=2, B=2, v_in=v_a, want_v_out=True, **kw)
+    assert torch.equal(full[:2], a) and torch.equal(full[2:], b) and torch.equal(v_full, v_b)
+    assert 0.02 < float(full.float().mean()) < 0.9
+
+
+def test_simt_and_umma_agree():
+    from stereospike_b200 import ops, _lib
+    geom, x, w_kn, w_um = _mk_block(3, 2, seed=3)
+    kw = dict(in_layout=0, neuron=_lib.SS_NEURON_IF, gain=4.0, v_th=1.0, v_reset=0.0, T=3, B=2, want_h=True, planes=3)
+    o1, _, h1 = ops.conv_neuron_fwd(x, geom, w_kn, w_um, impl=_lib.SS_IMPL_SIMT, **kw)
+    o2, _, h2 = ops.conv_neuron_fwd(x, geom, w_kn, w_um, impl=_lib.SS_IMPL_UMMA, **kw)
+    assert float((h1[0] - h2[0]).abs().max()) < 1e-5
+    assert float((o1 != o2).float().mean()) < 1e-4
+
+
+def test_empty_batch_and_bad_arguments():
+    from stereospike_b200 import ops, _lib
+    geom, x, w_kn, w_um = _mk_block(1, 1)
+    out, _, _ = ops.conv_neuron_fwd(x[:, :0].contiguous(), geom, w_kn, w_um, T=1, B=0, in_layout=0, neuron=0, gain=1.0,
+                                    v_th=1.0, v_reset=0.0)
+    assert out.numel() == 0
+    with pytest.raises(RuntimeError, match='PLIF needs'):
+        ops.conv_neuron_fwd(x, geom, w_kn, w_um, T=1, B=1, in_layout=0, neuron=_lib.SS_NEURON_PLIF, gain=1.0, v_th=1.0,
+                            v_reset=0.0)
+
+
+@pytest.mark.parametrize('variant,mono,gain,T,B,impl', [
+    ('if', False, 5.0, 2, 1, 'umma'),
+    ('if', False, 5.0, 1, 2, 'simt'),
+    ('lif', False, 15.0, 3, 1, 'umma'),
+    ('plif', True, 15.0, 2, 2, 'umma'),
+])
+def test_model_end_to_end(variant, mono, gain, T, B, impl):
+    from tests._cases import model_case
+    r = model_case(variant, mono, gain, T, B, impl, 3)
+    assert abs(r['mde_ref'] - r['mde_got']) <= TOL_MDE, r
+    mm = r['mismatch(rate,firing)']
+    for k, (rate, firing) in mm.items():
+        assert 0.01 < firing < 0.7, (k, firing)             # live network
+    assert mm['out_bottom'][0] <= 1e-6 and mm['out_conv1'][0] <= 1e-5 and mm['out_conv2'][0] <= 1e-4, mm
+
+
+@pytest.mark.parametrize('variant,mono,gain,impl', [('if', False, 5.0, 'simt'), ('plif', False, 15.0, 'umma')])
+def test_model_gradients(variant, mono, gain, impl):
+    from tests._cases import model_case
+    r = model_case(variant, mono, gain, 2, 1, impl, 3, backward=True)
+    cos, name = r['grad_worst_cos']
+    assert cos >= 0.999, (cos, name, r['grad_rel'])
+
+
+@pytest.mark.parametrize('name', ['stereospike_if_T2', 'bino_lif_T2', 'mono_plif_T2'])
+def test_golden_fixture(name, golden_dir):
+    """Committed fixtures produced by the reference's own model files (oracle/make_golden.py)."""
+    from oracle import make_golden as mg, ref_model as rm, sj_compat as sj
+    import stereospike_b200 as sb
+    gold = np.load(os.path.join(golden_dir, name + '.npz'))
+    variant, mono, gain, tau, T, seed = mg.CASES[name]
+    torch.manual_seed(seed)
+    oracle = rm.SpikingUNet(variant, mono, surrogate_function=sj.ATan() if variant == 'if' else None, tau=tau,
+                            multiply_factor=gain)
+    if not np.array_equal(mg.weight_checksum(oracle), gold['weight_checksum']):
+        pytest.skip('torch default-init RNG differs from the container that generated the fixture')
+    if variant == 'if':
+        net = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), multiply_factor=gain)
+    elif mono:
+        net = sb.fromZero_feedforward_multiscale_tempo_monocular_SpikeFlowNetLike(use_plif=variant == 'plif', tau=tau,
+                                                                                  multiply_factor=gain)
+    else:
+        net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=variant == 'plif', tau=tau,
+                                                                              multiply_factor=gain)
+    net.load_state_dict(oracle.state_dict())
+    net = net.cuda()
+    x = torch.from_numpy(gold['x'].astype(np.float32)).cuda()
+    label = torch.from_numpy(gold['label'])
+    with torch.no_grad():
+        sb.functional.reset_net(net)
+        out = net.forward_seq(x)
+    depths = out if mono else out[0]
+    mde = float(rm.mean_depth_error(depths[0].cpu(), label))
+    assert abs(mde - float(gold['mde'])) <= TOL_MDE, (mde, float(gold['mde']))
+    rel = abs(float(depths[0].double().sum()) - gold['depth_sums'][0]) / gold['depth_abs_sums'][0]
+    assert rel < 2e-3, rel
+    if not mono:
+        nz = np.array([int(s.count_nonzero()) for s in out[1]])
+        assert np.all(np.abs(nz - gold['spk_nonzero']) <= 0.03 * gold['spk_nonzero']), (nz, gold['spk_nonzero'])
+
+
+def test_forward_single_step_contract():
+    """forward(x) reads frame 0 only and is stateful across calls: T calls == one forward_seq over T frames."""
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm
+    torch.manual_seed(3)
+    net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=False, tau=3.0, multiply_factor=15.0).cuda()
+    x = rm.synthetic_inputs(1, 3, 4, seed=9).cuda()
+    with torch.no_grad():
+        sb.functional.reset_net(net)
+        d_seq, s_seq = net.forward_seq(x)
+        sb.functional.reset_net(net)
+        for t in range(3):
+            d_it, s_it = net(x[:, t:])            # extra frames on dim 1 are ignored, like the reference
+    for a, b in zip(d_seq, d_it):
+        assert torch.equal(a, b)
+    for a, b in zip(s_seq, s_it):
+        assert torch.equal(a.float(), b) and b.dtype == torch.float32 and b.shape[1] in (512, 256, 128, 64, 32)
+    assert tuple(d_it[0].shape) == (1, 1, 260, 346)
+    assert isinstance(net.conv1[2].v, torch.Tensor) and tuple(net.conv1[2].v.shape) == (1, 64, 130, 173)
+    sb.functional.reset_net(net)
+    assert net.conv1[2].v == 0.0
+    rates = net.calculate_firing_rates(x)
+    assert set(rates) == set(sb.models.LAYER_NAMES) and 0.01 < rates['out_conv1'] < 0.7
+
+
+def test_full_size_properties():
+    """BASELINE config (binocular T=5, batch 8): determinism and batch independence, bit-exact."""
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm
+    torch.manual_seed(0)
+    net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=False, tau=3.0, multiply_factor=15.0).cuda()
+    x = rm.synthetic_inputs(8, 5, 4, seed=21).cuda()
+    with torch.no_grad():
+        sb.functional.reset_net(net)
+        d1, s1 = net.forward_seq(x)
+        sb.functional.reset_net(net)
+        d2, s2 = net.forward_seq(x)
+        sb.functional.reset_net(net)
+        d3, s3 = net.forward_seq(x[5:6].contiguous())
+    assert all(torch.equal(a, b) for a, b in zip(d1, d2)) and all(torch.equal(a, b) for a, b in zip(s1, s2))
+    assert all(torch.equal(a[5:6], b) for a, b in zip(d1, d3)), 'samples of a batch must not interact'
+    assert torch.isfinite(d1[0]).all() and 0.05 < float((s1[0] != 0).float().mean()) < 0.9
+
+
+def test_standalone_blocks():
+    """The block classes stay usable on their own with the reference's NCHW fp32 tensors."""
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm, sj_compat as sj
+    torch.manual_seed(1)
+    o = rm.SEWBlock(64, lambda: sj.IFNode(1.0, 0.0, sj.Sigmoid(), True), 4.0)
+    blk = sb.SEWResBlock(64, multiply_factor=4.0)
+    blk.load_state_dict(o.state_dict())
+    blk = blk.cuda()
+    x = (torch.rand(2, 64, 9, 7) < 0.2).float()
+    with torch.no_grad():
+        ref = o(x.clone())
+        got = blk(x.cuda()).cpu()
+    assert float((ref != got).float().mean()) < 1e-3 and 0.02 < float((ref > 0).float().mean())
+    up_o = rm.UpConv(32, 1, 3, (20, 26), bias=True)
+    up = sb.NNConvUpsampling(32, 1, 3, (20, 26), bias=True)
+    up.load_state_dict(up_o.state_dict())
+    xs = (torch.rand(1, 32, 10, 13) < 0.3).float()
+    with torch.no_grad():
+        torch.testing.assert_close(up.cuda()(xs.cuda()).cpu(), up_o(xs), rtol=1e-5, atol=1e-5)
+    node = sb.neuron.IFNode(v_threshold=float('inf'))
+    node(torch.ones(3, device='cuda'))
+    node(torch.ones(3, device='cuda') * 2)
+    assert torch.equal(node.v.cpu(), torch.full((3,), 3.0))

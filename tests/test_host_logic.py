@@ -1,0 +1,116 @@
+"""CPU: host-side logic of the drop-in modules -- gather tables, weight packing, state-dict compatibility, helpers."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import stereospike_b200 as sb
+from stereospike_b200 import ops
+from oracle import ref_model as rm
+from oracle import sj_compat as sj
+
+PAIRS = [(17, 33), (22, 44), (33, 65), (44, 87), (65, 130), (87, 173), (130, 260), (173, 346)]
+
+
+@pytest.mark.parametrize('n_in,n_out', PAIRS + [(33, 260), (44, 346), (260, 260), (346, 346)])
+@pytest.mark.parametrize('ks', [3, 5])
+def test_upsample_map_matches_aten(n_in, n_out, ks):
+    """The gather table must reproduce torch's nearest-neighbour index rule for every size pair the model uses."""
+    n_up = n_out + ks - 1
+    src = torch.arange(n_in, dtype=torch.float32).view(1, 1, n_in, 1)
+    up = F.interpolate(src, size=(n_up, 1), mode='nearest').view(-1).long().numpy()
+    m = ops.upsample_axis_map(n_in, n_out, ks)
+    assert m.shape == (n_out, ks)
+    for k in range(ks):
+        assert np.array_equal(m[:, k], up[k:k + n_out])
+
+
+def test_conv_map_equals_unfold():
+    m = ops.conv_axis_map(11, ops.conv_out_size(11, 5, 2, 2), 5, 2, 2)
+    assert m.shape == (6, 5)
+    assert list(m[0]) == [-1, -1, 0, 1, 2] and list(m[5]) == [8, 9, 10, -1, -1]
+
+
+def test_maps_reproduce_conv_and_upconv():
+    """conv via (ymap,xmap) gather + [K][Cout] weights == F.conv2d, for both block kinds (pure torch, CPU)."""
+    torch.manual_seed(0)
+    for kind in ('conv', 'upconv'):
+        Cin, Cout, ks = 8, 32, 5
+        x = torch.randn(2, Cin, 9, 11)
+        w = torch.randn(Cout, Cin, ks, ks)
+        if kind == 'conv':
+            ref = F.conv2d(x, w, stride=2, padding=2)
+            Ho, Wo = ref.shape[2:]
+            ym, xm = ops.conv_axis_map(9, Ho, ks, 2, 2), ops.conv_axis_map(11, Wo, ks, 2, 2)
+        else:
+            Ho, Wo = 19, 23
+            ref = F.conv2d(F.interpolate(x, size=(Ho + ks - 1, Wo + ks - 1), mode='nearest'), w)
+            ym, xm = ops.upsample_axis_map(9, Ho, ks), ops.upsample_axis_map(11, Wo, ks)
+        w_kn = ops.weight_to_kn(w)
+        xp = torch.cat([x, torch.zeros(2, Cin, 1, 11)], 2)
+        xp = torch.cat([xp, torch.zeros(2, Cin, 10, 1)], 3)       # index -1 -> the zero row / column
+        cols = []
+        for ky in range(ks):
+            for kx in range(ks):
+                g = xp[:, :, torch.from_numpy(ym[:, ky]).long()][:, :, :, torch.from_numpy(xm[:, kx]).long()]
+                cols.append(g)                                   # [B,Cin,Ho,Wo]
+        A = torch.stack(cols, 1).permute(0, 3, 4, 1, 2).reshape(2 * Ho * Wo, ks * ks * Cin)
+        got = (A @ w_kn).reshape(2, Ho, Wo, Cout).permute(0, 3, 1, 2)
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+        assert torch.equal(ops.kn_to_weight(w_kn, Cout, Cin, ks), w)
+
+
+@pytest.mark.parametrize('cls,kw,variant,mono', [
+    (sb.StereoSpike, dict(multiply_factor=5.0), 'if', False),
+    (sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike, dict(use_plif=True, tau=3.0), 'plif', False),
+    (sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike, dict(use_plif=False, tau=3.0), 'lif', False),
+    (sb.fromZero_feedforward_multiscale_tempo_monocular_SpikeFlowNetLike, dict(use_plif=False, tau=3.0), 'lif', True)])
+def test_state_dict_is_interchangeable_with_reference_layout(cls, kw, variant, mono):
+    net = cls(**kw)
+    oracle = rm.SpikingUNet(variant, mono, tau=3.0)
+    sd_o, sd_n = oracle.state_dict(), net.state_dict()
+    assert list(sd_o) == list(sd_n)
+    for k in sd_o:
+        assert sd_o[k].shape == sd_n[k].shape, k
+    net.load_state_dict(sd_o)
+    oracle.load_state_dict(net.state_dict())
+    assert net.count_trainable_params() == sum(p.numel() for p in oracle.parameters())
+
+
+def test_constructor_quirks_match_reference():
+    # SNN_models.py:71-72: StereoSpike never forwards v_threshold / v_reset
+    n = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), v_threshold=0.5, v_reset=0.3)
+    assert n.bottom[2].v_threshold == 1.0 and n.bottom[2].v_reset == 0.0
+    # blocks.py:142: bottleneck neurons silently use the default Sigmoid surrogate
+    assert isinstance(n.bottleneck[0].sn1.surrogate_function, sb.surrogate.Sigmoid)
+    assert isinstance(n.bottom[2].surrogate_function, sb.surrogate.ATan)
+    assert n.Ineurons.v_threshold == float('inf')
+    m = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=False, tau=3.0)
+    assert isinstance(m.conv1[2], sb.neuron.LIFNode) and isinstance(m.bottleneck[1].sn2, sb.neuron.ParametricLIFNode)
+    assert float(m.bottleneck[0].sn1.w) == pytest.approx(float(sj.ParametricLIFNode(3.0).w))
+
+
+def test_reset_and_state_helpers():
+    n = sb.StereoSpike()
+    nodes = [m for m in n.modules() if hasattr(m, 'reset')]
+    assert len(nodes) == 14                       # 13 spiking layers + the I-neuron pool
+    n.conv1[2].v = torch.ones(1, 64, 130, 173)
+    n.set_init_depths_potentials(torch.full((1, 1, 260, 346), 2.0))
+    assert len(n.get_network_state()) == 14
+    sb.functional.reset_net(n)
+    assert n.conv1[2].v == 0.0 and n.Ineurons.v == 0.0
+    n.increment_epoch()
+    n.update_max_accuracy(0.5)
+    assert n.epoch == 1 and n.get_max_accuracy() == 0.5
+
+
+def test_engine_wiring():
+    e = sb.StereoSpike().engine
+    assert [s.name for s in e.sites] == ['bottom', 'conv1', 'conv2', 'conv3', 'conv4', 'bottleneck.0.conv1',
+                                         'bottleneck.0.conv2', 'bottleneck.1.conv1', 'bottleneck.1.conv2', 'deconv4',
+                                         'deconv3', 'deconv2', 'deconv1']
+    assert [(s.src, s.resid) for s in e.sites[-4:]] == [('out_rconv', 'out_conv3'), ('out_add4', 'out_conv2'),
+                                                        ('out_add3', 'out_conv1'), ('out_add2', 'out_bottom')]
+    g = e.sites[-1].geom(130, 173)
+    assert (g.Hout, g.Wout, g.K) == (260, 346, 1600)
+    assert [h.src for h in e.heads] == ['out_add4', 'out_add3', 'out_add2', 'out_add1']

@@ -102,7 +102,12 @@ extern "C" int ss_pack_weights_umma(const float* w_kn, int32_t K, int32_t Cout, 
 extern "C" int ss_conv_neuron_fwd(const ss_conv_geom* g, const void* x, const int32_t* ymap, const int32_t* xmap,
                                   const float* w_kn, const void* w_umma, const float* decay, const float* v_in,
                                   float* v_out, const void* resid, void* out, float* h_seq, void* stream) {
-    if (g == nullptr || x == nullptr || ymap == nullptr || xmap == nullptr || out == nullptr) {
+    if (g == nullptr) {
+        set_error("ss_conv_neuron_fwd: null geometry");
+        return SS_EINVAL;
+    }
+    if (g->T == 0 || g->B == 0) return SS_OK;  // empty batch / sequence: nothing to do (empty tensors have null pointers)
+    if (x == nullptr || ymap == nullptr || xmap == nullptr || out == nullptr) {
         set_error("ss_conv_neuron_fwd: null argument");
         return SS_EINVAL;
     }
@@ -123,7 +128,6 @@ extern "C" int ss_conv_neuron_fwd(const ss_conv_geom* g, const void* x, const in
         set_error("ss_conv_neuron_fwd: LIF needs tau > 1");
         return SS_EINVAL;
     }
-    if (g->T == 0 || g->B == 0) return SS_OK;  // empty batch / sequence: nothing to do
     ConvParams p;
     p.T = g->T; p.B = g->B; p.Hin = g->Hin; p.Win = g->Win; p.Cin = g->Cin;
     p.Hout = g->Hout; p.Wout = g->Wout; p.Cout = g->Cout; p.ks = g->ks;

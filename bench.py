@@ -155,7 +155,7 @@ def run_reference(args):
 def workload_config(args, per_gpu_B):
     return {'workload': f'StereoSpike spiking U-Net forward (fused conv+{args.neuron.upper()} blocks + heads/I-neurons), '
                         f'binocular 4x{H0}x{W0} event frames, T={args.T}, batch {per_gpu_B} per GPU, fp32-parity inference '
-                        f'(bf16 spikes x {args.planes} bf16 weight planes, fp32 accumulate)',
+                        f'(u8 spikes x {args.planes} int8 weight digit planes on the int8 tensor cores, exact s32 accumulate, one fp32 rounding)',
             'neuron': args.neuron, 'T': args.T, 'batch_per_gpu': per_gpu_B, 'global_batch': per_gpu_B * args.gpus,
             'weight_planes': args.planes, 'multiply_factor': args.gain, 'tau': args.tau,
             'l2': f'rotating {args.input_sets} input sets per step; per-step activation stream (~2 GB) exceeds the 126 MB L2',
@@ -254,18 +254,18 @@ def run_ours(args):
         frames = B * T * world
         value = frames * args.steps / (ms / 1e3)
         e2e_val = frames * args.steps / (ms_e2e / 1e3)
-        umma_sites = [k for k in per_site if k not in ('bottom', 'heads')]
+        umma_sites = [k for k in per_site if k != 'heads']
         umma_ms = sum(statistics.mean(per_site[k]) for k in umma_sites)
         umma_gflop = sum(MFLOP_PER_FRAME[k] for k in umma_sites) / 1e3 * B * T
         ach = umma_gflop / umma_ms if umma_ms > 0 else 0.0      # GFLOP/ms == TFLOP/s
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get('conv_neuron_umma_bytes_per_launch')
+            traffic = json.load(open(tp)).get('conv_i8_bytes_per_launch')
         line = {
             'metric': 'event-frames/sec', 'value': value, 'unit': 'event-frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16 spikes x bf16 weight planes, f32 accumulate', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'u8 x s8 -> s32 (tcgen05 kind::i8), fp32 neuron state', 'data': 'synthetic',
             'config': workload_config(args, B),
             'e2e': {'value': e2e_val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': xs_host[0].numel() * 4,
                     'd2h_bytes_per_step': depth_host.numel() * 4, 'ms_per_step': ms_e2e / args.steps},
@@ -273,7 +273,7 @@ def run_ours(args):
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                          'frac': ach / peaks['bf16_sustained'], 'traffic': traffic,
-                         'kernel': 'conv_neuron_umma_kernel (12 launches/step: conv1-4, bottleneck x4, deconv4-1)',
+                         'kernel': 'conv_i8_kernel (13 launches/step: bottom, conv1-4, bottleneck x4, deconv4-1)',
                          'peak_source': peaks['source'] + ' sustained bf16 (MEASURED_PEAKS.json)',
                          'algorithmic_gflop_per_step': umma_gflop, 'kernel_ms_per_step': umma_ms,
                          'executed_flop_factor': args.planes,

@@ -12,10 +12,13 @@
  * ss_last_error() returns a thread-local description of the last failure.
  *
  * Data layout in HBM
- *   spikes / activations : bf16, [T][B][H][W][C]  (timestep-major NHWC; values are small integers
- *                          {0..3} -- exact in bf16)
+ *   spikes / activations : u8,   [T][B][H][W][C]  (timestep-major NHWC; values are small non-negative
+ *                          integers: spikes {0,1}, spike sums {0..3}, event counts {0..255} -- exact)
  *   first-layer input    : fp32, [B][T][C][H][W]  (the reference's own NCHW event-count frames,
- *                          train.py:201-218), read directly by the first block
+ *                          train.py:201-218); ss_pack_events turns it into u8 [T][B][H][W][32] for the
+ *                          tensor-core path, the SIMT path reads it directly
+ *   weights              : fp32 OIHW as in the reference's state dict; ss_pack_weights_i8 derives the
+ *                          int8 digit planes + per-channel power-of-two scale the tensor-core path uses
  *   membrane potentials  : fp32, [B][H][W][C]
  *   pre-reset potentials : fp32, [T][B][H][W][C]  (optional, saved for the surrogate backward)
  *   depth (I-neurons)    : fp32, [B][H][W]
@@ -30,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 1
+#define SS_ABI_VERSION 2
 
 /* error codes */
 #define SS_OK 0
@@ -50,14 +53,64 @@ extern "C" {
 #define SS_SURR_SIGMOID 1
 
 /* input layouts of ss_conv_neuron_fwd */
-#define SS_IN_BF16_TBHWC 0
+#define SS_IN_U8_TBHWC 0
 #define SS_IN_F32_BTCHW 1
 
 /* implementations */
 #define SS_IMPL_AUTO 0
 #define SS_IMPL_SIMT 1      /* fp32 CUDA-core implicit GEMM (exact fp32 weights) */
-#define SS_IMPL_UMMA 2      /* tcgen05 tensor-core implicit GEMM, bf16 weight planes, fp32 TMEM accumulate */
+#define SS_IMPL_UMMA 2      /* tcgen05 tensor-core implicit GEMM (ss_conv_i8_fwd) */
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused spiking block on the tensor cores (the hot path).
+ * Replaces  nn.Sequential(Conv2d(bias=False) | NNConvUpsampling, MultiplyBy, neuron)  called once per
+ * timestep (network/SNN_models.py:75-129, network/blocks.py:110-132,145-157) and, through `resid`, the
+ * skip additions (SNN_models.py:171,176,181,186) and the SEW 'ADD' connect (blocks.py:170-171).
+ * All T timesteps run in ONE launch; the membrane potential stays in registers across the time loop. */
+typedef struct ss_block_desc {
+    int32_t T, B;
+    int32_t Hin, Win, Cin;       /* source activation, u8 [T][B][Hin][Win][Cin], Cin % 32 == 0 */
+    int32_t Hout, Wout, Cout;    /* block output,     u8 [T][B][Hout][Wout][Cout], Cout % 32 == 0 */
+    int32_t ks;                  /* 3 or 5 */
+    int32_t stride;              /* 1 or 2 (2: ks 5, even pad) */
+    int32_t pad;                 /* zero padding of the plain conv; ignored when upsample != 0 */
+    int32_t upsample;            /* != 0: NNConvUpsampling -- nearest-neighbour upsample of the source to
+                                    (Hout+ks-1, Wout+ks-1) (ATen index rule) followed by a valid conv */
+    int32_t neuron;              /* SS_NEURON_* */
+    int32_t planes;              /* int8 digit planes per weight: 2 (16-bit), 3 (24-bit, fp32-class), 4 (32-bit) */
+    float gain;                  /* MultiplyBy scalar, applied to the conv result (blocks.py:106-107) */
+    float v_th, v_reset, tau;
+} ss_block_desc;
+
+/* channel-block bytes the kernel will use for (Cin, ks); ss_pack_weights_i8 uses the same rule */
+int ss_conv_i8_rowbytes(int32_t Cin, int32_t ks);
+
+/* fp32 OIHW weights -> `planes` balanced base-256 digit planes of a per-output-channel power-of-two fixed
+ * point, laid out [Cout/32][Cin/RB][ks*ks][planes*32][RB] and pre-swizzled as the kernel wants them in shared
+ * memory (Cout*Cin*ks*ks*planes bytes).  wscale[n] = 2^wexp[n]:  w[n][...] ~= wscale[n] * sum_p digit_p * 256^(planes-1-p),
+ * absolute error <= wscale[n] / 2. */
+int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, void* w_i8,
+                       float* wscale, int32_t* wexp, void* stream);
+
+/* fp32 [B][T][C][H][W] event-count frames (C <= 4) -> u8 [T][B][H][W][32] (channels >= C zero).  Counts are
+ * rounded and clamped to 0..255; if any input is not already such an integer, bit 0 of *status (device int,
+ * may be NULL) is set. */
+int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw32,
+                   int32_t* status, void* stream);
+
+/*   x      : u8 [T][B][Hin][Win][Cin]
+ *   w_i8, wscale : from ss_pack_weights_i8 (same Cout, Cin, ks, planes)
+ *   decay  : device scalar, PLIF only (sigmoid(w))
+ *   v_in   : fp32 [B][Hout][Wout][Cout] initial membrane potential or NULL (= v_reset); v_out: final potential or NULL
+ *   resid  : u8 [T][B][Hout][Wout][Cout] added to the spikes before they are written, or NULL
+ *   out    : u8 [T][B][Hout][Wout][Cout]
+ *   h_seq  : fp32 [T][B][Hout][Wout][Cout] pre-reset potential h_t (for the backward), or NULL */
+int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, const float* wscale, const float* decay,
+                   const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Same block on the CUDA cores in plain fp32 (exact fp32 weights, ascending-k accumulation): the first-layer
+ * path for non-integer inputs and the on-device cross-check of the tensor-core path. */
 typedef struct ss_conv_geom {
     int32_t T, B;
     int32_t Hin, Win, Cin;       /* source activation */
@@ -65,39 +118,29 @@ typedef struct ss_conv_geom {
     int32_t ks;                  /* taps per axis; GEMM K = ks*ks*Cin, k = (ky*ks+kx)*Cin + c */
     int32_t in_layout;           /* SS_IN_* */
     int32_t neuron;              /* SS_NEURON_* */
-    int32_t impl;                /* SS_IMPL_* */
-    float gain;                  /* MultiplyBy scalar, applied to the conv result (blocks.py:106-107) */
+    int32_t reserved0;
+    float gain;                  /* MultiplyBy scalar */
     float v_th, v_reset, tau;
-    int32_t weight_planes;       /* UMMA: number of bf16 planes per weight (1 = bf16, 2, 3 = fp32-exact split) */
-    int32_t reserved;
+    int32_t reserved1, reserved2;
 } ss_conv_geom;
 
-/* Fused spiking block, forward, all T timesteps in one launch.
- * Replaces  nn.Sequential(Conv2d(bias=False) | NNConvUpsampling, MultiplyBy, neuron)  called once per
- * timestep (network/SNN_models.py:75-129, network/blocks.py:110-132,145-157) and, through `resid`, the
- * skip additions (SNN_models.py:171,176,181,186) and the SEW 'ADD' connect (blocks.py:170-171).
- *
- *   ymap [Hout*ks], xmap [Wout*ks] : source row / column read by output row oy at tap ky (resp. ox, kx),
+/*   ymap [Hout*ks], xmap [Wout*ks] : source row / column read by output row oy at tap ky (resp. ox, kx),
  *                                    or -1 for a zero-padded tap.  One table pair expresses strided
  *                                    zero-padded convs and the nearest-neighbour-upsampled valid convs.
- *   w_kn   : fp32 [K][Cout]                      (SIMT)      k ordered (ky,kx,c)
- *   w_umma : bf16 [planes][Cout][Kpad]           (UMMA)      Kpad = K rounded up to 64, zero padded
- *   decay  : device scalar, PLIF only
- *   v_in   : initial membrane potential or NULL (= v_reset); v_out: final potential or NULL
- *   resid  : bf16 [T][B][Hout][Wout][Cout] added to the spikes before they are written, or NULL
- *   out    : bf16 [T][B][Hout][Wout][Cout]
- *   h_seq  : fp32 pre-reset potential h_t (for the backward), or NULL
- */
+ *   x      : u8 [T][B][Hin][Win][Cin] (SS_IN_U8_TBHWC, Cin % 8 == 0) or fp32 [B][T][Cin][Hin][Win] (SS_IN_F32_BTCHW)
+ *   w_kn   : fp32 [K][Cout], k ordered (ky,kx,c)
+ *   other arguments as ss_conv_i8_fwd */
 int ss_conv_neuron_fwd(const ss_conv_geom* g, const void* x, const int32_t* ymap, const int32_t* xmap,
-                       const float* w_kn, const void* w_umma, const float* decay,
-                       const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,
-                       void* stream);
+                       const float* w_kn, const float* decay, const float* v_in, float* v_out, const void* resid,
+                       void* out, float* h_seq, void* stream);
 
 /* Prediction heads + I-neuron readout, forward, all T timesteps.
  * Replaces  Ineurons(predict_depthK(out_addK))  for K = 4,3,2,1 (SNN_models.py:133-150,172-188):
  * v += gain * (conv3x3(NNupsample(out_addK)) + bias_K), in that order, every timestep.
- *   acts[i], C[i], Hs[i], Ws[i], w[i] (fp32 [9][C]), bias[i] (device scalar), ymap[i] [H*3], xmap[i] [W*3]
- *   for i = 0..3 in execution order (head 4 first).
+ *   acts[i] (u8 [T][B][Hs][Ws][C]), C[i], Hs[i], Ws[i], w[i] (fp32 [9][C]), bias[i] (device scalar),
+ *   ymap[i] [H*3], xmap[i] [W*3] for i = 0..3 in execution order (head 4 first).
+ *   taps[i]: fp32 workspace [T][B][9][Hs][Ws] -- the 9 per-tap channel dots are taken at SOURCE resolution
+ *   (9*Hs*Ws*C MACs instead of 9*H*W*C) and gathered per output pixel; same math up to fp32 reassociation.
  *   v_io   : fp32 [B][H][W] I-neuron potential, updated in place (caller zero-fills / sets the prior)
  *   depths : fp32 [4][B][H][W]; depths[i] = potential right after head i of the LAST timestep
  */
@@ -110,6 +153,7 @@ typedef struct ss_heads_args {
     const float* bias[4];
     const int32_t* ymap[4];
     const int32_t* xmap[4];
+    float* taps[4];
 } ss_heads_args;
 int ss_heads_fwd(const ss_heads_args* a, float* v_io, float* depths, void* stream);
 
@@ -144,14 +188,11 @@ int ss_conv_wgrad(const ss_conv_geom* g, const void* x, const int32_t* ymap, con
 
 /* Backward of ss_heads_fwd (autograd through predict_depthK + the I-neuron running sum).
  *   g_depths fp32 [4][B][H][W]: gradient w.r.t. the four returned depth maps (execution order)
- *   g_acts[i] fp32 [T][B][Hs][Ws][C] accumulated; g_w[i] fp32 [9][C] accumulated; g_bias[i] scalar accumulated
+ *   g_acts[i] fp32 [T][B][Hs][Ws][C] accumulated (acts u8 as in ss_heads_fwd; taps unused); g_w[i] fp32 [9][C] accumulated; g_bias[i] scalar accumulated
  *   bins[i]   fp32 [2][B][Hs][Ws][9] zero-filled workspace
  */
 int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float* const* g_acts, float* const* g_w,
                  float* const* g_bias, float* const* bins, void* stream);
-
-/* Repack weights for the UMMA path: fp32 [K][Cout] -> bf16 [planes][Cout][Kpad] (residual split). */
-int ss_pack_weights_umma(const float* w_kn, int32_t K, int32_t Cout, int32_t planes, void* w_umma, void* stream);
 
 int ss_abi_version(void);
 const char* ss_last_error(void);

@@ -11,12 +11,23 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libstereospike_b200.so')
 
 SS_NEURON_IF, SS_NEURON_LIF, SS_NEURON_PLIF = 0, 1, 2
 SS_SURR_ATAN, SS_SURR_SIGMOID = 0, 1
-SS_IN_BF16_TBHWC, SS_IN_F32_BTCHW = 0, 1
+SS_IN_U8_TBHWC, SS_IN_F32_BTCHW = 0, 1
 SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
-SYMBOLS = ('ss_conv_neuron_fwd', 'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_conv_dgrad', 'ss_conv_wgrad',
-           'ss_heads_bwd', 'ss_pack_weights_umma', 'ss_abi_version', 'ss_last_error', 'ss_launch_count')
+SYMBOLS = ('ss_conv_i8_fwd', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
+           'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
+           'ss_abi_version', 'ss_last_error', 'ss_launch_count')
+
+
+class BlockDesc(ctypes.Structure):
+    _fields_ = [('T', ctypes.c_int32), ('B', ctypes.c_int32),
+                ('Hin', ctypes.c_int32), ('Win', ctypes.c_int32), ('Cin', ctypes.c_int32),
+                ('Hout', ctypes.c_int32), ('Wout', ctypes.c_int32), ('Cout', ctypes.c_int32),
+                ('ks', ctypes.c_int32), ('stride', ctypes.c_int32), ('pad', ctypes.c_int32),
+                ('upsample', ctypes.c_int32), ('neuron', ctypes.c_int32), ('planes', ctypes.c_int32),
+                ('gain', ctypes.c_float), ('v_th', ctypes.c_float), ('v_reset', ctypes.c_float),
+                ('tau', ctypes.c_float)]
 
 
 class ConvGeom(ctypes.Structure):
@@ -24,10 +35,10 @@ class ConvGeom(ctypes.Structure):
                 ('Hin', ctypes.c_int32), ('Win', ctypes.c_int32), ('Cin', ctypes.c_int32),
                 ('Hout', ctypes.c_int32), ('Wout', ctypes.c_int32), ('Cout', ctypes.c_int32),
                 ('ks', ctypes.c_int32), ('in_layout', ctypes.c_int32), ('neuron', ctypes.c_int32),
-                ('impl', ctypes.c_int32),
+                ('reserved0', ctypes.c_int32),
                 ('gain', ctypes.c_float), ('v_th', ctypes.c_float), ('v_reset', ctypes.c_float),
                 ('tau', ctypes.c_float),
-                ('weight_planes', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('reserved1', ctypes.c_int32), ('reserved2', ctypes.c_int32)]
 
 
 class HeadsArgs(ctypes.Structure):
@@ -35,7 +46,7 @@ class HeadsArgs(ctypes.Structure):
                 ('gain', ctypes.c_float),
                 ('C', ctypes.c_int32 * 4), ('Hs', ctypes.c_int32 * 4), ('Ws', ctypes.c_int32 * 4),
                 ('acts', ctypes.c_void_p * 4), ('w', ctypes.c_void_p * 4), ('bias', ctypes.c_void_p * 4),
-                ('ymap', ctypes.c_void_p * 4), ('xmap', ctypes.c_void_p * 4)]
+                ('ymap', ctypes.c_void_p * 4), ('xmap', ctypes.c_void_p * 4), ('taps', ctypes.c_void_p * 4)]
 
 
 class LibraryMissing(RuntimeError):
@@ -56,7 +67,15 @@ def lib():
             'There is no CPU or PyTorch fallback for the stereospike_b200 hot path.')
     L = ctypes.CDLL(LIB_PATH)
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
-    L.ss_conv_neuron_fwd.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 12
+    L.ss_conv_i8_fwd.argtypes = [ctypes.POINTER(BlockDesc)] + [vp] * 10
+    L.ss_conv_i8_fwd.restype = ctypes.c_int
+    L.ss_conv_i8_rowbytes.argtypes = [i32, i32]
+    L.ss_conv_i8_rowbytes.restype = ctypes.c_int
+    L.ss_pack_weights_i8.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.ss_pack_weights_i8.restype = ctypes.c_int
+    L.ss_pack_events.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.ss_pack_events.restype = ctypes.c_int
+    L.ss_conv_neuron_fwd.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 11
     L.ss_conv_neuron_fwd.restype = ctypes.c_int
     L.ss_heads_fwd.argtypes = [ctypes.POINTER(HeadsArgs), vp, vp, vp]
     L.ss_heads_fwd.restype = ctypes.c_int
@@ -70,8 +89,6 @@ def lib():
     L.ss_conv_dgrad.restype = ctypes.c_int
     L.ss_conv_wgrad.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 6
     L.ss_conv_wgrad.restype = ctypes.c_int
-    L.ss_pack_weights_umma.argtypes = [vp, i32, i32, i32, vp, vp]
-    L.ss_pack_weights_umma.restype = ctypes.c_int
     L.ss_abi_version.restype = ctypes.c_int
     L.ss_last_error.restype = ctypes.c_char_p
     L.ss_launch_count.restype = ctypes.c_int64

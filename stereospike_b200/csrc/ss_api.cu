@@ -30,20 +30,6 @@ int check_launch(const char* what) {
 
 namespace {
 
-__global__ void pack_weights_umma_kernel(const float* __restrict__ w_kn, int K, int Cout, int Kpad, int planes,
-                                         __nv_bfloat16* __restrict__ out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)Cout * Kpad) return;
-    const int n = (int)(idx / Kpad);
-    const int k = (int)(idx - (long long)n * Kpad);
-    float r = (k < K) ? w_kn[(size_t)k * Cout + n] : 0.0f;
-    for (int pl = 0; pl < planes; ++pl) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(r);
-        out[((size_t)pl * Cout + n) * Kpad + k] = h;
-        r = r - __bfloat162float(h);  // exact: the residual of a round-to-nearest split is representable
-    }
-}
-
 // Stand-alone neuron layer (the reference calls IFNode directly for its I-neuron pool, SNN_models.py:150,172).
 __global__ void __launch_bounds__(256) neuron_fwd_kernel(int T, long long N, int neuron, float v_th, float v_reset, float tau,
                                                          const float* __restrict__ decay_p, const float* __restrict__ x,
@@ -85,23 +71,9 @@ extern "C" int ss_abi_version(void) { return SS_ABI_VERSION; }
 extern "C" const char* ss_last_error(void) { return g_err; }
 extern "C" int64_t ss_launch_count(void) { return (int64_t)g_launches.load(); }
 
-extern "C" int ss_pack_weights_umma(const float* w_kn, int32_t K, int32_t Cout, int32_t planes, void* w_umma,
-                                    void* stream) {
-    if (w_kn == nullptr || w_umma == nullptr || K <= 0 || Cout <= 0 || planes < 1 || planes > 3) {
-        set_error("ss_pack_weights_umma: bad argument");
-        return SS_EINVAL;
-    }
-    const int Kpad = (K + 63) / 64 * 64;
-    const long long n = (long long)Cout * Kpad;
-    pack_weights_umma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        w_kn, K, Cout, Kpad, planes, reinterpret_cast<__nv_bfloat16*>(w_umma));
-    count_launch();
-    return check_launch("pack_weights_umma");
-}
-
 extern "C" int ss_conv_neuron_fwd(const ss_conv_geom* g, const void* x, const int32_t* ymap, const int32_t* xmap,
-                                  const float* w_kn, const void* w_umma, const float* decay, const float* v_in,
-                                  float* v_out, const void* resid, void* out, float* h_seq, void* stream) {
+                                  const float* w_kn, const float* decay, const float* v_in, float* v_out,
+                                  const void* resid, void* out, float* h_seq, void* stream) {
     if (g == nullptr) {
         set_error("ss_conv_neuron_fwd: null geometry");
         return SS_EINVAL;
@@ -140,21 +112,10 @@ extern "C" int ss_conv_neuron_fwd(const ss_conv_geom* g, const void* x, const in
     p.M = (int)M;
     p.neuron = g->neuron; p.gain = g->gain; p.v_th = g->v_th; p.v_reset = g->v_reset; p.tau = g->tau;
     p.x = x; p.ymap = ymap; p.xmap = xmap; p.w_kn = w_kn; p.decay = decay; p.v_in = v_in; p.v_out = v_out;
-    p.resid = reinterpret_cast<const __nv_bfloat16*>(resid);
-    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.resid = reinterpret_cast<const uint8_t*>(resid);
+    p.out = reinterpret_cast<uint8_t*>(out);
     p.h_seq = h_seq;
 
-    int impl = g->impl;
-    const bool umma_ok = g->in_layout == SS_IN_BF16_TBHWC && (g->Cin % 8) == 0 && (g->Cout % 32) == 0 &&
-                         w_umma != nullptr && g->weight_planes >= 1 && g->weight_planes <= 3;
-    if (impl == SS_IMPL_AUTO) impl = umma_ok ? SS_IMPL_UMMA : SS_IMPL_SIMT;
-    if (impl == SS_IMPL_UMMA) {
-        if (!umma_ok) {
-            set_error("ss_conv_neuron_fwd: geometry/arguments not supported by the UMMA path");
-            return SS_EUNSUPPORTED;
-        }
-        return launch_conv_neuron_umma(p, w_umma, g->weight_planes, (cudaStream_t)stream);
-    }
     if (w_kn == nullptr) {
         set_error("ss_conv_neuron_fwd: SIMT path needs w_kn");
         return SS_EINVAL;

@@ -184,9 +184,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvParams p, con
                 const int sy = __ldg(p.ymap + oy * p.ks + ky);
                 const int sx = __ldg(p.xmap + ox * p.ks + kx);
                 if (sy >= 0 && sx >= 0) {
-                    if (IN_LAYOUT == SS_IN_BF16_TBHWC)
-                        a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
-                            p.x)[((((size_t)t * p.B + b) * p.Hin + sy) * p.Win + sx) * p.Cin + c]);
+                    if (IN_LAYOUT == SS_IN_U8_TBHWC)
+                        a = (float)reinterpret_cast<const uint8_t*>(
+                            p.x)[((((size_t)t * p.B + b) * p.Hin + sy) * p.Win + sx) * p.Cin + c];
                     else
                         a = __ldg(reinterpret_cast<const float*>(p.x) +
                                   ((((size_t)b * p.T + t) * p.Cin + c) * p.Hin + sy) * p.Win + sx);
@@ -229,7 +229,7 @@ struct HeadsBwdParams {
     int T, B, H, W;
     float gain;
     int C[4], Hs[4], Ws[4];
-    const __nv_bfloat16* acts[4];
+    const uint8_t* acts[4];
     const float* w[4];
     const int* ymap[4];
     const int* xmap[4];
@@ -317,14 +317,12 @@ __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, 
             any |= bn[k] != 0.0f;
         }
         const size_t eo = ((size_t)t * S + s) * C + c0;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.acts[head] + eo));
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + eo));
         float a[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(h2[e]);
-            a[2 * e] = f.x;
-            a[2 * e + 1] = f.y;
+            a[e] = (float)((raw.x >> (8 * e)) & 0xFFu);
+            a[4 + e] = (float)((raw.y >> (8 * e)) & 0xFFu);
         }
         float ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (any) {
@@ -429,8 +427,8 @@ extern "C" int ss_conv_wgrad(const ss_conv_geom* g, const void* x, const int32_t
         return SS_EINVAL;
     }
     dim3 grid((p.K + WG_BK - 1) / WG_BK, (p.Cout + WG_BN - 1) / WG_BN, (unsigned)splits);
-    if (g->in_layout == SS_IN_BF16_TBHWC)
-        conv_wgrad_kernel<SS_IN_BF16_TBHWC><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g_acc, g_w, (int)rows);
+    if (g->in_layout == SS_IN_U8_TBHWC)
+        conv_wgrad_kernel<SS_IN_U8_TBHWC><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g_acc, g_w, (int)rows);
     else
         conv_wgrad_kernel<SS_IN_F32_BTCHW><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g_acc, g_w, (int)rows);
     count_launch();
@@ -451,7 +449,7 @@ extern "C" int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float
             return SS_EINVAL;
         }
         p.C[i] = a->C[i]; p.Hs[i] = a->Hs[i]; p.Ws[i] = a->Ws[i];
-        p.acts[i] = reinterpret_cast<const __nv_bfloat16*>(a->acts[i]);
+        p.acts[i] = reinterpret_cast<const uint8_t*>(a->acts[i]);
         p.w[i] = a->w[i]; p.ymap[i] = a->ymap[i]; p.xmap[i] = a->xmap[i];
         p.g_acts[i] = g_acts[i]; p.g_w[i] = g_w[i]; p.g_bias[i] = g_bias[i]; p.bins[i] = bins[i];
     }

@@ -1,6 +1,5 @@
 // Shared declarations for the stereospike_b200 CUDA sources (sm_100a only).
 #pragma once
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,8 +20,8 @@ struct ConvParams {
     const float* decay;
     const float* v_in;
     float* v_out;
-    const __nv_bfloat16* resid;
-    __nv_bfloat16* out;
+    const uint8_t* resid;
+    uint8_t* out;
     float* h_seq;
 };
 
@@ -31,7 +30,6 @@ void count_launch(int n = 1);
 int check_launch(const char* what);
 
 int launch_conv_neuron_simt(const ConvParams& p, int in_layout, cudaStream_t st);
-int launch_conv_neuron_umma(const ConvParams& p, const void* w_umma, int planes, cudaStream_t st);
 
 // One neuron step (SpikingJelly BaseNode.forward: charge -> fire -> hard reset), fp32.
 // Returns the spike (0/1); v is updated in place; h_out receives the pre-reset potential.

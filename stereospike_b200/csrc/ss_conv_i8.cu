@@ -1,0 +1,827 @@
+// tcgen05 (5th-gen tensor core) implementation of the fused spiking block for sm_100a -- integer edition.
+//
+// Replaces: Conv2d / NNConvUpsampling -> MultiplyBy -> IF/LIF/PLIF node, once per timestep, plus the skip / SEW
+// additions (reference network/SNN_models.py:75-129,171-186; network/blocks.py:110-132,145-171).
+//
+// Arithmetic.  Every conv input on this path is a small non-negative integer (spikes {0,1}, spike sums {0..3},
+// event counts), so activations live in HBM as u8 NHWC and are EXACT.  fp32 weights are converted once to
+// `planes` signed base-256 digits of a per-output-channel power-of-two fixed point (3 planes = 24 bits).  The
+// contraction runs on the tensor cores as  u8 x s8 -> s32  (tcgen05.mma kind::i8, twice the bf16 MAC rate), one
+// accumulator column block per digit plane stacked along the MMA N dimension; integer accumulation is exact and
+// order independent, the epilogue recombines the planes in 64-bit arithmetic and rounds ONCE to fp32.  The result
+// is the correctly rounded dot product of the quantised weights -- closer to the exact value than any fp32
+// summation order, deterministic, and independent of the tiling.
+//
+// Data movement (implicit GEMM without im2col re-reads).  A CTA owns an output tile of 16 rows x 8 columns
+// (M = 128) x 32 output channels.  For each 32/64-channel block of the input the producer warps gather the tile's
+// receptive field ONCE into shared memory as a swizzled "halo patch" ([patch pixel][channel block], one swizzle
+// row per pixel); every tap (ky,kx) of the filter is then just a different START ADDRESS of the same patch in the
+// MMA's shared-memory descriptor (8-row groups = 8 consecutive pixels of one output row, stride-byte-offset = one
+// patch row), so each input byte is fetched from L2 once per tile instead of ks*ks times.  Zero padding is
+// zero-filled cp.async; stride 2 is a parity-split patch row (even | odd columns) with a 2-row group stride; the
+// nearest-neighbour upsampling of the decoder is a gather table (the upsampled tensor is never materialised);
+// the batch is stacked vertically so tiles straddle images and the 17x22 / 33x44 layers waste < 15 % of a tile.
+//
+// Time loop.  Weights dominate the traffic of the deep layers, so the T timesteps of a tile are processed against
+// each weight block while it is resident: TMEM holds up to 512 / (planes*32) accumulator slots, one per timestep.
+// The epilogue warps then run the neuron recurrence over those slots with the membrane potential in REGISTERS
+// (it never touches HBM between timesteps), add the residual and store u8 spikes.  Layers whose weights fit in
+// shared memory (<= 2 channel blocks) keep them resident across tiles and pipeline MMA(t+1) with epilogue(t).
+//
+// Warp roles (mbarrier pipelines, no __syncthreads in the steady state):
+//   warps 0-3  patch producers (cp.async gather, zero fill)     warp 4  MMA issuer (one lane), owns TMEM
+//   warp 5     weight producer (cp.async.bulk of pre-swizzled images)      warps 8-15  epilogue (TMEM -> neuron -> HBM)
+#include <cuda.h>
+
+#include "ss_common.cuh"
+
+namespace ss {
+namespace {
+
+constexpr int NWB = 2;        // weight buffers
+constexpr int MAXPP = 6;      // patch pixels per producer thread (700 / 128 rounded up)
+constexpr int LAG = 2;        // cp.async groups in flight per producer thread
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_SLOTS = 8;
+constexpr int THREADS = 512;
+
+struct I8Params {
+    int T, B, Hin, Win, Cin, Hout, Wout, Cout;
+    int ks, stride, pad, upsample;
+    int N;                 // planes * 32
+    int RB, ncb, ntaps;
+    int PH, PWp, PWhalf, ppix;
+    int HsO, Hup, Wup;
+    int tiles_x, mtiles, nitems;
+    int TC, NPS, WB, PB;
+    int resident;
+    float yscale, xscale;
+    int neuron;
+    float gain, v_th, v_reset, tau;
+    const uint8_t* x;
+    const int8_t* w;
+    const float* wscale;
+    const float* decay;
+    const float* v_in;
+    float* v_out;
+    const uint8_t* resid;
+    uint8_t* out;
+    float* h_seq;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major shared-memory matrix descriptor (sm_100 "version 1").  Rows are `RB` bytes (one swizzle row each); the
+// swizzle (32B / 64B / 128B, = RB) is applied by the hardware on ABSOLUTE shared-memory address bits, so the start
+// address may point at any row of a patch (probe: tools/umma_probe_i8.cu).  sbo = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t swizzle_off(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
+
+// ------------------------------------------------------------------------------------------------ geometry
+// Source row (b*Hin + iy) read by patch row `pr` of tile row `ty`, or -1 (zero padding / gap between stacked images).
+__device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr) {
+    const int gi = ty * 16 * p.stride + pr;
+    const int per = p.stride * p.HsO;
+    const int b = gi / per;
+    if (b >= p.B) return -1;
+    const int local = gi - b * per;
+    if (p.upsample) {
+        if (local >= p.Hup) return -1;
+        // ATen upsample_nearest: min(int(floorf(dst * scale)), in - 1), scale = float(in) / out
+        const int iy = min((int)floorf((float)local * p.yscale), p.Hin - 1);
+        return b * p.Hin + iy;
+    }
+    const int iy = local - p.pad;
+    return (iy >= 0 && iy < p.Hin) ? b * p.Hin + iy : -1;
+}
+__device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
+    if (p.upsample) {
+        const int u = tx * 8 + pc;
+        if (u >= p.Wup) return -1;
+        return min((int)floorf((float)u * p.xscale), p.Win - 1);
+    }
+    int ix;
+    if (p.stride == 1) {
+        ix = tx * 8 + pc - p.pad;
+    } else {
+        // parity-split row: [even-type columns | odd-type columns]; input col = 2*(ox0 - pad/2 + idx) + plane
+        const int plane = pc / p.PWhalf;
+        const int idx = pc - plane * p.PWhalf;
+        ix = 2 * (tx * 8 - p.pad / 2 + idx) + plane;
+    }
+    return (ix >= 0 && ix < p.Win) ? ix : -1;
+}
+// patch pixel at which the A operand of tap (ky,kx) starts
+__device__ __forceinline__ int tap_offset(const I8Params& p, int ky, int kx) {
+    if (p.stride == 1) return ky * p.PWp + kx;
+    return ky * p.PWp + (kx & 1) * p.PWhalf + (kx >> 1);
+}
+
+template <int PLANES>
+__global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_addr);
+
+    const uint32_t w_base = base;
+    const uint32_t patch_base = base + NWB * p.WB;
+    uint8_t* tail = sm + (size_t)NWB * p.WB + (size_t)p.NPS * p.PB;
+    int* rowsrc = reinterpret_cast<int*>(tail);              // [2][40]
+    int* colsrc = rowsrc + 80;                               // [2][24]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
+    // bars: full_p[8], empty_p[8], full_w[2], empty_w[2], full_a[8], empty_a[8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t bar_full_p = smem_u32(bars);
+    const uint32_t bar_empty_p = smem_u32(bars + 8);
+    const uint32_t bar_full_w = smem_u32(bars + 16);
+    const uint32_t bar_empty_w = smem_u32(bars + 18);
+    const uint32_t bar_full_a = smem_u32(bars + 20);
+    const uint32_t bar_empty_a = smem_u32(bars + 28);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            mbar_init(bar_full_p + 8 * s, 128);
+            mbar_init(bar_empty_p + 8 * s, 1);
+        }
+        for (int s = 0; s < NWB; ++s) {
+            mbar_init(bar_full_w + 8 * s, 1);
+            mbar_init(bar_empty_w + 8 * s, 1);
+        }
+        for (int s = 0; s < MAX_SLOTS; ++s) {
+            mbar_init(bar_full_a + 8 * s, 1);
+            mbar_init(bar_empty_a + 8 * s, 256);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t swz_mask = (uint32_t)(p.RB >> 4) - 1u;  // 32 -> 1, 64 -> 3, 128 -> 7
+
+    if (warp < 4) {
+        // ================================================================== patch producers
+        const int tid = threadIdx.x;
+        const size_t t_stride = (size_t)p.B * p.Hin * p.Win * p.Cin;
+        const int chunks = p.RB >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int issued = 0, arrive_stage = 0, itcount = 0;
+        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x, ++itcount) {
+            const int ntile = it / p.mtiles;
+            const int mt = it - ntile * p.mtiles;
+            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            int* rs = rowsrc + (itcount & 1) * 40;
+            int* cs = colsrc + (itcount & 1) * 24;
+            if (tid < p.PH) rs[tid] = row_source(p, ty, tid);
+            if (tid >= 64 && tid - 64 < p.PWp) cs[tid - 64] = col_source(p, tx, tid - 64);
+            named_sync(1, 128);
+            int goff[MAXPP];
+#pragma unroll
+            for (int i = 0; i < MAXPP; ++i) {
+                const int pix = tid + i * 128;
+                goff[i] = -2;
+                if (pix < p.ppix) {
+                    const int pr = pix / p.PWp;
+                    const int pc = pix - pr * p.PWp;
+                    const int r = rs[pr], c = cs[pc];
+                    goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * p.Cin : -1;
+                }
+            }
+            for (int t0 = 0; t0 < p.T; t0 += p.TC) {
+                const int tc = min(p.TC, p.T - t0);
+                const int n_outer = p.resident ? tc : p.ncb;
+                const int n_inner = p.resident ? p.ncb : tc;
+                for (int o = 0; o < n_outer; ++o) {
+                    for (int in = 0; in < n_inner; ++in) {
+                        const int cb = p.resident ? in : o;
+                        const int t = t0 + (p.resident ? o : in);
+                        mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
+                        const uint8_t* xt = p.x + (size_t)t * t_stride + cb * p.RB;
+                        const uint32_t dst0 = patch_base + (uint32_t)stage * p.PB;
+#pragma unroll
+                        for (int i = 0; i < MAXPP; ++i) {
+                            if (goff[i] != -2) {
+                                const uint32_t off = (uint32_t)(tid + i * 128) * p.RB;
+                                const bool ok = goff[i] >= 0;
+                                const uint8_t* src = ok ? xt + goff[i] : p.x;
+                                for (int c = 0; c < chunks; ++c)
+                                    cp_async_16(dst0 + swizzle_off(off + c * 16, swz_mask), ok ? src + c * 16 : src, ok ? 16u : 0u);
+                            }
+                        }
+                        cp_async_commit();
+                        ++issued;
+                        if (issued > LAG) {
+                            cp_async_wait<LAG>();
+                            fence_proxy_async();
+                            mbar_arrive(bar_full_p + 8 * arrive_stage);
+                            if (++arrive_stage == p.NPS) arrive_stage = 0;
+                        }
+                        if (++stage == p.NPS) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        const int pending = issued < LAG ? issued : LAG;
+        for (int i = 0; i < pending; ++i) {
+            mbar_arrive(bar_full_p + 8 * arrive_stage);
+            if (++arrive_stage == p.NPS) arrive_stage = 0;
+        }
+    } else if (warp == 4) {
+        // ================================================================== MMA issuer
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t layout = p.RB == 128 ? 2u : (p.RB == 64 ? 4u : 6u);
+        const uint32_t a_sbo = (uint32_t)(p.stride * p.PWp * p.RB);
+        const uint32_t b_sbo = (uint32_t)(8 * p.RB);
+        const int ksteps = p.RB >> 5;
+        const uint32_t tap_bytes = (uint32_t)(p.N * p.RB);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t slot_phase = 0;   // bit s: parity to wait on empty_a[s] (starts "free")
+        uint32_t wu = 0;           // streaming: weight-use counter;  resident: number of loads done
+        int loaded_ntile = -1;
+        uint32_t w_pending = 0;    // resident: bit cb set while full_w[cb] has not been observed for the current load
+
+        auto do_stage = [&](int wbuf, int slot, bool first) {
+            mbar_wait(bar_full_p + 8 * stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t a0 = make_desc(patch_base + (uint32_t)stage * p.PB, a_sbo, layout);
+                const uint64_t b0 = make_desc(w_base + (uint32_t)wbuf * p.WB, b_sbo, layout);
+                const uint32_t d = tmem_base + (uint32_t)(slot * p.N);
+                int tap = 0;
+                for (int ky = 0; ky < p.ks; ++ky) {
+                    for (int kx = 0; kx < p.ks; ++kx, ++tap) {
+                        const uint32_t aoff = (uint32_t)tap_offset(p, ky, kx) * p.RB;
+                        const uint32_t boff = (uint32_t)tap * tap_bytes;
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_i8(d, a0 + ((aoff + k * 32) >> 4), b0 + ((boff + k * 32) >> 4), idesc,
+                                    (first && tap == 0 && k == 0) ? 0u : 1u);
+                    }
+                }
+                umma_commit(bar_empty_p + 8 * stage);
+            }
+            __syncwarp();
+            if (++stage == p.NPS) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        };
+
+        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+            const int ntile = it / p.mtiles;
+            if (p.resident && ntile != loaded_ntile) {
+                loaded_ntile = ntile;
+                w_pending = (1u << p.ncb) - 1u;
+                ++wu;
+            }
+            for (int t0 = 0; t0 < p.T; t0 += p.TC) {
+                const int tc = min(p.TC, p.T - t0);
+                if (p.resident) {
+                    for (int s = 0; s < tc; ++s) {
+                        mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                        slot_phase ^= 1u << s;
+                        tc_fence_after();
+                        for (int cb = 0; cb < p.ncb; ++cb) {
+                            if (w_pending & (1u << cb)) {
+                                mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
+                                w_pending &= ~(1u << cb);
+                            }
+                            do_stage(cb, s, cb == 0);
+                        }
+                        if (lane == 0) umma_commit(bar_full_a + 8 * s);
+                        __syncwarp();
+                    }
+                } else {
+                    for (int cb = 0; cb < p.ncb; ++cb) {
+                        const int buf = (int)(wu % NWB);
+                        mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+                        for (int s = 0; s < tc; ++s) {
+                            if (cb == 0) {
+                                mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                                slot_phase ^= 1u << s;
+                                tc_fence_after();
+                            }
+                            do_stage(buf, s, cb == 0);
+                            if (cb == p.ncb - 1) {
+                                if (lane == 0) umma_commit(bar_full_a + 8 * s);
+                                __syncwarp();
+                            }
+                        }
+                        if (lane == 0) umma_commit(bar_empty_w + 8 * buf);
+                        __syncwarp();
+                        ++wu;
+                    }
+                }
+            }
+            if (p.resident) {
+                const int nxt = it + gridDim.x;
+                if (nxt < p.nitems && nxt / p.mtiles != ntile) {
+                    if (lane == 0)
+                        for (int cb = 0; cb < p.ncb; ++cb) umma_commit(bar_empty_w + 8 * cb);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================================================================== weight producer (bulk copies)
+        if (lane == 0) {
+            uint32_t wu = 0;
+            int loaded_ntile = -1;
+            auto load = [&](int buf, int ntile, int cb) {
+                const uint32_t full = bar_full_w + 8 * buf;
+                mbar_arrive_expect_tx(full, (uint32_t)p.WB);
+                const int8_t* src = p.w + (size_t)(ntile * p.ncb + cb) * p.WB;
+                const uint32_t dst = w_base + (uint32_t)buf * p.WB;
+                for (int o = 0; o < p.WB; o += 16384) bulk_load(dst + o, src + o, (uint32_t)min(16384, p.WB - o), full);
+            };
+            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+                const int ntile = it / p.mtiles;
+                if (p.resident) {
+                    if (ntile != loaded_ntile) {
+                        for (int cb = 0; cb < p.ncb; ++cb) {
+                            if (wu > 0) mbar_wait(bar_empty_w + 8 * cb, (wu - 1u) & 1u);
+                            load(cb, ntile, cb);
+                        }
+                        loaded_ntile = ntile;
+                        ++wu;
+                    }
+                } else {
+                    for (int t0 = 0; t0 < p.T; t0 += p.TC) {
+                        for (int cb = 0; cb < p.ncb; ++cb) {
+                            const int buf = (int)(wu % NWB);
+                            if (wu >= NWB) mbar_wait(bar_empty_w + 8 * buf, ((wu / NWB) - 1u) & 1u);
+                            load(buf, ntile, cb);
+                            ++wu;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================================================== epilogue: TMEM -> neuron -> HBM
+        const int ew = warp - 8;
+        const int quarter = ew & 3;   // == warp % 4: the TMEM lanes this warp may touch
+        const int hf = ew >> 2;       // which 16 of the tile's 32 output channels
+        const int m = quarter * 32 + lane;
+        const int g = m >> 3, j = m & 7;
+        const int M = p.B * p.Hout * p.Wout;
+        float decay = 0.0f;
+        if (p.neuron == SS_NEURON_PLIF) decay = __ldg(p.decay);
+        uint32_t slot_phase = 0;
+        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+            const int ntile = it / p.mtiles;
+            const int mt = it - ntile * p.mtiles;
+            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            const int so = ty * 16 + g;
+            const int b = so / p.HsO;
+            const int oy = so - b * p.HsO;
+            const int ox = tx * 8 + j;
+            const bool live = b < p.B && oy < p.Hout && ox < p.Wout;
+            const int nb = ntile * 32 + hf * 16;
+            const size_t pix = live ? ((size_t)(b * p.Hout + oy) * p.Wout + ox) : 0;
+            float sc[16], v[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p.wscale + nb) + i);
+                sc[4 * i] = q.x; sc[4 * i + 1] = q.y; sc[4 * i + 2] = q.z; sc[4 * i + 3] = q.w;
+            }
+            if (p.v_in != nullptr && live) {
+                const float4* vi = reinterpret_cast<const float4*>(p.v_in + pix * p.Cout + nb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 q = __ldg(vi + i);
+                    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = p.v_reset;
+            }
+            for (int t0 = 0; t0 < p.T; t0 += p.TC) {
+                const int tc = min(p.TC, p.T - t0);
+                for (int s = 0; s < tc; ++s) {
+                    const int t = t0 + s;
+                    mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
+                    slot_phase ^= 1u << s;
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * p.N + hf * 16);
+                    int d[PLANES][16];
+#pragma unroll
+                    for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(taddr + pl * 32, d[pl]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_empty_a + 8 * s);   // the slot is in registers now: hand it back to the MMA warp
+                    if (!live) continue;
+                    const size_t o = ((size_t)t * M + pix) * p.Cout + nb;
+                    uint32_t rsd[4] = {0u, 0u, 0u, 0u};
+                    if (p.resid != nullptr) {
+                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.resid + o));
+                        rsd[0] = q.x; rsd[1] = q.y; rsd[2] = q.z; rsd[3] = q.w;
+                    }
+                    uint32_t packed[4] = {0u, 0u, 0u, 0u};
+                    float hbuf[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        // recombine the base-256 digit planes exactly, round once to fp32
+                        float conv;
+                        if (PLANES == 2) {
+                            conv = __int2float_rn(d[0][i] * 256 + d[1][i]);
+                        } else if (PLANES == 3) {
+                            conv = __double2float_rn(fma((double)(d[0][i] * 256 + d[1][i]), 256.0, (double)d[2][i]));
+                        } else {
+                            conv = __double2float_rn(
+                                fma((double)(d[0][i] * 256 + d[1][i]), 65536.0, (double)(d[PLANES - 2][i] * 256 + d[PLANES - 1][i])));
+                        }
+                        conv = __fmul_rn(conv, sc[i]);
+                        float h;
+                        const float s_out = neuron_step(p.neuron, __fmul_rn(conv, p.gain), v[i], p.v_th, p.v_reset, p.tau, decay, h);
+                        hbuf[i] = h;
+                        const uint32_t r8 = (rsd[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+                        const uint32_t o8 = (s_out != 0.0f ? 1u : 0u) + r8;
+                        packed[i >> 2] |= o8 << ((i & 3) * 8);
+                    }
+                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    if (p.h_seq != nullptr) {
+                        float4* hp = reinterpret_cast<float4*>(p.h_seq + o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) hp[i] = make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]);
+                    }
+                }
+            }
+            if (p.v_out != nullptr && live) {
+                float4* vo = reinterpret_cast<float4*>(p.v_out + pix * p.Cout + nb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// per output channel: exponent e such that every |w| * 2^-e fits `planes` balanced base-256 digits
+__global__ void __launch_bounds__(256) weight_exponent_kernel(const float* __restrict__ w, int Cout, int per_out, int planes,
+                                                              float* __restrict__ wscale, int* __restrict__ wexp) {
+    const int n = blockIdx.x;
+    float m = 0.0f;
+    for (int i = threadIdx.x; i < per_out; i += blockDim.x) m = fmaxf(m, fabsf(w[(size_t)n * per_out + i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) m = fmaxf(m, red[i]);
+        int e = 0;
+        if (m > 0.0f) {
+            int ex;
+            frexpf(m, &ex);                    // m = f * 2^ex, f in [0.5, 1)
+            e = ex - (8 * planes - 1);         // |q| < 2^(8*planes-1)
+            // balanced digits carry upwards: the top digit must stay <= 127 for the largest magnitude
+            const long long q = llrint(ldexp((double)m, -e));
+            long long rest = q;
+            for (int pl = planes - 1; pl > 0; --pl) {
+                const long long dgt = ((rest + 128) & 255) - 128;
+                rest = (rest - dgt) >> 8;
+            }
+            if (rest > 127) ++e;
+        }
+        wexp[n] = e;
+        wscale[n] = ldexpf(1.0f, e);
+    }
+}
+
+// [ntile][cb][tap][N = planes x 32 rows][RB bytes], swizzled exactly as it must sit in shared memory
+__global__ void __launch_bounds__(256) weight_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int ks, int planes, int RB,
+                                                          const int* __restrict__ wexp, int8_t* __restrict__ out) {
+    const int ntaps = ks * ks;
+    const int ncb = Cin / RB;
+    const long long total = (long long)Cout * Cin * ntaps;   // one thread per weight
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // decompose idx as (ntile, cb, tap, r32, c)
+    long long r = idx;
+    const int c = (int)(r % RB); r /= RB;
+    const int r32 = (int)(r % 32); r /= 32;
+    const int tap = (int)(r % ntaps); r /= ntaps;
+    const int cb = (int)(r % ncb); r /= ncb;
+    const int ntile = (int)r;
+    const int n = ntile * 32 + r32;
+    const int ch = cb * RB + c;
+    const int ky = tap / ks, kx = tap - ky * ks;
+    const float wv = w[(((size_t)n * Cin + ch) * ks + ky) * ks + kx];   // OIHW
+    long long q = llrint(ldexp((double)wv, -wexp[n]));
+    const int N = planes * 32;
+    const size_t buf = (size_t)(ntile * ncb + cb) * ((size_t)ntaps * N * RB);
+    const uint32_t mask = (uint32_t)(RB >> 4) - 1u;
+    for (int pl = planes - 1; pl >= 0; --pl) {
+        long long dgt;
+        if (pl > 0) {
+            dgt = ((q + 128) & 255) - 128;
+            q = (q - dgt) >> 8;
+        } else {
+            dgt = q;
+        }
+        const uint32_t off = (uint32_t)((tap * N + pl * 32 + r32) * RB + c);
+        out[buf + (off ^ (((off >> 7) & mask) << 4))] = (int8_t)dgt;
+    }
+}
+
+// fp32 NCHW event-count frames [B][T][C][H][W] (reference layout, train.py:201-218) -> u8 NHWC [T][B][H][W][32]
+__global__ void __launch_bounds__(256) pack_events_kernel(const float* __restrict__ x, int B, int T, int C, int H, int W,
+                                                          uint8_t* __restrict__ out, int* __restrict__ status) {
+    const long long HW = (long long)H * W;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)T * B * HW) return;
+    const long long hw = idx % HW;
+    const int b = (int)((idx / HW) % B);
+    const int t = (int)(idx / (HW * B));
+    uint32_t lo = 0;
+    bool bad = false;
+    for (int c = 0; c < C; ++c) {
+        const float f = __ldg(x + (((size_t)b * T + t) * C + c) * HW + hw);
+        const float r = fminf(fmaxf(rintf(f), 0.0f), 255.0f);
+        bad |= (r != f);
+        lo |= (uint32_t)r << (8 * c);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)idx * 32);
+    o[0] = make_uint4(lo, 0u, 0u, 0u);
+    o[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (bad && status != nullptr) atomicOr(status, 1);
+}
+
+int rowbytes_for(int Cin, int ks) { return (ks <= 3 && Cin % 64 == 0) ? 64 : 32; }
+
+}  // namespace
+}  // namespace ss
+
+using namespace ss;
+
+extern "C" int ss_conv_i8_rowbytes(int32_t Cin, int32_t ks) { return rowbytes_for(Cin, ks); }
+
+extern "C" int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, void* w_i8,
+                                  float* wscale, int32_t* wexp, void* stream) {
+    if (w_oihw == nullptr || w_i8 == nullptr || wscale == nullptr || wexp == nullptr || Cout <= 0 || Cin <= 0 || ks <= 0 ||
+        planes < 2 || planes > 4 || Cout % 32 != 0 || Cin % 32 != 0) {
+        set_error("ss_pack_weights_i8: bad argument (Cout %% 32, Cin %% 32, planes 2..4)");
+        return SS_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int RB = rowbytes_for(Cin, ks);
+    weight_exponent_kernel<<<Cout, 256, 0, st>>>(w_oihw, Cout, Cin * ks * ks, planes, wscale, wexp);
+    count_launch();
+    if (check_launch("weight_exponent") != SS_OK) return SS_ECUDA;
+    const long long total = (long long)Cout * Cin * ks * ks;
+    weight_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_oihw, Cout, Cin, ks, planes, RB, wexp,
+                                                                       reinterpret_cast<int8_t*>(w_i8));
+    count_launch();
+    return check_launch("weight_pack");
+}
+
+extern "C" int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw32,
+                              int32_t* status, void* stream) {
+    if (x_btchw == nullptr || out_tbhw32 == nullptr || C <= 0 || C > 4 || B < 0 || T < 0 || H <= 0 || W <= 0) {
+        set_error("ss_pack_events: bad argument (1 <= C <= 4)");
+        return SS_EINVAL;
+    }
+    const long long n = (long long)T * B * H * W;
+    if (n == 0) return SS_OK;
+    pack_events_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_btchw, B, T, C, H, W,
+                                                                                      reinterpret_cast<uint8_t*>(out_tbhw32), status);
+    count_launch();
+    return check_launch("pack_events");
+}
+
+extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, const float* wscale, const float* decay,
+                              const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* stream) {
+    if (g == nullptr) {
+        set_error("ss_conv_i8_fwd: null descriptor");
+        return SS_EINVAL;
+    }
+    if (g->T == 0 || g->B == 0) return SS_OK;
+    if (x == nullptr || w_i8 == nullptr || wscale == nullptr || out == nullptr) {
+        set_error("ss_conv_i8_fwd: null argument");
+        return SS_EINVAL;
+    }
+    if (g->T < 0 || g->B < 0 || g->Hin <= 0 || g->Win <= 0 || g->Hout <= 0 || g->Wout <= 0 || g->Cin <= 0 || g->Cout <= 0) {
+        set_error("ss_conv_i8_fwd: bad geometry");
+        return SS_EINVAL;
+    }
+    if (g->Cin % 32 != 0 || g->Cout % 32 != 0) {
+        set_error("ss_conv_i8_fwd: Cin and Cout must be multiples of 32 (got %d, %d)", g->Cin, g->Cout);
+        return SS_EUNSUPPORTED;
+    }
+    if (g->planes < 2 || g->planes > 4) {
+        set_error("ss_conv_i8_fwd: planes must be 2, 3 or 4");
+        return SS_EINVAL;
+    }
+    if (g->neuron < SS_NEURON_IF || g->neuron > SS_NEURON_PLIF) {
+        set_error("ss_conv_i8_fwd: unknown neuron kind %d", g->neuron);
+        return SS_EINVAL;
+    }
+    if (g->neuron == SS_NEURON_PLIF && decay == nullptr) {
+        set_error("ss_conv_i8_fwd: PLIF needs the decay scalar");
+        return SS_EINVAL;
+    }
+    if (g->neuron == SS_NEURON_LIF && !(g->tau > 1.0f)) {
+        set_error("ss_conv_i8_fwd: LIF needs tau > 1");
+        return SS_EINVAL;
+    }
+    const bool up = g->upsample != 0;
+    if (!(g->ks == 3 || g->ks == 5) || !(g->stride == 1 || g->stride == 2) || (up && g->stride != 1) ||
+        (g->stride == 2 && (g->pad % 2 != 0 || g->ks != 5))) {
+        set_error("ss_conv_i8_fwd: unsupported conv shape (ks %d stride %d pad %d upsample %d)", g->ks, g->stride, g->pad, g->upsample);
+        return SS_EUNSUPPORTED;
+    }
+    I8Params p;
+    p.T = g->T; p.B = g->B; p.Hin = g->Hin; p.Win = g->Win; p.Cin = g->Cin;
+    p.Hout = g->Hout; p.Wout = g->Wout; p.Cout = g->Cout;
+    p.ks = g->ks; p.stride = g->stride; p.pad = up ? 0 : g->pad; p.upsample = up ? 1 : 0;
+    if (!up) {
+        const int ho = (g->Hin + 2 * g->pad - g->ks) / g->stride + 1, wo = (g->Win + 2 * g->pad - g->ks) / g->stride + 1;
+        if (ho != g->Hout || wo != g->Wout) {
+            set_error("ss_conv_i8_fwd: Hout/Wout (%d,%d) do not match the conv geometry (%d,%d)", g->Hout, g->Wout, ho, wo);
+            return SS_EINVAL;
+        }
+    }
+    p.N = g->planes * 32;
+    p.RB = rowbytes_for(g->Cin, g->ks);
+    p.ncb = g->Cin / p.RB;
+    p.ntaps = g->ks * g->ks;
+    p.PH = 15 * g->stride + g->ks;
+    p.PWhalf = 8 + (g->ks - 1) / 2;
+    p.PWp = (g->stride == 1) ? 8 + g->ks - 1 : 2 * p.PWhalf;
+    p.ppix = p.PH * p.PWp;
+    p.Hup = g->Hout + g->ks - 1;
+    p.Wup = g->Wout + g->ks - 1;
+    if (up) {
+        p.HsO = p.Hup;
+    } else {
+        // Stacked output rows per image.  Rows of the next image start stride*HsO input rows later; that must be
+        // past this image's real rows (Hin + pad) and far enough that a tap reaching below the last output row
+        // lands in the next image's top padding (local index < pad), which is zero-filled like ours.
+        const int need = g->Hin + p.pad;
+        const int reach = g->stride * (g->Hout - 1) + g->ks - p.pad;
+        const int span = need > reach ? need : reach;
+        p.HsO = (span + g->stride - 1) / g->stride;
+        if (p.HsO < g->Hout) p.HsO = g->Hout;
+    }
+    const long long rows = (long long)p.HsO * g->B;
+    const int tiles_y = (int)((rows + 15) / 16);
+    p.tiles_x = (g->Wout + 7) / 8;
+    p.mtiles = tiles_y * p.tiles_x;
+    const int ntiles = g->Cout / 32;
+    const long long nitems = (long long)p.mtiles * ntiles;
+    if (nitems > 0x7fffffffLL || (long long)g->B * g->Hin * g->Win * g->Cin > 0x7fffffffLL) {
+        set_error("ss_conv_i8_fwd: problem too large for 32-bit indexing");
+        return SS_EINVAL;
+    }
+    p.nitems = (int)nitems;
+    p.TC = 512 / p.N;
+    if (p.TC > MAX_SLOTS) p.TC = MAX_SLOTS;
+    p.WB = p.ntaps * p.N * p.RB;
+    p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
+    p.resident = p.ncb <= NWB ? 1 : 0;
+    if (p.PH > 40 || p.PWp > 24 || p.ppix > MAXPP * 128) {
+        set_error("ss_conv_i8_fwd: patch too large");
+        return SS_EUNSUPPORTED;
+    }
+    const int tail_bytes = 512 + 40 * 8 + 64;
+    const int budget = 227 * 1024 - 1024 - tail_bytes - NWB * p.WB;
+    int nps = budget / p.PB;
+    if (nps > MAX_STAGES) nps = MAX_STAGES;
+    if (nps < LAG + 1) {
+        set_error("ss_conv_i8_fwd: not enough shared memory (weights %d B x %d, patch %d B)", p.WB, NWB, p.PB);
+        return SS_EUNSUPPORTED;
+    }
+    p.NPS = nps;
+    p.yscale = up ? (float)g->Hin / (float)p.Hup : 1.0f;
+    p.xscale = up ? (float)g->Win / (float)p.Wup : 1.0f;
+    p.neuron = g->neuron; p.gain = g->gain; p.v_th = g->v_th; p.v_reset = g->v_reset; p.tau = g->tau;
+    p.x = reinterpret_cast<const uint8_t*>(x);
+    p.w = reinterpret_cast<const int8_t*>(w_i8);
+    p.wscale = wscale; p.decay = decay; p.v_in = v_in; p.v_out = v_out;
+    p.resid = reinterpret_cast<const uint8_t*>(resid);
+    p.out = reinterpret_cast<uint8_t*>(out);
+    p.h_seq = h_seq;
+
+    const size_t smem = 1024 + (size_t)NWB * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+        cudaFuncSetAttribute(conv_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_i8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (check_launch("conv_i8: cudaFuncSetAttribute") != SS_OK) {
+            num_sms = 0;
+            return SS_ECUDA;
+        }
+    }
+    const int grid = p.nitems < num_sms ? p.nitems : num_sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g->planes == 2) conv_i8_kernel<2><<<grid, THREADS, smem, st>>>(p);
+    else if (g->planes == 3) conv_i8_kernel<3><<<grid, THREADS, smem, st>>>(p);
+    else conv_i8_kernel<4><<<grid, THREADS, smem, st>>>(p);
+    count_launch();
+    return check_launch("conv_i8");
+}

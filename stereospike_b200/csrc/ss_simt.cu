@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NT) conv_neuron_simt_kernel(const ConvParams p
                 for (int e = 0; e < 8; ++e) a[e] = 0.0f;
                 const int k0 = kb * BK + lchk * 8;
                 if (l_b >= 0) {
-                    if (IN_LAYOUT == SS_IN_BF16_TBHWC) {
+                    if (IN_LAYOUT == SS_IN_U8_TBHWC) {
                         // Cin % 8 == 0: the 8 elements share one tap
                         const int tap = k0 / p.Cin;
                         const int c = k0 - tap * p.Cin;
@@ -90,15 +90,13 @@ __global__ void __launch_bounds__(NT) conv_neuron_simt_kernel(const ConvParams p
                             const int sy = __ldg(p.ymap + l_oy * p.ks + ky);
                             const int sx = __ldg(p.xmap + l_ox * p.ks + kx);
                             if (sy >= 0 && sx >= 0) {
-                                const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.x) +
+                                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.x) +
                                     ((((size_t)t * p.B + l_b) * p.Hin + sy) * p.Win + sx) * p.Cin + c;
-                                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
-                                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src));
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
-                                    const float2 f = __bfloat1622float2(h2[e]);
-                                    a[2 * e] = f.x;
-                                    a[2 * e + 1] = f.y;
+                                    a[e] = (float)((raw.x >> (8 * e)) & 0xFFu);
+                                    a[4 + e] = (float)((raw.y >> (8 * e)) & 0xFFu);
                                 }
                             }
                         }
@@ -165,11 +163,11 @@ __global__ void __launch_bounds__(NT) conv_neuron_simt_kernel(const ConvParams p
             }
             if (p.resid != nullptr) {
 #pragma unroll
-                for (int j = 0; j < TN; ++j) s[j] += __bfloat162float(p.resid[o + j]);
+                for (int j = 0; j < TN; ++j) s[j] += (float)p.resid[o + j];
             }
 #pragma unroll
             for (int j = 0; j < TN; j += 2)
-                *reinterpret_cast<__nv_bfloat162*>(p.out + o + j) = __floats2bfloat162_rn(s[j], s[j + 1]);
+                *reinterpret_cast<uchar2*>(p.out + o + j) = make_uchar2((unsigned char)s[j], (unsigned char)s[j + 1]);
         }
     }
 
@@ -187,8 +185,8 @@ __global__ void __launch_bounds__(NT) conv_neuron_simt_kernel(const ConvParams p
 template <int BN>
 int launch_bn(const ConvParams& p, int in_layout, cudaStream_t st) {
     dim3 grid((p.M + BM - 1) / BM, p.Cout / BN);
-    if (in_layout == SS_IN_BF16_TBHWC)
-        conv_neuron_simt_kernel<BN, SS_IN_BF16_TBHWC><<<grid, NT, 0, st>>>(p);
+    if (in_layout == SS_IN_U8_TBHWC)
+        conv_neuron_simt_kernel<BN, SS_IN_U8_TBHWC><<<grid, NT, 0, st>>>(p);
     else
         conv_neuron_simt_kernel<BN, SS_IN_F32_BTCHW><<<grid, NT, 0, st>>>(p);
     count_launch();
@@ -198,8 +196,8 @@ int launch_bn(const ConvParams& p, int in_layout, cudaStream_t st) {
 }  // namespace
 
 int launch_conv_neuron_simt(const ConvParams& p, int in_layout, cudaStream_t st) {
-    if (in_layout == SS_IN_BF16_TBHWC && (p.Cin % 8) != 0) {
-        set_error("simt: bf16 input needs Cin %% 8 == 0 (got %d)", p.Cin);
+    if (in_layout == SS_IN_U8_TBHWC && (p.Cin % 8) != 0) {
+        set_error("simt: u8 input needs Cin %% 8 == 0 (got %d)", p.Cin);
         return SS_EINVAL;
     }
     if (p.Cout % 32 != 0) {

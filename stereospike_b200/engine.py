@@ -2,7 +2,8 @@
 timesteps, then block l+1 -- mathematically identical to the reference's timestep loop because the network is
 feed-forward in depth) and calls one CUDA kernel per block through the C ABI.
 
-Forward : ss_conv_neuron_fwd per spiking block, ss_heads_fwd for the four heads + I-neurons.
+Forward : ss_pack_events + ss_conv_i8_fwd (tcgen05 int8 tensor-core kernel) per spiking block -- or ss_conv_neuron_fwd
+          (fp32 CUDA cores) when impl='simt' -- then ss_heads_fwd for the four heads + I-neurons.
 Backward: ss_heads_bwd, then per block in reverse order ss_neuron_bwd (surrogate BPTT scan), ss_conv_wgrad,
           ss_conv_dgrad.  Replaces PyTorch autograd through the reference modules.
 """
@@ -11,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
-from ._lib import SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA, SS_IN_BF16_TBHWC, SS_IN_F32_BTCHW
+from ._lib import SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA, SS_IN_U8_TBHWC, SS_IN_F32_BTCHW
 from .ops import BlockGeom, _ptr, _stream, conv_out_size
 
 IMPLS = {'auto': SS_IMPL_AUTO, 'simt': SS_IMPL_SIMT, 'umma': SS_IMPL_UMMA}
@@ -34,14 +35,18 @@ class Site:
         return BlockGeom('conv', c.in_channels, c.out_channels, ks, Hin, Win, conv_out_size(Hin, ks, st, pd),
                          conv_out_size(Win, ks, st, pd), st, pd)
 
-    def packed(self, planes, need_umma):
-        """(w_kn fp32 [K][Cout], w_umma bf16 [planes][Cout][Kpad] or None), cached on the weight's version."""
+    def packed(self, planes, need_i8, need_kn=True):
+        """(w_kn fp32 [K][Cout] or None, (w_i8, wscale) or None), cached on the weight's version."""
         w = self.conv.weight
-        key = (w.data_ptr(), w._version, planes, need_umma, str(w.device))
+        key = (w.data_ptr(), w._version, planes, need_i8, need_kn, str(w.device))
         if self._pack is None or self._pack[0] != key:
-            w_kn = ops.weight_to_kn(w)
-            w_um = ops.pack_weights_umma(w_kn, planes) if need_umma else None
-            self._pack = (key, w_kn, w_um)
+            w_kn = ops.weight_to_kn(w) if need_kn else None
+            w_i8 = None
+            if need_i8:
+                cin = w.shape[1]
+                q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=(cin + 31) // 32 * 32)
+                w_i8 = (q, sc)
+            self._pack = (key, w_kn, w_i8)
         return self._pack[1], self._pack[2]
 
 
@@ -100,6 +105,7 @@ class Engine:
         self.weight_planes = 3
         self.keep_state = True
         self.timing = None          # bench.py: list of (site name, start event, end event) when not None
+        self.event_status = None    # optional device int32[1]: bit 0 set when an input frame was not integer counts 0..255
 
     # ------------------------------------------------------------------ parameter flattening
     def _flat_params(self):
@@ -140,8 +146,8 @@ class Engine:
             g = s.geom(Hin, Win)
             if first and int(x_seq.shape[2]) != g.Cin:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
-            use_umma = (not first) and impl != SS_IMPL_SIMT
-            w_kn, w_um = s.packed(self.weight_planes, use_umma)
+            use_i8 = impl != SS_IMPL_SIMT
+            w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=want_h or not use_i8)
             decay = params[2 * i + 1]
             if decay is not None:
                 decay = decay.detach().contiguous()
@@ -151,12 +157,16 @@ class Engine:
             if self.timing is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            out, v_out, h_seq = ops.conv_neuron_fwd(
-                xin, g, w_kn, w_um, T=T, B=B, in_layout=SS_IN_F32_BTCHW if first else SS_IN_BF16_TBHWC,
-                neuron=node.kind, gain=s.gain_mod.gain(), v_th=node.v_threshold, v_reset=node.v_reset,
-                tau=node._tau_value(), decay=decay, v_in=v_in, want_v_out=self.keep_state, resid=resid, want_h=want_h,
-                impl=SS_IMPL_SIMT if first else (impl if impl != SS_IMPL_AUTO else SS_IMPL_UMMA),
-                planes=self.weight_planes)
+            common = dict(T=T, B=B, neuron=node.kind, gain=s.gain_mod.gain(), v_th=node.v_threshold, v_reset=node.v_reset,
+                          tau=node._tau_value(), decay=decay, v_in=v_in, want_v_out=self.keep_state, resid=resid, want_h=want_h)
+            if use_i8:
+                if first:
+                    xin = ops.pack_events(x_seq, self.event_status)     # fp32 NCHW counts -> u8 NHWC32
+                out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
+                                                    cin=32 if first else g.Cin, **common)
+            else:
+                out, v_out, h_seq = ops.conv_neuron_fwd(xin, g, w_kn, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC,
+                                                        **common)
             if self.timing is not None:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
@@ -263,8 +273,8 @@ class Engine:
                     g[s.resid] = g_out      # donate: the residual branch passes the gradient through unchanged
             first = s.src == 'x'
             cg = _lib.ConvGeom(T=T, B=B, Hin=gm.Hin, Win=gm.Win, Cin=gm.Cin, Hout=gm.Hout, Wout=gm.Wout, Cout=gm.Cout,
-                               ks=gm.ks, in_layout=SS_IN_F32_BTCHW if first else SS_IN_BF16_TBHWC, neuron=node.kind,
-                               impl=0, gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0, weight_planes=0, reserved=0)
+                               ks=gm.ks, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC, neuron=node.kind,
+                               reserved0=0, gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0, reserved1=0, reserved2=0)
             ym, xm = gm.maps(dev)
             g_wkn = torch.zeros((gm.K, gm.Cout), dtype=torch.float32, device=dev)
             rc = L.ss_conv_wgrad(ctypes.byref(cg), _ptr(acts[s.src]), _ptr(ym), _ptr(xm), _ptr(g_acc), _ptr(g_wkn), _stream())
@@ -282,9 +292,9 @@ class Engine:
 
 # ---------------------------------------------------------------------------------------- stand-alone blocks
 def _nchw_to_tbhwc(x):
-    """[B,C,H,W] fp32 spikes -> bf16 [1,B,H,W,C] (layout plumbing for stand-alone block calls)."""
+    """[B,C,H,W] fp32 spikes -> u8 [1,B,H,W,C] (layout plumbing for stand-alone block calls)."""
     ops._require_cuda(x, 'x')
-    return x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous().unsqueeze(0)
+    return x.detach().permute(0, 2, 3, 1).to(ops.ACT_DTYPE).contiguous().unsqueeze(0)
 
 
 def _tbhwc_to_nchw(a):
@@ -295,13 +305,17 @@ def _run_site_single(site, x_bf, resid=None, planes=3):
     _, B, Hin, Win, _ = x_bf.shape
     g = site.geom(Hin, Win)
     node = site.node
-    w_kn, w_um = site.packed(planes, True)
     v_in = _node_v_in(node, (B, g.Hout, g.Wout, g.Cout), x_bf.device)
     decay = node.decay_tensor()
-    out, v_out, _ = ops.conv_neuron_fwd(x_bf, g, w_kn, w_um, T=1, B=B, in_layout=SS_IN_BF16_TBHWC, neuron=node.kind,
-                                        gain=site.gain_mod.gain(), v_th=node.v_threshold, v_reset=node.v_reset,
-                                        tau=node._tau_value(), decay=decay.detach() if decay is not None else None,
-                                        v_in=v_in, want_v_out=True, resid=resid, planes=planes)
+    common = dict(T=1, B=B, neuron=node.kind, gain=site.gain_mod.gain(), v_th=node.v_threshold, v_reset=node.v_reset,
+                  tau=node._tau_value(), decay=decay.detach() if decay is not None else None, v_in=v_in, want_v_out=True,
+                  resid=resid)
+    if g.Cin % 32 == 0 and g.Cout % 32 == 0:
+        _, w_i8 = site.packed(planes, True, need_kn=False)
+        out, v_out, _ = ops.conv_i8_fwd(x_bf, g, w_i8[0], w_i8[1], planes=planes, **common)
+    else:
+        w_kn, _ = site.packed(planes, False)
+        out, v_out, _ = ops.conv_neuron_fwd(x_bf, g, w_kn, in_layout=SS_IN_U8_TBHWC, **common)
     node.v = v_out.permute(0, 3, 1, 2)
     return out
 

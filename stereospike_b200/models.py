@@ -126,14 +126,15 @@ class _SpikingUNet(NeuromorphicNet):
         return self._engine
 
     def set_kernel_options(self, impl=None, weight_planes=None, keep_state=None):
-        """impl: 'umma' (tcgen05; default) or 'simt' (exact-fp32 CUDA cores).  weight_planes: 3 = fp32-exact
-        weights (default), 2, or 1 = plain bf16 weights (the bf16 training configuration)."""
+        """impl: 'umma' (tcgen05 int8 tensor-core kernel; default) or 'simt' (exact-fp32 CUDA cores).
+        weight_planes: int8 digit planes per weight -- 3 = 24-bit fixed point, fp32-class (default);
+        2 = 16-bit (the reduced-precision training configuration); 4 = 32-bit."""
         e = self.engine
         if impl is not None:
             assert impl in ('auto', 'umma', 'simt')
             e.impl = impl
         if weight_planes is not None:
-            assert weight_planes in (1, 2, 3)
+            assert weight_planes in (2, 3, 4)
             e.weight_planes = weight_planes
         if keep_state is not None:
             e.keep_state = bool(keep_state)
@@ -147,7 +148,7 @@ class _SpikingUNet(NeuromorphicNet):
         acts = side['acts']
         spks = []
         for k in ('out_rconv', 'out_add4', 'out_add3', 'out_add2', 'out_add1'):
-            s = acts[k][-1].permute(0, 3, 1, 2)        # last timestep, NCHW-shaped view of the bf16 NHWC buffer
+            s = acts[k][-1].permute(0, 3, 1, 2)        # last timestep, NCHW-shaped view of the u8 NHWC buffer
             spks.append(s.float() if spikes_fp32 else s)
         return d, spks
 
@@ -159,7 +160,7 @@ class _SpikingUNet(NeuromorphicNet):
     def forward_seq(self, x_seq, spikes_fp32=False):
         """T-loop over ``x_seq[:, t]`` without reset, fused: one kernel per block for all T timesteps.
         Returns what the LAST ``forward`` call of the equivalent loop would return.  Spike tensors are
-        NCHW-shaped bf16 views unless ``spikes_fp32``."""
+        NCHW-shaped u8 views unless ``spikes_fp32``."""
         depths, side = self.engine.run(x_seq)
         return self._package(depths, side, spikes_fp32)
 

@@ -10,8 +10,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA, SS_IN_BF16_TBHWC, SS_IN_F32_BTCHW,
+from ._lib import (SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA, SS_IN_U8_TBHWC, SS_IN_F32_BTCHW,
                    SS_NEURON_IF, SS_NEURON_LIF, SS_NEURON_PLIF)
+
+ACT_DTYPE = torch.uint8          # spikes / spike sums / event counts in HBM: u8 NHWC, exact
 
 
 def _ptr(t):
@@ -90,44 +92,90 @@ def kn_to_weight(w_kn, co, ci, ks):
     return w_kn.reshape(ks, ks, ci, co).permute(3, 2, 0, 1).contiguous()
 
 
-def pack_weights_umma(w_kn, planes):
-    K, Cout = w_kn.shape
-    Kpad = (K + 63) // 64 * 64
-    out = torch.empty((planes, Cout, Kpad), dtype=torch.bfloat16, device=w_kn.device)
-    _lib.check(_lib.lib().ss_pack_weights_umma(_ptr(w_kn), K, Cout, planes, _ptr(out), _stream()),
-               'ss_pack_weights_umma')
+def pack_weights_i8(weight, planes, cin_pad=None):
+    """OIHW fp32 -> (int8 digit planes in the kernel's shared-memory image, wscale fp32 [Cout], wexp int32 [Cout]).
+    ``cin_pad``: zero-pad the input channels up to this count (the first layer's 2/4 channels -> 32)."""
+    w = weight.detach().float()
+    co, ci, kh, kw = w.shape
+    if cin_pad is not None and cin_pad > ci:
+        w = torch.cat([w, w.new_zeros(co, cin_pad - ci, kh, kw)], dim=1)
+        ci = cin_pad
+    w = w.contiguous()
+    out = torch.empty(co * ci * kh * kw * planes, dtype=torch.int8, device=w.device)
+    wscale = torch.empty(co, dtype=torch.float32, device=w.device)
+    wexp = torch.empty(co, dtype=torch.int32, device=w.device)
+    _lib.check(_lib.lib().ss_pack_weights_i8(_ptr(w), co, ci, kh, planes, _ptr(out), _ptr(wscale), _ptr(wexp), _stream()),
+               'ss_pack_weights_i8')
+    return out, wscale, wexp
+
+
+def pack_events(x_seq, status=None):
+    """fp32 [B,T,C,H,W] event-count frames -> u8 [T,B,H,W,32] (the first block's tensor-core input)."""
+    _require_cuda(x_seq, 'x')
+    B, T, C, H, W = x_seq.shape
+    out = torch.empty((T, B, H, W, 32), dtype=torch.uint8, device=x_seq.device)
+    _lib.check(_lib.lib().ss_pack_events(_ptr(x_seq), B, T, C, H, W, _ptr(out), _ptr(status), _stream()), 'ss_pack_events')
     return out
 
 
+def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
+    if resid is not None:
+        assert resid.dtype == ACT_DTYPE and resid.is_contiguous() and tuple(resid.shape) == out_shape
+    if v_in is not None:
+        assert v_in.dtype == torch.float32 and v_in.is_contiguous() and tuple(v_in.shape) == (B, g.Hout, g.Wout, g.Cout)
+    if decay is not None:
+        assert decay.dtype == torch.float32 and decay.numel() == 1 and decay.is_cuda
+
+
 # ----------------------------------------------------------------------------------------- fused block
-def conv_neuron_fwd(x, geom, w_kn, w_umma, *, T, B, in_layout, neuron, gain, v_th, v_reset, tau=2.0, decay=None,
-                    v_in=None, want_v_out=False, resid=None, want_h=False, impl=SS_IMPL_AUTO, planes=3):
-    """Run one fused spiking block over all T timesteps.  Returns (out bf16 [T,B,Hout,Wout,Cout], v_out, h_seq)."""
+def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau=2.0, decay=None, v_in=None,
+                want_v_out=False, resid=None, want_h=False, planes=3, cin=None):
+    """Tensor-core fused block over all T timesteps (ss_conv_i8_fwd).  x: u8 [T,B,Hin,Win,Cin].
+    Returns (out u8 [T,B,Hout,Wout,Cout], v_out, h_seq)."""
     _require_cuda(x, 'x')
     dev = x.device
     g = geom
-    if in_layout == SS_IN_BF16_TBHWC:
-        assert x.dtype == torch.bfloat16 and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, g.Cin), \
+    cin = g.Cin if cin is None else cin
+    assert x.dtype == ACT_DTYPE and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, cin), \
+        (x.dtype, tuple(x.shape), (T, B, g.Hin, g.Win, cin))
+    out_shape = (T, B, g.Hout, g.Wout, g.Cout)
+    out = torch.empty(out_shape, dtype=ACT_DTYPE, device=dev)
+    v_out = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=torch.float32, device=dev) if want_v_out else None
+    h_seq = torch.empty(out_shape, dtype=torch.float32, device=dev) if want_h else None
+    _check_block_io(x, g, T, B, resid, v_in, decay, out_shape)
+    d = _lib.BlockDesc(T=T, B=B, Hin=g.Hin, Win=g.Win, Cin=cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
+                       stride=g.stride, pad=g.pad, upsample=1 if g.kind == 'upconv' else 0, neuron=neuron, planes=planes,
+                       gain=gain, v_th=v_th, v_reset=v_reset, tau=tau)
+    rc = _lib.lib().ss_conv_i8_fwd(ctypes.byref(d), _ptr(x), _ptr(w_i8), _ptr(wscale), _ptr(decay), _ptr(v_in), _ptr(v_out),
+                                   _ptr(resid), _ptr(out), _ptr(h_seq), _stream())
+    _lib.check(rc, 'ss_conv_i8_fwd')
+    return out, v_out, h_seq
+
+
+def conv_neuron_fwd(x, geom, w_kn, *, T, B, in_layout, neuron, gain, v_th, v_reset, tau=2.0, decay=None,
+                    v_in=None, want_v_out=False, resid=None, want_h=False):
+    """fp32 CUDA-core fused block (ss_conv_neuron_fwd): exact fp32 weights; also reads the reference's fp32 NCHW frames.
+    Returns (out u8 [T,B,Hout,Wout,Cout], v_out, h_seq)."""
+    _require_cuda(x, 'x')
+    dev = x.device
+    g = geom
+    if in_layout == SS_IN_U8_TBHWC:
+        assert x.dtype == ACT_DTYPE and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, g.Cin), \
             (x.dtype, tuple(x.shape), (T, B, g.Hin, g.Win, g.Cin))
     else:
         assert x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (B, T, g.Cin, g.Hin, g.Win), \
             (x.dtype, tuple(x.shape), (B, T, g.Cin, g.Hin, g.Win))
     ymap, xmap = g.maps(dev)
-    out = torch.empty((T, B, g.Hout, g.Wout, g.Cout), dtype=torch.bfloat16, device=dev)
+    out_shape = (T, B, g.Hout, g.Wout, g.Cout)
+    out = torch.empty(out_shape, dtype=ACT_DTYPE, device=dev)
     v_out = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=torch.float32, device=dev) if want_v_out else None
-    h_seq = torch.empty((T, B, g.Hout, g.Wout, g.Cout), dtype=torch.float32, device=dev) if want_h else None
-    if resid is not None:
-        assert resid.dtype == torch.bfloat16 and resid.is_contiguous() and resid.shape == out.shape
-    if v_in is not None:
-        assert v_in.dtype == torch.float32 and v_in.is_contiguous() and tuple(v_in.shape) == (B, g.Hout, g.Wout, g.Cout)
-    if decay is not None:
-        assert decay.dtype == torch.float32 and decay.numel() == 1 and decay.is_cuda
+    h_seq = torch.empty(out_shape, dtype=torch.float32, device=dev) if want_h else None
+    _check_block_io(x, g, T, B, resid, v_in, decay, out_shape)
     cg = _lib.ConvGeom(T=T, B=B, Hin=g.Hin, Win=g.Win, Cin=g.Cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
-                       in_layout=in_layout, neuron=neuron, impl=impl, gain=gain, v_th=v_th, v_reset=v_reset,
-                       tau=tau, weight_planes=planes if w_umma is not None else 0, reserved=0)
-    rc = _lib.lib().ss_conv_neuron_fwd(ctypes.byref(cg), _ptr(x), _ptr(ymap), _ptr(xmap), _ptr(w_kn), _ptr(w_umma),
-                                       _ptr(decay), _ptr(v_in), _ptr(v_out), _ptr(resid), _ptr(out), _ptr(h_seq),
-                                       _stream())
+                       in_layout=in_layout, neuron=neuron, reserved0=0, gain=gain, v_th=v_th, v_reset=v_reset,
+                       tau=tau, reserved1=0, reserved2=0)
+    rc = _lib.lib().ss_conv_neuron_fwd(ctypes.byref(cg), _ptr(x), _ptr(ymap), _ptr(xmap), _ptr(w_kn), _ptr(decay),
+                                       _ptr(v_in), _ptr(v_out), _ptr(resid), _ptr(out), _ptr(h_seq), _stream())
     _lib.check(rc, 'ss_conv_neuron_fwd')
     return out, v_out, h_seq
 
@@ -141,10 +189,12 @@ def heads_fwd(acts, geoms, weights_9c, biases, *, T, B, H, W, gain, v_io):
     keep = []
     for i in range(4):
         g = geoms[i]
-        assert acts[i].dtype == torch.bfloat16 and acts[i].is_contiguous() and \
+        assert acts[i].dtype == ACT_DTYPE and acts[i].is_contiguous() and \
             tuple(acts[i].shape) == (T, B, g.Hin, g.Win, g.Cin)
         ym, xm = g.maps(dev)
-        keep += [ym, xm]
+        tp = torch.empty((T, B, 9, g.Hin, g.Win), dtype=torch.float32, device=dev)
+        keep += [ym, xm, tp]
+        a.taps[i] = tp.data_ptr()
         a.C[i], a.Hs[i], a.Ws[i] = g.Cin, g.Hin, g.Win
         a.acts[i] = acts[i].data_ptr()
         a.w[i] = weights_9c[i].data_ptr()

@@ -8,7 +8,7 @@ def block_case(kind, Cin, Cout, ks, Hin, Win, stride, pad, up, neuron, T, B, imp
     import torch.nn.functional as F
     from oracle import sj_compat as sj
     from stereospike_b200 import ops
-    from stereospike_b200._lib import SS_IN_BF16_TBHWC, SS_IMPL_SIMT, SS_IMPL_UMMA
+    from stereospike_b200._lib import SS_IN_U8_TBHWC
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device('cuda')
@@ -51,16 +51,21 @@ def block_case(kind, Cin, Cout, ks, Hin, Win, stride, pad, up, neuron, T, B, imp
     o_ref = torch.stack(outs).permute(0, 1, 3, 4, 2).contiguous()
     v_ref = node.v.permute(0, 2, 3, 1).contiguous()
     # device
-    xb = x.permute(0, 1, 3, 4, 2).contiguous().to(dev, torch.bfloat16)
-    w_kn = ops.weight_to_kn(w.to(dev))
-    w_um = ops.pack_weights_umma(w_kn, planes) if impl == 'umma' else None
-    rb = r.permute(0, 1, 3, 4, 2).contiguous().to(dev, torch.bfloat16) if resid else None
+    xb = x.permute(0, 1, 3, 4, 2).contiguous().to(dev, torch.uint8)
+    rb = r.permute(0, 1, 3, 4, 2).contiguous().to(dev, torch.uint8) if resid else None
     decay = node.w.detach().sigmoid().reshape(1).float().to(dev) if neuron == 2 else None
-    t0 = time.time()
-    out, v_out, h_seq = ops.conv_neuron_fwd(xb, geom, w_kn, w_um, T=T, B=B, in_layout=SS_IN_BF16_TBHWC, neuron=neuron,
-                                            gain=gain, v_th=1.0, v_reset=0.0, tau=3.0, decay=decay, want_v_out=True,
-                                            resid=rb, want_h=True, impl=SS_IMPL_UMMA if impl == 'umma' else SS_IMPL_SIMT,
-                                            planes=planes)
+    common = dict(T=T, B=B, neuron=neuron, gain=gain, v_th=1.0, v_reset=0.0, tau=3.0, decay=decay, want_v_out=True,
+                  resid=rb, want_h=True)
+    if impl == 'umma':
+        w_i8, wscale, _ = ops.pack_weights_i8(w.to(dev), planes)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out, v_out, h_seq = ops.conv_i8_fwd(xb, geom, w_i8, wscale, planes=planes, **common)
+    else:
+        w_kn = ops.weight_to_kn(w.to(dev))
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out, v_out, h_seq = ops.conv_neuron_fwd(xb, geom, w_kn, in_layout=SS_IN_U8_TBHWC, **common)
     torch.cuda.synchronize()
     dt = time.time() - t0
     h = h_seq.cpu()

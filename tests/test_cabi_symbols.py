@@ -30,7 +30,7 @@ def test_header_matches_binding_and_library(lib):
 
 
 def test_abi_version_and_launch_counter(lib):
-    assert lib.ss_abi_version() == 1
+    assert lib.ss_abi_version() == 2
     assert lib.ss_launch_count() >= 0
     assert isinstance(lib.ss_last_error(), bytes)
 
@@ -38,19 +38,26 @@ def test_abi_version_and_launch_counter(lib):
 def test_argument_validation_without_gpu(lib):
     """Entry points validate before touching the device: null / malformed arguments return SS_EINVAL (-1)."""
     from stereospike_b200 import _lib
-    g = _lib.ConvGeom(T=1, B=1, Hin=4, Win=4, Cin=8, Hout=4, Wout=4, Cout=32, ks=3, in_layout=0, neuron=0, impl=1,
-                      gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0, weight_planes=0, reserved=0)
-    rc = lib.ss_conv_neuron_fwd(ctypes.byref(g), None, None, None, None, None, None, None, None, None, None, None, None)
+    g = _lib.ConvGeom(T=1, B=1, Hin=4, Win=4, Cin=8, Hout=4, Wout=4, Cout=32, ks=3, in_layout=0, neuron=0, reserved0=0,
+                      gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0, reserved1=0, reserved2=0)
+    rc = lib.ss_conv_neuron_fwd(ctypes.byref(g), None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b'null' in lib.ss_last_error()
-    assert lib.ss_pack_weights_umma(None, 0, 0, 0, None, None) == -1
+    d = _lib.BlockDesc(T=1, B=1, Hin=4, Win=4, Cin=32, Hout=4, Wout=4, Cout=32, ks=3, stride=1, pad=1, upsample=0, neuron=0,
+                       planes=3, gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0)
+    rc = lib.ss_conv_i8_fwd(ctypes.byref(d), None, None, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b'null' in lib.ss_last_error()
+    assert lib.ss_pack_weights_i8(None, 0, 0, 0, 0, None, None, None, None) == -1
+    assert lib.ss_pack_events(None, 1, 1, 4, 2, 2, None, None, None) == -1
+    assert lib.ss_conv_i8_rowbytes(512, 3) == 64 and lib.ss_conv_i8_rowbytes(64, 5) == 32
     assert lib.ss_neuron_bwd(1, 1, 0, 0, 2.0, 1.0, 1.0, 0.0, 2.0, None, None, None, None, None, None, None, None, None) == -1
 
 
 def test_struct_layout_matches_header():
     from stereospike_b200 import _lib
     assert ctypes.sizeof(_lib.ConvGeom) == 18 * 4
-    # ss_heads_args: 4 int32 + float + 12 int32 (+4 pad) + 20 pointers
-    assert ctypes.sizeof(_lib.HeadsArgs) == 72 + 20 * 8
+    assert ctypes.sizeof(_lib.BlockDesc) == 18 * 4
+    # ss_heads_args: 4 int32 + float + 12 int32 (+4 pad) + 24 pointers
+    assert ctypes.sizeof(_lib.HeadsArgs) == 72 + 24 * 8
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

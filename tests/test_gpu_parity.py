@@ -34,18 +34,22 @@ def _cuda():
 
 
 BLOCKS = {
-    # strided 5x5 conv, Cin=32 (two taps per 64-wide K block, K tail zero-filled), M not a multiple of 128
+    # strided 5x5 conv (parity-split patch), Cin=32 (one channel block, weights resident), ragged tiles, batch stacking
     'conv5_s2_c32': dict(kind='conv', Cin=32, Cout=64, ks=5, Hin=20, Win=27, stride=2, pad=2, up=None, neuron=0, T=3, B=2, resid=False),
-    # NN-upsampled decoder conv, Cout=32 tile, LIF, skip add
+    # NN-upsampled decoder conv, LIF, skip add, two channel blocks
     'upconv5_lif_skip': dict(kind='upconv', Cin=64, Cout=32, ks=5, Hin=9, Win=11, stride=1, pad=0, up=(19, 23), neuron=1, T=3, B=2, resid=True),
-    # SEW-style 3x3, PLIF, residual
-    'conv3_plif_res': dict(kind='conv', Cin=64, Cout=128, ks=3, Hin=12, Win=13, stride=1, pad=1, up=None, neuron=2, T=4, B=1, resid=True),
-    # bottleneck geometry at full size: 512 -> 512 @ 17x22 (4 N tiles)
-    'bottleneck_512': dict(kind='conv', Cin=512, Cout=512, ks=3, Hin=17, Win=22, stride=1, pad=1, up=None, neuron=0, T=2, B=1, resid=True),
-    # deconv3 geometry at full size: 33x44 -> 65x87
+    # SEW-style 3x3 (64-byte channel blocks), PLIF, residual, T > one TMEM chunk
+    'conv3_plif_res': dict(kind='conv', Cin=64, Cout=128, ks=3, Hin=12, Win=13, stride=1, pad=1, up=None, neuron=2, T=7, B=1, resid=True),
+    # bottleneck geometry at full size: 512 -> 512 @ 17x22 (streamed weights, 16 output-channel tiles)
+    'bottleneck_512': dict(kind='conv', Cin=512, Cout=512, ks=3, Hin=17, Win=22, stride=1, pad=1, up=None, neuron=0, T=2, B=3, resid=True),
+    # deconv3 geometry at full size: 33x44 -> 65x87 (streamed weights, upsample gather)
     'deconv3_full': dict(kind='upconv', Cin=256, Cout=128, ks=5, Hin=33, Win=44, stride=1, pad=0, up=(65, 87), neuron=1, T=2, B=1, resid=True),
+    # conv4 geometry: stride 2, 256 -> 512, 33x44 -> 17x22 (streamed weights, parity-split patch)
+    'conv4_full': dict(kind='conv', Cin=256, Cout=512, ks=5, Hin=33, Win=44, stride=2, pad=2, up=None, neuron=0, T=2, B=2, resid=False),
+    # first-layer geometry: 5x5 stride 1 pad 2, Cin=32
+    'conv5_s1_pad2': dict(kind='conv', Cin=32, Cout=32, ks=5, Hin=21, Win=30, stride=1, pad=2, up=None, neuron=0, T=2, B=2, resid=False),
     # single pixel row / single timestep / ragged tiny M
-    'tiny': dict(kind='conv', Cin=8, Cout=32, ks=3, Hin=3, Win=5, stride=1, pad=1, up=None, neuron=0, T=1, B=1, resid=False),
+    'tiny': dict(kind='conv', Cin=32, Cout=32, ks=3, Hin=3, Win=5, stride=1, pad=1, up=None, neuron=0, T=1, B=1, resid=False),
 }
 
 
@@ -61,58 +65,97 @@ def test_block_teacher_forced(name, impl, planes):
     assert r['spike_mismatch_all'] <= max(2, 2e-5 * r['n']), r
 
 
-@pytest.mark.parametrize('planes,tol', [(1, 2e-2), (2, 2e-4)])
-def test_block_reduced_weight_planes(planes, tol):
-    """1 plane = plain bf16 weights (the bf16 training configuration), 2 planes = 16-bit weight mantissa."""
+@pytest.mark.parametrize('planes,tol', [(2, 2e-3), (4, 2e-5)])
+def test_block_other_weight_planes(planes, tol):
+    """2 planes = 16-bit fixed-point weights (reduced-precision configuration), 4 planes = 32-bit."""
     from tests._cases import block_case
     r = block_case(impl='umma', planes=planes, **BLOCKS['conv3_plif_res'])
     assert r['max_dh_t0'] <= tol * max(1.0, r['h_absmax']), r
 
 
-def _mk_block(T, B, seed=0, Cin=64, Cout=64, H=10, W=13, neuron=1):
+def _mk_block(T, B, seed=0, Cin=64, Cout=64, H=10, W=13):
     from stereospike_b200 import ops
     g = torch.Generator().manual_seed(seed)
     geom = ops.BlockGeom('conv', Cin, Cout, 3, H, W, H, W, 1, 1)
-    x = ((torch.rand(T, B, H, W, Cin, generator=g) < 0.2).float()).to('cuda', torch.bfloat16)
+    x = ((torch.rand(T, B, H, W, Cin, generator=g) < 0.2).to(torch.uint8)).cuda()
     w = ((torch.rand(Cout, Cin, 3, 3, generator=g) * 2 - 1) / 8).cuda()
-    w_kn = ops.weight_to_kn(w)
-    return geom, x, w_kn, ops.pack_weights_umma(w_kn, 3)
+    return geom, x, w
+
+
+def _run(impl, geom, x, w, **kw):
+    from stereospike_b200 import ops
+    if impl == 'umma':
+        q, sc, _ = ops.pack_weights_i8(w, 3)
+        return ops.conv_i8_fwd(x, geom, q, sc, planes=3, **kw)
+    return ops.conv_neuron_fwd(x, geom, ops.weight_to_kn(w), in_layout=0, **kw)
 
 
 @pytest.mark.parametrize('impl', ['simt', 'umma'])
 def test_state_carry_equals_one_long_sequence(impl):
     """Running T=4 in one launch is bit-identical to 2 + 2 with v_out -> v_in (the register-resident membrane
     potential is the same state the reference keeps in ``node.v`` between calls)."""
-    from stereospike_b200 import ops, _lib
-    geom, x, w_kn, w_um = _mk_block(4, 2)
-    kw = dict(in_layout=0, neuron=_lib.SS_NEURON_LIF, gain=4.0, v_th=1.0, v_reset=0.0, tau=3.0,
-              impl=_lib.SS_IMPL_UMMA if impl == 'umma' else _lib.SS_IMPL_SIMT, planes=3)
-    full, v_full, _ = ops.conv_neuron_fwd(x, geom, w_kn, w_um, T=4, B=2, want_v_out=True, **kw)
-    a, v_a, _ = ops.conv_neuron_fwd(x[:2].contiguous(), geom, w_kn, w_um, T=2, B=2, want_v_out=True, **kw)
-    b, v_b, _ = ops.conv_neuron_fwd(x[2:].contiguous(), geom, w_kn, w_um, T=2, B=2, v_in=v_a, want_v_out=True, **kw)
+    from stereospike_b200 import _lib
+    geom, x, w = _mk_block(4, 2)
+    kw = dict(neuron=_lib.SS_NEURON_LIF, gain=4.0, v_th=1.0, v_reset=0.0, tau=3.0, want_v_out=True)
+    full, v_full, _ = _run(impl, geom, x, w, T=4, B=2, **kw)
+    a, v_a, _ = _run(impl, geom, x[:2].contiguous(), w, T=2, B=2, **kw)
+    b, v_b, _ = _run(impl, geom, x[2:].contiguous(), w, T=2, B=2, v_in=v_a, **kw)
     assert torch.equal(full[:2], a) and torch.equal(full[2:], b) and torch.equal(v_full, v_b)
     assert 0.02 < float(full.float().mean()) < 0.9
 
 
 def test_simt_and_umma_agree():
-    from stereospike_b200 import ops, _lib
-    geom, x, w_kn, w_um = _mk_block(3, 2, seed=3)
-    kw = dict(in_layout=0, neuron=_lib.SS_NEURON_IF, gain=4.0, v_th=1.0, v_reset=0.0, T=3, B=2, want_h=True, planes=3)
-    o1, _, h1 = ops.conv_neuron_fwd(x, geom, w_kn, w_um, impl=_lib.SS_IMPL_SIMT, **kw)
-    o2, _, h2 = ops.conv_neuron_fwd(x, geom, w_kn, w_um, impl=_lib.SS_IMPL_UMMA, **kw)
+    from stereospike_b200 import _lib
+    geom, x, w = _mk_block(3, 2, seed=3)
+    kw = dict(neuron=_lib.SS_NEURON_IF, gain=4.0, v_th=1.0, v_reset=0.0, T=3, B=2, want_h=True)
+    o1, _, h1 = _run('simt', geom, x, w, **kw)
+    o2, _, h2 = _run('umma', geom, x, w, **kw)
     assert float((h1[0] - h2[0]).abs().max()) < 1e-5
     assert float((o1 != o2).float().mean()) < 1e-4
 
 
+def test_i8_result_is_exact_and_tiling_independent():
+    """Integer accumulation: the tensor-core block equals the exact (float64) dot product of the quantised weights
+    rounded once to fp32 -- bit for bit -- and does not depend on batch stacking / tile position."""
+    from stereospike_b200 import ops, _lib
+    geom, x, w = _mk_block(1, 3, seed=5, Cin=64, Cout=32, H=17, W=22)
+    q, sc, wexp = ops.pack_weights_i8(w, 3)
+    kw = dict(neuron=_lib.SS_NEURON_IF, gain=4.0, v_th=1.0, v_reset=0.0, want_h=True, planes=3)
+    _, _, h = ops.conv_i8_fwd(x, geom, q, sc, T=1, B=3, **kw)
+    wq = torch.round(w.double() / sc.double().view(-1, 1, 1, 1)) * sc.double().view(-1, 1, 1, 1)     # quantised weights
+    ref = torch.nn.functional.conv2d(x[0].permute(0, 3, 1, 2).double(), wq, padding=1)
+    ref = (ref.float() * 4.0).permute(0, 2, 3, 1)        # one rounding to fp32, then the MultiplyBy gain in fp32
+    assert torch.equal(h[0], ref.contiguous())
+    _, _, h1 = ops.conv_i8_fwd(x[:, 1:2].contiguous(), geom, q, sc, T=1, B=1, **kw)
+    assert torch.equal(h[0, 1:2], h1[0])
+
+
 def test_empty_batch_and_bad_arguments():
     from stereospike_b200 import ops, _lib
-    geom, x, w_kn, w_um = _mk_block(1, 1)
-    out, _, _ = ops.conv_neuron_fwd(x[:, :0].contiguous(), geom, w_kn, w_um, T=1, B=0, in_layout=0, neuron=0, gain=1.0,
-                                    v_th=1.0, v_reset=0.0)
+    geom, x, w = _mk_block(1, 1)
+    q, sc, _ = ops.pack_weights_i8(w, 3)
+    out, _, _ = ops.conv_i8_fwd(x[:, :0].contiguous(), geom, q, sc, T=1, B=0, neuron=0, gain=1.0, v_th=1.0, v_reset=0.0)
     assert out.numel() == 0
     with pytest.raises(RuntimeError, match='PLIF needs'):
-        ops.conv_neuron_fwd(x, geom, w_kn, w_um, T=1, B=1, in_layout=0, neuron=_lib.SS_NEURON_PLIF, gain=1.0, v_th=1.0,
-                            v_reset=0.0)
+        ops.conv_i8_fwd(x, geom, q, sc, T=1, B=1, neuron=_lib.SS_NEURON_PLIF, gain=1.0, v_th=1.0, v_reset=0.0)
+    with pytest.raises(RuntimeError, match='planes'):
+        ops.conv_i8_fwd(x, geom, q, sc, T=1, B=1, neuron=0, gain=1.0, v_th=1.0, v_reset=0.0, planes=5)
+    with pytest.raises(RuntimeError, match='multiples of 32'):
+        g8 = ops.BlockGeom('conv', 8, 32, 3, 10, 13, 10, 13, 1, 1)
+        ops.conv_i8_fwd(x[..., :8].contiguous(), g8, q, sc, T=1, B=1, neuron=0, gain=1.0, v_th=1.0, v_reset=0.0)
+
+
+def test_pack_events_flags_non_integer_input():
+    from stereospike_b200 import ops
+    x = torch.zeros(1, 2, 4, 6, 7, device='cuda')
+    x[0, 1, 2, 3, 4] = 3.0
+    st = torch.zeros(1, dtype=torch.int32, device='cuda')
+    p = ops.pack_events(x, st)
+    assert p.shape == (2, 1, 6, 7, 32) and int(p[1, 0, 3, 4, 2]) == 3 and int(p.sum()) == 3 and int(st) == 0
+    x[0, 0, 0, 0, 0] = 0.5
+    x[0, 0, 1, 0, 0] = 300.0
+    ops.pack_events(x, st)
+    assert int(st) == 1
 
 
 @pytest.mark.parametrize('variant,mono,gain,T,B,impl', [
@@ -169,11 +212,19 @@ def test_golden_fixture(name, golden_dir):
     depths = out if mono else out[0]
     mde = float(rm.mean_depth_error(depths[0].cpu(), label))
     assert abs(mde - float(gold['mde'])) <= TOL_MDE, (mde, float(gold['mde']))
-    rel = abs(float(depths[0].double().sum()) - gold['depth_sums'][0]) / gold['depth_abs_sums'][0]
-    assert rel < 2e-3, rel
+    # Depth-map checksum.  The threshold makes some configurations chaotic (bino_lif_T2: the reference's own fp32 and
+    # float64 evaluations differ in 3-4 % of the decoder spikes and 1 % of this checksum while their MDEs agree to
+    # 4e-4), so the checksum must match EITHER evaluation of the reference files; the integer tensor-core path,
+    # which does no rounding inside the dot products, lands on the float64 one.
+    got = float(depths[0].double().sum())
+    rel32 = abs(got - gold['depth_sums'][0]) / gold['depth_abs_sums'][0]
+    rel64 = abs(got - gold['depth_sums64'][0]) / gold['depth_abs_sums'][0]
+    assert min(rel32, rel64) < 2e-3, (rel32, rel64)
     if not mono:
         nz = np.array([int(s.count_nonzero()) for s in out[1]])
-        assert np.all(np.abs(nz - gold['spk_nonzero']) <= 0.03 * gold['spk_nonzero']), (nz, gold['spk_nonzero'])
+        ok32 = np.all(np.abs(nz - gold['spk_nonzero']) <= 0.03 * gold['spk_nonzero'])
+        ok64 = np.all(np.abs(nz - gold['spk_nonzero64']) <= 0.03 * gold['spk_nonzero64'])
+        assert ok32 or ok64, (nz, gold['spk_nonzero'], gold['spk_nonzero64'])
 
 
 def test_forward_single_step_contract():

@@ -18,7 +18,7 @@ CASES = {
     'simt_conv_s2_if': dict(kind='conv', Cin=32, Cout=64, ks=5, Hin=20, Win=27, stride=2, pad=2, up=None, neuron=0, T=3, B=2, impl='simt', planes=0, resid=False),
     'simt_up_lif_res': dict(kind='upconv', Cin=64, Cout=32, ks=5, Hin=9, Win=11, stride=1, pad=0, up=(19, 23), neuron=1, T=3, B=2, impl='simt', planes=0, resid=True),
     'simt_3x3_plif': dict(kind='conv', Cin=64, Cout=64, ks=3, Hin=7, Win=9, stride=1, pad=1, up=None, neuron=2, T=4, B=1, impl='simt', planes=0, resid=True),
-    'umma_conv64_if_T1': dict(kind='conv', Cin=64, Cout=128, ks=3, Hin=12, Win=13, stride=1, pad=1, up=None, neuron=0, T=1, B=1, impl='umma', planes=1, resid=False),
+    'umma_conv64_if_T1': dict(kind='conv', Cin=64, Cout=128, ks=3, Hin=12, Win=13, stride=1, pad=1, up=None, neuron=0, T=1, B=1, impl='umma', planes=2, resid=False),
     'umma_conv64_if_p3': dict(kind='conv', Cin=64, Cout=128, ks=3, Hin=12, Win=13, stride=1, pad=1, up=None, neuron=0, T=3, B=2, impl='umma', planes=3, resid=False),
     'umma_conv32_s2_if': dict(kind='conv', Cin=32, Cout=64, ks=5, Hin=20, Win=27, stride=2, pad=2, up=None, neuron=0, T=3, B=2, impl='umma', planes=3, resid=False),
     'umma_up_lif_res_n32': dict(kind='upconv', Cin=64, Cout=32, ks=5, Hin=9, Win=11, stride=1, pad=0, up=(19, 23), neuron=1, T=3, B=2, impl='umma', planes=3, resid=True),
@@ -29,6 +29,7 @@ CASES = {
     'model_plif_mono_umma': dict(model=True, variant='plif', mono=True, gain=15.0, T=2, B=2, impl='umma', planes=3),
     'model_if_simt_bwd': dict(model=True, variant='if', mono=False, gain=5.0, T=2, B=1, impl='simt', planes=3, backward=True),
     'model_plif_umma_bwd': dict(model=True, variant='plif', mono=False, gain=15.0, T=2, B=1, impl='umma', planes=3, backward=True),
+    'umma_conv4_s2': dict(kind='conv', Cin=256, Cout=512, ks=5, Hin=33, Win=44, stride=2, pad=2, up=None, neuron=0, T=2, B=2, impl='umma', planes=3, resid=False),
     'umma_big_up': dict(kind='upconv', Cin=128, Cout=64, ks=5, Hin=33, Win=44, stride=1, pad=0, up=(65, 87), neuron=0, T=2, B=2, impl='umma', planes=3, resid=True),
 }
 

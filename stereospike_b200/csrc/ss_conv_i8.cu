@@ -39,7 +39,6 @@ namespace ss {
 namespace {
 
 constexpr int NWB = 2;        // weight buffers
-constexpr int MAXPP = 6;      // patch pixels per producer thread (700 / 128 rounded up)
 constexpr int LAG = 2;        // cp.async groups in flight per producer thread
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_SLOTS = 8;
@@ -136,6 +135,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one elected lane of a converged warp (the compiler knows exactly one lane is active in the guarded region)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -156,9 +165,10 @@ __device__ __forceinline__ uint32_t swizzle_off(uint32_t off, uint32_t mask) { r
 
 // ------------------------------------------------------------------------------------------------ geometry
 // Source row (b*Hin + iy) read by patch row `pr` of tile row `ty`, or -1 (zero padding / gap between stacked images).
+template <int STRIDE>
 __device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr) {
-    const int gi = ty * 16 * p.stride + pr;
-    const int per = p.stride * p.HsO;
+    const int gi = ty * 16 * STRIDE + pr;
+    const int per = STRIDE * p.HsO;
     const int b = gi / per;
     if (b >= p.B) return -1;
     const int local = gi - b * per;
@@ -171,6 +181,7 @@ __device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr) {
     const int iy = local - p.pad;
     return (iy >= 0 && iy < p.Hin) ? b * p.Hin + iy : -1;
 }
+template <int STRIDE, int PWHALF>
 __device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
     if (p.upsample) {
         const int u = tx * 8 + pc;
@@ -178,32 +189,44 @@ __device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
         return min((int)floorf((float)u * p.xscale), p.Win - 1);
     }
     int ix;
-    if (p.stride == 1) {
+    if (STRIDE == 1) {
         ix = tx * 8 + pc - p.pad;
     } else {
         // parity-split row: [even-type columns | odd-type columns]; input col = 2*(ox0 - pad/2 + idx) + plane
-        const int plane = pc / p.PWhalf;
-        const int idx = pc - plane * p.PWhalf;
+        const int plane = pc / PWHALF;
+        const int idx = pc - plane * PWHALF;
         ix = 2 * (tx * 8 - p.pad / 2 + idx) + plane;
     }
     return (ix >= 0 && ix < p.Win) ? ix : -1;
 }
 // patch pixel at which the A operand of tap (ky,kx) starts
-__device__ __forceinline__ int tap_offset(const I8Params& p, int ky, int kx) {
-    if (p.stride == 1) return ky * p.PWp + kx;
-    return ky * p.PWp + (kx & 1) * p.PWhalf + (kx >> 1);
+template <int STRIDE, int PWP, int PWHALF>
+__device__ __forceinline__ constexpr int tap_offset(int ky, int kx) {
+    return STRIDE == 1 ? ky * PWP + kx : ky * PWP + (kx & 1) * PWHALF + (kx >> 1);
 }
 
-template <int PLANES>
+template <int PLANES, int KS, int STRIDE, int RB>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
+    // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
+    constexpr int cN = PLANES * 32;
+    constexpr int cNTAPS = KS * KS;
+    constexpr int cPWhalf = 8 + (KS - 1) / 2;
+    constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
+    constexpr int cPH = 15 * STRIDE + KS;
+    constexpr int cPPIX = cPH * cPWp;
+    constexpr int cWB = cNTAPS * cN * RB;
+    constexpr int cPB = (cPPIX * RB + 1023) / 1024 * 1024;
+    constexpr int cTC = (512 / cN) < MAX_SLOTS ? (512 / cN) : MAX_SLOTS;
+    constexpr int cKSTEPS = RB / 32;
+    constexpr int cNPIX = (cPPIX + 127) / 128;   // patch pixels per producer thread
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
 
     const uint32_t w_base = base;
-    const uint32_t patch_base = base + NWB * p.WB;
-    uint8_t* tail = sm + (size_t)NWB * p.WB + (size_t)p.NPS * p.PB;
+    const uint32_t patch_base = base + NWB * cWB;
+    uint8_t* tail = sm + (size_t)NWB * cWB + (size_t)p.NPS * cPB;
     int* rowsrc = reinterpret_cast<int*>(tail);              // [2][40]
     int* colsrc = rowsrc + 80;                               // [2][24]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
@@ -243,13 +266,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t swz_mask = (uint32_t)(p.RB >> 4) - 1u;  // 32 -> 1, 64 -> 3, 128 -> 7
+    constexpr uint32_t swz_mask = (uint32_t)(RB >> 4) - 1u;  // 32 -> 1, 64 -> 3, 128 -> 7
 
     if (warp < 4) {
         // ================================================================== patch producers
         const int tid = threadIdx.x;
         const size_t t_stride = (size_t)p.B * p.Hin * p.Win * p.Cin;
-        const int chunks = p.RB >> 4;
+        constexpr int chunks = RB >> 4;
         int stage = 0;
         uint32_t phase = 0;
         int issued = 0, arrive_stage = 0, itcount = 0;
@@ -259,23 +282,23 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
             int* rs = rowsrc + (itcount & 1) * 40;
             int* cs = colsrc + (itcount & 1) * 24;
-            if (tid < p.PH) rs[tid] = row_source(p, ty, tid);
-            if (tid >= 64 && tid - 64 < p.PWp) cs[tid - 64] = col_source(p, tx, tid - 64);
+            if (tid < cPH) rs[tid] = row_source<STRIDE>(p, ty, tid);
+            if (tid >= 64 && tid - 64 < cPWp) cs[tid - 64] = col_source<STRIDE, cPWhalf>(p, tx, tid - 64);
             named_sync(1, 128);
-            int goff[MAXPP];
+            int goff[cNPIX];
 #pragma unroll
-            for (int i = 0; i < MAXPP; ++i) {
+            for (int i = 0; i < cNPIX; ++i) {
                 const int pix = tid + i * 128;
                 goff[i] = -2;
-                if (pix < p.ppix) {
-                    const int pr = pix / p.PWp;
-                    const int pc = pix - pr * p.PWp;
+                if (pix < cPPIX) {
+                    const int pr = pix / cPWp;
+                    const int pc = pix - pr * cPWp;
                     const int r = rs[pr], c = cs[pc];
                     goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * p.Cin : -1;
                 }
             }
-            for (int t0 = 0; t0 < p.T; t0 += p.TC) {
-                const int tc = min(p.TC, p.T - t0);
+            for (int t0 = 0; t0 < p.T; t0 += cTC) {
+                const int tc = min(cTC, p.T - t0);
                 const int n_outer = p.resident ? tc : p.ncb;
                 const int n_inner = p.resident ? p.ncb : tc;
                 for (int o = 0; o < n_outer; ++o) {
@@ -283,14 +306,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         const int cb = p.resident ? in : o;
                         const int t = t0 + (p.resident ? o : in);
                         mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
-                        const uint8_t* xt = p.x + (size_t)t * t_stride + cb * p.RB;
-                        const uint32_t dst0 = patch_base + (uint32_t)stage * p.PB;
+                        const uint8_t* xt = p.x + (size_t)t * t_stride + cb * RB;
+                        const uint32_t dst0 = patch_base + (uint32_t)stage * cPB;
 #pragma unroll
-                        for (int i = 0; i < MAXPP; ++i) {
+                        for (int i = 0; i < cNPIX; ++i) {
                             if (goff[i] != -2) {
-                                const uint32_t off = (uint32_t)(tid + i * 128) * p.RB;
+                                const uint32_t off = (uint32_t)(tid + i * 128) * RB;
                                 const bool ok = goff[i] >= 0;
                                 const uint8_t* src = ok ? xt + goff[i] : p.x;
+#pragma unroll
                                 for (int c = 0; c < chunks; ++c)
                                     cp_async_16(dst0 + swizzle_off(off + c * 16, swz_mask), ok ? src + c * 16 : src, ok ? 16u : 0u);
                             }
@@ -320,12 +344,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         }
     } else if (warp == 4) {
         // ================================================================== MMA issuer
-        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t layout = p.RB == 128 ? 2u : (p.RB == 64 ? 4u : 6u);
-        const uint32_t a_sbo = (uint32_t)(p.stride * p.PWp * p.RB);
-        const uint32_t b_sbo = (uint32_t)(8 * p.RB);
-        const int ksteps = p.RB >> 5;
-        const uint32_t tap_bytes = (uint32_t)(p.N * p.RB);
+        constexpr uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
+        constexpr uint32_t a_sbo = (uint32_t)(STRIDE * cPWp * RB);
+        constexpr uint32_t b_sbo = (uint32_t)(8 * RB);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t slot_phase = 0;   // bit s: parity to wait on empty_a[s] (starts "free")
@@ -336,18 +358,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         auto do_stage = [&](int wbuf, int slot, bool first) {
             mbar_wait(bar_full_p + 8 * stage, phase);
             tc_fence_after();
-            if (lane == 0) {
-                const uint64_t a0 = make_desc(patch_base + (uint32_t)stage * p.PB, a_sbo, layout);
-                const uint64_t b0 = make_desc(w_base + (uint32_t)wbuf * p.WB, b_sbo, layout);
-                const uint32_t d = tmem_base + (uint32_t)(slot * p.N);
-                int tap = 0;
-                for (int ky = 0; ky < p.ks; ++ky) {
-                    for (int kx = 0; kx < p.ks; ++kx, ++tap) {
-                        const uint32_t aoff = (uint32_t)tap_offset(p, ky, kx) * p.RB;
-                        const uint32_t boff = (uint32_t)tap * tap_bytes;
-                        for (int k = 0; k < ksteps; ++k)
-                            umma_i8(d, a0 + ((aoff + k * 32) >> 4), b0 + ((boff + k * 32) >> 4), idesc,
-                                    (first && tap == 0 && k == 0) ? 0u : 1u);
+            if (elect_one()) {
+                const uint64_t a0 = make_desc(patch_base + (uint32_t)stage * cPB, a_sbo, layout);
+                const uint64_t b0 = make_desc(w_base + (uint32_t)wbuf * cWB, b_sbo, layout);
+                const uint32_t d = tmem_base + (uint32_t)(slot * cN);
+                umma_i8(d, a0, b0, idesc, first ? 0u : 1u);
+#pragma unroll
+                for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+                    for (int kx = 0; kx < KS; ++kx) {
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const uint32_t aoff = (uint32_t)(tap_offset<STRIDE, cPWp, cPWhalf>(ky, kx) * RB);
+                        const uint32_t boff = (uint32_t)((ky * KS + kx) * cN * RB);
+#pragma unroll
+                        for (int k = 0; k < cKSTEPS; ++k) {
+                            if (ky == 0 && kx == 0 && k == 0) continue;   // issued above with the accumulate flag
+                            umma_i8(d, a0 + ((aoff + k * 32) >> 4), b0 + ((boff + k * 32) >> 4), idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(bar_empty_p + 8 * stage);
@@ -366,8 +394,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 w_pending = (1u << p.ncb) - 1u;
                 ++wu;
             }
-            for (int t0 = 0; t0 < p.T; t0 += p.TC) {
-                const int tc = min(p.TC, p.T - t0);
+            for (int t0 = 0; t0 < p.T; t0 += cTC) {
+                const int tc = min(cTC, p.T - t0);
                 if (p.resident) {
                     for (int s = 0; s < tc; ++s) {
                         mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
@@ -380,7 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             }
                             do_stage(cb, s, cb == 0);
                         }
-                        if (lane == 0) umma_commit(bar_full_a + 8 * s);
+                        if (elect_one()) umma_commit(bar_full_a + 8 * s);
                         __syncwarp();
                     }
                 } else {
@@ -395,11 +423,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             }
                             do_stage(buf, s, cb == 0);
                             if (cb == p.ncb - 1) {
-                                if (lane == 0) umma_commit(bar_full_a + 8 * s);
+                                if (elect_one()) umma_commit(bar_full_a + 8 * s);
                                 __syncwarp();
                             }
                         }
-                        if (lane == 0) umma_commit(bar_empty_w + 8 * buf);
+                        if (elect_one()) umma_commit(bar_empty_w + 8 * buf);
                         __syncwarp();
                         ++wu;
                     }
@@ -408,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             if (p.resident) {
                 const int nxt = it + gridDim.x;
                 if (nxt < p.nitems && nxt / p.mtiles != ntile) {
-                    if (lane == 0)
+                    if (elect_one())
                         for (int cb = 0; cb < p.ncb; ++cb) umma_commit(bar_empty_w + 8 * cb);
                     __syncwarp();
                 }
@@ -421,10 +449,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             int loaded_ntile = -1;
             auto load = [&](int buf, int ntile, int cb) {
                 const uint32_t full = bar_full_w + 8 * buf;
-                mbar_arrive_expect_tx(full, (uint32_t)p.WB);
-                const int8_t* src = p.w + (size_t)(ntile * p.ncb + cb) * p.WB;
-                const uint32_t dst = w_base + (uint32_t)buf * p.WB;
-                for (int o = 0; o < p.WB; o += 16384) bulk_load(dst + o, src + o, (uint32_t)min(16384, p.WB - o), full);
+                mbar_arrive_expect_tx(full, (uint32_t)cWB);
+                const int8_t* src = p.w + (size_t)(ntile * p.ncb + cb) * cWB;
+                const uint32_t dst = w_base + (uint32_t)buf * cWB;
+                for (int o = 0; o < cWB; o += 16384) bulk_load(dst + o, src + o, (uint32_t)min(16384, cWB - o), full);
             };
             for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
                 const int ntile = it / p.mtiles;
@@ -438,7 +466,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         ++wu;
                     }
                 } else {
-                    for (int t0 = 0; t0 < p.T; t0 += p.TC) {
+                    for (int t0 = 0; t0 < p.T; t0 += cTC) {
                         for (int cb = 0; cb < p.ncb; ++cb) {
                             const int buf = (int)(wu % NWB);
                             if (wu >= NWB) mbar_wait(bar_empty_w + 8 * buf, ((wu / NWB) - 1u) & 1u);
@@ -488,14 +516,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = p.v_reset;
             }
-            for (int t0 = 0; t0 < p.T; t0 += p.TC) {
-                const int tc = min(p.TC, p.T - t0);
+            for (int t0 = 0; t0 < p.T; t0 += cTC) {
+                const int tc = min(cTC, p.T - t0);
                 for (int s = 0; s < tc; ++s) {
                     const int t = t0 + s;
                     mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
                     slot_phase ^= 1u << s;
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * p.N + hf * 16);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * cN + hf * 16);
                     int d[PLANES][16];
 #pragma unroll
                     for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(taddr + pl * 32, d[pl]);
@@ -779,7 +807,7 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     p.WB = p.ntaps * p.N * p.RB;
     p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
     p.resident = p.ncb <= NWB ? 1 : 0;
-    if (p.PH > 40 || p.PWp > 24 || p.ppix > MAXPP * 128) {
+    if (p.PH > 40 || p.PWp > 24) {
         set_error("ss_conv_i8_fwd: patch too large");
         return SS_EUNSUPPORTED;
     }
@@ -809,19 +837,30 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
-        cudaFuncSetAttribute(conv_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_i8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (check_launch("conv_i8: cudaFuncSetAttribute") != SS_OK) {
-            num_sms = 0;
-            return SS_ECUDA;
-        }
     }
     const int grid = p.nitems < num_sms ? p.nitems : num_sms;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g->planes == 2) conv_i8_kernel<2><<<grid, THREADS, smem, st>>>(p);
-    else if (g->planes == 3) conv_i8_kernel<3><<<grid, THREADS, smem, st>>>(p);
-    else conv_i8_kernel<4><<<grid, THREADS, smem, st>>>(p);
+    bool launched = false;
+#define SS_TRY(PL, KS_, ST_, RB_)                                                                                          \
+    if (!launched && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {                                 \
+        static bool attr = false;                                                                                          \
+        if (!attr) {                                                                                                       \
+            cudaFuncSetAttribute(conv_i8_kernel<PL, KS_, ST_, RB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            attr = true;                                                                                                   \
+        }                                                                                                                  \
+        conv_i8_kernel<PL, KS_, ST_, RB_><<<grid, THREADS, smem, st>>>(p);                                                 \
+        launched = true;                                                                                                   \
+    }
+#define SS_TRY_PL(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
+    SS_TRY_PL(2)
+    SS_TRY_PL(3)
+    SS_TRY_PL(4)
+#undef SS_TRY_PL
+#undef SS_TRY
+    if (!launched) {
+        set_error("ss_conv_i8_fwd: no kernel instance for planes %d ks %d stride %d rowbytes %d", g->planes, g->ks, g->stride, p.RB);
+        return SS_EUNSUPPORTED;
+    }
     count_launch();
     return check_launch("conv_i8");
 }

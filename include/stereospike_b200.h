@@ -15,7 +15,7 @@
  *   spikes / activations : u8,   [T][B][H][W][C]  (timestep-major NHWC; values are small non-negative
  *                          integers: spikes {0,1}, spike sums {0..3}, event counts {0..255} -- exact)
  *   first-layer input    : fp32, [B][T][C][H][W]  (the reference's own NCHW event-count frames,
- *                          train.py:201-218); ss_pack_events turns it into u8 [T][B][H][W][32] for the
+ *                          train.py:201-218); ss_pack_events turns it into u8 [T][B][H][W][4] for the
  *                          tensor-core path, the SIMT path reads it directly
  *   weights              : fp32 OIHW as in the reference's state dict; ss_pack_weights_i8 derives the
  *                          int8 digit planes + per-channel power-of-two scale the tensor-core path uses
@@ -69,7 +69,8 @@ extern "C" {
  * All T timesteps run in ONE launch; the membrane potential stays in registers across the time loop. */
 typedef struct ss_block_desc {
     int32_t T, B;
-    int32_t Hin, Win, Cin;       /* source activation, u8 [T][B][Hin][Win][Cin], Cin % 32 == 0 */
+    int32_t Hin, Win, Cin;       /* source activation, u8 [T][B][Hin][Win][Cin], Cin % 32 == 0 -- or Cin == 4:
+                                    first-layer mode (packed event frames, 5x5 stride-1 conv) */
     int32_t Hout, Wout, Cout;    /* block output,     u8 [T][B][Hout][Wout][Cout], Cout % 32 == 0 */
     int32_t ks;                  /* 3 or 5 */
     int32_t stride;              /* 1 or 2 (2: ks 5, even pad) */
@@ -87,15 +88,16 @@ int ss_conv_i8_rowbytes(int32_t Cin, int32_t ks);
 
 /* fp32 OIHW weights -> `planes` balanced base-256 digit planes of a per-output-channel power-of-two fixed
  * point, laid out [Cout/32][Cin/RB][ks*ks][planes*32][RB] and pre-swizzled as the kernel wants them in shared
- * memory (Cout*Cin*ks*ks*planes bytes).  wscale[n] = 2^wexp[n]:  w[n][...] ~= wscale[n] * sum_p digit_p * 256^(planes-1-p),
+ * memory (Cout*Cin*ks*ks*planes bytes; first-layer mode Cin <= 4, ks 5: [Cout/32][planes*32][128],
+ * Cout*128*planes bytes, input channels zero-padded to 4).  wscale[n] = 2^wexp[n]:  w[n][...] ~= wscale[n] * sum_p digit_p * 256^(planes-1-p),
  * absolute error <= wscale[n] / 2. */
 int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, void* w_i8,
                        float* wscale, int32_t* wexp, void* stream);
 
-/* fp32 [B][T][C][H][W] event-count frames (C <= 4) -> u8 [T][B][H][W][32] (channels >= C zero).  Counts are
+/* fp32 [B][T][C][H][W] event-count frames (C <= 4) -> u8 [T][B][H][W][4] (channels >= C zero).  Counts are
  * rounded and clamped to 0..255; if any input is not already such an integer, bit 0 of *status (device int,
  * may be NULL) is set. */
-int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw32,
+int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw4,
                    int32_t* status, void* stream);
 
 /*   x      : u8 [T][B][Hin][Win][Cin]

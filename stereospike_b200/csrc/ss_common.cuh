@@ -31,24 +31,60 @@ int check_launch(const char* what);
 
 int launch_conv_neuron_simt(const ConvParams& p, int in_layout, cudaStream_t st);
 
+// Correctly rounded a / b for a loop-invariant divisor b:  y = refined reciprocal of b (div_const_prepare), two
+// fused residual corrections (the fast path of div.rn.f32 with the reciprocal hoisted out of the loop).  Bit-identical
+// to IEEE division away from the exponent extremes, where it falls back to the full division.
+__device__ __forceinline__ float div_const_prepare(float b) {
+    float y = __frcp_rn(b);
+    const float e = fmaf(-b, y, 1.0f);
+    return fmaf(e, y, y);
+}
+__device__ __forceinline__ float div_const(float a, float b, float y) {
+    const float aa = fabsf(a);
+    if (!(aa > 1e-30f && aa < 1e30f)) return __fdiv_rn(a, b);
+    float q = __fmul_rn(a, y);
+    float r = fmaf(-b, q, a);
+    q = fmaf(r, y, q);
+    r = fmaf(-b, q, a);
+    return fmaf(r, y, q);
+}
+
+// Loop-invariant neuron parameters (rtau = div_const_prepare(tau)).
+struct NeuronConst {
+    float gain, v_th, v_reset, tau, rtau, decay;
+};
+
 // One neuron step (SpikingJelly BaseNode.forward: charge -> fire -> hard reset), fp32.
 // Returns the spike (0/1); v is updated in place; h_out receives the pre-reset potential.
-__device__ __forceinline__ float neuron_step(int kind, float x, float& v, float v_th, float v_reset,
-                                             float tau, float decay, float& h_out) {
+template <int KIND>
+__device__ __forceinline__ float neuron_step_t(float x, float& v, const NeuronConst& c, float& h_out) {
     float h;
-    if (kind == SS_NEURON_IF) {
-        h = v + x;
-    } else if (kind == SS_NEURON_LIF) {
+    if (KIND == SS_NEURON_IF) {
+        h = __fadd_rn(v, x);
+    } else if (KIND == SS_NEURON_LIF) {
         // true division: (x - v) / tau is not (x - v) * (1 / tau) in fp32
-        h = (v_reset == 0.0f) ? v + __fdiv_rn(x - v, tau) : v + __fdiv_rn(x - (v - v_reset), tau);
+        const float dv = (c.v_reset == 0.0f) ? __fsub_rn(x, v) : __fsub_rn(x, __fsub_rn(v, c.v_reset));
+        h = __fadd_rn(v, div_const(dv, c.tau, c.rtau));
     } else {
-        h = (v_reset == 0.0f) ? __fadd_rn(v, __fmul_rn(x - v, decay))
-                              : __fadd_rn(v, __fmul_rn(x - (v - v_reset), decay));
+        const float dv = (c.v_reset == 0.0f) ? __fsub_rn(x, v) : __fsub_rn(x, __fsub_rn(v, c.v_reset));
+        h = __fadd_rn(v, __fmul_rn(dv, c.decay));
     }
     h_out = h;
-    const float s = (h - v_th >= 0.0f) ? 1.0f : 0.0f;
-    v = (s != 0.0f) ? v_reset : h;
-    return s;
+    const bool fire = __fsub_rn(h, c.v_th) >= 0.0f;
+    v = fire ? c.v_reset : h;
+    return fire ? 1.0f : 0.0f;
+}
+
+__device__ __forceinline__ float neuron_step(int kind, float x, float& v, float v_th, float v_reset, float tau, float decay,
+                                             float& h_out) {
+    NeuronConst c;
+    c.gain = 1.0f; c.v_th = v_th; c.v_reset = v_reset; c.tau = tau; c.rtau = 0.0f; c.decay = decay;
+    if (kind == SS_NEURON_IF) return neuron_step_t<SS_NEURON_IF>(x, v, c, h_out);
+    if (kind == SS_NEURON_LIF) {
+        c.rtau = div_const_prepare(tau);
+        return neuron_step_t<SS_NEURON_LIF>(x, v, c, h_out);
+    }
+    return neuron_step_t<SS_NEURON_PLIF>(x, v, c, h_out);
 }
 
 }  // namespace ss

@@ -39,7 +39,6 @@ namespace ss {
 namespace {
 
 constexpr int NWB = 2;        // weight buffers
-constexpr int LAG = 2;        // cp.async groups in flight per producer thread
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_SLOTS = 8;
 constexpr int THREADS = 512;
@@ -54,6 +53,7 @@ struct I8Params {
     int tiles_x, mtiles, nitems;
     int TC, NPS, WB, PB;
     int resident;
+    int nwb;               // weight buffers allocated in shared memory (1 when a single channel block is resident)
     float yscale, xscale;
     int neuron;
     float gain, v_th, v_reset, tau;
@@ -101,10 +101,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// mbarrier arrival triggered by the completion of all prior cp.async of this thread (counts as one expected arrival)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -205,7 +204,10 @@ __device__ __forceinline__ constexpr int tap_offset(int ky, int kx) {
     return STRIDE == 1 ? ky * PWP + kx : ky * PWP + (kx & 1) * PWHALF + (kx >> 1);
 }
 
-template <int PLANES, int KS, int STRIDE, int RB>
+// FIRST: the first layer (Cin <= 4, event-count frames u8 [T][B][H][W][4]).  Its K = ks*ks*4 <= 128 is one swizzle row,
+// so the producers assemble an explicit im2col tile (KS = 1 "tap", RB = 128: row = output pixel, byte = tap*4 + c) with
+// L1-cached 4-byte loads instead of a halo patch -- 4 MMAs per tile instead of ks*ks*(32-channel padded blocks).
+template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
@@ -225,8 +227,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     uint8_t* sm = smem_raw + (base - raw_addr);
 
     const uint32_t w_base = base;
-    const uint32_t patch_base = base + NWB * cWB;
-    uint8_t* tail = sm + (size_t)NWB * cWB + (size_t)p.NPS * cPB;
+    const uint32_t patch_base = base + (uint32_t)p.nwb * cWB;
+    uint8_t* tail = sm + (size_t)p.nwb * cWB + (size_t)p.NPS * cPB;
     int* rowsrc = reinterpret_cast<int*>(tail);              // [2][40]
     int* colsrc = rowsrc + 80;                               // [2][24]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
@@ -268,14 +270,67 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t swz_mask = (uint32_t)(RB >> 4) - 1u;  // 32 -> 1, 64 -> 3, 128 -> 7
 
-    if (warp < 4) {
+    if (warp < 4 && FIRST) {
+        // ================================================================== first-layer im2col producers
+        const int r = threadIdx.x;               // tile row = output pixel
+        const size_t t_stride = (size_t)p.B * p.Hin * p.Win * 4;
+        constexpr int ks = 5;                    // real filter (the template's KS is the single im2col "tap")
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+            const int mt = it % p.mtiles;
+            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            const int so = ty * 16 + (r >> 3);
+            const int b = so / p.HsO;
+            const int oy = so - b * p.HsO;
+            const int ox = tx * 8 + (r & 7);
+            const bool live = b < p.B && oy < p.Hout && ox < p.Wout;
+            // validity of each tap (zero padding) and the offset of tap (0,0)
+            uint32_t vmask = 0;
+            if (live) {
+                for (int ky = 0; ky < ks; ++ky)
+                    for (int kx = 0; kx < ks; ++kx) {
+                        const int iy = oy + ky - p.pad, ix = ox + kx - p.pad;
+                        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) vmask |= 1u << (ky * ks + kx);
+                    }
+            }
+            const long long o00 = ((long long)(b * p.Hin + oy - p.pad) * p.Win + (ox - p.pad)) * 4;
+            for (int t = 0; t < p.T; ++t) {
+                mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
+                const uint8_t* xt = p.x + (size_t)t * t_stride;
+                uint32_t wds[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) wds[i] = 0u;
+#pragma unroll
+                for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) {
+                        constexpr int dummy2 = 0;
+                        (void)dummy2;
+                        const int tap = ky * ks + kx;
+                        if ((vmask >> tap) & 1u)
+                            wds[tap] = __ldg(reinterpret_cast<const uint32_t*>(xt + o00 + ((long long)ky * p.Win + kx) * 4));
+                    }
+                uint8_t* dst = sm + (size_t)p.nwb * cWB + (size_t)stage * cPB + (size_t)r * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(dst + ((c ^ (r & 7)) << 4)) = make_uint4(wds[4 * c], wds[4 * c + 1], wds[4 * c + 2], wds[4 * c + 3]);
+                fence_proxy_async();
+                mbar_arrive(bar_full_p + 8 * stage);
+                if (++stage == p.NPS) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp < 4) {
         // ================================================================== patch producers
         const int tid = threadIdx.x;
         const size_t t_stride = (size_t)p.B * p.Hin * p.Win * p.Cin;
         constexpr int chunks = RB >> 4;
         int stage = 0;
         uint32_t phase = 0;
-        int issued = 0, arrive_stage = 0, itcount = 0;
+        int itcount = 0;
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x, ++itcount) {
             const int ntile = it / p.mtiles;
             const int mt = it - ntile * p.mtiles;
@@ -319,14 +374,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                                     cp_async_16(dst0 + swizzle_off(off + c * 16, swz_mask), ok ? src + c * 16 : src, ok ? 16u : 0u);
                             }
                         }
-                        cp_async_commit();
-                        ++issued;
-                        if (issued > LAG) {
-                            cp_async_wait<LAG>();
-                            fence_proxy_async();
-                            mbar_arrive(bar_full_p + 8 * arrive_stage);
-                            if (++arrive_stage == p.NPS) arrive_stage = 0;
-                        }
+                        // the barrier arrival fires when this thread's copies have landed; nobody blocks here
+                        cp_async_arrive_noinc(bar_full_p + 8 * stage);
                         if (++stage == p.NPS) {
                             stage = 0;
                             phase ^= 1u;
@@ -334,13 +383,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     }
                 }
             }
-        }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        const int pending = issued < LAG ? issued : LAG;
-        for (int i = 0; i < pending; ++i) {
-            mbar_arrive(bar_full_p + 8 * arrive_stage);
-            if (++arrive_stage == p.NPS) arrive_stage = 0;
         }
     } else if (warp == 4) {
         // ================================================================== MMA issuer
@@ -357,6 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
 
         auto do_stage = [&](int wbuf, int slot, bool first) {
             mbar_wait(bar_full_p + 8 * stage, phase);
+            fence_proxy_async();   // cp.async wrote the patch through the generic proxy; the MMA reads it through the async proxy
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t a0 = make_desc(patch_base + (uint32_t)stage * cPB, a_sbo, layout);
@@ -485,8 +528,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         const int m = quarter * 32 + lane;
         const int g = m >> 3, j = m & 7;
         const int M = p.B * p.Hout * p.Wout;
-        float decay = 0.0f;
-        if (p.neuron == SS_NEURON_PLIF) decay = __ldg(p.decay);
+        NeuronConst nc;
+        nc.gain = p.gain; nc.v_th = p.v_th; nc.v_reset = p.v_reset; nc.tau = p.tau;
+        nc.rtau = div_const_prepare(p.tau);
+        nc.decay = (p.neuron == SS_NEURON_PLIF) ? __ldg(p.decay) : 0.0f;
+        const size_t t_out = (size_t)M * p.Cout;
         uint32_t slot_phase = 0;
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
             const int ntile = it / p.mtiles;
@@ -499,6 +545,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const bool live = b < p.B && oy < p.Hout && ox < p.Wout;
             const int nb = ntile * 32 + hf * 16;
             const size_t pix = live ? ((size_t)(b * p.Hout + oy) * p.Wout + ox) : 0;
+            const size_t o0 = pix * p.Cout + nb;                  // element offset inside one timestep
+            const bool use_resid = p.resid != nullptr && live;
+            uint4 rs_next = make_uint4(0u, 0u, 0u, 0u);
+            if (use_resid) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + o0));
             float sc[16], v[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -506,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 sc[4 * i] = q.x; sc[4 * i + 1] = q.y; sc[4 * i + 2] = q.z; sc[4 * i + 3] = q.w;
             }
             if (p.v_in != nullptr && live) {
-                const float4* vi = reinterpret_cast<const float4*>(p.v_in + pix * p.Cout + nb);
+                const float4* vi = reinterpret_cast<const float4*>(p.v_in + o0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 q = __ldg(vi + i);
@@ -520,6 +570,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 const int tc = min(cTC, p.T - t0);
                 for (int s = 0; s < tc; ++s) {
                     const int t = t0 + s;
+                    // residual of this step was requested one step ago; request the next one before blocking
+                    const uint4 rs_cur = rs_next;
+                    if (use_resid && t + 1 < p.T) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + (size_t)(t + 1) * t_out + o0));
                     mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
                     slot_phase ^= 1u << s;
                     tc_fence_after();
@@ -531,35 +584,42 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     tc_fence_before();
                     mbar_arrive(bar_empty_a + 8 * s);   // the slot is in registers now: hand it back to the MMA warp
                     if (!live) continue;
-                    const size_t o = ((size_t)t * M + pix) * p.Cout + nb;
-                    uint32_t rsd[4] = {0u, 0u, 0u, 0u};
-                    if (p.resid != nullptr) {
-                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.resid + o));
-                        rsd[0] = q.x; rsd[1] = q.y; rsd[2] = q.z; rsd[3] = q.w;
-                    }
-                    uint32_t packed[4] = {0u, 0u, 0u, 0u};
-                    float hbuf[16];
+                    float x[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        // recombine the base-256 digit planes exactly, round once to fp32
+                        // recombine the base-256 digit planes exactly, round once to fp32, then scale and gain
                         float conv;
                         if (PLANES == 2) {
                             conv = __int2float_rn(d[0][i] * 256 + d[1][i]);
                         } else if (PLANES == 3) {
-                            conv = __double2float_rn(fma((double)(d[0][i] * 256 + d[1][i]), 256.0, (double)d[2][i]));
+                            conv = __ll2float_rn((long long)(d[0][i] * 256 + d[1][i]) * 256LL + (long long)d[2][i]);
                         } else {
-                            conv = __double2float_rn(
-                                fma((double)(d[0][i] * 256 + d[1][i]), 65536.0, (double)(d[PLANES - 2][i] * 256 + d[PLANES - 1][i])));
+                            conv = __ll2float_rn((long long)(d[0][i] * 256 + d[1][i]) * 65536LL +
+                                                 (long long)(d[PLANES - 2][i] * 256 + d[PLANES - 1][i]));
                         }
-                        conv = __fmul_rn(conv, sc[i]);
-                        float h;
-                        const float s_out = neuron_step(p.neuron, __fmul_rn(conv, p.gain), v[i], p.v_th, p.v_reset, p.tau, decay, h);
-                        hbuf[i] = h;
-                        const uint32_t r8 = (rsd[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-                        const uint32_t o8 = (s_out != 0.0f ? 1u : 0u) + r8;
-                        packed[i >> 2] |= o8 << ((i & 3) * 8);
+                        x[i] = __fmul_rn(__fmul_rn(conv, sc[i]), nc.gain);
                     }
-                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    float hbuf[16];
+                    uint32_t fired = 0;
+                    if (p.neuron == SS_NEURON_IF) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) fired |= (neuron_step_t<SS_NEURON_IF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u) << i;
+                    } else if (p.neuron == SS_NEURON_LIF) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) fired |= (neuron_step_t<SS_NEURON_LIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u) << i;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) fired |= (neuron_step_t<SS_NEURON_PLIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u) << i;
+                    }
+                    // 16 spike bits -> 16 bytes (+ residual bytes; sums stay <= 3, no carry between bytes)
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t nib = (fired >> (4 * q)) & 0xFu;
+                        pk[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                    }
+                    const size_t o = (size_t)t * t_out + o0;
+                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(pk[0] + rs_cur.x, pk[1] + rs_cur.y, pk[2] + rs_cur.z, pk[3] + rs_cur.w);
                     if (p.h_seq != nullptr) {
                         float4* hp = reinterpret_cast<float4*>(p.h_seq + o);
 #pragma unroll
@@ -568,7 +628,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 }
             }
             if (p.v_out != nullptr && live) {
-                float4* vo = reinterpret_cast<float4*>(p.v_out + pix * p.Cout + nb);
+                float4* vo = reinterpret_cast<float4*>(p.v_out + o0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
@@ -652,9 +712,35 @@ __global__ void __launch_bounds__(256) weight_pack_kernel(const float* __restric
     }
 }
 
-// fp32 NCHW event-count frames [B][T][C][H][W] (reference layout, train.py:201-218) -> u8 NHWC [T][B][H][W][32]
+// first layer (Cin <= 4): [ntile][planes x 32 rows][128 B], byte k = (ky*5+kx)*4 + c, bytes 100..127 zero
+__global__ void __launch_bounds__(256) weight_pack_first_kernel(const float* __restrict__ w, int Cout, int Cin, int planes,
+                                                                const int* __restrict__ wexp, int8_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Cout * 128) return;
+    const int k = idx & 127;
+    const int n = idx >> 7;
+    const int ntile = n >> 5, r32 = n & 31;
+    const int tap = k >> 2, c = k & 3;
+    long long q = 0;
+    if (tap < 25 && c < Cin) q = llrint(ldexp((double)w[((size_t)n * Cin + c) * 25 + tap], -wexp[n]));
+    const int N = planes * 32;
+    const size_t buf = (size_t)ntile * N * 128;
+    for (int pl = planes - 1; pl >= 0; --pl) {
+        long long dgt;
+        if (pl > 0) {
+            dgt = ((q + 128) & 255) - 128;
+            q = (q - dgt) >> 8;
+        } else {
+            dgt = q;
+        }
+        const uint32_t off = (uint32_t)((pl * 32 + r32) * 128 + k);
+        out[buf + (off ^ (((off >> 7) & 7u) << 4))] = (int8_t)dgt;
+    }
+}
+
+// fp32 NCHW event-count frames [B][T][C][H][W] (reference layout, train.py:201-218) -> u8 NHWC [T][B][H][W][4]
 __global__ void __launch_bounds__(256) pack_events_kernel(const float* __restrict__ x, int B, int T, int C, int H, int W,
-                                                          uint8_t* __restrict__ out, int* __restrict__ status) {
+                                                          uint32_t* __restrict__ out, int* __restrict__ status) {
     const long long HW = (long long)H * W;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)T * B * HW) return;
@@ -669,9 +755,7 @@ __global__ void __launch_bounds__(256) pack_events_kernel(const float* __restric
         bad |= (r != f);
         lo |= (uint32_t)r << (8 * c);
     }
-    uint4* o = reinterpret_cast<uint4*>(out + (size_t)idx * 32);
-    o[0] = make_uint4(lo, 0u, 0u, 0u);
-    o[1] = make_uint4(0u, 0u, 0u, 0u);
+    out[idx] = lo;
     if (bad && status != nullptr) atomicOr(status, 1);
 }
 
@@ -686,9 +770,10 @@ extern "C" int ss_conv_i8_rowbytes(int32_t Cin, int32_t ks) { return rowbytes_fo
 
 extern "C" int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, void* w_i8,
                                   float* wscale, int32_t* wexp, void* stream) {
+    const bool first = Cin >= 1 && Cin <= 4;
     if (w_oihw == nullptr || w_i8 == nullptr || wscale == nullptr || wexp == nullptr || Cout <= 0 || Cin <= 0 || ks <= 0 ||
-        planes < 2 || planes > 4 || Cout % 32 != 0 || Cin % 32 != 0) {
-        set_error("ss_pack_weights_i8: bad argument (Cout %% 32, Cin %% 32, planes 2..4)");
+        planes < 2 || planes > 4 || Cout % 32 != 0 || (!first && Cin % 32 != 0) || (first && ks != 5)) {
+        set_error("ss_pack_weights_i8: bad argument (Cout %% 32; Cin %% 32, or Cin <= 4 with ks 5; planes 2..4)");
         return SS_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -696,6 +781,12 @@ extern "C" int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin
     weight_exponent_kernel<<<Cout, 256, 0, st>>>(w_oihw, Cout, Cin * ks * ks, planes, wscale, wexp);
     count_launch();
     if (check_launch("weight_exponent") != SS_OK) return SS_ECUDA;
+    if (first) {
+        weight_pack_first_kernel<<<(Cout * 128 + 255) / 256, 256, 0, st>>>(w_oihw, Cout, Cin, planes, wexp,
+                                                                            reinterpret_cast<int8_t*>(w_i8));
+        count_launch();
+        return check_launch("weight_pack_first");
+    }
     const long long total = (long long)Cout * Cin * ks * ks;
     weight_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_oihw, Cout, Cin, ks, planes, RB, wexp,
                                                                        reinterpret_cast<int8_t*>(w_i8));
@@ -703,16 +794,16 @@ extern "C" int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin
     return check_launch("weight_pack");
 }
 
-extern "C" int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw32,
+extern "C" int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw4,
                               int32_t* status, void* stream) {
-    if (x_btchw == nullptr || out_tbhw32 == nullptr || C <= 0 || C > 4 || B < 0 || T < 0 || H <= 0 || W <= 0) {
+    if (x_btchw == nullptr || out_tbhw4 == nullptr || C <= 0 || C > 4 || B < 0 || T < 0 || H <= 0 || W <= 0) {
         set_error("ss_pack_events: bad argument (1 <= C <= 4)");
         return SS_EINVAL;
     }
     const long long n = (long long)T * B * H * W;
     if (n == 0) return SS_OK;
     pack_events_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_btchw, B, T, C, H, W,
-                                                                                      reinterpret_cast<uint8_t*>(out_tbhw32), status);
+                                                                                      reinterpret_cast<uint32_t*>(out_tbhw4), status);
     count_launch();
     return check_launch("pack_events");
 }
@@ -732,8 +823,14 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
         set_error("ss_conv_i8_fwd: bad geometry");
         return SS_EINVAL;
     }
-    if (g->Cin % 32 != 0 || g->Cout % 32 != 0) {
-        set_error("ss_conv_i8_fwd: Cin and Cout must be multiples of 32 (got %d, %d)", g->Cin, g->Cout);
+    const bool first = g->Cin == 4;
+    if ((!first && g->Cin % 32 != 0) || g->Cout % 32 != 0) {
+        set_error("ss_conv_i8_fwd: Cin and Cout must be multiples of 32 (got %d, %d); Cin == 4 selects the first-layer mode", g->Cin,
+                  g->Cout);
+        return SS_EUNSUPPORTED;
+    }
+    if (first && (g->ks != 5 || g->stride != 1 || g->upsample != 0)) {
+        set_error("ss_conv_i8_fwd: the first-layer mode (Cin == 4) is a 5x5 stride-1 conv");
         return SS_EUNSUPPORTED;
     }
     if (g->planes < 2 || g->planes > 4) {
@@ -770,17 +867,23 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
         }
     }
     p.N = g->planes * 32;
-    p.RB = rowbytes_for(g->Cin, g->ks);
-    p.ncb = g->Cin / p.RB;
-    p.ntaps = g->ks * g->ks;
-    p.PH = 15 * g->stride + g->ks;
-    p.PWhalf = 8 + (g->ks - 1) / 2;
-    p.PWp = (g->stride == 1) ? 8 + g->ks - 1 : 2 * p.PWhalf;
+    if (first) {
+        p.RB = 128; p.ncb = 1; p.ntaps = 1; p.PH = 16; p.PWhalf = 8; p.PWp = 8;
+    } else {
+        p.RB = rowbytes_for(g->Cin, g->ks);
+        p.ncb = g->Cin / p.RB;
+        p.ntaps = g->ks * g->ks;
+        p.PH = 15 * g->stride + g->ks;
+        p.PWhalf = 8 + (g->ks - 1) / 2;
+        p.PWp = (g->stride == 1) ? 8 + g->ks - 1 : 2 * p.PWhalf;
+    }
     p.ppix = p.PH * p.PWp;
     p.Hup = g->Hout + g->ks - 1;
     p.Wup = g->Wout + g->ks - 1;
     if (up) {
         p.HsO = p.Hup;
+    } else if (first) {
+        p.HsO = g->Hout;   // explicit im2col rows: no halo shared between rows, so no gap rows between stacked images
     } else {
         // Stacked output rows per image.  Rows of the next image start stride*HsO input rows later; that must be
         // past this image's real rows (Hin + pad) and far enough that a tap reaching below the last output row
@@ -807,16 +910,17 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     p.WB = p.ntaps * p.N * p.RB;
     p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
     p.resident = p.ncb <= NWB ? 1 : 0;
+    p.nwb = p.ncb < NWB ? p.ncb : NWB;
     if (p.PH > 40 || p.PWp > 24) {
         set_error("ss_conv_i8_fwd: patch too large");
         return SS_EUNSUPPORTED;
     }
     const int tail_bytes = 512 + 40 * 8 + 64;
-    const int budget = 227 * 1024 - 1024 - tail_bytes - NWB * p.WB;
+    const int budget = 227 * 1024 - 1024 - tail_bytes - p.nwb * p.WB;
     int nps = budget / p.PB;
     if (nps > MAX_STAGES) nps = MAX_STAGES;
-    if (nps < LAG + 1) {
-        set_error("ss_conv_i8_fwd: not enough shared memory (weights %d B x %d, patch %d B)", p.WB, NWB, p.PB);
+    if (nps < 2) {
+        set_error("ss_conv_i8_fwd: not enough shared memory (weights %d B x %d, patch %d B)", p.WB, p.nwb, p.PB);
         return SS_EUNSUPPORTED;
     }
     p.NPS = nps;
@@ -830,7 +934,7 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     p.out = reinterpret_cast<uint8_t*>(out);
     p.h_seq = h_seq;
 
-    const size_t smem = 1024 + (size_t)NWB * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
+    const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -851,11 +955,22 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
         conv_i8_kernel<PL, KS_, ST_, RB_><<<grid, THREADS, smem, st>>>(p);                                                 \
         launched = true;                                                                                                   \
     }
-#define SS_TRY_PL(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
+#define SS_TRY_FIRST(PL)                                                                                                   \
+    if (!launched && first && g->planes == PL) {                                                                           \
+        static bool attr = false;                                                                                          \
+        if (!attr) {                                                                                                       \
+            cudaFuncSetAttribute(conv_i8_kernel<PL, 1, 1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            attr = true;                                                                                                   \
+        }                                                                                                                  \
+        conv_i8_kernel<PL, 1, 1, 128, true><<<grid, THREADS, smem, st>>>(p);                                               \
+        launched = true;                                                                                                   \
+    }
+#define SS_TRY_PL(PL) SS_TRY_FIRST(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
     SS_TRY_PL(2)
     SS_TRY_PL(3)
     SS_TRY_PL(4)
 #undef SS_TRY_PL
+#undef SS_TRY_FIRST
 #undef SS_TRY
     if (!launched) {
         set_error("ss_conv_i8_fwd: no kernel instance for planes %d ks %d stride %d rowbytes %d", g->planes, g->ks, g->stride, p.RB);

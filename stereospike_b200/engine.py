@@ -44,7 +44,7 @@ class Site:
             w_i8 = None
             if need_i8:
                 cin = w.shape[1]
-                q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=(cin + 31) // 32 * 32)
+                q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=4 if cin <= 4 else (cin + 31) // 32 * 32)
                 w_i8 = (q, sc)
             self._pack = (key, w_kn, w_i8)
         return self._pack[1], self._pack[2]
@@ -161,9 +161,9 @@ class Engine:
                           tau=node._tau_value(), decay=decay, v_in=v_in, want_v_out=self.keep_state, resid=resid, want_h=want_h)
             if use_i8:
                 if first:
-                    xin = ops.pack_events(x_seq, self.event_status)     # fp32 NCHW counts -> u8 NHWC32
+                    xin = ops.pack_events(x_seq, self.event_status)     # fp32 NCHW counts -> u8 NHWC4
                 out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
-                                                    cin=32 if first else g.Cin, **common)
+                                                    cin=4 if first else g.Cin, **common)
             else:
                 out, v_out, h_seq = ops.conv_neuron_fwd(xin, g, w_kn, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC,
                                                         **common)

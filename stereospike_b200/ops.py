@@ -94,14 +94,15 @@ def kn_to_weight(w_kn, co, ci, ks):
 
 def pack_weights_i8(weight, planes, cin_pad=None):
     """OIHW fp32 -> (int8 digit planes in the kernel's shared-memory image, wscale fp32 [Cout], wexp int32 [Cout]).
-    ``cin_pad``: zero-pad the input channels up to this count (the first layer's 2/4 channels -> 32)."""
+    ``cin_pad``: zero-pad the input channels up to this count (the first layer's 2 channels -> 4)."""
     w = weight.detach().float()
     co, ci, kh, kw = w.shape
     if cin_pad is not None and cin_pad > ci:
         w = torch.cat([w, w.new_zeros(co, cin_pad - ci, kh, kw)], dim=1)
         ci = cin_pad
     w = w.contiguous()
-    out = torch.empty(co * ci * kh * kw * planes, dtype=torch.int8, device=w.device)
+    nbytes = co * 128 * planes if ci <= 4 else co * ci * kh * kw * planes
+    out = torch.empty(nbytes, dtype=torch.int8, device=w.device)
     wscale = torch.empty(co, dtype=torch.float32, device=w.device)
     wexp = torch.empty(co, dtype=torch.int32, device=w.device)
     _lib.check(_lib.lib().ss_pack_weights_i8(_ptr(w), co, ci, kh, planes, _ptr(out), _ptr(wscale), _ptr(wexp), _stream()),
@@ -110,10 +111,10 @@ def pack_weights_i8(weight, planes, cin_pad=None):
 
 
 def pack_events(x_seq, status=None):
-    """fp32 [B,T,C,H,W] event-count frames -> u8 [T,B,H,W,32] (the first block's tensor-core input)."""
+    """fp32 [B,T,C,H,W] event-count frames -> u8 [T,B,H,W,4] (the first block's tensor-core input)."""
     _require_cuda(x_seq, 'x')
     B, T, C, H, W = x_seq.shape
-    out = torch.empty((T, B, H, W, 32), dtype=torch.uint8, device=x_seq.device)
+    out = torch.empty((T, B, H, W, 4), dtype=torch.uint8, device=x_seq.device)
     _lib.check(_lib.lib().ss_pack_events(_ptr(x_seq), B, T, C, H, W, _ptr(out), _ptr(status), _stream()), 'ss_pack_events')
     return out
 

@@ -52,15 +52,19 @@ def block_case(kind, Cin, Cout, ks, Hin, Win, stride, pad, up, neuron, T, B, imp
     v_ref = node.v.permute(0, 2, 3, 1).contiguous()
     # device
     xb = x.permute(0, 1, 3, 4, 2).contiguous().to(dev, torch.uint8)
+    cin_dev = None
+    if Cin < 4:       # first-layer mode wants 4 packed channels
+        xb = torch.cat([xb, xb.new_zeros(T, B, Hin, Win, 4 - Cin)], dim=-1).contiguous()
+        cin_dev = 4
     rb = r.permute(0, 1, 3, 4, 2).contiguous().to(dev, torch.uint8) if resid else None
     decay = node.w.detach().sigmoid().reshape(1).float().to(dev) if neuron == 2 else None
     common = dict(T=T, B=B, neuron=neuron, gain=gain, v_th=1.0, v_reset=0.0, tau=3.0, decay=decay, want_v_out=True,
                   resid=rb, want_h=True)
     if impl == 'umma':
-        w_i8, wscale, _ = ops.pack_weights_i8(w.to(dev), planes)
+        w_i8, wscale, _ = ops.pack_weights_i8(w.to(dev), planes, cin_pad=cin_dev)
         torch.cuda.synchronize()
         t0 = time.time()
-        out, v_out, h_seq = ops.conv_i8_fwd(xb, geom, w_i8, wscale, planes=planes, **common)
+        out, v_out, h_seq = ops.conv_i8_fwd(xb, geom, w_i8, wscale, planes=planes, cin=cin_dev, **common)
     else:
         w_kn = ops.weight_to_kn(w.to(dev))
         torch.cuda.synchronize()

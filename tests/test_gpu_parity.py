@@ -65,6 +65,17 @@ def test_block_teacher_forced(name, impl, planes):
     assert r['spike_mismatch_all'] <= max(2, 2e-5 * r['n']), r
 
 
+@pytest.mark.parametrize('cin', [4, 2])
+def test_first_layer_mode(cin):
+    """First-layer mode of the tensor-core kernel: 4-channel packed event frames, explicit im2col tile (K = 100 -> 128)."""
+    from tests._cases import block_case
+    r = block_case(kind='conv', Cin=cin, Cout=32, ks=5, Hin=37, Win=29, stride=1, pad=2, up=None, neuron=1, T=6, B=3,
+                   impl='umma', planes=3, resid=False, gain=6.0)
+    assert 0.02 < r['rate'] < 0.9, r
+    assert r['max_dh_t0'] <= TOL_H * max(1.0, r['h_absmax']), r
+    assert r['spike_mismatch_outside_band'] == 0, r
+
+
 @pytest.mark.parametrize('planes,tol', [(2, 2e-3), (4, 2e-5)])
 def test_block_other_weight_planes(planes, tol):
     """2 planes = 16-bit fixed-point weights (reduced-precision configuration), 4 planes = 32-bit."""
@@ -151,7 +162,7 @@ def test_pack_events_flags_non_integer_input():
     x[0, 1, 2, 3, 4] = 3.0
     st = torch.zeros(1, dtype=torch.int32, device='cuda')
     p = ops.pack_events(x, st)
-    assert p.shape == (2, 1, 6, 7, 32) and int(p[1, 0, 3, 4, 2]) == 3 and int(p.sum()) == 3 and int(st) == 0
+    assert p.shape == (2, 1, 6, 7, 4) and int(p[1, 0, 3, 4, 2]) == 3 and int(p.sum()) == 3 and int(st) == 0
     x[0, 0, 0, 0, 0] = 0.5
     x[0, 0, 1, 0, 0] = 300.0
     ops.pack_events(x, st)

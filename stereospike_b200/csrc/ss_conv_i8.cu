@@ -295,32 +295,40 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     }
             }
             const long long o00 = ((long long)(b * p.Hin + oy - p.pad) * p.Win + (ox - p.pad)) * 4;
-            for (int t = 0; t < p.T; ++t) {
-                mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
-                const uint8_t* xt = p.x + (size_t)t * t_stride;
-                uint32_t wds[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) wds[i] = 0u;
+            // software pipeline: the 25 loads of timestep t+1 are in flight while timestep t is written to shared memory
+            uint32_t cur[25], nxt[25];
+            auto issue = [&](int t, uint32_t (&w)[25]) {
+                const uint8_t* xt = p.x + (size_t)t * t_stride + o00;
 #pragma unroll
                 for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 5; ++kx) {
-                        constexpr int dummy2 = 0;
-                        (void)dummy2;
-                        const int tap = ky * ks + kx;
-                        if ((vmask >> tap) & 1u)
-                            wds[tap] = __ldg(reinterpret_cast<const uint32_t*>(xt + o00 + ((long long)ky * p.Win + kx) * 4));
+                        const int tap = ky * 5 + kx;
+                        w[tap] = ((vmask >> tap) & 1u) ? __ldg(reinterpret_cast<const uint32_t*>(xt + ((long long)ky * p.Win + kx) * 4)) : 0u;
                     }
+            };
+            issue(0, cur);
+            for (int t = 0; t < p.T; ++t) {
+                if (t + 1 < p.T) issue(t + 1, nxt);
+                mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
                 uint8_t* dst = sm + (size_t)p.nwb * cWB + (size_t)stage * cPB + (size_t)r * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<uint4*>(dst + ((c ^ (r & 7)) << 4)) = make_uint4(wds[4 * c], wds[4 * c + 1], wds[4 * c + 2], wds[4 * c + 3]);
+                for (int c = 0; c < 8; ++c) {
+                    uint4 q;
+                    q.x = 4 * c < 25 ? cur[(4 * c) % 25] : 0u;
+                    q.y = 4 * c + 1 < 25 ? cur[(4 * c + 1) % 25] : 0u;
+                    q.z = 4 * c + 2 < 25 ? cur[(4 * c + 2) % 25] : 0u;
+                    q.w = 4 * c + 3 < 25 ? cur[(4 * c + 3) % 25] : 0u;
+                    *reinterpret_cast<uint4*>(dst + ((c ^ (r & 7)) << 4)) = q;
+                }
                 fence_proxy_async();
                 mbar_arrive(bar_full_p + 8 * stage);
                 if (++stage == p.NPS) {
                     stage = 0;
                     phase ^= 1u;
                 }
+#pragma unroll
+                for (int i = 0; i < 25; ++i) cur[i] = nxt[i];
             }
         }
     } else if (warp < 4) {

@@ -58,13 +58,17 @@ __global__ void __launch_bounds__(TAPS_NT) head_taps_kernel(const HeadsParams p)
     for (int c16 = 0; c16 < C / 16; ++c16) {
         const uint4 raw = __ldg(src + c16);
         const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
-        if ((raw.x | raw.y | raw.z | raw.w) == 0u) continue;   // all-silent channel group
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const float a = (float)((wds[e >> 2] >> ((e & 3) * 8)) & 0xFFu);
-            const float* wc = wt + c16 * 16 + e;
+        for (int q = 0; q < 4; ++q) {
+            if (wds[q] == 0u) continue;                       // four silent channels
+            const float a0 = (float)(wds[q] & 0xFFu), a1 = (float)((wds[q] >> 8) & 0xFFu);
+            const float a2 = (float)((wds[q] >> 16) & 0xFFu), a3 = (float)(wds[q] >> 24);
+            const float* wc = wt + c16 * 16 + q * 4;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) acc[k] = fmaf(a, wc[k * C], acc[k]);
+            for (int k = 0; k < 9; ++k) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wc + k * C);
+                acc[k] = fmaf(a3, w4.w, fmaf(a2, w4.z, fmaf(a1, w4.y, fmaf(a0, w4.x, acc[k]))));
+            }
         }
     }
     float* dst = p.taps[hd] + (size_t)tb * 9 * S + s;

@@ -122,6 +122,18 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with the per-tap descriptor offsets (in 16-byte units) folded into the asm statement so that the two 64-bit adds
+// stay next to their MMA instead of being hoisted in front of the whole tap sequence.
+template <uint32_t AOFF, uint32_t BOFF>
+__device__ __forceinline__ void umma_i8_off(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t"
+        "add.s64 da, %1, %4;\n\t"
+        "add.s64 db, %2, %5;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, 1;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "n"(AOFF), "n"(BOFF)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -202,6 +214,24 @@ __device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
 template <int STRIDE, int PWP, int PWHALF>
 __device__ __forceinline__ constexpr int tap_offset(int ky, int kx) {
     return STRIDE == 1 ? ky * PWP + kx : ky * PWP + (kx & 1) * PWHALF + (kx >> 1);
+}
+
+// Issues every MMA of one (patch stage, weight buffer) pair except the very first one (tap 0, k-step 0), which the
+// caller issues itself because it carries the run-time accumulate flag.
+template <int KS, int STRIDE, int RB, int CN, int PWP, int PWHALF, int TAP = 0, int K = 1>
+__device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0, uint32_t idesc) {
+    constexpr int KSTEPS = RB / 32;
+    if constexpr (TAP < KS * KS) {
+        if constexpr (K < KSTEPS) {
+            constexpr int ky = TAP / KS, kx = TAP % KS;
+            constexpr uint32_t aoff = (uint32_t)(tap_offset<STRIDE, PWP, PWHALF>(ky, kx) * RB + K * 32) >> 4;
+            constexpr uint32_t boff = (uint32_t)(TAP * CN * RB + K * 32) >> 4;
+            umma_i8_off<aoff, boff>(d, a0, b0, idesc);
+            issue_taps<KS, STRIDE, RB, CN, PWP, PWHALF, TAP, K + 1>(d, a0, b0, idesc);
+        } else {
+            issue_taps<KS, STRIDE, RB, CN, PWP, PWHALF, TAP + 1, 0>(d, a0, b0, idesc);
+        }
+    }
 }
 
 // FIRST: the first layer (Cin <= 4, event-count frames u8 [T][B][H][W][4]).  Its K = ks*ks*4 <= 128 is one swizzle row,
@@ -393,106 +423,86 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             }
         }
     } else if (warp == 4) {
-        // ================================================================== MMA issuer
-        constexpr uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
-        constexpr uint32_t a_sbo = (uint32_t)(STRIDE * cPWp * RB);
-        constexpr uint32_t b_sbo = (uint32_t)(8 * RB);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t slot_phase = 0;   // bit s: parity to wait on empty_a[s] (starts "free")
-        uint32_t wu = 0;           // streaming: weight-use counter;  resident: number of loads done
-        int loaded_ntile = -1;
-        uint32_t w_pending = 0;    // resident: bit cb set while full_w[cb] has not been observed for the current load
+        // ================================================================== MMA issuer (ONE elected thread runs the whole role)
+        if (elect_one()) {
+            constexpr uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
+            constexpr uint32_t a_sbo = (uint32_t)(STRIDE * cPWp * RB);
+            constexpr uint32_t b_sbo = (uint32_t)(8 * RB);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t slot_phase = 0;   // bit s: parity to wait on empty_a[s] (starts "free")
+            uint32_t wu = 0;           // streaming: weight-use counter;  resident: number of loads done
+            int loaded_ntile = -1;
+            uint32_t w_pending = 0;    // resident: bit cb set while full_w[cb] has not been observed for the current load
+            const uint64_t a_stage0 = make_desc(patch_base, a_sbo, layout);
+            const uint64_t b_buf0 = make_desc(w_base, b_sbo, layout);
 
-        auto do_stage = [&](int wbuf, int slot, bool first) {
-            mbar_wait(bar_full_p + 8 * stage, phase);
-            fence_proxy_async();   // cp.async wrote the patch through the generic proxy; the MMA reads it through the async proxy
-            tc_fence_after();
-            if (elect_one()) {
-                const uint64_t a0 = make_desc(patch_base + (uint32_t)stage * cPB, a_sbo, layout);
-                const uint64_t b0 = make_desc(w_base + (uint32_t)wbuf * cWB, b_sbo, layout);
+            auto do_stage = [&](int wbuf, int slot, bool first) {
+                mbar_wait(bar_full_p + 8 * stage, phase);
+                fence_proxy_async();   // cp.async wrote the patch through the generic proxy; the MMA reads it through the async proxy
+                tc_fence_after();
+                const uint64_t a0 = a_stage0 + (uint64_t)((uint32_t)stage * (cPB >> 4));
+                const uint64_t b0 = b_buf0 + (uint64_t)((uint32_t)wbuf * (cWB >> 4));
                 const uint32_t d = tmem_base + (uint32_t)(slot * cN);
                 umma_i8(d, a0, b0, idesc, first ? 0u : 1u);
-#pragma unroll
-                for (int ky = 0; ky < KS; ++ky) {
-#pragma unroll
-                    for (int kx = 0; kx < KS; ++kx) {
-                        constexpr int dummy = 0;
-                        (void)dummy;
-                        const uint32_t aoff = (uint32_t)(tap_offset<STRIDE, cPWp, cPWhalf>(ky, kx) * RB);
-                        const uint32_t boff = (uint32_t)((ky * KS + kx) * cN * RB);
-#pragma unroll
-                        for (int k = 0; k < cKSTEPS; ++k) {
-                            if (ky == 0 && kx == 0 && k == 0) continue;   // issued above with the accumulate flag
-                            umma_i8(d, a0 + ((aoff + k * 32) >> 4), b0 + ((boff + k * 32) >> 4), idesc, 1u);
-                        }
-                    }
-                }
+                issue_taps<KS, STRIDE, RB, cN, cPWp, cPWhalf>(d, a0, b0, idesc);
                 umma_commit(bar_empty_p + 8 * stage);
-            }
-            __syncwarp();
-            if (++stage == p.NPS) {
-                stage = 0;
-                phase ^= 1u;
-            }
-        };
+                if (++stage == p.NPS) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            };
 
-        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-            const int ntile = it / p.mtiles;
-            if (p.resident && ntile != loaded_ntile) {
-                loaded_ntile = ntile;
-                w_pending = (1u << p.ncb) - 1u;
-                ++wu;
-            }
-            for (int t0 = 0; t0 < p.T; t0 += cTC) {
-                const int tc = min(cTC, p.T - t0);
-                if (p.resident) {
-                    for (int s = 0; s < tc; ++s) {
-                        mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
-                        slot_phase ^= 1u << s;
-                        tc_fence_after();
-                        for (int cb = 0; cb < p.ncb; ++cb) {
-                            if (w_pending & (1u << cb)) {
-                                mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
-                                w_pending &= ~(1u << cb);
-                            }
-                            do_stage(cb, s, cb == 0);
-                        }
-                        if (elect_one()) umma_commit(bar_full_a + 8 * s);
-                        __syncwarp();
-                    }
-                } else {
-                    for (int cb = 0; cb < p.ncb; ++cb) {
-                        const int buf = (int)(wu % NWB);
-                        mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+                const int ntile = it / p.mtiles;
+                if (p.resident && ntile != loaded_ntile) {
+                    loaded_ntile = ntile;
+                    w_pending = (1u << p.ncb) - 1u;
+                    ++wu;
+                }
+                for (int t0 = 0; t0 < p.T; t0 += cTC) {
+                    const int tc = min(cTC, p.T - t0);
+                    if (p.resident) {
                         for (int s = 0; s < tc; ++s) {
-                            if (cb == 0) {
-                                mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
-                                slot_phase ^= 1u << s;
-                                tc_fence_after();
+                            mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                            slot_phase ^= 1u << s;
+                            tc_fence_after();
+                            for (int cb = 0; cb < p.ncb; ++cb) {
+                                if (w_pending & (1u << cb)) {
+                                    mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
+                                    w_pending &= ~(1u << cb);
+                                }
+                                do_stage(cb, s, cb == 0);
                             }
-                            do_stage(buf, s, cb == 0);
-                            if (cb == p.ncb - 1) {
-                                if (elect_one()) umma_commit(bar_full_a + 8 * s);
-                                __syncwarp();
-                            }
+                            umma_commit(bar_full_a + 8 * s);
                         }
-                        if (elect_one()) umma_commit(bar_empty_w + 8 * buf);
-                        __syncwarp();
-                        ++wu;
+                    } else {
+                        for (int cb = 0; cb < p.ncb; ++cb) {
+                            const int buf = (int)(wu % NWB);
+                            mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+                            for (int s = 0; s < tc; ++s) {
+                                if (cb == 0) {
+                                    mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                                    slot_phase ^= 1u << s;
+                                    tc_fence_after();
+                                }
+                                do_stage(buf, s, cb == 0);
+                                if (cb == p.ncb - 1) umma_commit(bar_full_a + 8 * s);
+                            }
+                            umma_commit(bar_empty_w + 8 * buf);
+                            ++wu;
+                        }
                     }
                 }
-            }
-            if (p.resident) {
-                const int nxt = it + gridDim.x;
-                if (nxt < p.nitems && nxt / p.mtiles != ntile) {
-                    if (elect_one())
+                if (p.resident) {
+                    const int nxt = it + gridDim.x;
+                    if (nxt < p.nitems && nxt / p.mtiles != ntile)
                         for (int cb = 0; cb < p.ncb; ++cb) umma_commit(bar_empty_w + 8 * cb);
-                    __syncwarp();
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 5) {
         // ================================================================== weight producer (bulk copies)
         if (lane == 0) {

@@ -113,14 +113,14 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* patch_g, int 
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
 }
 
-__global__ void __launch_bounds__(128) rate_kernel(int n, int iters, int rb, long long* cycles_out) {
+__global__ void __launch_bounds__(128) rate_kernel(int n, int iters, int rb, int a_sbo, int a_shift, long long* cycles_out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x;
-    for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (base - raw))[i] = 0x01010101u;
+    for (int i = tid; i < (65536 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (base - raw))[i] = 0x01010101u;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(128) rate_kernel(int n, int iters, int rb, lon
     if (tid == 0) {
         const uint32_t idesc = idesc_i8(n, 0, 1);
         const uint32_t lay = layout_code(rb);
-        const uint64_t ad = make_desc(base, 8u * rb, lay);
-        const uint64_t bd = make_desc(base + 16384, 8u * rb, lay);
+        const uint64_t ad = make_desc(base + a_shift, (uint32_t)a_sbo, lay);
+        const uint64_t bd = make_desc(base + 65536, 8u * rb, lay);
         const int ks = rb / 32;
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
@@ -157,24 +157,30 @@ int main() {
     // ---- rate
     long long* dc;
     cudaMalloc(&dc, 148 * sizeof(long long));
-    const int smem_r = 1024 + 16384 + 32768;
+    const int smem_r = 1024 + 65536 + 32768;
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
-    for (int rb : {128, 32})
-        for (int n : {32, 64, 96, 128, 192, 256}) {
+    struct Cfg { int rb, sbo, shift; const char* what; };
+    const Cfg cfgs[] = {{32, 256, 0, "canonical rb32"},   {32, 384, 0, "5x5 s1 patch (12 px rows)"}, {32, 384, 13 * 32, "5x5 s1 patch, tap shift"},
+                        {32, 1280, 0, "5x5 s2 patch (2 x 20 px rows)"}, {32, 1280, 33 * 32, "5x5 s2 patch, tap shift"},
+                        {64, 512, 0, "canonical rb64"},   {64, 640, 0, "3x3 patch rb64 (10 px rows)"}, {64, 640, 11 * 64, "3x3 patch rb64, tap shift"},
+                        {32, 320, 0, "3x3 patch rb32"},   {128, 1024, 0, "canonical rb128 (first layer)"}};
+    for (const Cfg& c : cfgs)
+        for (int n : {64, 96, 128}) {
             const int iters = 2000;
-            rate_kernel<<<148, 128, smem_r>>>(n, iters, rb, dc);
+            rate_kernel<<<148, 128, smem_r>>>(n, iters, c.rb, c.sbo, c.shift, dc);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) {
                 printf("rate i8 N=%d: CUDA error %s\n", n, cudaGetErrorString(e));
                 return 1;
             }
-            std::vector<long long> c(148);
-            cudaMemcpy(c.data(), dc, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+            std::vector<long long> cc(148);
+            cudaMemcpy(cc.data(), dc, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
             long long mx = 0;
-            for (long long v : c) mx = v > mx ? v : mx;
+            for (long long v : cc) mx = v > mx ? v : mx;
             const double per = (double)mx / (iters * 4.0);
-            printf("rate i8 rowbytes=%3d grid=148 N=%3d: %.1f cycles per 128xNx32 MMA (N/2 = %.1f)\n", rb, n, per, n / 2.0);
+            printf("rate i8 %-34s rowbytes=%3d sbo=%4d N=%3d: %.1f cycles per 128xNx32 MMA (N/2 = %.1f)\n", c.what, c.rb, c.sbo, n, per, n / 2.0);
         }
+    return 0;
     // ---- correctness
     const int MAXROWS = 16 * 24 + 16;
     std::vector<uint8_t> patch(MAXROWS * 128);

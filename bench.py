@@ -55,9 +55,17 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+
+    def mark(self):
+        """Only samples taken after this call count (the timed region)."""
+        self.f.flush()
+        try:
+            self.skip = sum(1 for _ in open(self.f.name))
+        except OSError:
+            self.skip = 0
 
     def stop(self):
         if self.p is None:
@@ -68,7 +76,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()][getattr(self, 'skip', 0):]
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -167,7 +175,7 @@ def run_ours(args):
     import torch.distributed as dist
     import stereospike_b200 as sb
     from stereospike_b200 import _lib
-    from oracle import ref_model as rm
+    from oracle import ref_model as rm          # synthetic-input recipe only (shared with the CPU arm)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -179,6 +187,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     _lib.lib()   # fail loudly if the extension is missing
+    sampler = ClockSampler(local) if rank == 0 else None      # started early so that it has samples under load
 
     torch.manual_seed(0)
     if args.neuron == 'if':
@@ -191,7 +200,6 @@ def run_ours(args):
     B, T = args.batch, args.T
     xs_host = [rm.synthetic_inputs(B, T, 4, seed=100 + rank * 16 + i).pin_memory() for i in range(args.input_sets)]
     xs = [x.to(dev) for x in xs_host]
-    depth_host = torch.empty((B, 1, H0, W0), dtype=torch.float32).pin_memory()
 
     def step(x):
         sb.functional.reset_net(net)
@@ -208,7 +216,8 @@ def run_ours(args):
     barrier()
 
     # ---- device-resident throughput
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -221,22 +230,24 @@ def run_ours(args):
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if sampler else None
 
-    # ---- end to end: pinned host frames in, finest depth map out, every step
+    # ---- end to end through the public API: pinned host frames in (copy overlapped with the previous step's kernels on a
+    #      second stream), finest depth map back to pinned host memory, every step
+    pipe = sb.pipeline.HostPipeline(net, tuple(xs_host[0].shape), dev)
+    for i in range(2):
+        pipe.step(xs_host[i % len(xs_host)])
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
-        xg = xs_host[i % len(xs_host)].to(dev, non_blocking=True)
-        out = step(xg)
-        depth_host.copy_(out[0][0], non_blocking=True)
+        depth_host = pipe.step(xs_host[i % len(xs_host)])
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
 
-    # ---- per-kernel timing of the tcgen05 blocks (roofline)
+    # ---- per-kernel timing of the tensor-core blocks (roofline)
     eng = net.engine
     eng.timing = []
-    for i in range(min(args.steps, 5)):
+    for i in range(min(args.steps, 10)):
         step(xs[i % len(xs)])
     torch.cuda.synchronize()
     per_site = {}
@@ -254,38 +265,41 @@ def run_ours(args):
         frames = B * T * world
         value = frames * args.steps / (ms / 1e3)
         e2e_val = frames * args.steps / (ms_e2e / 1e3)
-        umma_sites = [k for k in per_site if k != 'heads']
-        umma_ms = sum(statistics.mean(per_site[k]) for k in umma_sites)
-        umma_gflop = sum(MFLOP_PER_FRAME[k] for k in umma_sites) / 1e3 * B * T
-        ach = umma_gflop / umma_ms if umma_ms > 0 else 0.0      # GFLOP/ms == TFLOP/s
+        conv_sites = [k for k in per_site if k != 'heads']
+        conv_ms = sum(statistics.mean(per_site[k]) for k in conv_sites)
+        conv_gflop = sum(MFLOP_PER_FRAME[k] for k in conv_sites) / 1e3 * B * T
+        ach = conv_gflop / conv_ms if conv_ms > 0 else 0.0      # GFLOP/ms == TFLOP/s
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get('conv_i8_bytes_per_launch')
+            traffic = json.load(open(tp)).get('conv_i8_dram_bytes_per_step')
         line = {
             'metric': 'event-frames/sec', 'value': value, 'unit': 'event-frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'u8 x s8 -> s32 (tcgen05 kind::i8), fp32 neuron state', 'data': 'synthetic',
-            'config': workload_config(args, B),
+            'vs_baseline': None, 'dtype': 'u8 x s8 -> s32 (tcgen05 kind::i8, %d weight digit planes), fp32 neuron state' % args.planes,
+            'data': 'synthetic', 'config': workload_config(args, B),
             'e2e': {'value': e2e_val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': xs_host[0].numel() * 4,
-                    'd2h_bytes_per_step': depth_host.numel() * 4, 'ms_per_step': ms_e2e / args.steps},
+                    'd2h_bytes_per_step': depth_host.numel() * 4, 'ms_per_step': ms_e2e / args.steps,
+                    'api': 'stereospike_b200.pipeline.HostPipeline.step (pinned fp32 frames -> forward_seq -> pinned depth map)'},
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                          'frac': ach / peaks['bf16_sustained'], 'traffic': traffic,
-                         'kernel': 'conv_i8_kernel (13 launches/step: bottom, conv1-4, bottleneck x4, deconv4-1)',
-                         'peak_source': peaks['source'] + ' sustained bf16 (MEASURED_PEAKS.json)',
-                         'algorithmic_gflop_per_step': umma_gflop, 'kernel_ms_per_step': umma_ms,
-                         'executed_flop_factor': args.planes,
+                         'kernel': 'conv_i8_kernel (13 launches/step: bottom, conv1-4, bottleneck x4, deconv4-1); achieved, '
+                                   'traffic and algorithmic work are summed over those 13 launches',
+                         'peak_source': peaks['source'] + ' sustained dense bf16 (MEASURED_PEAKS.json; the kernel runs int8 MMAs, '
+                                        '3 digit planes = 1.5 bf16-equivalents per algorithmic FLOP)',
+                         'algorithmic_gflop_per_step': conv_gflop, 'kernel_ms_per_step': conv_ms,
+                         'executed_int8_mac_factor': args.planes,
                          'per_block_ms': {k: round(statistics.mean(v), 4) for k, v in per_site.items()},
                          'per_block_tflops': {k: round(MFLOP_PER_FRAME[k] / 1e3 * B * T / statistics.mean(v), 1)
                                               for k, v in per_site.items() if k in MFLOP_PER_FRAME}},
             'model_gflop_per_frame': TOTAL_GFLOP_PER_FRAME,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, dt = cpu_oracle_rate(args.neuron, args.gain, args.tau, T, 1, 2)
+            v, cores, dt = cpu_oracle_rate(args.neuron, args.gain, args.tau, T, 1, 8)
             line['cpu_baseline'] = {'value': v, 'unit': 'event-frames/s', 'cores': cores, 'kind': 'port',
-                                    'sample': f'oracle/ref_model.py forward, B=1 x T={T} frames, median of 2 after 1 warm-up '
+                                    'sample': f'oracle/ref_model.py forward, B=1 x T={T} frames, median of 8 after 1 warm-up '
                                               f'({dt:.2f} s each), torch CPU fp32, {cores} threads'}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -295,8 +309,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='samples per GPU')
     ap.add_argument('--T', type=int, default=5)

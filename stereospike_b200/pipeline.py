@@ -1,0 +1,51 @@
+"""Host -> device streaming of event-frame batches for the fused forward path.
+
+The reference moves every batch with a blocking ``.to(device)`` before it calls the network (train.py:193-198,
+test.py:113-118).  Here the copy of batch i+1 runs on a second CUDA stream while batch i is being computed, and the
+finest depth map is copied back asynchronously, so that the PCIe transfer is hidden behind the kernels:
+
+    pipe = HostPipeline(net, batch_shape=(8, 5, 4, 260, 346))
+    for depth in pipe.run(batches):          # batches: iterable of pinned fp32 host tensors [B,T,C,H,W]
+        ...                                   # depth: pinned host tensor [B,1,H,W], valid after pipe.sync()
+"""
+import torch
+
+from . import functional
+
+
+class HostPipeline:
+    def __init__(self, net, batch_shape, device=None, depth=2):
+        self.net = net
+        self.device = torch.device(device) if device is not None else next(net.parameters()).device
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.bufs = [torch.empty(batch_shape, dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        B, _, _, H, W = batch_shape
+        self.depth_host = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self._i = 0
+
+    def step(self, x_host):
+        """Enqueue one batch (pinned host tensor); returns the pinned host depth map it will land in."""
+        k = self._i % len(self.bufs)
+        self._i += 1
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[k])          # the kernels that read this buffer have finished
+            self.bufs[k].copy_(x_host, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        main.wait_event(self.ready[k])
+        functional.reset_net(self.net)
+        with torch.no_grad():
+            out = self.net.forward_seq(self.bufs[k])
+        self.free[k].record(main)
+        depths = out if not isinstance(out, tuple) else out[0]
+        self.depth_host[k].copy_(depths[0], non_blocking=True)
+        return self.depth_host[k]
+
+    def run(self, batches):
+        for x in batches:
+            yield self.step(x)
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libstereospike_b200.so')
+LIB_PATH = os.environ.get('STEREOSPIKE_B200_LIB', os.path.join(_HERE, 'lib', 'libstereospike_b200.so'))   # env: instrumented builds
 
 SS_NEURON_IF, SS_NEURON_LIF, SS_NEURON_PLIF = 0, 1, 2
 SS_SURR_ATAN, SS_SURR_SIGMOID = 0, 1

@@ -32,6 +32,7 @@
 //   warps 0-3  patch producers (cp.async gather, zero fill)     warp 4  MMA issuer (one lane), owns TMEM
 //   warp 5     weight producer (cp.async.bulk of pre-swizzled images)      warps 8-15  epilogue (TMEM -> neuron -> HBM)
 #include <cuda.h>
+#include <cstdio>
 
 #include "ss_common.cuh"
 
@@ -262,8 +263,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     int* rowsrc = reinterpret_cast<int*>(tail);              // [2][40]
     int* colsrc = rowsrc + 80;                               // [2][24]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
-    // bars: full_p[8], empty_p[8], full_w[2], empty_w[2], full_a[8], empty_a[8]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+    // bars: full_p[8], empty_p[8], full_w[2], empty_w[2], full_a[8], empty_a[8], tok[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     const uint32_t bar_empty_w = smem_u32(bars + 18);
     const uint32_t bar_full_a = smem_u32(bars + 20);
     const uint32_t bar_empty_a = smem_u32(bars + 28);
+    const uint32_t bar_tok = smem_u32(bars + 36);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
@@ -287,6 +289,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             mbar_init(bar_full_a + 8 * s, 1);
             mbar_init(bar_empty_a + 8 * s, 256);
         }
+        mbar_init(bar_tok, 1);
+        mbar_init(bar_tok + 8, 1);
         fence_barrier_init();
     }
     if (warp == 4) {
@@ -307,39 +311,51 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         constexpr int ks = 5;                    // real filter (the template's KS is the single im2col "tap")
         int stage = 0;
         uint32_t phase = 0;
-        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+        // geometry of one work item for this thread: validity of each tap (zero padding) and the offset of tap (0,0)
+        auto geometry = [&](int it, uint32_t& vmask, long long& o00) {
             const int mt = it % p.mtiles;
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
             const int so = ty * 16 + (r >> 3);
             const int b = so / p.HsO;
             const int oy = so - b * p.HsO;
             const int ox = tx * 8 + (r & 7);
-            const bool live = b < p.B && oy < p.Hout && ox < p.Wout;
-            // validity of each tap (zero padding) and the offset of tap (0,0)
-            uint32_t vmask = 0;
-            if (live) {
+            vmask = 0;
+            if (b < p.B && oy < p.Hout && ox < p.Wout) {
                 for (int ky = 0; ky < ks; ++ky)
                     for (int kx = 0; kx < ks; ++kx) {
                         const int iy = oy + ky - p.pad, ix = ox + kx - p.pad;
                         if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) vmask |= 1u << (ky * ks + kx);
                     }
             }
-            const long long o00 = ((long long)(b * p.Hin + oy - p.pad) * p.Win + (ox - p.pad)) * 4;
-            // software pipeline: the 25 loads of timestep t+1 are in flight while timestep t is written to shared memory
-            uint32_t cur[25], nxt[25];
-            auto issue = [&](int t, uint32_t (&w)[25]) {
-                const uint8_t* xt = p.x + (size_t)t * t_stride + o00;
+            o00 = ((long long)(b * p.Hin + oy - p.pad) * p.Win + (ox - p.pad)) * 4;
+        };
+        auto issue = [&](int t, uint32_t vmask, long long o00, uint32_t (&w)[25]) {
+            const uint8_t* xt = p.x + (size_t)t * t_stride + o00;
 #pragma unroll
-                for (int ky = 0; ky < 5; ++ky)
+            for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx) {
-                        const int tap = ky * 5 + kx;
-                        w[tap] = ((vmask >> tap) & 1u) ? __ldg(reinterpret_cast<const uint32_t*>(xt + ((long long)ky * p.Win + kx) * 4)) : 0u;
-                    }
-            };
-            issue(0, cur);
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int tap = ky * 5 + kx;
+                    w[tap] = ((vmask >> tap) & 1u) ? __ldg(reinterpret_cast<const uint32_t*>(xt + ((long long)ky * p.Win + kx) * 4)) : 0u;
+                }
+        };
+        // software pipeline over the flat (item, t) sequence: the 25 loads of the NEXT step (also across items) are in
+        // flight while the current step is written to shared memory
+        uint32_t cur[25], nxt[25];
+        uint32_t vm = 0, vm_n = 0;
+        long long o0 = 0, o0_n = 0;
+        if ((int)blockIdx.x < p.nitems) {
+            geometry(blockIdx.x, vm, o0);
+            issue(0, vm, o0, cur);
+        }
+        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
             for (int t = 0; t < p.T; ++t) {
-                if (t + 1 < p.T) issue(t + 1, nxt);
+                if (t + 1 < p.T) {
+                    issue(t + 1, vm, o0, nxt);
+                } else if (it + (int)gridDim.x < p.nitems) {
+                    geometry(it + gridDim.x, vm_n, o0_n);
+                    issue(0, vm_n, o0_n, nxt);
+                }
                 mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
                 uint8_t* dst = sm + (size_t)p.nwb * cWB + (size_t)stage * cPB + (size_t)r * 128;
 #pragma unroll
@@ -360,6 +376,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
 #pragma unroll
                 for (int i = 0; i < 25; ++i) cur[i] = nxt[i];
             }
+            vm = vm_n;
+            o0 = o0_n;
         }
     } else if (warp < 4) {
         // ================================================================== patch producers
@@ -422,9 +440,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 }
             }
         }
-    } else if (warp == 4) {
-        // ================================================================== MMA issuer (ONE elected thread runs the whole role)
+    } else if (warp == 4 || warp == 6) {
+        // ================================================================== MMA issuers: two elected threads (warps 4 and 6) ping-pong
+        // The tensor pipe's issue queue is only ~3 MMAs deep and the bookkeeping between two stages (barrier waits, proxy
+        // fence, descriptor set-up) costs ~500 cycles, which left the pipe idle ~330 cycles per 1400-cycle stage with a single
+        // issuing thread (measured with the SS_MMA_TIMING build).  So stage g is issued by thread g & 1: while one thread's
+        // 25 MMAs drain, the other has already waited for its patch, fenced and built its descriptors, and only waits for the
+        // "issued" token of its predecessor.  Both threads walk the same loop nest and keep identical phase bookkeeping.
         if (elect_one()) {
+            const uint32_t role = warp == 4 ? 0u : 1u;
             constexpr uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
             constexpr uint32_t a_sbo = (uint32_t)(STRIDE * cPWp * RB);
@@ -435,23 +459,38 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             uint32_t wu = 0;           // streaming: weight-use counter;  resident: number of loads done
             int loaded_ntile = -1;
             uint32_t w_pending = 0;    // resident: bit cb set while full_w[cb] has not been observed for the current load
+            uint32_t g = 0;            // global stage counter
+            uint32_t mine = 0;         // stages issued by this thread so far
+            const uint32_t tok_wait = bar_tok + 8 * (role ^ 1u);   // predecessor's "issued" token
+            const uint32_t tok_post = bar_tok + 8 * role;
             const uint64_t a_stage0 = make_desc(patch_base, a_sbo, layout);
             const uint64_t b_buf0 = make_desc(w_base, b_sbo, layout);
 
-            auto do_stage = [&](int wbuf, int slot, bool first) {
-                mbar_wait(bar_full_p + 8 * stage, phase);
-                fence_proxy_async();   // cp.async wrote the patch through the generic proxy; the MMA reads it through the async proxy
-                tc_fence_after();
-                const uint64_t a0 = a_stage0 + (uint64_t)((uint32_t)stage * (cPB >> 4));
-                const uint64_t b0 = b_buf0 + (uint64_t)((uint32_t)wbuf * (cWB >> 4));
-                const uint32_t d = tmem_base + (uint32_t)(slot * cN);
-                umma_i8(d, a0, b0, idesc, first ? 0u : 1u);
-                issue_taps<KS, STRIDE, RB, cN, cPWp, cPWhalf>(d, a0, b0, idesc);
-                umma_commit(bar_empty_p + 8 * stage);
+            // returns true when this thread issued the stage
+            auto do_stage = [&](int wbuf, int slot, bool first) -> bool {
+                const bool own = (g & 1u) == role;
+                ++g;
+                if (own) {
+                    mbar_wait(bar_full_p + 8 * stage, phase);
+                    fence_proxy_async();   // cp.async wrote the patch through the generic proxy; the MMA reads it through the async proxy
+                    const uint64_t a0 = a_stage0 + (uint64_t)((uint32_t)stage * (uint32_t)(cPB >> 4));
+                    const uint64_t b0 = b_buf0 + (uint64_t)((uint32_t)wbuf * (uint32_t)(cWB >> 4));
+                    const uint32_t d = tmem_base + (uint32_t)(slot * cN);
+                    // everything is ready: wait until the other thread has issued the previous stage
+                    mbar_wait(tok_wait, role == 0 ? ((mine & 1u) ^ 1u) : (mine & 1u));
+                    ++mine;
+                    tc_fence_after();
+                    umma_i8(d, a0, b0, idesc, first ? 0u : 1u);
+                    issue_taps<KS, STRIDE, RB, cN, cPWp, cPWhalf>(d, a0, b0, idesc);
+                    tc_fence_before();
+                    mbar_arrive(tok_post);
+                    umma_commit(bar_empty_p + 8 * stage);
+                }
                 if (++stage == p.NPS) {
                     stage = 0;
                     phase ^= 1u;
                 }
+                return own;
             };
 
             for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
@@ -465,39 +504,40 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     const int tc = min(cTC, p.T - t0);
                     if (p.resident) {
                         for (int s = 0; s < tc; ++s) {
+                            // BOTH threads wait for every slot hand-back (and every weight fill below), not only the thread that
+                            // issues into it: a parity wait is only meaningful if the waiter is at most one phase behind.
                             mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
                             slot_phase ^= 1u << s;
-                            tc_fence_after();
+                            bool last_own = false;
                             for (int cb = 0; cb < p.ncb; ++cb) {
-                                if (w_pending & (1u << cb)) {
-                                    mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
-                                    w_pending &= ~(1u << cb);
-                                }
-                                do_stage(cb, s, cb == 0);
+                                if (w_pending & (1u << cb)) mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
+                                w_pending &= ~(1u << cb);
+                                last_own = do_stage(cb, s, cb == 0);
                             }
-                            umma_commit(bar_full_a + 8 * s);
+                            if (last_own) umma_commit(bar_full_a + 8 * s);
                         }
                     } else {
                         for (int cb = 0; cb < p.ncb; ++cb) {
                             const int buf = (int)(wu % NWB);
                             mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+                            bool last_own = false;
                             for (int s = 0; s < tc; ++s) {
                                 if (cb == 0) {
                                     mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
                                     slot_phase ^= 1u << s;
-                                    tc_fence_after();
                                 }
-                                do_stage(buf, s, cb == 0);
-                                if (cb == p.ncb - 1) umma_commit(bar_full_a + 8 * s);
+                                last_own = do_stage(buf, s, cb == 0);
+                                if (cb == p.ncb - 1 && last_own) umma_commit(bar_full_a + 8 * s);
                             }
-                            umma_commit(bar_empty_w + 8 * buf);
+                            if (last_own) umma_commit(bar_empty_w + 8 * buf);
                             ++wu;
                         }
                     }
                 }
                 if (p.resident) {
                     const int nxt = it + gridDim.x;
-                    if (nxt < p.nitems && nxt / p.mtiles != ntile)
+                    // the thread that issued the last stage releases the resident weight buffers before a reload
+                    if (nxt < p.nitems && nxt / p.mtiles != ntile && ((g - 1u) & 1u) == role)
                         for (int cb = 0; cb < p.ncb; ++cb) umma_commit(bar_empty_w + 8 * cb);
                 }
             }

@@ -106,9 +106,10 @@ int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_
  *   v_in   : fp32 [B][Hout][Wout][Cout] initial membrane potential or NULL (= v_reset); v_out: final potential or NULL
  *   resid  : u8 [T][B][Hout][Wout][Cout] added to the spikes before they are written, or NULL
  *   out    : u8 [T][B][Hout][Wout][Cout]
- *   h_seq  : fp32 [T][B][Hout][Wout][Cout] pre-reset potential h_t (for the backward), or NULL */
+ *   h_seq  : fp32 [T][B][Hout][Wout][Cout] pre-reset potential h_t (for the backward), or NULL
+ *   tsum   : u8 [B][Hout][Wout][Cout] = sum over the first T-1 timesteps of `out` (needs 3*(T-1) <= 255), or NULL */
 int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, const float* wscale, const float* decay,
-                   const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* stream);
+                   const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* tsum, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Same block on the CUDA cores in plain fp32 (exact fp32 weights, ascending-k accumulation): the first-layer
@@ -141,7 +142,7 @@ int ss_conv_neuron_fwd(const ss_conv_geom* g, const void* x, const int32_t* ymap
  * v += gain * (conv3x3(NNupsample(out_addK)) + bias_K), in that order, every timestep.
  *   acts[i] (u8 [T][B][Hs][Ws][C]), C[i], Hs[i], Ws[i], w[i] (fp32 [9][C]), bias[i] (device scalar),
  *   ymap[i] [H*3], xmap[i] [W*3] for i = 0..3 in execution order (head 4 first).
- *   taps[i]: fp32 workspace [T][B][9][Hs][Ws] -- the 9 per-tap channel dots are taken at SOURCE resolution
+ *   taps[i]: fp32 workspace [T][B][9][Hs][Ws] ([2][B][9][Hs][Ws] suffices with acts_sum) -- the 9 per-tap channel dots are taken at SOURCE resolution
  *   (9*Hs*Ws*C MACs instead of 9*H*W*C) and gathered per output pixel; same math up to fp32 reassociation.
  *   v_io   : fp32 [B][H][W] I-neuron potential, updated in place (caller zero-fills / sets the prior)
  *   depths : fp32 [4][B][H][W]; depths[i] = potential right after head i of the LAST timestep
@@ -156,6 +157,9 @@ typedef struct ss_heads_args {
     const int32_t* ymap[4];
     const int32_t* xmap[4];
     float* taps[4];
+    const void* acts_sum[4];     /* optional (all four or none): u8 [B][Hs][Ws][C] = sum of acts over the first T-1 timesteps
+                                    (ss_conv_i8_fwd's `tsum` output).  The readout is linear and never fires, so the heads are
+                                    then evaluated on that sum and on the last timestep only (2 passes instead of T). */
 } ss_heads_args;
 int ss_heads_fwd(const ss_heads_args* a, float* v_io, float* depths, void* stream);
 

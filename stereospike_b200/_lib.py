@@ -46,7 +46,8 @@ class HeadsArgs(ctypes.Structure):
                 ('gain', ctypes.c_float),
                 ('C', ctypes.c_int32 * 4), ('Hs', ctypes.c_int32 * 4), ('Ws', ctypes.c_int32 * 4),
                 ('acts', ctypes.c_void_p * 4), ('w', ctypes.c_void_p * 4), ('bias', ctypes.c_void_p * 4),
-                ('ymap', ctypes.c_void_p * 4), ('xmap', ctypes.c_void_p * 4), ('taps', ctypes.c_void_p * 4)]
+                ('ymap', ctypes.c_void_p * 4), ('xmap', ctypes.c_void_p * 4), ('taps', ctypes.c_void_p * 4),
+                ('acts_sum', ctypes.c_void_p * 4)]
 
 
 class LibraryMissing(RuntimeError):
@@ -67,7 +68,7 @@ def lib():
             'There is no CPU or PyTorch fallback for the stereospike_b200 hot path.')
     L = ctypes.CDLL(LIB_PATH)
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
-    L.ss_conv_i8_fwd.argtypes = [ctypes.POINTER(BlockDesc)] + [vp] * 10
+    L.ss_conv_i8_fwd.argtypes = [ctypes.POINTER(BlockDesc)] + [vp] * 11
     L.ss_conv_i8_fwd.restype = ctypes.c_int
     L.ss_conv_i8_rowbytes.argtypes = [i32, i32]
     L.ss_conv_i8_rowbytes.restype = ctypes.c_int

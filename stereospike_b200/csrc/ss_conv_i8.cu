@@ -67,6 +67,7 @@ struct I8Params {
     const uint8_t* resid;
     uint8_t* out;
     float* h_seq;
+    uint8_t* tsum;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -101,6 +102,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 // mbarrier arrival triggered by the completion of all prior cp.async of this thread (counts as one expected arrival)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
@@ -306,20 +310,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
 
     if (warp < 4 && FIRST) {
         // ================================================================== first-layer im2col producers
-        const int r = threadIdx.x;               // tile row = output pixel
+        // Thread r owns tile row r (one output pixel): 25 asynchronous 4-byte copies (one per tap, zero-filled outside the
+        // image) straight into the swizzled 128-byte im2col row; bytes 100..127 of every row are zeroed once.  No register
+        // staging and no producer-side fence, so nothing in this loop waits for memory.
+        const int r = threadIdx.x;
         const size_t t_stride = (size_t)p.B * p.Hin * p.Win * 4;
         constexpr int ks = 5;                    // real filter (the template's KS is the single im2col "tap")
         int stage = 0;
         uint32_t phase = 0;
-        // geometry of one work item for this thread: validity of each tap (zero padding) and the offset of tap (0,0)
-        auto geometry = [&](int it, uint32_t& vmask, long long& o00) {
+        for (int st = 0; st < p.NPS; ++st) {
+            uint8_t* row = sm + (size_t)p.nwb * cWB + (size_t)st * cPB + (size_t)r * 128;
+            *reinterpret_cast<uint4*>(row + ((6 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // bytes 96..111 (tap 24 lands in 96..99)
+            *reinterpret_cast<uint4*>(row + ((7 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // bytes 112..127
+        }
+        fence_proxy_async();
+        named_sync(1, 128);
+        const uint32_t row_base = patch_base + (uint32_t)r * 128u;
+        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
             const int mt = it % p.mtiles;
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
             const int so = ty * 16 + (r >> 3);
             const int b = so / p.HsO;
             const int oy = so - b * p.HsO;
             const int ox = tx * 8 + (r & 7);
-            vmask = 0;
+            uint32_t vmask = 0;
             if (b < p.B && oy < p.Hout && ox < p.Wout) {
                 for (int ky = 0; ky < ks; ++ky)
                     for (int kx = 0; kx < ks; ++kx) {
@@ -327,57 +341,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) vmask |= 1u << (ky * ks + kx);
                     }
             }
-            o00 = ((long long)(b * p.Hin + oy - p.pad) * p.Win + (ox - p.pad)) * 4;
-        };
-        auto issue = [&](int t, uint32_t vmask, long long o00, uint32_t (&w)[25]) {
-            const uint8_t* xt = p.x + (size_t)t * t_stride + o00;
-#pragma unroll
-            for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 5; ++kx) {
-                    const int tap = ky * 5 + kx;
-                    w[tap] = ((vmask >> tap) & 1u) ? __ldg(reinterpret_cast<const uint32_t*>(xt + ((long long)ky * p.Win + kx) * 4)) : 0u;
-                }
-        };
-        // software pipeline over the flat (item, t) sequence: the 25 loads of the NEXT step (also across items) are in
-        // flight while the current step is written to shared memory
-        uint32_t cur[25], nxt[25];
-        uint32_t vm = 0, vm_n = 0;
-        long long o0 = 0, o0_n = 0;
-        if ((int)blockIdx.x < p.nitems) {
-            geometry(blockIdx.x, vm, o0);
-            issue(0, vm, o0, cur);
-        }
-        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+            const long long o00 = ((long long)(b * p.Hin + oy - p.pad) * p.Win + (ox - p.pad)) * 4;
             for (int t = 0; t < p.T; ++t) {
-                if (t + 1 < p.T) {
-                    issue(t + 1, vm, o0, nxt);
-                } else if (it + (int)gridDim.x < p.nitems) {
-                    geometry(it + gridDim.x, vm_n, o0_n);
-                    issue(0, vm_n, o0_n, nxt);
-                }
                 mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
-                uint8_t* dst = sm + (size_t)p.nwb * cWB + (size_t)stage * cPB + (size_t)r * 128;
+                const uint8_t* xt = p.x + (size_t)t * t_stride + o00;
+                const uint32_t dst = row_base + (uint32_t)stage * cPB;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    uint4 q;
-                    q.x = 4 * c < 25 ? cur[(4 * c) % 25] : 0u;
-                    q.y = 4 * c + 1 < 25 ? cur[(4 * c + 1) % 25] : 0u;
-                    q.z = 4 * c + 2 < 25 ? cur[(4 * c + 2) % 25] : 0u;
-                    q.w = 4 * c + 3 < 25 ? cur[(4 * c + 3) % 25] : 0u;
-                    *reinterpret_cast<uint4*>(dst + ((c ^ (r & 7)) << 4)) = q;
-                }
-                fence_proxy_async();
-                mbar_arrive(bar_full_p + 8 * stage);
+                for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) {
+                        const int tap = ky * 5 + kx;
+                        const bool ok = (vmask >> tap) & 1u;
+                        const uint32_t d = dst + ((((uint32_t)tap >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)tap & 3u) * 4u;
+                        cp_async_4(d, ok ? xt + ((long long)ky * p.Win + kx) * 4 : p.x, ok ? 4u : 0u);
+                    }
+                cp_async_arrive_noinc(bar_full_p + 8 * stage);
                 if (++stage == p.NPS) {
                     stage = 0;
                     phase ^= 1u;
                 }
-#pragma unroll
-                for (int i = 0; i < 25; ++i) cur[i] = nxt[i];
             }
-            vm = vm_n;
-            o0 = o0_n;
         }
     } else if (warp < 4) {
         // ================================================================== patch producers
@@ -607,6 +590,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const bool use_resid = p.resid != nullptr && live;
             uint4 rs_next = make_uint4(0u, 0u, 0u, 0u);
             if (use_resid) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + o0));
+            uint32_t ts[4] = {0u, 0u, 0u, 0u};   // running byte-wise sum of the first T-1 output steps (feeds the linear heads)
             float sc[16], v[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -677,7 +661,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         pk[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
                     }
                     const size_t o = (size_t)t * t_out + o0;
-                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(pk[0] + rs_cur.x, pk[1] + rs_cur.y, pk[2] + rs_cur.z, pk[3] + rs_cur.w);
+                    pk[0] += rs_cur.x; pk[1] += rs_cur.y; pk[2] += rs_cur.z; pk[3] += rs_cur.w;
+                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (t + 1 < p.T) {
+                        ts[0] += pk[0]; ts[1] += pk[1]; ts[2] += pk[2]; ts[3] += pk[3];
+                    }
                     if (p.h_seq != nullptr) {
                         float4* hp = reinterpret_cast<float4*>(p.h_seq + o);
 #pragma unroll
@@ -685,6 +673,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     }
                 }
             }
+            if (p.tsum != nullptr && live) *reinterpret_cast<uint4*>(p.tsum + o0) = make_uint4(ts[0], ts[1], ts[2], ts[3]);
             if (p.v_out != nullptr && live) {
                 float4* vo = reinterpret_cast<float4*>(p.v_out + o0);
 #pragma unroll
@@ -867,7 +856,7 @@ extern "C" int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_
 }
 
 extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, const float* wscale, const float* decay,
-                              const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* stream) {
+                              const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* tsum, void* stream) {
     if (g == nullptr) {
         set_error("ss_conv_i8_fwd: null descriptor");
         return SS_EINVAL;
@@ -906,6 +895,10 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     if (g->neuron == SS_NEURON_LIF && !(g->tau > 1.0f)) {
         set_error("ss_conv_i8_fwd: LIF needs tau > 1");
         return SS_EINVAL;
+    }
+    if (tsum != nullptr && 3 * (g->T - 1) > 255) {
+        set_error("ss_conv_i8_fwd: tsum needs 3*(T-1) <= 255 (got T = %d)", g->T);
+        return SS_EUNSUPPORTED;
     }
     const bool up = g->upsample != 0;
     if (!(g->ks == 3 || g->ks == 5) || !(g->stride == 1 || g->stride == 2) || (up && g->stride != 1) ||
@@ -991,6 +984,7 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     p.resid = reinterpret_cast<const uint8_t*>(resid);
     p.out = reinterpret_cast<uint8_t*>(out);
     p.h_seq = h_seq;
+    p.tsum = reinterpret_cast<uint8_t*>(tsum);
 
     const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
     static int num_sms = 0;

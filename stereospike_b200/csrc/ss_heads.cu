@@ -7,7 +7,11 @@
 // per-tap channel dots  P[tap][sy][sx] = sum_c act[sy][sx][c] * w[tap][c]  are taken once per SOURCE pixel
 // (9*Hs*Ws*C MACs instead of 9*H*W*C: 8x fewer over the four heads), and every output pixel then just gathers
 // 9 of those scalars per head.  Same math up to fp32 reassociation (tap-major instead of interleaved).
-//   kernel 1  head_taps_kernel   : u8 NHWC spikes -> fp32 taps[t][b][tap][sy][sx]      (one launch, all heads)
+// The readout is LINEAR and never fires, so the time loop can be folded as well: sum_t conv(act_t) = conv(sum_t act_t).
+// When the producing blocks hand over  acts_sum = sum_{t < T-1} act_t  (u8, accumulated for free in their epilogues) the
+// heads are evaluated on two pseudo-timesteps only -- the summed past (bias counted T-1 times) and the last step, which
+// the four running-sum outputs need separately -- instead of T.  Again the same math up to fp32 reassociation.
+//   kernel 1  head_taps_kernel   : u8 NHWC spikes -> fp32 taps[e][b][tap][sy][sx]      (one launch, all heads)
 //   kernel 2  heads_gather_kernel: one thread per output pixel, potential in a register across heads and
 //                                  timesteps, 36 coalesced gathers per timestep, depth planes written at the
 //                                  last timestep.  HBM/L2-bound.
@@ -20,8 +24,12 @@ struct HeadsParams {
     int T, B, H, W;
     float gain;
     int C[4], Hs[4], Ws[4], woff[4];
-    long long pix_begin[5];   // prefix sums of T*B*Hs*Ws over the heads (kernel 1 work partition)
+    int NE;                   // evaluated (pseudo-)timesteps: T, or 2 when acts_sum is given and T > 1
+    int summed;               // 1: step 0 = acts_sum (first T-1 steps), step 1 = last timestep of acts
+    float bias_mul[2];        // summed mode: {T-1, 1}
+    long long pix_begin[5];   // prefix sums of NE*B*Hs*Ws over the heads (kernel 1 work partition)
     const uint8_t* acts[4];
+    const uint8_t* acts_sum[4];
     const float* w[4];
     const float* bias[4];
     const int* ymap[4];
@@ -45,12 +53,18 @@ __global__ void __launch_bounds__(TAPS_NT) head_taps_kernel(const HeadsParams p)
 #pragma unroll
     for (int i = 1; i < 4; ++i)
         if (gid >= p.pix_begin[i]) hd = i;
-    const long long q = gid - p.pix_begin[hd];          // (t*B + b)*Hs*Ws + s
+    const long long q = gid - p.pix_begin[hd];          // (e*B + b)*Hs*Ws + s
     const int C = p.C[hd];
     const int S = p.Hs[hd] * p.Ws[hd];
     const long long tb = q / S;
     const int s = (int)(q - tb * S);
-    const uint4* src = reinterpret_cast<const uint4*>(p.acts[hd] + (size_t)q * C);
+    const uint8_t* a0 = p.acts[hd] + (size_t)q * C;
+    if (p.summed) {
+        const long long e = tb / p.B, b = tb - e * p.B;
+        a0 = (e == 0) ? p.acts_sum[hd] + ((size_t)b * S + s) * C
+                      : p.acts[hd] + (((size_t)(p.T - 1) * p.B + b) * S + s) * C;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(a0);
     const float* wt = wsm + p.woff[hd];
     float acc[9];
 #pragma unroll
@@ -103,17 +117,18 @@ __global__ void __launch_bounds__(GATHER_NT) heads_gather_kernel(const HeadsPara
         }
     }
     float v = p.v_io[pix];
-    for (int t = 0; t < p.T; ++t) {
+    for (int e = 0; e < p.NE; ++e) {
+        const float bm = p.summed ? p.bias_mul[e] : 1.0f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float* base = p.taps[i] + ((size_t)t * p.B + b) * 9 * p.Hs[i] * p.Ws[i];
+            const float* base = p.taps[i] + ((size_t)e * p.B + b) * 9 * p.Hs[i] * p.Ws[i];
             float acc = 0.0f;
 #pragma unroll
             for (int k = 0; k < 9; ++k)
                 if (off[i][k] >= 0) acc += __ldg(base + off[i][k]);
             // (conv + bias) * gain, then IF charge with v_threshold = inf: v = v + x, never fires
-            v = __fadd_rn(v, __fmul_rn(__fadd_rn(acc, bias[i]), p.gain));
-            if (t == p.T - 1) p.depths[(size_t)i * p.B * HW + pix] = v;
+            v = __fadd_rn(v, __fmul_rn(fmaf(bm, bias[i], acc), p.gain));
+            if (e == p.NE - 1) p.depths[(size_t)i * p.B * HW + pix] = v;
         }
     }
     p.v_io[pix] = v;
@@ -132,7 +147,16 @@ extern "C" int ss_heads_fwd(const ss_heads_args* a, float* v_io, float* depths, 
     p.T = a->T; p.B = a->B; p.H = a->H; p.W = a->W; p.gain = a->gain;
     int off = 0;
     p.pix_begin[0] = 0;
+    p.summed = (a->T > 1 && a->acts_sum[0] != nullptr) ? 1 : 0;
+    p.NE = p.summed ? 2 : a->T;
+    p.bias_mul[0] = (float)(a->T - 1);
+    p.bias_mul[1] = 1.0f;
     for (int i = 0; i < 4; ++i) {
+        if (p.summed && a->acts_sum[i] == nullptr) {
+            set_error("ss_heads_fwd: acts_sum must be given for all four heads or for none");
+            return SS_EINVAL;
+        }
+        p.acts_sum[i] = reinterpret_cast<const uint8_t*>(a->acts_sum[i]);
         if (a->C[i] % 16 != 0 || a->C[i] <= 0) {
             set_error("ss_heads_fwd: head %d channels %d not a multiple of 16", i, a->C[i]);
             return SS_EINVAL;
@@ -144,7 +168,7 @@ extern "C" int ss_heads_fwd(const ss_heads_args* a, float* v_io, float* depths, 
         p.C[i] = a->C[i]; p.Hs[i] = a->Hs[i]; p.Ws[i] = a->Ws[i];
         p.woff[i] = off;
         off += 9 * a->C[i];
-        p.pix_begin[i + 1] = p.pix_begin[i] + (long long)a->T * a->B * a->Hs[i] * a->Ws[i];
+        p.pix_begin[i + 1] = p.pix_begin[i] + (long long)p.NE * a->B * a->Hs[i] * a->Ws[i];
         p.acts[i] = reinterpret_cast<const uint8_t*>(a->acts[i]);
         p.w[i] = a->w[i]; p.bias[i] = a->bias[i]; p.ymap[i] = a->ymap[i]; p.xmap[i] = a->xmap[i];
         p.taps[i] = a->taps[i];

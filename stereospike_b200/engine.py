@@ -106,6 +106,8 @@ class Engine:
         self.keep_state = True
         self.timing = None          # bench.py: list of (site name, start event, end event) when not None
         self.event_status = None    # optional device int32[1]: bit 0 set when an input frame was not integer counts 0..255
+        self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
+        #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
 
     # ------------------------------------------------------------------ parameter flattening
     def _flat_params(self):
@@ -139,6 +141,8 @@ class Engine:
         impl = IMPLS[self.impl]
         acts = {'x': x_seq}
         saved = {'B': B, 'T': T, 'sites': [], 'acts': acts}
+        head_srcs = {h.src for h in self.heads}
+        tsums = {}
         for i, s in enumerate(self.sites):
             xin = acts[s.src]
             first = s.src == 'x'
@@ -162,8 +166,12 @@ class Engine:
             if use_i8:
                 if first:
                     xin = ops.pack_events(x_seq, self.event_status)     # fp32 NCHW counts -> u8 NHWC4
+                tsum = None
+                if s.out in head_srcs and self.heads_time_sum and 1 < T <= 86:
+                    tsum = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=ops.ACT_DTYPE, device=dev)
+                    tsums[s.out] = tsum
                 out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
-                                                    cin=4 if first else g.Cin, **common)
+                                                    cin=4 if first else g.Cin, tsum=tsum, **common)
             else:
                 out, v_out, h_seq = ops.conv_neuron_fwd(xin, g, w_kn, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC,
                                                         **common)
@@ -195,7 +203,8 @@ class Engine:
         if self.timing is not None:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
-        depths = ops.heads_fwd(hacts, hg, hw, hb, T=T, B=B, H=H, W=W, gain=gain, v_io=v_io)
+        acts_sum = [tsums[h.src] for h in self.heads] if len(tsums) == len(self.heads) else None
+        depths = ops.heads_fwd(hacts, hg, hw, hb, T=T, B=B, H=H, W=W, gain=gain, v_io=v_io, acts_sum=acts_sum)
         if self.timing is not None:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()

@@ -130,8 +130,9 @@ def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
 
 # ----------------------------------------------------------------------------------------- fused block
 def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau=2.0, decay=None, v_in=None,
-                want_v_out=False, resid=None, want_h=False, planes=3, cin=None):
+                want_v_out=False, resid=None, want_h=False, planes=3, cin=None, tsum=None):
     """Tensor-core fused block over all T timesteps (ss_conv_i8_fwd).  x: u8 [T,B,Hin,Win,Cin].
+    ``tsum``: optional u8 [B,Hout,Wout,Cout] receiving the sum of the first T-1 output steps (input of the linear heads).
     Returns (out u8 [T,B,Hout,Wout,Cout], v_out, h_seq)."""
     _require_cuda(x, 'x')
     dev = x.device
@@ -147,8 +148,10 @@ def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau
     d = _lib.BlockDesc(T=T, B=B, Hin=g.Hin, Win=g.Win, Cin=cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
                        stride=g.stride, pad=g.pad, upsample=1 if g.kind == 'upconv' else 0, neuron=neuron, planes=planes,
                        gain=gain, v_th=v_th, v_reset=v_reset, tau=tau)
+    if tsum is not None:
+        assert tsum.dtype == ACT_DTYPE and tsum.is_contiguous() and tuple(tsum.shape) == (B, g.Hout, g.Wout, g.Cout)
     rc = _lib.lib().ss_conv_i8_fwd(ctypes.byref(d), _ptr(x), _ptr(w_i8), _ptr(wscale), _ptr(decay), _ptr(v_in), _ptr(v_out),
-                                   _ptr(resid), _ptr(out), _ptr(h_seq), _stream())
+                                   _ptr(resid), _ptr(out), _ptr(h_seq), _ptr(tsum), _stream())
     _lib.check(rc, 'ss_conv_i8_fwd')
     return out, v_out, h_seq
 
@@ -181,8 +184,9 @@ def conv_neuron_fwd(x, geom, w_kn, *, T, B, in_layout, neuron, gain, v_th, v_res
     return out, v_out, h_seq
 
 
-def heads_fwd(acts, geoms, weights_9c, biases, *, T, B, H, W, gain, v_io):
+def heads_fwd(acts, geoms, weights_9c, biases, *, T, B, H, W, gain, v_io, acts_sum=None):
     """Four prediction heads + I-neuron accumulation.  acts/geoms/weights/biases in execution order (head 4 first).
+    ``acts_sum``: optional list of u8 [B,Hs,Ws,C] sums over the first T-1 timesteps -> 2 head passes instead of T.
     v_io fp32 [B,H,W] is updated in place.  Returns depths fp32 [4,B,H,W] (potential after each head, last step)."""
     dev = v_io.device
     a = _lib.HeadsArgs()
@@ -193,9 +197,14 @@ def heads_fwd(acts, geoms, weights_9c, biases, *, T, B, H, W, gain, v_io):
         assert acts[i].dtype == ACT_DTYPE and acts[i].is_contiguous() and \
             tuple(acts[i].shape) == (T, B, g.Hin, g.Win, g.Cin)
         ym, xm = g.maps(dev)
-        tp = torch.empty((T, B, 9, g.Hin, g.Win), dtype=torch.float32, device=dev)
+        ne = 2 if (acts_sum is not None and T > 1) else T
+        tp = torch.empty((ne, B, 9, g.Hin, g.Win), dtype=torch.float32, device=dev)
         keep += [ym, xm, tp]
         a.taps[i] = tp.data_ptr()
+        if acts_sum is not None and T > 1:
+            assert acts_sum[i].dtype == ACT_DTYPE and acts_sum[i].is_contiguous() and \
+                tuple(acts_sum[i].shape) == (B, g.Hin, g.Win, g.Cin)
+            a.acts_sum[i] = acts_sum[i].data_ptr()
         a.C[i], a.Hs[i], a.Ws[i] = g.Cin, g.Hin, g.Win
         a.acts[i] = acts[i].data_ptr()
         a.w[i] = weights_9c[i].data_ptr()

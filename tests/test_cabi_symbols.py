@@ -44,7 +44,7 @@ def test_argument_validation_without_gpu(lib):
     assert rc == -1 and b'null' in lib.ss_last_error()
     d = _lib.BlockDesc(T=1, B=1, Hin=4, Win=4, Cin=32, Hout=4, Wout=4, Cout=32, ks=3, stride=1, pad=1, upsample=0, neuron=0,
                        planes=3, gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0)
-    rc = lib.ss_conv_i8_fwd(ctypes.byref(d), None, None, None, None, None, None, None, None, None, None)
+    rc = lib.ss_conv_i8_fwd(ctypes.byref(d), None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b'null' in lib.ss_last_error()
     assert lib.ss_pack_weights_i8(None, 0, 0, 0, 0, None, None, None, None) == -1
     assert lib.ss_pack_events(None, 1, 1, 4, 2, 2, None, None, None) == -1
@@ -56,8 +56,8 @@ def test_struct_layout_matches_header():
     from stereospike_b200 import _lib
     assert ctypes.sizeof(_lib.ConvGeom) == 18 * 4
     assert ctypes.sizeof(_lib.BlockDesc) == 18 * 4
-    # ss_heads_args: 4 int32 + float + 12 int32 (+4 pad) + 24 pointers
-    assert ctypes.sizeof(_lib.HeadsArgs) == 72 + 24 * 8
+    # ss_heads_args: 4 int32 + float + 12 int32 (+4 pad) + 28 pointers
+    assert ctypes.sizeof(_lib.HeadsArgs) == 72 + 28 * 8
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

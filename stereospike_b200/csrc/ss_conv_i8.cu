@@ -575,6 +575,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         nc.decay = (p.neuron == SS_NEURON_PLIF) ? __ldg(p.decay) : 0.0f;
         const size_t t_out = (size_t)M * p.Cout;
         uint32_t slot_phase = 0;
+        int sc_ntile = -1;
+        float sc[16];                 // wscale * gain (wscale is a power of two, so this product is exact)
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
             const int ntile = it / p.mtiles;
             const int mt = it - ntile * p.mtiles;
@@ -591,11 +593,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             uint4 rs_next = make_uint4(0u, 0u, 0u, 0u);
             if (use_resid) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + o0));
             uint32_t ts[4] = {0u, 0u, 0u, 0u};   // running byte-wise sum of the first T-1 output steps (feeds the linear heads)
-            float sc[16], v[16];
+            float v[16];
+            if (ntile != sc_ntile) {
+                sc_ntile = ntile;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(p.wscale + nb) + i);
-                sc[4 * i] = q.x; sc[4 * i + 1] = q.y; sc[4 * i + 2] = q.z; sc[4 * i + 3] = q.w;
+                for (int i = 0; i < 4; ++i) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(p.wscale + nb) + i);
+                    sc[4 * i] = q.x * nc.gain; sc[4 * i + 1] = q.y * nc.gain; sc[4 * i + 2] = q.z * nc.gain; sc[4 * i + 3] = q.w * nc.gain;
+                }
             }
             if (p.v_in != nullptr && live) {
                 const float4* vi = reinterpret_cast<const float4*>(p.v_in + o0);
@@ -639,7 +644,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             conv = __ll2float_rn((long long)(d[0][i] * 256 + d[1][i]) * 65536LL +
                                                  (long long)(d[PLANES - 2][i] * 256 + d[PLANES - 1][i]));
                         }
-                        x[i] = __fmul_rn(__fmul_rn(conv, sc[i]), nc.gain);
+                        x[i] = __fmul_rn(conv, sc[i]);   // == (conv * wscale) * gain: the first product is exact
                     }
                     float hbuf[16];
                     uint32_t fired = 0;

@@ -134,17 +134,40 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     net = build_oracle(args.neuron, args.gain, args.tau)
-    sample_B = 1
+    on_gpu = args.reference_device == 'cuda'
+    sample_B = args.batch if on_gpu else 1
     x = rm.synthetic_inputs(sample_B, args.T, 4, seed=0)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            sj.reset_net(net)
-            net.forward_seq(x)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            sj.reset_net(net)
-            net.forward_seq(x)
-        dt = time.perf_counter() - t0
+    label = rm.synthetic_label(sample_B, seed=1)
+    if on_gpu:
+        # what the reference itself executes on cuda:0: cuDNN convs + unfused elementwise neuron kernels (true fp32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        net, x, label = net.cuda(), x.cuda(), label.cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4) if args.mode == 'train' else None
+
+    def ref_step():
+        sj.reset_net(net)
+        if args.mode == 'train':
+            depths = net.forward_seq(x)[0]
+            masked_l1(depths, label).backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        else:
+            with torch.no_grad():
+                net.forward_seq(x)
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ref_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref_step()
+    sync()
+    dt = time.perf_counter() - t0
     val = sample_B * args.T * args.steps / dt
     line = {
         'impl': 'reference', 'metric': 'event-frames/sec', 'value': val, 'unit': 'event-frames/s', 'n_gpus': args.gpus,
@@ -152,19 +175,34 @@ def run_reference(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, per_gpu_B=args.batch),
         'cpu_baseline': {'value': val, 'unit': 'event-frames/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'each step = B={sample_B} sample x T={args.T} frames of the same workload, forward, '
-                                   f'torch {torch.__version__} CPU fp32, {cores} threads'},
+                         'sample': f'each step = B={sample_B} sample x T={args.T} frames of the same workload, {args.mode}, '
+                                   f'torch {torch.__version__} ' + ('CUDA eager (cuDNN fp32, allow_tf32=False) -- the reference\'s own GPU '
+                                   'execution model, NOT the CPU arm' if on_gpu else f'CPU fp32, {cores} threads')},
+        'reference_device': args.reference_device,
         'e2e': {'value': val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def masked_l1(depths, label):
+    """Sum over the four scales of the NaN-masked mean absolute error (network/metrics.py:83-95 per scale); stands in for
+    network/loss.py::Total_Loss, which cannot run on CPU tensors on a GPU box (SURVEY.md section 0)."""
+    import torch
+    mask = ~torch.isnan(label)
+    n = mask.count_nonzero()
+    lab = torch.nan_to_num(label)
+    tot = 0.0
+    for d in depths:
+        tot = tot + ((d - lab).abs() * mask).sum() / n
+    return tot
+
+
 def workload_config(args, per_gpu_B):
     return {'workload': f'StereoSpike spiking U-Net forward (fused conv+{args.neuron.upper()} blocks + heads/I-neurons), '
-                        f'binocular 4x{H0}x{W0} event frames, T={args.T}, batch {per_gpu_B} per GPU, fp32-parity inference '
+                        f'binocular 4x{H0}x{W0} event frames, T={args.T}, batch {per_gpu_B} per GPU, fp32-parity ' + ('inference ' if args.mode == 'infer' else 'training step (forward + surrogate backward + Adam) ') +
                         f'(u8 spikes x {args.planes} int8 weight digit planes on the int8 tensor cores, exact s32 accumulate, one fp32 rounding)',
-            'neuron': args.neuron, 'T': args.T, 'batch_per_gpu': per_gpu_B, 'global_batch': per_gpu_B * args.gpus,
+            'mode': args.mode, 'neuron': args.neuron, 'T': args.T, 'batch_per_gpu': per_gpu_B, 'global_batch': per_gpu_B * args.gpus,
             'weight_planes': args.planes, 'multiply_factor': args.gain, 'tau': args.tau,
             'l2': f'rotating {args.input_sets} input sets per step; per-step activation stream (~2 GB) exceeds the 126 MB L2',
             'parallelism': f'replicas x{args.gpus} (batch shards, no data-path collective)'}
@@ -201,8 +239,22 @@ def run_ours(args):
     xs_host = [rm.synthetic_inputs(B, T, 4, seed=100 + rank * 16 + i).pin_memory() for i in range(args.input_sets)]
     xs = [x.to(dev) for x in xs_host]
 
+    train = args.mode == 'train'
+    if train:
+        label = rm.synthetic_label(B, seed=1).to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+        sync = sb.parallel.GradientSynchronizer(net.parameters()) if world > 1 else None
+
     def step(x):
         sb.functional.reset_net(net)
+        if train:
+            out = net.forward_seq(x)
+            masked_l1(out[0], label).backward()
+            if sync is not None:
+                sync.sync(local_samples=B, global_samples=B * world)     # NCCL all-reduce of the gradients
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return out
         with torch.no_grad():
             return net.forward_seq(x)
 
@@ -232,23 +284,40 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host frames in (copy overlapped with the previous step's kernels on a
     #      second stream), finest depth map back to pinned host memory, every step
-    pipe = sb.pipeline.HostPipeline(net, tuple(xs_host[0].shape), dev)
-    for i in range(2):
-        pipe.step(xs_host[i % len(xs_host)])
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(args.steps):
-        depth_host = pipe.step(xs_host[i % len(xs_host)])
-    e3.record()
-    barrier()
+    if train:
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(args.steps):
+            xg = xs_host[i % len(xs_host)].to(dev, non_blocking=True)
+            out = step(xg)
+            depth_host = out[0][0]
+            loss_host.copy_(out[0][0].mean(), non_blocking=True)
+        e3.record()
+        barrier()
+        d2h_bytes = 4
+    else:
+        pipe = sb.pipeline.HostPipeline(net, tuple(xs_host[0].shape), dev)
+        for i in range(2):
+            pipe.step(xs_host[i % len(xs_host)])
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(args.steps):
+            depth_host = pipe.step(xs_host[i % len(xs_host)])
+        e3.record()
+        barrier()
+        d2h_bytes = depth_host.numel() * 4
     ms_e2e = e2.elapsed_time(e3)
 
     # ---- per-kernel timing of the tensor-core blocks (roofline)
     eng = net.engine
     eng.timing = []
     for i in range(min(args.steps, 10)):
-        step(xs[i % len(xs)])
+        with torch.no_grad():
+            sb.functional.reset_net(net)
+            net.forward_seq(xs[i % len(xs)])
     torch.cuda.synchronize()
     per_site = {}
     for name, a, b in eng.timing:
@@ -279,7 +348,7 @@ def run_ours(args):
             'vs_baseline': None, 'dtype': 'u8 x s8 -> s32 (tcgen05 kind::i8, %d weight digit planes), fp32 neuron state' % args.planes,
             'data': 'synthetic', 'config': workload_config(args, B),
             'e2e': {'value': e2e_val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': xs_host[0].numel() * 4,
-                    'd2h_bytes_per_step': depth_host.numel() * 4, 'ms_per_step': ms_e2e / args.steps,
+                    'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': ms_e2e / args.steps,
                     'api': 'stereospike_b200.pipeline.HostPipeline.step (pinned fp32 frames -> forward_seq -> pinned depth map)'},
             'gpu_launches': launches,
             'clocks': clocks,
@@ -313,6 +382,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='samples per GPU')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'])
+    ap.add_argument('--reference-device', default='cpu', choices=['cpu', 'cuda'],
+                    help='--impl reference only: cuda = the oracle in PyTorch eager on the GPU (extra comparison point)')
     ap.add_argument('--T', type=int, default=5)
     ap.add_argument('--neuron', default='lif', choices=['if', 'lif', 'plif'])
     ap.add_argument('--gain', type=float, default=15.0)

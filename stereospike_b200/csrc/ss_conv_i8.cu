@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the previous
+    // kernel in the stream; from here on we read what it wrote.  Let our own dependents start their prologue early as well.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr uint32_t swz_mask = (uint32_t)(RB >> 4) - 1u;  // 32 -> 1, 64 -> 3, 128 -> 7
 
     if (warp < 4 && FIRST) {
@@ -1002,6 +1006,16 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     const int grid = p.nitems < num_sms ? p.nitems : num_sms;
     cudaStream_t st = (cudaStream_t)stream;
     bool launched = false;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: our prologue may overlap the previous kernel's tail
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
 #define SS_TRY(PL, KS_, ST_, RB_)                                                                                          \
     if (!launched && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {                                 \
         static bool attr = false;                                                                                          \
@@ -1009,7 +1023,7 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
             cudaFuncSetAttribute(conv_i8_kernel<PL, KS_, ST_, RB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr = true;                                                                                                   \
         }                                                                                                                  \
-        conv_i8_kernel<PL, KS_, ST_, RB_><<<grid, THREADS, smem, st>>>(p);                                                 \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, ST_, RB_>, p);                                                    \
         launched = true;                                                                                                   \
     }
 #define SS_TRY_FIRST(PL)                                                                                                   \
@@ -1019,7 +1033,7 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
             cudaFuncSetAttribute(conv_i8_kernel<PL, 1, 1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr = true;                                                                                                   \
         }                                                                                                                  \
-        conv_i8_kernel<PL, 1, 1, 128, true><<<grid, THREADS, smem, st>>>(p);                                               \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 1, 1, 128, true>, p);                                                  \
         launched = true;                                                                                                   \
     }
 #define SS_TRY_PL(PL) SS_TRY_FIRST(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)

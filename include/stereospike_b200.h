@@ -111,6 +111,39 @@ int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_
 int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, const float* wscale, const float* decay,
                    const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* tsum, void* stream);
 
+/* Tile iteration of ss_conv_i8_fwd_ex.  NNConvUpsampling (blocks.py:110-132) by ~2x replicates every source pixel 2 (rarely
+ * 3) times, so the 5x5 conv over the upsampled image reads only 3x3 DISTINCT source pixels per output: with the integer
+ * weights of the replicated taps summed (exactly), the block folds into four 3x3 convs on the SOURCE image, one per
+ * (row class, column class) of the output -- 9 taps instead of 25, bit-identical integer sums.  Output rows/columns next to a
+ * 3-fold replication (a few % of the image) do not fit that pattern and are computed by the general kernel on bands.
+ *   SS_TILES_FOLDED   : g = the virtual conv (ks 3, stride 1, pad 0, upsample 0, Hin/Win = source, Hout/Wout = REAL output);
+ *                       w_i8 holds 4 weight sets per output-channel tile (packed with Cout' = 4*Cout, set = tile*4 + class,
+ *                       class = 2*row_class + col_class); ymap_out [2][Hin-2], xmap_out [2][Win-2]: real output row / column of
+ *                       virtual position s for class 0 / 1, or -1
+ *   SS_TILES_ROW_BANDS: g = the real upsampled conv; only output rows band_start[i] .. +band_len[i] (band_len <= band_rows)
+ *   SS_TILES_COL_BANDS: same for output columns (band_len <= 8) */
+#define SS_TILES_PLAIN 0
+#define SS_TILES_FOLDED 1
+#define SS_TILES_ROW_BANDS 2
+#define SS_TILES_COL_BANDS 3
+typedef struct ss_tile_maps {
+    int32_t mode;
+    int32_t nbands, band_rows;
+    int32_t reserved;
+    const int32_t* ymap_out;
+    const int32_t* xmap_out;
+    const int32_t* band_start;
+    const int32_t* band_len;
+} ss_tile_maps;
+int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
+                      const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,
+                      void* tsum, void* stream);
+
+/* Digit planes of ALREADY QUANTISED integer weights (fp32 holding exact integers, |q| < 2^(8*planes-1)), same layout as
+ * ss_pack_weights_i8; zero_exp: device int32 [Cout] of zeros.  Used for the folded weight sets (sums of quantised taps). */
+int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, const int32_t* zero_exp,
+                      void* w_i8, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Same block on the CUDA cores in plain fp32 (exact fp32 weights, ascending-k accumulation): the first-layer
  * path for non-integer inputs and the on-device cross-check of the tensor-core path. */

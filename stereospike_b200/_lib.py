@@ -15,7 +15,7 @@ SS_IN_U8_TBHWC, SS_IN_F32_BTCHW = 0, 1
 SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
-SYMBOLS = ('ss_conv_i8_fwd', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
+SYMBOLS = ('ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
            'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
            'ss_abi_version', 'ss_last_error', 'ss_launch_count')
 
@@ -28,6 +28,15 @@ class BlockDesc(ctypes.Structure):
                 ('upsample', ctypes.c_int32), ('neuron', ctypes.c_int32), ('planes', ctypes.c_int32),
                 ('gain', ctypes.c_float), ('v_th', ctypes.c_float), ('v_reset', ctypes.c_float),
                 ('tau', ctypes.c_float)]
+
+
+class TileMaps(ctypes.Structure):
+    _fields_ = [('mode', ctypes.c_int32), ('nbands', ctypes.c_int32), ('band_rows', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('ymap_out', ctypes.c_void_p), ('xmap_out', ctypes.c_void_p), ('band_start', ctypes.c_void_p),
+                ('band_len', ctypes.c_void_p)]
+
+
+SS_TILES_PLAIN, SS_TILES_FOLDED, SS_TILES_ROW_BANDS, SS_TILES_COL_BANDS = 0, 1, 2, 3
 
 
 class ConvGeom(ctypes.Structure):
@@ -70,6 +79,10 @@ def lib():
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
     L.ss_conv_i8_fwd.argtypes = [ctypes.POINTER(BlockDesc)] + [vp] * 11
     L.ss_conv_i8_fwd.restype = ctypes.c_int
+    L.ss_conv_i8_fwd_ex.argtypes = [ctypes.POINTER(BlockDesc), ctypes.POINTER(TileMaps)] + [vp] * 11
+    L.ss_conv_i8_fwd_ex.restype = ctypes.c_int
+    L.ss_pack_digits_i8.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+    L.ss_pack_digits_i8.restype = ctypes.c_int
     L.ss_conv_i8_rowbytes.argtypes = [i32, i32]
     L.ss_conv_i8_rowbytes.restype = ctypes.c_int
     L.ss_pack_weights_i8.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]

@@ -40,6 +40,8 @@ namespace ss {
 namespace {
 
 constexpr int NWB = 2;        // weight buffers
+
+// tile iteration modes: SS_TILES_PLAIN / FOLDED / ROW_BANDS / COL_BANDS (include/stereospike_b200.h)
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_SLOTS = 8;
 constexpr int THREADS = 512;
@@ -52,6 +54,14 @@ struct I8Params {
     int PH, PWp, PWhalf, ppix;
     int HsO, Hup, Wup;
     int tiles_x, mtiles, nitems;
+    int Hv, Wv;            // iteration space of the tiles (== Hout, Wout except for the folded / band passes of an upsampled conv)
+    int mode;              // SS_TILES_*
+    int nclass;            // weight sets per output-channel tile (folded pass: 4 = {L,M} x {L,M}), else 1
+    int nbands, band_rows; // band passes
+    const int* ymap_out;   // folded: [2][Hv] real output row of virtual row s for class L, M, or -1
+    const int* xmap_out;   // folded: [2][Wv]
+    const int* band_start; // band passes: first output row / column of each band
+    const int* band_len;   // band passes: rows / columns in each band
     int TC, NPS, WB, PB;
     int resident;
     int nwb;               // weight buffers allocated in shared memory (1 when a single channel block is resident)
@@ -185,9 +195,15 @@ template <int STRIDE>
 __device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr) {
     const int gi = ty * 16 * STRIDE + pr;
     const int per = STRIDE * p.HsO;
-    const int b = gi / per;
+    int b = gi / per;
+    int local = gi - b * per;
+    if (p.mode == SS_TILES_ROW_BANDS) {
+        // stacked mini-images: (sample, band); `local` indexes the upsampled rows band_start .. band_start + band_rows + ks - 2
+        const int band = b % p.nbands;
+        b /= p.nbands;
+        local += __ldg(p.band_start + band);
+    }
     if (b >= p.B) return -1;
-    const int local = gi - b * per;
     if (p.upsample) {
         if (local >= p.Hup) return -1;
         // ATen upsample_nearest: min(int(floorf(dst * scale)), in - 1), scale = float(in) / out
@@ -200,7 +216,7 @@ __device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr) {
 template <int STRIDE, int PWHALF>
 __device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
     if (p.upsample) {
-        const int u = tx * 8 + pc;
+        const int u = (p.mode == SS_TILES_COL_BANDS ? __ldg(p.band_start + tx) : tx * 8) + pc;
         if (u >= p.Wup) return -1;
         return min((int)floorf((float)u * p.xscale), p.Win - 1);
     }
@@ -481,7 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             };
 
             for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-                const int ntile = it / p.mtiles;
+                const int ntile = it / p.mtiles;   // weight-set index: (output-channel tile, class)
                 if (p.resident && ntile != loaded_ntile) {
                     loaded_ntile = ntile;
                     w_pending = (1u << p.ncb) - 1u;
@@ -585,12 +601,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const int ntile = it / p.mtiles;
             const int mt = it - ntile * p.mtiles;
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            const int wset = ntile;                       // it / mtiles: (output-channel tile, class)
+            const int cls = wset % p.nclass;
             const int so = ty * 16 + g;
-            const int b = so / p.HsO;
-            const int oy = so - b * p.HsO;
-            const int ox = tx * 8 + j;
-            const bool live = b < p.B && oy < p.Hout && ox < p.Wout;
-            const int nb = ntile * 32 + hf * 16;
+            int b = so / p.HsO;
+            int oy = so - b * p.HsO;
+            int ox = tx * 8 + j;
+            bool live = oy < p.Hv && ox < p.Wv;
+            if (p.mode == SS_TILES_FOLDED) {
+                // virtual (class, source position) -> real output pixel; -1 = not a regular position of this class
+                oy = live ? __ldg(p.ymap_out + (cls >> 1) * p.Hv + oy) : -1;
+                ox = live ? __ldg(p.xmap_out + (cls & 1) * p.Wv + ox) : -1;
+                live = oy >= 0 && ox >= 0;
+            } else if (p.mode == SS_TILES_ROW_BANDS) {
+                const int band = b % p.nbands;
+                b /= p.nbands;
+                live = live && oy < __ldg(p.band_len + band);
+                oy += __ldg(p.band_start + band);
+            } else if (p.mode == SS_TILES_COL_BANDS) {
+                live = live && j < __ldg(p.band_len + tx);
+                ox = __ldg(p.band_start + tx) + j;
+            }
+            live = live && b < p.B && oy < p.Hout && ox < p.Wout;
+            const int nb = (wset / p.nclass) * 32 + hf * 16;
             const size_t pix = live ? ((size_t)(b * p.Hout + oy) * p.Wout + ox) : 0;
             const size_t o0 = pix * p.Cout + nb;                  // element offset inside one timestep
             const bool use_resid = p.resid != nullptr && live;
@@ -864,8 +897,9 @@ extern "C" int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_
     return check_launch("pack_events");
 }
 
-extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, const float* wscale, const float* decay,
-                              const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* tsum, void* stream) {
+static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
+                          const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,
+                          void* tsum, void* stream) {
     if (g == nullptr) {
         set_error("ss_conv_i8_fwd: null descriptor");
         return SS_EINVAL;
@@ -910,6 +944,21 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
         return SS_EUNSUPPORTED;
     }
     const bool up = g->upsample != 0;
+    const int mode = tm != nullptr ? tm->mode : SS_TILES_PLAIN;
+    if (mode < SS_TILES_PLAIN || mode > SS_TILES_COL_BANDS) {
+        set_error("ss_conv_i8_fwd_ex: unknown tile mode %d", mode);
+        return SS_EINVAL;
+    }
+    if (mode == SS_TILES_FOLDED && (tm->ymap_out == nullptr || tm->xmap_out == nullptr || g->ks != 3 || g->stride != 1 || g->pad != 0 ||
+                                    up || g->Hin < 3 || g->Win < 3)) {
+        set_error("ss_conv_i8_fwd_ex: the folded pass is a 3x3 stride-1 pad-0 conv on the source with output maps");
+        return SS_EINVAL;
+    }
+    if ((mode == SS_TILES_ROW_BANDS || mode == SS_TILES_COL_BANDS) &&
+        (!up || tm->band_start == nullptr || tm->band_len == nullptr || tm->nbands <= 0 || tm->band_rows <= 0)) {
+        set_error("ss_conv_i8_fwd_ex: band passes need an upsampled conv and the band tables");
+        return SS_EINVAL;
+    }
     if (!(g->ks == 3 || g->ks == 5) || !(g->stride == 1 || g->stride == 2) || (up && g->stride != 1) ||
         (g->stride == 2 && (g->pad % 2 != 0 || g->ks != 5))) {
         set_error("ss_conv_i8_fwd: unsupported conv shape (ks %d stride %d pad %d upsample %d)", g->ks, g->stride, g->pad, g->upsample);
@@ -919,7 +968,7 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     p.T = g->T; p.B = g->B; p.Hin = g->Hin; p.Win = g->Win; p.Cin = g->Cin;
     p.Hout = g->Hout; p.Wout = g->Wout; p.Cout = g->Cout;
     p.ks = g->ks; p.stride = g->stride; p.pad = up ? 0 : g->pad; p.upsample = up ? 1 : 0;
-    if (!up) {
+    if (!up && mode != SS_TILES_FOLDED) {
         const int ho = (g->Hin + 2 * g->pad - g->ks) / g->stride + 1, wo = (g->Win + 2 * g->pad - g->ks) / g->stride + 1;
         if (ho != g->Hout || wo != g->Wout) {
             set_error("ss_conv_i8_fwd: Hout/Wout (%d,%d) do not match the conv geometry (%d,%d)", g->Hout, g->Wout, ho, wo);
@@ -940,7 +989,24 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     p.ppix = p.PH * p.PWp;
     p.Hup = g->Hout + g->ks - 1;
     p.Wup = g->Wout + g->ks - 1;
-    if (up) {
+    p.mode = mode;
+    p.nclass = mode == SS_TILES_FOLDED ? 4 : 1;
+    p.Hv = g->Hout; p.Wv = g->Wout;
+    p.nbands = 1; p.band_rows = 0;
+    p.ymap_out = p.xmap_out = p.band_start = p.band_len = nullptr;
+    if (mode == SS_TILES_FOLDED) {
+        p.Hv = g->Hin - 2; p.Wv = g->Win - 2;
+        p.ymap_out = tm->ymap_out; p.xmap_out = tm->xmap_out;
+    } else if (mode != SS_TILES_PLAIN) {
+        p.nbands = tm->nbands; p.band_rows = tm->band_rows;
+        p.band_start = tm->band_start; p.band_len = tm->band_len;
+    }
+    if (mode == SS_TILES_FOLDED) {
+        p.HsO = g->Hin;                       // virtual 3x3 pad-0 conv: image b's rows are Hin apart, no shared padding
+    } else if (mode == SS_TILES_ROW_BANDS) {
+        p.Hv = tm->band_rows;
+        p.HsO = tm->band_rows + g->ks - 1;    // one stacked mini-image per (sample, band)
+    } else if (up) {
         p.HsO = p.Hup;
     } else if (first) {
         p.HsO = g->Hout;   // explicit im2col rows: no halo shared between rows, so no gap rows between stacked images
@@ -954,12 +1020,16 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
         p.HsO = (span + g->stride - 1) / g->stride;
         if (p.HsO < g->Hout) p.HsO = g->Hout;
     }
-    const long long rows = (long long)p.HsO * g->B;
+    const long long rows = (long long)p.HsO * g->B * (mode == SS_TILES_ROW_BANDS ? p.nbands : 1);
     const int tiles_y = (int)((rows + 15) / 16);
-    p.tiles_x = (g->Wout + 7) / 8;
+    p.tiles_x = (p.Wv + 7) / 8;
+    if (mode == SS_TILES_COL_BANDS) {
+        p.tiles_x = p.nbands;
+        p.Wv = 8 * p.nbands;
+    }
     p.mtiles = tiles_y * p.tiles_x;
     const int ntiles = g->Cout / 32;
-    const long long nitems = (long long)p.mtiles * ntiles;
+    const long long nitems = (long long)p.mtiles * ntiles * p.nclass;
     if (nitems > 0x7fffffffLL || (long long)g->B * g->Hin * g->Win * g->Cin > 0x7fffffffLL) {
         set_error("ss_conv_i8_fwd: problem too large for 32-bit indexing");
         return SS_EINVAL;
@@ -1049,4 +1119,30 @@ extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void*
     }
     count_launch();
     return check_launch("conv_i8");
+}
+
+extern "C" int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, const float* wscale, const float* decay,
+                              const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* tsum, void* stream) {
+    return conv_i8_launch(g, nullptr, x, w_i8, wscale, decay, v_in, v_out, resid, out, h_seq, tsum, stream);
+}
+
+extern "C" int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
+                                 const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,
+                                 void* tsum, void* stream) {
+    return conv_i8_launch(g, tm, x, w_i8, wscale, decay, v_in, v_out, resid, out, h_seq, tsum, stream);
+}
+
+extern "C" int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, const int32_t* zero_exp,
+                                 void* w_i8, void* stream) {
+    if (q_oihw == nullptr || w_i8 == nullptr || zero_exp == nullptr || Cout <= 0 || Cin <= 0 || ks <= 0 || planes < 2 || planes > 4 ||
+        Cout % 32 != 0 || Cin % 32 != 0) {
+        set_error("ss_pack_digits_i8: bad argument (Cout %% 32, Cin %% 32, planes 2..4)");
+        return SS_EINVAL;
+    }
+    const int RB = rowbytes_for(Cin, ks);
+    const long long total = (long long)Cout * Cin * ks * ks;
+    weight_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q_oihw, Cout, Cin, ks, planes, RB, zero_exp,
+                                                                                           reinterpret_cast<int8_t*>(w_i8));
+    count_launch();
+    return check_launch("pack_digits");
 }

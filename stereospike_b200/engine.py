@@ -35,14 +35,16 @@ class Site:
         return BlockGeom('conv', c.in_channels, c.out_channels, ks, Hin, Win, conv_out_size(Hin, ks, st, pd),
                          conv_out_size(Win, ks, st, pd), st, pd)
 
-    def packed(self, planes, need_i8, need_kn=True):
-        """(w_kn fp32 [K][Cout] or None, (w_i8, wscale) or None), cached on the weight's version."""
+    def packed(self, planes, need_i8, need_kn=True, fold=False):
+        """(w_kn fp32 [K][Cout] or None, (w_i8, wscale) or (w_fold, w_full, wscale) or None), cached on the weight's version."""
         w = self.conv.weight
-        key = (w.data_ptr(), w._version, planes, need_i8, need_kn, str(w.device))
+        key = (w.data_ptr(), w._version, planes, need_i8, need_kn, fold, str(w.device))
         if self._pack is None or self._pack[0] != key:
             w_kn = ops.weight_to_kn(w) if need_kn else None
             w_i8 = None
-            if need_i8:
+            if need_i8 and fold:
+                w_i8 = ops.pack_weights_folded(w, planes)
+            elif need_i8:
                 cin = w.shape[1]
                 q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=4 if cin <= 4 else (cin + 31) // 32 * 32)
                 w_i8 = (q, sc)
@@ -106,6 +108,7 @@ class Engine:
         self.keep_state = True
         self.timing = None          # bench.py: list of (site name, start event, end event) when not None
         self.event_status = None    # optional device int32[1]: bit 0 set when an input frame was not integer counts 0..255
+        self.fold_upsample = True   # NNConvUpsampling blocks as four folded 3x3 convs on the source + band passes (9 taps instead of 25)
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
         #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
 
@@ -151,7 +154,9 @@ class Engine:
             if first and int(x_seq.shape[2]) != g.Cin:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
             use_i8 = impl != SS_IMPL_SIMT
-            w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=want_h or not use_i8)
+            fold = use_i8 and self.fold_upsample and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
+                min(g.Hin, g.Win) >= 8 and abs(g.Hout + 4 - 2 * g.Hin) <= g.Hin // 8 and abs(g.Wout + 4 - 2 * g.Win) <= g.Win // 8
+            w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=want_h or not use_i8, fold=fold)
             decay = params[2 * i + 1]
             if decay is not None:
                 decay = decay.detach().contiguous()
@@ -170,8 +175,12 @@ class Engine:
                 if s.out in head_srcs and self.heads_time_sum and 1 < T <= 86:
                     tsum = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=ops.ACT_DTYPE, device=dev)
                     tsums[s.out] = tsum
-                out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
-                                                    cin=4 if first else g.Cin, tsum=tsum, **common)
+                if fold:
+                    out, v_out, h_seq = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], planes=self.weight_planes,
+                                                               tsum=tsum, **common)
+                else:
+                    out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
+                                                        cin=4 if first else g.Cin, tsum=tsum, **common)
             else:
                 out, v_out, h_seq = ops.conv_neuron_fwd(xin, g, w_kn, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC,
                                                         **common)

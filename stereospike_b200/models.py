@@ -125,7 +125,7 @@ class _SpikingUNet(NeuromorphicNet):
             object.__setattr__(self, '_engine', Engine(sites, heads, self.Ineurons))
         return self._engine
 
-    def set_kernel_options(self, impl=None, weight_planes=None, keep_state=None, heads_time_sum=None):
+    def set_kernel_options(self, impl=None, weight_planes=None, keep_state=None, heads_time_sum=None, fold_upsample=None):
         """impl: 'umma' (tcgen05 int8 tensor-core kernel; default) or 'simt' (exact-fp32 CUDA cores).
         weight_planes: int8 digit planes per weight -- 3 = 24-bit fixed point, fp32-class (default);
         2 = 16-bit (the reduced-precision training configuration); 4 = 32-bit."""
@@ -140,6 +140,8 @@ class _SpikingUNet(NeuromorphicNet):
             e.keep_state = bool(keep_state)
         if heads_time_sum is not None:
             e.heads_time_sum = bool(heads_time_sum)
+        if fold_upsample is not None:
+            e.fold_upsample = bool(fold_upsample)
         return self
 
     # ---- forward

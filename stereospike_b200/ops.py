@@ -119,6 +119,103 @@ def pack_events(x_seq, status=None):
     return out
 
 
+# ----------------------------------------------------------------------------------------- folded upsampled conv
+_FOLD_GROUPS = {0: ((0,), (1, 2), (3, 4)),      # class L: the output sits on the LAST copy of its source pixel  (pattern 0,1,1,2,2)
+                1: ((0, 1), (2, 3), (4,))}      # class M: ... on the second-to-last copy                          (pattern 0,0,1,1,2)
+_FOLD_PATTERNS = {0: (0, 1, 1, 2, 2), 1: (0, 0, 1, 1, 2)}
+
+
+def fold_axis(n_in, n_out, ks=5):
+    """Regular / irregular structure of  UpsamplingNearest2d(n_out+ks-1) -> valid conv(ks)  along one axis.
+    Returns (omap int32 [2][n_in-2]: output coordinate of source position s for class L / M or -1, bands [(start, len)] of
+    the output coordinates that do not follow either regular pattern)."""
+    assert ks == 5
+    n_up = n_out + ks - 1
+    scale = np.float32(n_in) / np.float32(n_up)
+    src = np.minimum(np.floor(np.arange(n_up, dtype=np.float32) * scale).astype(np.int64), n_in - 1)
+    omap = np.full((2, n_in - 2), -1, dtype=np.int32)
+    irregular = []
+    for o in range(n_out):
+        pat = tuple(int(src[o + k] - src[o]) for k in range(ks))
+        s0 = int(src[o])
+        hit = [c for c, pt in _FOLD_PATTERNS.items() if pt == pat]
+        if hit and s0 < n_in - 2 and omap[hit[0], s0] < 0:
+            omap[hit[0], s0] = o
+        else:
+            irregular.append(o)
+    bands = []
+    for o in irregular:
+        if bands and o == bands[-1][0] + bands[-1][1]:
+            bands[-1][1] += 1
+        else:
+            bands.append([o, 1])
+    return omap, [tuple(b) for b in bands]
+
+
+class FoldPlan:
+    """Device tables of one folded NNConvUpsampling geometry (cached per (Hin, Win, Hout, Wout, device))."""
+
+    def __init__(self, Hin, Win, Hout, Wout, device):
+        ymap, ybands = fold_axis(Hin, Hout)
+        xmap, xbands = fold_axis(Win, Wout)
+        xb = []
+        for st, ln in xbands:                      # column bands are at most one 8-wide tile each
+            while ln > 0:
+                xb.append((st, min(ln, 8)))
+                st, ln = st + 8, ln - 8
+        dev = torch.device(device)
+        t = lambda a: torch.tensor(a, dtype=torch.int32, device=dev).contiguous()
+        self.ymap, self.xmap = t(ymap), t(xmap)
+        self.yband_start, self.yband_len = t([b[0] for b in ybands]), t([b[1] for b in ybands])
+        self.xband_start, self.xband_len = t([b[0] for b in xb]), t([b[1] for b in xb])
+        self.n_ybands, self.n_xbands = len(ybands), len(xb)
+        self.yband_rows = max([b[1] for b in ybands]) if ybands else 0
+        self.covered = float((ymap >= 0).sum()) / Hout * float((xmap >= 0).sum()) / Wout      # fraction of regular outputs
+
+
+@functools.lru_cache(maxsize=None)
+def fold_plan(Hin, Win, Hout, Wout, device):
+    return FoldPlan(Hin, Win, Hout, Wout, device)
+
+
+def pack_weights_folded(weight, planes):
+    """Quantises a 5x5 NNConvUpsampling weight (OIHW) with 3 bits of head-room and returns
+    (w_fold: digit planes of the four folded 3x3 weight sets, w_full: digit planes of the 5x5 taps (band passes),
+    wscale fp32 [Cout]).  The folded sets are exact integer sums of the quantised taps, so both passes produce
+    identical integers for every output they share."""
+    w = weight.detach().double()
+    co, ci, kh, kw = w.shape
+    assert kh == 5 and kw == 5 and co % 32 == 0 and ci % 32 == 0
+    m = w.abs().amax(dim=(1, 2, 3))
+    ex = torch.where(m > 0, torch.floor(torch.log2(m)) + 1, torch.zeros_like(m))          # m < 2^ex
+    e = ex - (8 * planes - 1) + 3
+    q = torch.round(w * torch.pow(2.0, -e).view(-1, 1, 1, 1))
+    assert float(q.abs().max()) < 2 ** (8 * planes - 4) + 1
+    sets = []
+    for cy in (0, 1):
+        for cx in (0, 1):
+            f = q.new_zeros(co, ci, 3, 3)
+            for dy, kys in enumerate(_FOLD_GROUPS[cy]):
+                for dx, kxs in enumerate(_FOLD_GROUPS[cx]):
+                    for ky in kys:
+                        for kx in kxs:
+                            f[:, :, dy, dx] += q[:, :, ky, kx]
+            sets.append(f)
+    # weight-set index = output-channel tile * 4 + class  ->  stack as [tile][class][32] "output channels"
+    fold = torch.stack(sets, dim=1).view(co // 32, 32, 4, ci, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(4 * co, ci, 3, 3)
+    dev = weight.device
+    zeros = torch.zeros(4 * co, dtype=torch.int32, device=dev)
+    fold32 = fold.float().contiguous()
+    full32 = q.float().contiguous()
+    w_fold = torch.empty(4 * co * ci * 9 * planes, dtype=torch.int8, device=dev)
+    w_full = torch.empty(co * ci * 25 * planes, dtype=torch.int8, device=dev)
+    L = _lib.lib()
+    _lib.check(L.ss_pack_digits_i8(_ptr(fold32), 4 * co, ci, 3, planes, _ptr(zeros), _ptr(w_fold), _stream()), 'ss_pack_digits_i8')
+    _lib.check(L.ss_pack_digits_i8(_ptr(full32), co, ci, 5, planes, _ptr(zeros), _ptr(w_full), _stream()), 'ss_pack_digits_i8')
+    wscale = torch.pow(2.0, e).float().contiguous()
+    return w_fold, w_full, wscale
+
+
 def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
     if resid is not None:
         assert resid.dtype == ACT_DTYPE and resid.is_contiguous() and tuple(resid.shape) == out_shape
@@ -130,7 +227,8 @@ def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
 
 # ----------------------------------------------------------------------------------------- fused block
 def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau=2.0, decay=None, v_in=None,
-                want_v_out=False, resid=None, want_h=False, planes=3, cin=None, tsum=None):
+                want_v_out=False, resid=None, want_h=False, planes=3, cin=None, tsum=None, outputs=None, tile_maps=None,
+                desc_override=None):
     """Tensor-core fused block over all T timesteps (ss_conv_i8_fwd).  x: u8 [T,B,Hin,Win,Cin].
     ``tsum``: optional u8 [B,Hout,Wout,Cout] receiving the sum of the first T-1 output steps (input of the linear heads).
     Returns (out u8 [T,B,Hout,Wout,Cout], v_out, h_seq)."""
@@ -141,19 +239,52 @@ def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau
     assert x.dtype == ACT_DTYPE and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, cin), \
         (x.dtype, tuple(x.shape), (T, B, g.Hin, g.Win, cin))
     out_shape = (T, B, g.Hout, g.Wout, g.Cout)
-    out = torch.empty(out_shape, dtype=ACT_DTYPE, device=dev)
-    v_out = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=torch.float32, device=dev) if want_v_out else None
-    h_seq = torch.empty(out_shape, dtype=torch.float32, device=dev) if want_h else None
+    if outputs is not None:
+        out, v_out, h_seq = outputs           # a later pass of the same block writes into the first pass's tensors
+    else:
+        out = torch.empty(out_shape, dtype=ACT_DTYPE, device=dev)
+        v_out = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=torch.float32, device=dev) if want_v_out else None
+        h_seq = torch.empty(out_shape, dtype=torch.float32, device=dev) if want_h else None
     _check_block_io(x, g, T, B, resid, v_in, decay, out_shape)
     d = _lib.BlockDesc(T=T, B=B, Hin=g.Hin, Win=g.Win, Cin=cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
                        stride=g.stride, pad=g.pad, upsample=1 if g.kind == 'upconv' else 0, neuron=neuron, planes=planes,
                        gain=gain, v_th=v_th, v_reset=v_reset, tau=tau)
+    if desc_override:
+        for k, v in desc_override.items():
+            setattr(d, k, v)
     if tsum is not None:
         assert tsum.dtype == ACT_DTYPE and tsum.is_contiguous() and tuple(tsum.shape) == (B, g.Hout, g.Wout, g.Cout)
-    rc = _lib.lib().ss_conv_i8_fwd(ctypes.byref(d), _ptr(x), _ptr(w_i8), _ptr(wscale), _ptr(decay), _ptr(v_in), _ptr(v_out),
-                                   _ptr(resid), _ptr(out), _ptr(h_seq), _ptr(tsum), _stream())
+    if tile_maps is None:
+        rc = _lib.lib().ss_conv_i8_fwd(ctypes.byref(d), _ptr(x), _ptr(w_i8), _ptr(wscale), _ptr(decay), _ptr(v_in), _ptr(v_out),
+                                       _ptr(resid), _ptr(out), _ptr(h_seq), _ptr(tsum), _stream())
+    else:
+        rc = _lib.lib().ss_conv_i8_fwd_ex(ctypes.byref(d), ctypes.byref(tile_maps), _ptr(x), _ptr(w_i8), _ptr(wscale), _ptr(decay),
+                                          _ptr(v_in), _ptr(v_out), _ptr(resid), _ptr(out), _ptr(h_seq), _ptr(tsum), _stream())
     _lib.check(rc, 'ss_conv_i8_fwd')
     return out, v_out, h_seq
+
+
+def conv_i8_fwd_folded(x, geom, w_fold, w_full, wscale, **kw):
+    """NNConvUpsampling block (5x5, ~2x) as four folded 3x3 convs on the source + the general kernel on the irregular
+    row / column bands (three launches writing the same output tensors).  Same arguments / results as conv_i8_fwd."""
+    g = geom
+    assert g.kind == 'upconv' and g.ks == 5
+    plan = fold_plan(g.Hin, g.Win, g.Hout, g.Wout, str(x.device))
+    tm = _lib.TileMaps(mode=_lib.SS_TILES_FOLDED, nbands=0, band_rows=0, reserved=0, ymap_out=plan.ymap.data_ptr(),
+                       xmap_out=plan.xmap.data_ptr(), band_start=0, band_len=0)
+    res = conv_i8_fwd(x, g, w_fold, wscale, tile_maps=tm, desc_override=dict(ks=3, stride=1, pad=0, upsample=0), **kw)
+    kw2 = dict(kw)
+    kw2.pop('want_v_out', None)
+    kw2.pop('want_h', None)
+    if plan.n_ybands:
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_BANDS, nbands=plan.n_ybands, band_rows=plan.yband_rows, reserved=0, ymap_out=0,
+                           xmap_out=0, band_start=plan.yband_start.data_ptr(), band_len=plan.yband_len.data_ptr())
+        conv_i8_fwd(x, g, w_full, wscale, tile_maps=tm, outputs=res, **kw2)
+    if plan.n_xbands:
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_COL_BANDS, nbands=plan.n_xbands, band_rows=8, reserved=0, ymap_out=0, xmap_out=0,
+                           band_start=plan.xband_start.data_ptr(), band_len=plan.xband_len.data_ptr())
+        conv_i8_fwd(x, g, w_full, wscale, tile_maps=tm, outputs=res, **kw2)
+    return res
 
 
 def conv_neuron_fwd(x, geom, w_kn, *, T, B, in_layout, neuron, gain, v_th, v_reset, tau=2.0, decay=None,

@@ -141,6 +141,29 @@ def test_i8_result_is_exact_and_tiling_independent():
     assert torch.equal(h[0, 1:2], h1[0])
 
 
+@pytest.mark.parametrize('Hin,Win,up,Cin,Cout,T,B', [(17, 22, (33, 44), 64, 32, 3, 2), (9, 11, (17, 21), 32, 64, 2, 3),
+                                                     (130, 173, (260, 346), 64, 32, 2, 1)])
+def test_folded_upsampled_conv_is_bit_identical(Hin, Win, up, Cin, Cout, T, B):
+    """NNConvUpsampling folded into four 3x3 convs on the source (+ band passes for the irregular rows / columns) gives
+    exactly the integers of the 25-tap kernel with the same quantised weights: identical h, spikes, state and time sums."""
+    from stereospike_b200 import ops, _lib
+    g = torch.Generator().manual_seed(Hin * 7 + Cin)
+    geom = ops.BlockGeom('upconv', Cin, Cout, 5, Hin, Win, up[0], up[1])
+    x = ((torch.rand(T, B, Hin, Win, Cin, generator=g) < 0.25).to(torch.uint8) * torch.randint(1, 4, (T, B, Hin, Win, Cin), generator=g).to(torch.uint8)).cuda()
+    w = ((torch.rand(Cout, Cin, 5, 5, generator=g) * 2 - 1) / (Cin * 25) ** 0.5).cuda()
+    r = (torch.rand(T, B, up[0], up[1], Cout, generator=g) < 0.3).to(torch.uint8).cuda()
+    w_fold, w_full, wscale = ops.pack_weights_folded(w, 3)
+    kw = dict(T=T, B=B, neuron=_lib.SS_NEURON_LIF, gain=5.0, v_th=1.0, v_reset=0.0, tau=3.0, resid=r, want_v_out=True, want_h=True, planes=3)
+    ts_a = torch.zeros((B, up[0], up[1], Cout), dtype=torch.uint8, device='cuda')
+    ts_b = torch.zeros_like(ts_a)
+    o_a, v_a, h_a = ops.conv_i8_fwd(x, geom, w_full, wscale, tsum=ts_a, **kw)
+    o_b, v_b, h_b = ops.conv_i8_fwd_folded(x, geom, w_fold, w_full, wscale, tsum=ts_b, **kw)
+    assert torch.equal(h_a, h_b) and torch.equal(o_a, o_b) and torch.equal(v_a, v_b) and torch.equal(ts_a, ts_b)
+    assert 0.02 < float((o_a > 0).float().mean()) < 0.95
+    plan = ops.fold_plan(Hin, Win, up[0], up[1], 'cuda:0')
+    assert plan.covered > (0.9 if Hin >= 100 else 0.3)
+
+
 def test_empty_batch_and_bad_arguments():
     from stereospike_b200 import ops, _lib
     geom, x, w = _mk_block(1, 1)

@@ -108,7 +108,9 @@ class Engine:
         self.keep_state = True
         self.timing = None          # bench.py: list of (site name, start event, end event) when not None
         self.event_status = None    # optional device int32[1]: bit 0 set when an input frame was not integer counts 0..255
-        self.fold_upsample = True   # NNConvUpsampling blocks as four folded 3x3 convs on the source + band passes (9 taps instead of 25)
+        self.fold_upsample = False  # NNConvUpsampling blocks as four folded 3x3 convs on the source + band passes (9 taps instead of
+        #                             25, bit-identical integers, 3 bits less weight precision); off by default: the full-resolution blocks
+        #                             are epilogue-bound, so the saved MMAs do not pay yet (profiles/r1e_fold_launches.txt)
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
         #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
 

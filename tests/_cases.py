@@ -86,7 +86,7 @@ def block_case(kind, Cin, Cout, ks, Hin, Win, stride, pad, up, neuron, T, B, imp
     return res
 
 
-def model_case(variant, mono, gain, T, B, impl, planes, seed=11, backward=False, tau=3.0):
+def model_case(variant, mono, gain, T, B, impl, planes, seed=11, backward=False, tau=3.0, with_fp64=False):
     import torch
     from oracle import ref_model as rm, sj_compat as sj
     from oracle.make_golden import simple_loss
@@ -126,6 +126,14 @@ def model_case(variant, mono, gain, T, B, impl, planes, seed=11, backward=False,
             res[f'depth{i + 1}_mean'] = float(diff.mean())
         res['depth_absmean'] = float(d_ref[0].detach().abs().mean())
         res['mde_ref'] = float(rm.mean_depth_error(d_ref[0].detach(), label))
+        if with_fp64:
+            # the same oracle evaluated in float64: |mde_ref - mde_ref64| measures how chaotic this configuration is
+            import copy
+            o64 = copy.deepcopy(o).double()
+            sj.reset_net(o64)
+            with torch.no_grad():
+                r64 = o64.forward_seq(x.double(), return_all=True)
+            res['mde_ref64'] = float(rm.mean_depth_error(r64[0][0].float(), label))
         res['mde_got'] = float(rm.mean_depth_error(d_got[0].detach().cpu(), label))
         acts = n.engine  # layer mismatch rates from the engine's last activations
         side_acts = None

@@ -100,6 +100,22 @@ int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t k
 int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw4,
                    int32_t* status, void* stream);
 
+/* Event stream -> event-count frames (the step in front of the path; replaces mvsecRectifyEvents and
+ * mvsecCumulateSpikesIntoFrames, datasets/MVSEC/utils.py:31-56,215-281).
+ *   events_xytp : fp64 [n][4] = (x, y, t, polarity) as the reference stores them
+ *   xmap, ymap  : fp64 [H][W] rectification look-up tables, or both NULL for already rectified events
+ *   t0          : subtracted from every timestamp (utils.py:251-253)
+ *   frame_start/_end : fp64 [n_frames]; an event is counted in frame f iff start[f] < t - t0 < end[f] (both strict, as upstream)
+ *   camera      : 0 = left (channels 0-1), 1 = right (channels 2-3); channel = 2*camera + (polarity == 1 ? 0 : 1)
+ *   counts_fhw4 : u32 [n_frames][H][W][4], ACCUMULATED into (caller zero-fills once, then calls once per camera)
+ * ss_events_pack turns the counts (frame f = b*T + t) into the first block's input u8 [T][B][H][W][4], saturating at 255
+ * (bit 1 of *status is set if it had to). */
+int ss_events_accumulate(const double* events_xytp, int64_t n_events, const double* xmap, const double* ymap, double t0,
+                         const double* frame_start, const double* frame_end, int32_t n_frames, int32_t H, int32_t W,
+                         int32_t camera, uint32_t* counts_fhw4, void* stream);
+int ss_events_pack(const uint32_t* counts_fhw4, int32_t B, int32_t T, int32_t H, int32_t W, void* out_tbhw4, int32_t* status,
+                   void* stream);
+
 /*   x      : u8 [T][B][Hin][Win][Cin]
  *   w_i8, wscale : from ss_pack_weights_i8 (same Cout, Cin, ks, planes)
  *   decay  : device scalar, PLIF only (sigmoid(w))

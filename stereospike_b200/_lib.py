@@ -15,7 +15,7 @@ SS_IN_U8_TBHWC, SS_IN_F32_BTCHW = 0, 1
 SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
-SYMBOLS = ('ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
+SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
            'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
            'ss_abi_version', 'ss_last_error', 'ss_launch_count')
 
@@ -83,6 +83,10 @@ def lib():
     L.ss_conv_i8_fwd_ex.restype = ctypes.c_int
     L.ss_pack_digits_i8.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     L.ss_pack_digits_i8.restype = ctypes.c_int
+    L.ss_events_accumulate.argtypes = [vp, i64, vp, vp, ctypes.c_double, vp, vp, i32, i32, i32, i32, vp, vp]
+    L.ss_events_accumulate.restype = ctypes.c_int
+    L.ss_events_pack.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+    L.ss_events_pack.restype = ctypes.c_int
     L.ss_conv_i8_rowbytes.argtypes = [i32, i32]
     L.ss_conv_i8_rowbytes.restype = ctypes.c_int
     L.ss_pack_weights_i8.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]

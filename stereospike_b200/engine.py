@@ -132,16 +132,25 @@ class Engine:
         ops._require_cuda(x_seq, 'x')
         if x_seq.dim() != 5:
             raise ValueError('expected x of shape [B, T, C, H, W]')
-        x_seq = x_seq.contiguous().float()
+        if x_seq.dtype == torch.uint8:
+            # packed event frames u8 [T, B, H, W, 4] (stereospike_b200.events / ss_pack_events): inference only
+            if x_seq.shape[-1] != 4 or IMPLS[self.impl] == SS_IMPL_SIMT:
+                raise ValueError('packed input must be u8 [T, B, H, W, 4] and needs the tensor-core path')
+            x_seq = x_seq.contiguous()
+        else:
+            x_seq = x_seq.contiguous().float()
         params, n_site = self._flat_params()
         need_grad = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params)
+        if need_grad and x_seq.dtype == torch.uint8:
+            raise NotImplementedError('packed u8 input is forward-only (the first layer\'s weight gradient reads the fp32 frames)')
         side = {'need_grad': need_grad, 'return_layers': return_layers}
         depths = _NetFunction.apply(self, x_seq, side, n_site, *params)
         return depths, side
 
     # ------------------------------------------------------------------ forward
     def _run_forward(self, x_seq, params, n_site, side, want_h):
-        B, T = int(x_seq.shape[0]), int(x_seq.shape[1])
+        packed_in = x_seq.dtype == torch.uint8
+        B, T = (int(x_seq.shape[1]), int(x_seq.shape[0])) if packed_in else (int(x_seq.shape[0]), int(x_seq.shape[1]))
         dev = x_seq.device
         impl = IMPLS[self.impl]
         acts = {'x': x_seq}
@@ -151,9 +160,9 @@ class Engine:
         for i, s in enumerate(self.sites):
             xin = acts[s.src]
             first = s.src == 'x'
-            Hin, Win = (int(xin.shape[3]), int(xin.shape[4])) if first else (int(xin.shape[2]), int(xin.shape[3]))
+            Hin, Win = (int(xin.shape[3]), int(xin.shape[4])) if (first and not packed_in) else (int(xin.shape[2]), int(xin.shape[3]))
             g = s.geom(Hin, Win)
-            if first and int(x_seq.shape[2]) != g.Cin:
+            if first and not packed_in and int(x_seq.shape[2]) != g.Cin:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
             use_i8 = impl != SS_IMPL_SIMT
             fold = use_i8 and self.fold_upsample and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
@@ -171,7 +180,7 @@ class Engine:
             common = dict(T=T, B=B, neuron=node.kind, gain=s.gain_mod.gain(), v_th=node.v_threshold, v_reset=node.v_reset,
                           tau=node._tau_value(), decay=decay, v_in=v_in, want_v_out=self.keep_state, resid=resid, want_h=want_h)
             if use_i8:
-                if first:
+                if first and not packed_in:
                     xin = ops.pack_events(x_seq, self.event_status)     # fp32 NCHW counts -> u8 NHWC4
                 tsum = None
                 if s.out in head_srcs and self.heads_time_sum and 1 < T <= 86:

@@ -163,6 +163,7 @@ class _SpikingUNet(NeuromorphicNet):
 
     def forward_seq(self, x_seq, spikes_fp32=False):
         """T-loop over ``x_seq[:, t]`` without reset, fused: one kernel per block for all T timesteps.
+        ``x_seq`` is the reference's fp32 ``[B, T, C, H, W]`` or the packed u8 ``[T, B, H, W, 4]`` of ``stereospike_b200.events``.
         Returns what the LAST ``forward`` call of the equivalent loop would return.  Spike tensors are
         NCHW-shaped u8 views unless ``spikes_fp32``."""
         depths, side = self.engine.run(x_seq)

@@ -179,6 +179,48 @@ def test_empty_batch_and_bad_arguments():
         ops.conv_i8_fwd(x[..., :8].contiguous(), g8, q, sc, T=1, B=1, neuron=0, gain=1.0, v_th=1.0, v_reset=0.0)
 
 
+@pytest.mark.parametrize('nfpdm,rect', [(1, False), (5, True)])
+def test_events_to_frames_bit_exact(nfpdm, rect):
+    """Event stream -> packed u8 frames on the device equals the oracle restatement of the reference's loops, count for count."""
+    from oracle import events_ref as er
+    from stereospike_b200 import events
+    n_chunks = 4
+    rng = np.random.default_rng(5)
+    evL = er.synthetic_events(40000, n_chunks, nfpdm, seed=1, raw=rect)
+    evR = er.synthetic_events(30000, n_chunks, nfpdm, seed=2, raw=rect)
+    maps = None
+    if rect:
+        maps = (rng.uniform(-5, 350, (260, 346)), rng.uniform(-5, 264, (260, 346)))
+        refL, refR = er.rectify_events(evL, *maps), er.rectify_events(evR, *maps)
+    else:
+        refL, refR = evL, evR
+    # the reference rectifies first, then shifts each stream by the first surviving timestamp and cumulates
+    wantL = er.cumulate_spikes_into_frames(refL, n_chunks, nfpdm)
+    wantR = er.cumulate_spikes_into_frames(refR, n_chunks, nfpdm)
+    tm = (torch.from_numpy(maps[0]).cuda(), torch.from_numpy(maps[1]).cuda()) if rect else None
+    got = events.cumulate_spikes_into_frames(torch.from_numpy(evL).cuda(), torch.from_numpy(evR).cuda(), n_chunks, nfpdm, tm, tm)
+    assert tuple(got.shape) == (nfpdm, n_chunks, 260, 346, 4)
+    g = got.cpu().numpy().astype(np.float64)                      # [T, B, H, W, 4]
+    want = np.concatenate([wantL, wantR], axis=2).transpose(1, 0, 3, 4, 2)   # [B,T,4,H,W] -> [T,B,H,W,4]
+    assert np.array_equal(g, np.minimum(want, 255)) and g.sum() > 20000
+
+
+def test_packed_event_input_equals_float_frames():
+    """forward_seq on the packed u8 [T,B,H,W,4] frames == forward_seq on the reference's fp32 [B,T,4,H,W] frames, bit for bit."""
+    import stereospike_b200 as sb
+    from stereospike_b200 import ops
+    from oracle import ref_model as rm
+    torch.manual_seed(2)
+    net = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), multiply_factor=5.0).cuda()
+    x = rm.synthetic_inputs(2, 3, 4, seed=31).cuda()
+    with torch.no_grad():
+        sb.functional.reset_net(net)
+        d0, s0 = net.forward_seq(x)
+        sb.functional.reset_net(net)
+        d1, s1 = net.forward_seq(ops.pack_events(x))
+    assert all(torch.equal(a, b) for a, b in zip(d0, d1)) and all(torch.equal(a, b) for a, b in zip(s0, s1))
+
+
 def test_pack_events_flags_non_integer_input():
     from stereospike_b200 import ops
     x = torch.zeros(1, 2, 4, 6, 7, device='cuda')

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 2
+#define SS_ABI_VERSION 3
 
 /* error codes */
 #define SS_OK 0
@@ -229,6 +229,12 @@ int ss_neuron_bwd(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float
                   float v_th, float v_reset, float tau, const float* decay, const float* h_seq,
                   const float* v_init, const float* g_s, const float* g_v_last, float* g_acc,
                   float* g_v_init, float* g_decay, void* stream);
+/* Same scan; additionally (or instead: g_acc may be NULL) writes g_acc rounded to bf16 [T][N], the operand of the
+ * tensor-core gradient kernels below. */
+int ss_neuron_bwd_ex(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain,
+                     float v_th, float v_reset, float tau, const float* decay, const float* h_seq,
+                     const float* v_init, const float* g_s, const float* g_v_last, float* g_acc, void* g_acc_bf16,
+                     float* g_v_init, float* g_decay, void* stream);
 
 /* Convolution gradients of the fused block (replaces cuDNN dgrad / wgrad and upsample_nearest2d_backward
  * reached through autograd; the (ymap, xmap) tables fold the upsampling into the gather / scatter).
@@ -240,6 +246,45 @@ int ss_conv_dgrad(const ss_conv_geom* g, const int32_t* ymap, const int32_t* xma
                   const float* g_acc, float* g_x, void* stream);
 int ss_conv_wgrad(const ss_conv_geom* g, const void* x, const int32_t* ymap, const int32_t* xmap,
                   const float* g_acc, float* g_w, void* stream);
+
+/* ---- tensor-core gradients (bf16 operands, fp32 accumulation; what train.py:239 reaches through cuDNN under autograd) ----
+ *
+ * ss_corr_bf16: stride-1 correlation of a zero-padded bf16 NHWC tensor with `nclass` weight sets, evaluated on a virtual
+ * grid Hv x Wv and routed to an fp32 NHWC destination through per-axis output maps.  Every data gradient of the path is
+ * one call:  same-padded 3x3 conv -> flipped/transposed weights, pad 1;  stride-2 5x5 conv -> four (row parity, column
+ * parity) classes of 3x3 weights on the output-resolution gradient, destination (2i+py, 2j+px);  NNConvUpsampling ->
+ * flipped 5x5 weights, pad 4, virtual grid = the upsampled image, destination = its nearest-neighbour source pixel
+ * (several virtual pixels share one: SS_CORR_ATOMIC).  Same kernel as ss_conv_i8_fwd (halo patch, taps by descriptor
+ * shift, T accumulator slots) with tcgen05 kind::f16 and a store epilogue.
+ *   src_bf16 bf16 [T][B][Hg][Wg][Cg];  w_img from ss_pack_weights_bf16 (OIHW fp32 [nsets*ntile][Cg][ks][ks], set index =
+ *   out-channel tile * nclass + class, class = 2*row_class + col_class);  ymap_out int32 [nclass > 1 ? 2 : 1][Hv], xmap_out
+ *   likewise [..][Wv]: destination row / column or -1 (NULL, NULL = identity, needs nclass 1 and Hv x Wv == Hdst x Wdst);
+ *   dst fp32 [T][B][Hdst][Wdst][Cdst]. */
+#define SS_CORR_STORE 0       /* dst  = result (every destination element written exactly once)   */
+#define SS_CORR_ACCUMULATE 1  /* dst += result, plain read-modify-write (destinations are unique) */
+#define SS_CORR_ATOMIC 2      /* dst += result with red.global.add (destinations may repeat)       */
+typedef struct ss_corr_desc {
+    int32_t T, B;
+    int32_t Hg, Wg, Cg;
+    int32_t Hv, Wv;
+    int32_t Hdst, Wdst, Cdst;
+    int32_t ks, pad;
+    int32_t nclass;      /* 1 or 4 */
+    int32_t out_mode;    /* SS_CORR_* */
+    int32_t ntile;       /* destination channels per weight set: 32 or 64 */
+    int32_t reserved;
+} ss_corr_desc;
+int ss_pack_weights_bf16(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t ntile, void* w_img, void* stream);
+int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const void* w_img, const int32_t* ymap_out,
+                 const int32_t* xmap_out, float* dst, void* stream);
+
+/* ss_conv_wgrad_bf16: weight gradient of one fused block (geometry as ss_conv_i8_fwd's descriptor; gain / neuron fields
+ * ignored).  The contraction runs over pixels, the slow dimension of NHWC, so both MMA operands are MN-major: A = a tile of
+ * g (pixels x 128 output channels), B = the halo patch of x converted to bf16 (pixels x 16 or 32 input channels), one
+ * accumulator per filter tap in TMEM; a tap is again a start-address shift of the patch.
+ *   x u8 [T][B][Hin][Win][Cin] (Cin % 16 == 0; Cin == 4: packed event frames);  g_bf16 bf16 [T][B][Hout][Wout][Cout];
+ *   g_w fp32 [ks*ks*Cin][Cout] accumulated with atomics. */
+int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const void* g_bf16, float* g_w, void* stream);
 
 /* Backward of ss_heads_fwd (autograd through predict_depthK + the I-neuron running sum).
  *   g_depths fp32 [4][B][H][W]: gradient w.r.t. the four returned depth maps (execution order)

@@ -16,7 +16,8 @@ SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
 SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
-           'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
+           'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_neuron_bwd_ex', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
+           'ss_pack_weights_bf16', 'ss_corr_bf16', 'ss_conv_wgrad_bf16',
            'ss_abi_version', 'ss_last_error', 'ss_launch_count')
 
 
@@ -48,6 +49,14 @@ class ConvGeom(ctypes.Structure):
                 ('gain', ctypes.c_float), ('v_th', ctypes.c_float), ('v_reset', ctypes.c_float),
                 ('tau', ctypes.c_float),
                 ('reserved1', ctypes.c_int32), ('reserved2', ctypes.c_int32)]
+
+
+class CorrDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('T', 'B', 'Hg', 'Wg', 'Cg', 'Hv', 'Wv', 'Hdst', 'Wdst', 'Cdst', 'ks', 'pad',
+                                               'nclass', 'out_mode', 'ntile', 'reserved')]
+
+
+SS_CORR_STORE, SS_CORR_ACCUMULATE, SS_CORR_ATOMIC = 0, 1, 2
 
 
 class HeadsArgs(ctypes.Structure):
@@ -103,6 +112,14 @@ def lib():
     L.ss_neuron_fwd.restype = ctypes.c_int
     L.ss_neuron_bwd.argtypes = [i32, i64, i32, i32, f32, f32, f32, f32, f32] + [vp] * 9
     L.ss_neuron_bwd.restype = ctypes.c_int
+    L.ss_neuron_bwd_ex.argtypes = [i32, i64, i32, i32, f32, f32, f32, f32, f32] + [vp] * 10
+    L.ss_neuron_bwd_ex.restype = ctypes.c_int
+    L.ss_pack_weights_bf16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.ss_pack_weights_bf16.restype = ctypes.c_int
+    L.ss_corr_bf16.argtypes = [ctypes.POINTER(CorrDesc)] + [vp] * 6
+    L.ss_corr_bf16.restype = ctypes.c_int
+    L.ss_conv_wgrad_bf16.argtypes = [ctypes.POINTER(BlockDesc)] + [vp] * 4
+    L.ss_conv_wgrad_bf16.restype = ctypes.c_int
     L.ss_conv_dgrad.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 6
     L.ss_conv_dgrad.restype = ctypes.c_int
     L.ss_conv_wgrad.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 6

@@ -4,6 +4,8 @@
 // autograd.Function.backward (ATan / Sigmoid evaluated at h - v_th, detach_reset=True), cuDNN dgrad / wgrad of
 // every Conv2d, and upsample_nearest2d_backward -- the (ymap, xmap) tables fold the upsampling into the conv
 // gradient, so no upsampled gradient tensor is ever materialised.
+#include <cuda_bf16.h>
+
 #include "ss_common.cuh"
 
 namespace ss {
@@ -24,7 +26,8 @@ __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int
                                                          const float* __restrict__ decay_p, const float* __restrict__ h_seq,
                                                          const float* __restrict__ v_init, const float* g_s,
                                                          const float* __restrict__ g_v_last, float* g_acc,
-                                                         float* __restrict__ g_v_init, float* __restrict__ g_decay) {
+                                                         __nv_bfloat16* __restrict__ g_acc_bf16, float* __restrict__ g_v_init,
+                                                         float* __restrict__ g_decay) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float gd_local = 0.0f;
     if (n < N) {
@@ -47,7 +50,8 @@ __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int
             const float s = (u >= 0.0f) ? 1.0f : 0.0f;
             const float g_h = g_s[(size_t)t * N + n] * surrogate_grad(surrogate, alpha, u) + g_v * (1.0f - s);
             const float g_x = (neuron == SS_NEURON_IF) ? g_h : g_h * r;
-            g_acc[(size_t)t * N + n] = g_x * gain;
+            if (g_acc != nullptr) g_acc[(size_t)t * N + n] = g_x * gain;
+            if (g_acc_bf16 != nullptr) g_acc_bf16[(size_t)t * N + n] = __float2bfloat16_rn(g_x * gain);
             if (neuron == SS_NEURON_PLIF) gd_local += g_h * ((h - v_prev) / r);  // d h / d r = x - (v - v_reset)
             g_v = g_h * keep;
             h = h_prev;
@@ -363,11 +367,11 @@ int fill_params(const ss_conv_geom* g, ConvParams& p) {
 
 using namespace ss;
 
-extern "C" int ss_neuron_bwd(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,
-                             float v_reset, float tau, const float* decay, const float* h_seq, const float* v_init,
-                             const float* g_s, const float* g_v_last, float* g_acc, float* g_v_init, float* g_decay,
-                             void* stream) {
-    if (h_seq == nullptr || g_s == nullptr || g_acc == nullptr || T < 0 || N < 0) {
+extern "C" int ss_neuron_bwd_ex(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,
+                                float v_reset, float tau, const float* decay, const float* h_seq, const float* v_init,
+                                const float* g_s, const float* g_v_last, float* g_acc, void* g_acc_bf16, float* g_v_init,
+                                float* g_decay, void* stream) {
+    if (h_seq == nullptr || g_s == nullptr || (g_acc == nullptr && g_acc_bf16 == nullptr) || T < 0 || N < 0) {
         set_error("ss_neuron_bwd: bad argument");
         return SS_EINVAL;
     }
@@ -377,10 +381,18 @@ extern "C" int ss_neuron_bwd(int32_t T, int64_t N, int32_t neuron, int32_t surro
     }
     if (T == 0 || N == 0) return SS_OK;
     neuron_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc, g_v_init,
-        g_decay);
+        T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
+        reinterpret_cast<__nv_bfloat16*>(g_acc_bf16), g_v_init, g_decay);
     count_launch();
     return check_launch("neuron_bwd");
+}
+
+extern "C" int ss_neuron_bwd(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,
+                             float v_reset, float tau, const float* decay, const float* h_seq, const float* v_init,
+                             const float* g_s, const float* g_v_last, float* g_acc, float* g_v_init, float* g_decay,
+                             void* stream) {
+    return ss_neuron_bwd_ex(T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
+                            nullptr, g_v_init, g_decay, stream);
 }
 
 extern "C" int ss_conv_dgrad(const ss_conv_geom* g, const int32_t* ymap, const int32_t* xmap, const float* w_kn,

@@ -32,9 +32,11 @@
 //   warps 0-3  patch producers (cp.async gather, zero fill)     warp 4  MMA issuer (one lane), owns TMEM
 //   warp 5     weight producer (cp.async.bulk of pre-swizzled images)      warps 8-15  epilogue (TMEM -> neuron -> HBM)
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdio>
 
 #include "ss_common.cuh"
+#include "ss_umma.cuh"
 
 namespace ss {
 namespace {
@@ -78,116 +80,12 @@ struct I8Params {
     uint8_t* out;
     float* h_seq;
     uint8_t* tsum;
+    float* g_dst;          // MODE_BF16 (gradient-side correlation): fp32 NHWC destination [T][B][Hout][Wout][Cout]
+    int g_mode;            // SS_CORR_STORE / SS_CORR_ACCUMULATE / SS_CORR_ATOMIC
 };
 
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 6000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// mbarrier arrival triggered by the completion of all prior cp.async of this thread (counts as one expected arrival)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Same, with the per-tap descriptor offsets (in 16-byte units) folded into the asm statement so that the two 64-bit adds
-// stay next to their MMA instead of being hoisted in front of the whole tap sequence.
-template <uint32_t AOFF, uint32_t BOFF>
-__device__ __forceinline__ void umma_i8_off(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .b64 da, db;\n\t"
-        "add.s64 da, %1, %4;\n\t"
-        "add.s64 db, %2, %5;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, 1;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "n"(AOFF), "n"(BOFF)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// one elected lane of a converged warp (the compiler knows exactly one lane is active in the guarded region)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void named_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// K-major shared-memory matrix descriptor (sm_100 "version 1").  Rows are `RB` bytes (one swizzle row each); the
-// swizzle (32B / 64B / 128B, = RB) is applied by the hardware on ABSOLUTE shared-memory address bits, so the start
-// address may point at any row of a patch (probe: tools/umma_probe_i8.cu).  sbo = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout << 61;
-    return d;
-}
-__device__ __forceinline__ uint32_t swizzle_off(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
+constexpr int MODE_I8 = 0;     // forward block: u8 activations x int8 weight digit planes -> s32, neuron epilogue
+constexpr int MODE_BF16 = 1;   // gradient-side correlation: bf16 gradients x bf16 weights -> f32, store / accumulate / atomic epilogue
 
 // ------------------------------------------------------------------------------------------------ geometry
 // Source row (b*Hin + iy) read by patch row `pr` of tile row `ty`, or -1 (zero padding / gap between stacked images).
@@ -239,7 +137,7 @@ __device__ __forceinline__ constexpr int tap_offset(int ky, int kx) {
 
 // Issues every MMA of one (patch stage, weight buffer) pair except the very first one (tap 0, k-step 0), which the
 // caller issues itself because it carries the run-time accumulate flag.
-template <int KS, int STRIDE, int RB, int CN, int PWP, int PWHALF, int TAP = 0, int K = 1>
+template <int MODE, int KS, int STRIDE, int RB, int CN, int PWP, int PWHALF, int TAP = 0, int K = 1>
 __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0, uint32_t idesc) {
     constexpr int KSTEPS = RB / 32;
     if constexpr (TAP < KS * KS) {
@@ -247,10 +145,10 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
             constexpr int ky = TAP / KS, kx = TAP % KS;
             constexpr uint32_t aoff = (uint32_t)(tap_offset<STRIDE, PWP, PWHALF>(ky, kx) * RB + K * 32) >> 4;
             constexpr uint32_t boff = (uint32_t)(TAP * CN * RB + K * 32) >> 4;
-            umma_i8_off<aoff, boff>(d, a0, b0, idesc);
-            issue_taps<KS, STRIDE, RB, CN, PWP, PWHALF, TAP, K + 1>(d, a0, b0, idesc);
+            umma_i8_off<aoff, boff, MODE>(d, a0, b0, idesc);
+            issue_taps<MODE, KS, STRIDE, RB, CN, PWP, PWHALF, TAP, K + 1>(d, a0, b0, idesc);
         } else {
-            issue_taps<KS, STRIDE, RB, CN, PWP, PWHALF, TAP + 1, 0>(d, a0, b0, idesc);
+            issue_taps<MODE, KS, STRIDE, RB, CN, PWP, PWHALF, TAP + 1, 0>(d, a0, b0, idesc);
         }
     }
 }
@@ -258,7 +156,7 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // FIRST: the first layer (Cin <= 4, event-count frames u8 [T][B][H][W][4]).  Its K = ks*ks*4 <= 128 is one swizzle row,
 // so the producers assemble an explicit im2col tile (KS = 1 "tap", RB = 128: row = output pixel, byte = tap*4 + c) with
 // L1-cached 4-byte loads instead of a halo patch -- 4 MMAs per tile instead of ks*ks*(32-channel padded blocks).
-template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false>
+template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
@@ -452,7 +350,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         // "issued" token of its predecessor.  Both threads walk the same loop nest and keep identical phase bookkeeping.
         if (elect_one()) {
             const uint32_t role = warp == 4 ? 0u : 1u;
-            constexpr uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptor: i8 = s32 accumulate, A u8, B s8;  bf16 = f32 accumulate, A and B bf16; both operands K-major
+            constexpr uint32_t idesc = (MODE == MODE_I8 ? ((2u << 4) | (0u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
+                                       ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
             constexpr uint32_t a_sbo = (uint32_t)(STRIDE * cPWp * RB);
             constexpr uint32_t b_sbo = (uint32_t)(8 * RB);
@@ -483,8 +383,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     mbar_wait(tok_wait, role == 0 ? ((mine & 1u) ^ 1u) : (mine & 1u));
                     ++mine;
                     tc_fence_after();
-                    umma_i8(d, a0, b0, idesc, first ? 0u : 1u);
-                    issue_taps<KS, STRIDE, RB, cN, cPWp, cPWhalf>(d, a0, b0, idesc);
+                    umma_i8<MODE>(d, a0, b0, idesc, first ? 0u : 1u);
+                    issue_taps<MODE, KS, STRIDE, RB, cN, cPWp, cPWhalf>(d, a0, b0, idesc);
                     tc_fence_before();
                     mbar_arrive(tok_post);
                     umma_commit(bar_empty_p + 8 * stage);
@@ -589,6 +489,70 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         const int m = quarter * 32 + lane;
         const int g = m >> 3, j = m & 7;
         const int M = p.B * p.Hout * p.Wout;
+        if constexpr (MODE == MODE_BF16) {
+            // ---------------------------------------------------------- gradient-side epilogue: fp32 accumulators -> HBM
+            // Thread = one virtual output pixel (TMEM lane) x half of the tile's cN output channels.  The pixel is routed
+            // through the (class, virtual position) -> destination maps (stride-2 parity classes, nearest-neighbour
+            // upsampling); several virtual pixels may share a destination (upsampling), hence the atomic mode.
+            constexpr int HALF = cN / 2;
+            constexpr int NCH = HALF / 16;
+            const size_t t_out = (size_t)M * p.Cout;
+            uint32_t slot_phase = 0;
+            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+                const int wset = it / p.mtiles;
+                const int mt = it - wset * p.mtiles;
+                const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                const int cls = wset % p.nclass;
+                const int so = ty * 16 + g;
+                const int b = so / p.HsO;
+                int oy = so - b * p.HsO;
+                int ox = tx * 8 + j;
+                bool live = oy < p.Hv && ox < p.Wv && b < p.B;
+                if (p.mode == SS_TILES_FOLDED) {
+                    oy = live ? __ldg(p.ymap_out + (cls >> 1) * p.Hv + oy) : -1;
+                    ox = live ? __ldg(p.xmap_out + (cls & 1) * p.Wv + ox) : -1;
+                    live = oy >= 0 && ox >= 0;
+                }
+                live = live && oy < p.Hout && ox < p.Wout;
+                const int nb = (wset / p.nclass) * cN + hf * HALF;
+                const size_t o0 = live ? ((size_t)(b * p.Hout + oy) * p.Wout + ox) * p.Cout + nb : 0;
+                for (int t0 = 0; t0 < p.T; t0 += cTC) {
+                    const int tc = min(cTC, p.T - t0);
+                    for (int s = 0; s < tc; ++s) {
+                        mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
+                        slot_phase ^= 1u << s;
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * cN + hf * HALF);
+                        int d[NCH][16];
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) tmem_ld16(taddr + c * 16, d[c]);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        mbar_arrive(bar_empty_a + 8 * s);
+                        if (!live) continue;
+                        float* dst = p.g_dst + (size_t)(t0 + s) * t_out + o0;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float4 v = make_float4(__int_as_float(d[c][4 * q]), __int_as_float(d[c][4 * q + 1]),
+                                                       __int_as_float(d[c][4 * q + 2]), __int_as_float(d[c][4 * q + 3]));
+                                float4* dp = reinterpret_cast<float4*>(dst + c * 16 + q * 4);
+                                if (p.g_mode == SS_CORR_ATOMIC) {
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                                                 : "memory");
+                                } else {
+                                    if (p.g_mode == SS_CORR_ACCUMULATE) {
+                                        const float4 old = *dp;
+                                        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                                    }
+                                    *dp = v;
+                                }
+                            }
+                    }
+                }
+            }
+        } else {
         NeuronConst nc;
         nc.gain = p.gain; nc.v_th = p.v_th; nc.v_reset = p.v_reset; nc.tau = p.tau;
         nc.rtau = div_const_prepare(p.tau);
@@ -722,6 +686,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 for (int i = 0; i < 4; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
         }
+        }   // MODE_I8
     }
 
     tc_fence_before();
@@ -848,7 +813,35 @@ __global__ void __launch_bounds__(256) pack_events_kernel(const float* __restric
     if (bad && status != nullptr) atomicOr(status, 1);
 }
 
+// bf16 weight image of the gradient-side correlation: [wset = Cout / NT][cb][tap][NT rows][RB bytes = RB/2 input channels],
+// swizzled exactly as it must sit in shared memory (same image layout as the int8 one, 2-byte elements)
+__global__ void __launch_bounds__(256) weight_pack_bf16_kernel(const float* __restrict__ w, int Cout, int Cin, int ks, int NT, int RB,
+                                                               uint16_t* __restrict__ out) {
+    const int ntaps = ks * ks;
+    const int cpr = RB / 2;                                   // input channels per swizzle row
+    const int ncb = Cin / cpr;
+    const long long total = (long long)Cout * Cin * ntaps;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    long long r = idx;
+    const int c = (int)(r % cpr); r /= cpr;
+    const int rn = (int)(r % NT); r /= NT;
+    const int tap = (int)(r % ntaps); r /= ntaps;
+    const int cb = (int)(r % ncb); r /= ncb;
+    const int wset = (int)r;
+    const int n = wset * NT + rn;
+    const int ch = cb * cpr + c;
+    const int ky = tap / ks, kx = tap - ky * ks;
+    const float wv = w[(((size_t)n * Cin + ch) * ks + ky) * ks + kx];   // OIHW
+    const size_t buf = (size_t)(wset * ncb + cb) * ((size_t)ntaps * NT * RB);
+    const uint32_t mask = (uint32_t)(RB >> 4) - 1u;
+    const uint32_t off = (uint32_t)((tap * NT + rn) * RB + c * 2);
+    out[(buf + (off ^ (((off >> 7) & mask) << 4))) >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(wv));
+}
+
 int rowbytes_for(int Cin, int ks) { return (ks <= 3 && Cin % 64 == 0) ? 64 : 32; }
+// gradient-side correlation: row bytes of the bf16 source patch (Cg channels = 2*Cg bytes per pixel)
+int corr_rowbytes_for(int Cg, int ks) { return (ks <= 3 && (2 * Cg) % 64 == 0) ? 64 : 32; }
 
 }  // namespace
 }  // namespace ss
@@ -964,7 +957,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         set_error("ss_conv_i8_fwd: unsupported conv shape (ks %d stride %d pad %d upsample %d)", g->ks, g->stride, g->pad, g->upsample);
         return SS_EUNSUPPORTED;
     }
-    I8Params p;
+    I8Params p{};
     p.T = g->T; p.B = g->B; p.Hin = g->Hin; p.Win = g->Win; p.Cin = g->Cin;
     p.Hout = g->Hout; p.Wout = g->Wout; p.Cout = g->Cout;
     p.ks = g->ks; p.stride = g->stride; p.pad = up ? 0 : g->pad; p.upsample = up ? 1 : 0;
@@ -1145,4 +1138,144 @@ extern "C" int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin,
                                                                                            reinterpret_cast<int8_t*>(w_i8));
     count_launch();
     return check_launch("pack_digits");
+}
+
+// ------------------------------------------------------------------------------------------------ gradient-side correlation
+extern "C" int ss_pack_weights_bf16(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t ntile, void* w_img,
+                                    void* stream) {
+    if (w_oihw == nullptr || w_img == nullptr || Cout <= 0 || Cin <= 0 || !(ks == 3 || ks == 5) || !(ntile == 32 || ntile == 64) ||
+        Cout % ntile != 0 || Cin % 16 != 0) {
+        set_error("ss_pack_weights_bf16: bad argument (ks 3 or 5, ntile 32 or 64, Cout %% ntile, Cin %% 16)");
+        return SS_EINVAL;
+    }
+    const int RB = corr_rowbytes_for(Cin, ks);
+    const long long total = (long long)Cout * Cin * ks * ks;
+    weight_pack_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, ks, ntile, RB,
+                                                                                                 reinterpret_cast<uint16_t*>(w_img));
+    count_launch();
+    return check_launch("weight_pack_bf16");
+}
+
+extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const void* w_img, const int32_t* ymap_out,
+                            const int32_t* xmap_out, float* dst, void* stream) {
+    if (d == nullptr) {
+        set_error("ss_corr_bf16: null descriptor");
+        return SS_EINVAL;
+    }
+    if (d->T == 0 || d->B == 0) return SS_OK;
+    if (src_bf16 == nullptr || w_img == nullptr || dst == nullptr) {
+        set_error("ss_corr_bf16: null argument");
+        return SS_EINVAL;
+    }
+    if (d->T < 0 || d->B < 0 || d->Hg <= 0 || d->Wg <= 0 || d->Cg <= 0 || d->Hv <= 0 || d->Wv <= 0 || d->Hdst <= 0 || d->Wdst <= 0 ||
+        d->Cdst <= 0 || !(d->ks == 3 || d->ks == 5) || d->pad < 0 || d->pad >= d->ks || !(d->nclass == 1 || d->nclass == 4) ||
+        !(d->ntile == 32 || d->ntile == 64) || d->Cdst % d->ntile != 0 || d->Cg % 16 != 0 || d->out_mode < SS_CORR_STORE ||
+        d->out_mode > SS_CORR_ATOMIC) {
+        set_error("ss_corr_bf16: bad descriptor");
+        return SS_EINVAL;
+    }
+    const bool mapped = ymap_out != nullptr && xmap_out != nullptr;
+    if (!mapped && (d->nclass != 1 || d->Hv != d->Hdst || d->Wv != d->Wdst)) {
+        set_error("ss_corr_bf16: classes / a virtual grid different from the destination need the output maps");
+        return SS_EINVAL;
+    }
+    I8Params p{};
+    p.T = d->T; p.B = d->B; p.Hin = d->Hg; p.Win = d->Wg; p.Cin = 2 * d->Cg;   // the producers count bytes
+    p.Hout = d->Hdst; p.Wout = d->Wdst; p.Cout = d->Cdst;
+    p.ks = d->ks; p.stride = 1; p.pad = d->pad; p.upsample = 0;
+    p.N = d->ntile;
+    p.RB = corr_rowbytes_for(d->Cg, d->ks);
+    p.ncb = p.Cin / p.RB;
+    p.ntaps = d->ks * d->ks;
+    p.PH = 15 + d->ks;
+    p.PWhalf = 8 + (d->ks - 1) / 2;
+    p.PWp = 8 + d->ks - 1;
+    p.ppix = p.PH * p.PWp;
+    p.Hup = p.Wup = 0;
+    p.mode = mapped ? SS_TILES_FOLDED : SS_TILES_PLAIN;
+    p.nclass = d->nclass;
+    p.Hv = d->Hv; p.Wv = d->Wv;
+    p.nbands = 1; p.band_rows = 0;
+    p.ymap_out = ymap_out; p.xmap_out = xmap_out; p.band_start = p.band_len = nullptr;
+    {
+        // stacked virtual rows per image: past the source rows + padding, and far enough that taps reaching below the last
+        // virtual row land in the next image's (zero) top padding
+        const int need = d->Hg + d->pad;
+        const int reach = (d->Hv - 1) + d->ks - d->pad;
+        int span = need > reach ? need : reach;
+        if (span < d->Hv) span = d->Hv;
+        p.HsO = span;
+    }
+    const long long rows = (long long)p.HsO * d->B;
+    const int tiles_y = (int)((rows + 15) / 16);
+    p.tiles_x = (p.Wv + 7) / 8;
+    p.mtiles = tiles_y * p.tiles_x;
+    const long long nitems = (long long)p.mtiles * (d->Cdst / d->ntile) * p.nclass;
+    if (nitems > 0x7fffffffLL || (long long)d->B * d->Hg * d->Wg * p.Cin > 0x7fffffffLL) {
+        set_error("ss_corr_bf16: problem too large for 32-bit indexing");
+        return SS_EINVAL;
+    }
+    p.nitems = (int)nitems;
+    p.TC = 512 / p.N;
+    if (p.TC > MAX_SLOTS) p.TC = MAX_SLOTS;
+    p.WB = p.ntaps * p.N * p.RB;
+    p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
+    p.resident = p.ncb <= NWB ? 1 : 0;
+    p.nwb = p.ncb < NWB ? p.ncb : NWB;
+    const int tail_bytes = 512 + 40 * 8 + 64;
+    const int budget = 227 * 1024 - 1024 - tail_bytes - p.nwb * p.WB;
+    int nps = budget / p.PB;
+    if (nps > MAX_STAGES) nps = MAX_STAGES;
+    if (nps < 2) {
+        set_error("ss_corr_bf16: not enough shared memory");
+        return SS_EUNSUPPORTED;
+    }
+    p.NPS = nps;
+    p.yscale = p.xscale = 1.0f;
+    p.neuron = SS_NEURON_IF; p.gain = 1.0f; p.v_th = 1.0f; p.v_reset = 0.0f; p.tau = 2.0f;
+    p.x = reinterpret_cast<const uint8_t*>(src_bf16);
+    p.w = reinterpret_cast<const int8_t*>(w_img);
+    p.g_dst = dst;
+    p.g_mode = d->out_mode;
+
+    const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
+    int dev = 0, num_sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(p.nitems < num_sms ? p.nitems : num_sms));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    bool launched = false;
+#define SS_TRY_CORR(PL, KS_, RB_)                                                                                                  \
+    if (!launched && d->ntile == PL * 32 && d->ks == KS_ && p.RB == RB_) {                                                         \
+        static bool attr = false;                                                                                                  \
+        if (!attr) {                                                                                                               \
+            cudaFuncSetAttribute(conv_i8_kernel<PL, KS_, 1, RB_, false, MODE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 227 * 1024);                                                                                      \
+            attr = true;                                                                                                           \
+        }                                                                                                                          \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, 1, RB_, false, MODE_BF16>, p);                                            \
+        launched = true;                                                                                                           \
+    }
+    SS_TRY_CORR(2, 5, 32)
+    SS_TRY_CORR(2, 3, 64)
+    SS_TRY_CORR(2, 3, 32)
+    SS_TRY_CORR(1, 5, 32)
+    SS_TRY_CORR(1, 3, 64)
+    SS_TRY_CORR(1, 3, 32)
+#undef SS_TRY_CORR
+    if (!launched) {
+        set_error("ss_corr_bf16: no kernel instance for ntile %d ks %d rowbytes %d", d->ntile, d->ks, p.RB);
+        return SS_EUNSUPPORTED;
+    }
+    count_launch();
+    return check_launch("corr_bf16");
 }

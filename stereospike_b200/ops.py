@@ -346,3 +346,94 @@ def heads_fwd(acts, geoms, weights_9c, biases, *, T, B, H, W, gain, v_io, acts_s
     rc = _lib.lib().ss_heads_fwd(ctypes.byref(a), _ptr(v_io), _ptr(depths), _stream())
     _lib.check(rc, 'ss_heads_fwd')
     return depths
+
+
+# ----------------------------------------------------------------------------------------- tensor-core gradients
+def _pack_bf16(w_eff, ks, ntile):
+    """OIHW fp32 [nsets*ntile][Cg][ks][ks] -> the correlation kernel's bf16 shared-memory image."""
+    w_eff = w_eff.contiguous().float()
+    co, ci = int(w_eff.shape[0]), int(w_eff.shape[1])
+    img = torch.empty(co * ci * ks * ks, dtype=torch.bfloat16, device=w_eff.device)
+    _lib.check(_lib.lib().ss_pack_weights_bf16(_ptr(w_eff), co, ci, ks, ntile, _ptr(img), _stream()), 'ss_pack_weights_bf16')
+    return img
+
+
+class DgradPlan:
+    """Data gradient of one fused block as a single ss_corr_bf16 call (include/stereospike_b200.h): correlation weights
+    derived from the block's OIHW weight, virtual grid, output maps.  ``geom`` is the block's forward BlockGeom."""
+
+    def __init__(self, weight, geom, device):
+        g = geom
+        w = weight.detach().float()
+        co, ci, ks, _ = w.shape
+        self.ntile = 64 if ci % 64 == 0 else 32
+        assert ci % 32 == 0 and co % 16 == 0
+        dev = torch.device(device)
+        t = lambda a: torch.tensor(a, dtype=torch.int32, device=dev).contiguous()
+        wt = w.flip(2, 3).transpose(0, 1)                       # [Cin][Cout][ks][ks]: correlation form of the transposed conv
+        self.ymap = self.xmap = None
+        if g.kind == 'conv' and g.stride == 1:
+            assert 2 * g.pad == ks - 1
+            self.ks, self.pad, self.nclass, self.mode = ks, ks - 1 - g.pad, 1, _lib.SS_CORR_ACCUMULATE
+            self.Hv, self.Wv = g.Hin, g.Win
+            w_eff = wt
+        elif g.kind == 'conv':
+            assert g.stride == 2 and ks == 5 and g.pad == 2
+            # input row y = 2i + py receives  sum_dy g[i - 1 + dy] * W[2*(2 - dy) + py]  (dy = 0..2; tap index > 4 -> absent)
+            self.ks, self.pad, self.nclass, self.mode = 3, 1, 4, _lib.SS_CORR_ACCUMULATE
+            self.Hv, self.Wv = (g.Hin + 1) // 2, (g.Win + 1) // 2
+            sets = []
+            for py in (0, 1):
+                for px in (0, 1):
+                    f = w.new_zeros(ci, co, 3, 3)
+                    for dy in range(3):
+                        for dx in range(3):
+                            ky, kx = 2 * (2 - dy) + py, 2 * (2 - dx) + px
+                            if ky <= 4 and kx <= 4:
+                                f[:, :, dy, dx] = w[:, :, ky, kx].transpose(0, 1)
+                    sets.append(f)
+            nt = self.ntile
+            w_eff = torch.stack(sets, 0).view(4, ci // nt, nt, co, 3, 3).permute(1, 0, 2, 3, 4, 5).reshape(4 * ci, co, 3, 3)
+            ym = np.full((2, self.Hv), -1, dtype=np.int32)
+            xm = np.full((2, self.Wv), -1, dtype=np.int32)
+            for par in (0, 1):
+                yy = 2 * np.arange(self.Hv) + par
+                xx = 2 * np.arange(self.Wv) + par
+                ym[par] = np.where(yy < g.Hin, yy, -1)
+                xm[par] = np.where(xx < g.Win, xx, -1)
+            self.ymap, self.xmap = t(ym), t(xm)
+        else:
+            # NNConvUpsampling: gradient w.r.t. the virtual upsampled image, routed to its nearest-neighbour source pixel
+            self.ks, self.pad, self.nclass, self.mode = ks, ks - 1, 1, _lib.SS_CORR_ATOMIC
+            self.Hv, self.Wv = g.Hout + ks - 1, g.Wout + ks - 1
+
+            def src(n_in, n_up):
+                scale = np.float32(n_in) / np.float32(n_up)
+                return np.minimum(np.floor(np.arange(n_up, dtype=np.float32) * scale).astype(np.int64), n_in - 1).astype(np.int32)
+            self.ymap, self.xmap = t(src(g.Hin, self.Hv)), t(src(g.Win, self.Wv))
+            w_eff = wt
+        self.w_img = _pack_bf16(w_eff, self.ks, self.ntile)
+        self.geom = g
+
+    def run(self, g_bf16, dst, T, B):
+        g = self.geom
+        assert g_bf16.dtype == torch.bfloat16 and g_bf16.is_contiguous() and tuple(g_bf16.shape) == (T, B, g.Hout, g.Wout, g.Cout)
+        assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape) == (T, B, g.Hin, g.Win, g.Cin)
+        d = _lib.CorrDesc(T=T, B=B, Hg=g.Hout, Wg=g.Wout, Cg=g.Cout, Hv=self.Hv, Wv=self.Wv, Hdst=g.Hin, Wdst=g.Win, Cdst=g.Cin,
+                          ks=self.ks, pad=self.pad, nclass=self.nclass, out_mode=self.mode, ntile=self.ntile, reserved=0)
+        _lib.check(_lib.lib().ss_corr_bf16(ctypes.byref(d), _ptr(g_bf16), _ptr(self.w_img), _ptr(self.ymap), _ptr(self.xmap),
+                                           _ptr(dst), _stream()), 'ss_corr_bf16')
+
+
+def conv_wgrad_bf16(x, g_bf16, geom, T, B, cin=None):
+    """Weight gradient of one fused block on the tensor cores -> fp32 [K][Cout] (k = (ky*ks + kx)*Cin + c)."""
+    g = geom
+    cin = g.Cin if cin is None else cin
+    assert x.dtype == ACT_DTYPE and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, cin)
+    assert g_bf16.dtype == torch.bfloat16 and g_bf16.is_contiguous() and tuple(g_bf16.shape) == (T, B, g.Hout, g.Wout, g.Cout)
+    g_w = torch.zeros((g.ks * g.ks * cin, g.Cout), dtype=torch.float32, device=x.device)
+    d = _lib.BlockDesc(T=T, B=B, Hin=g.Hin, Win=g.Win, Cin=cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
+                       stride=g.stride, pad=g.pad, upsample=1 if g.kind == 'upconv' else 0, neuron=0, planes=3,
+                       gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0)
+    _lib.check(_lib.lib().ss_conv_wgrad_bf16(ctypes.byref(d), _ptr(x), _ptr(g_bf16), _ptr(g_w), _stream()), 'ss_conv_wgrad_bf16')
+    return g_w

@@ -1,7 +1,466 @@
-// placeholder, replaced below
+// Weight gradient of the fused spiking block on the sm_100a tensor cores (tcgen05, bf16 x bf16 -> fp32).
+//
+// Replaces: autograd's cuDNN wgrad of every Conv2d on the path, including the convs behind UpsamplingNearest2d
+// (reference train.py:239 -> network/blocks.py:110-132, network/SNN_models.py:75-129).
+//
+//   g_w[ky][kx][c][n] = sum over (t, b, oy, ox) of  g[t][b][oy][ox][n] * x[t][b][src(oy, ky)][src(ox, kx)][c]
+//
+// The contraction runs over PIXELS, the slow dimension of NHWC, so both MMA operands are MN-major: a shared-memory row is
+// one pixel (a K index), its bytes are channels (the M / N index).  That is exactly the layout of the forward kernel's halo
+// patch, so the same trick applies: the input patch of a 16 x 8 output tile is staged ONCE per (tile, timestep, channel
+// chunk) and every filter tap is a different start address of the B descriptor (probe: tools/umma_probe_mn.cu -- the
+// hardware swizzles on absolute address bits for MN-major operands too).  Stride 2 = parity-split patch rows, upsampling =
+// gather in the producer, exactly as in ss_conv_i8.cu.
+//
+//   A = g tile      [K = 16 pixels (2 tile rows x 8)][M = 128 output channels]   bf16, SWIZZLE_128B, 2 channel blocks (LBO)
+//   B = x patch     [K = 16 pixels, shifted by tap  ][N = 16 / 32 input channels] u8 spikes converted to bf16 by the producer
+//   D = one fp32 accumulator [128][N] PER TAP in TMEM (25 x 16 or 9 x 32 columns), alive for the whole CTA
+//
+// A CTA owns one (128-channel block of Cout, N-channel chunk of Cin) pair and a contiguous range of (tile, timestep) units;
+// the accumulators never leave TMEM until the end, when four warps add them into g_w with coalesced atomics.
+//
+// Warp roles: 0-3 x-patch producers (LDG u8 -> bf16 -> swizzled STS), 4-7 g-tile producers (cp.async), 8 MMA issuer.
+#include <cuda_bf16.h>
+
 #include "ss_common.cuh"
+#include "ss_umma.cuh"
+
+namespace ss {
+namespace {
+
+constexpr int WG_THREADS = 288;
+constexpr int WG_MAX_STAGES = 6;
+constexpr int G_TILE_BYTES = 32768;          // 2 channel blocks x 128 pixels x 128 B
+
+struct WgParams {
+    int T, B, Hin, Win, Cin, Hout, Wout, Cout;
+    int pad, upsample;
+    int HsO, Hup, Wup;
+    int tiles_x, mtiles;
+    int nblk, nchunk, nsplit;    // grid = nblk * nchunk * nsplit
+    int NPS;
+    int cin_real;                // channels of x that exist in g_w's K index (Cin, or <= 4 for the packed first layer)
+    float yscale, xscale;
+    const uint8_t* x;
+    const __nv_bfloat16* g;
+    float* g_w;
+};
+
+// MN-major descriptor: lbo = bytes between channel blocks, sbo = bytes between 8-pixel groups
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int STRIDE>
+__device__ __forceinline__ int wg_row_source(const WgParams& p, int ty, int pr) {
+    const int gi = ty * 16 * STRIDE + pr;
+    const int per = STRIDE * p.HsO;
+    const int b = gi / per;
+    const int local = gi - b * per;
+    if (b >= p.B) return -1;
+    if (p.upsample) {
+        if (local >= p.Hup) return -1;
+        const int iy = min((int)floorf((float)local * p.yscale), p.Hin - 1);   // ATen upsample_nearest index rule
+        return b * p.Hin + iy;
+    }
+    const int iy = local - p.pad;
+    return (iy >= 0 && iy < p.Hin) ? b * p.Hin + iy : -1;
+}
+template <int STRIDE, int PWHALF>
+__device__ __forceinline__ int wg_col_source(const WgParams& p, int tx, int pc) {
+    if (p.upsample) {
+        const int u = tx * 8 + pc;
+        if (u >= p.Wup) return -1;
+        return min((int)floorf((float)u * p.xscale), p.Win - 1);
+    }
+    int ix;
+    if (STRIDE == 1) {
+        ix = tx * 8 + pc - p.pad;
+    } else {
+        const int plane = pc / PWHALF;
+        const int idx = pc - plane * PWHALF;
+        ix = 2 * (tx * 8 - p.pad / 2 + idx) + plane;
+    }
+    return (ix >= 0 && ix < p.Win) ? ix : -1;
+}
+
+// 16 u8 -> 16 bf16 (exact: values <= 255 have <= 8 significant bits)
+__device__ __forceinline__ void cvt16(const uint4 v, uint4& lo, uint4& hi) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn((float)(w[i] & 0xFFu), (float)((w[i] >> 8) & 0xFFu));
+        const __nv_bfloat162 b = __floats2bfloat162_rn((float)((w[i] >> 16) & 0xFFu), (float)(w[i] >> 24));
+        o[2 * i] = *reinterpret_cast<const uint32_t*>(&a);
+        o[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    lo = make_uint4(o[0], o[1], o[2], o[3]);
+    hi = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// NB: input channels per CTA (16 -> 32-byte patch rows, 32 -> 64-byte rows).  FIRST4: x is the packed first-layer input
+// u8 [..][4]; its 4 channels are widened to one 16-channel chunk (channels 4..15 zero).
+template <int KS, int STRIDE, int NB, bool FIRST4>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const WgParams p) {
+    constexpr int RBX = 2 * NB;
+    constexpr int cNTAPS = KS * KS;
+    constexpr int cPWhalf = 8 + (KS - 1) / 2;
+    constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
+    constexpr int cPH = 15 * STRIDE + KS;
+    constexpr int cPPIX = cPH * cPWp;
+    constexpr int cPBX = (cPPIX * RBX + 1023) / 1024 * 1024;
+    constexpr int cSTAGE = G_TILE_BYTES + cPBX;
+    constexpr int cNPIX = (cPPIX + 127) / 128;
+    constexpr uint32_t swz_mask = (uint32_t)(RBX >> 4) - 1u;
+    static_assert(cNTAPS * NB <= 512, "accumulators do not fit TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_addr);
+    uint8_t* tail = sm + (size_t)p.NPS * cSTAGE;
+    int* rowsrc = reinterpret_cast<int*>(tail);              // [40]
+    int* colsrc = rowsrc + 40;                               // [24]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WG_MAX_STAGES + 1);
+    const uint32_t bar_full_x = smem_u32(bars);
+    const uint32_t bar_full_g = smem_u32(bars + WG_MAX_STAGES);
+    const uint32_t bar_empty = smem_u32(bars + 2 * WG_MAX_STAGES);
+    const uint32_t bar_done = smem_u32(bars + 3 * WG_MAX_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_MAX_STAGES; ++s) {
+            mbar_init(bar_full_x + 8 * s, 128);
+            mbar_init(bar_full_g + 8 * s, 128);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this CTA's (output-channel block, input-channel chunk, unit range)
+    int item = blockIdx.x;
+    const int split = item % p.nsplit; item /= p.nsplit;
+    const int chunk = item % p.nchunk;
+    const int nblk = item / p.nchunk;
+    const long long U = (long long)p.mtiles * p.T;
+    const int u0 = (int)(U * split / p.nsplit);
+    const int u1 = (int)(U * (split + 1) / p.nsplit);
+    const int n0 = nblk * 128;
+    const int c0 = chunk * NB;
+
+    if (warp < 4) {
+        // ================================================================== x-patch producers
+        const int tid = threadIdx.x;
+        const int xpix_bytes = FIRST4 ? 4 : p.Cin;
+        const size_t t_stride = (size_t)p.B * p.Hin * p.Win * xpix_bytes;
+        int stage = 0;
+        uint32_t phase = 0;
+        int cur_mt = -1;
+        int goff[cNPIX];
+        for (int u = u0; u < u1; ++u) {
+            const int mt = u / p.T;
+            const int t = u - mt * p.T;
+            if (mt != cur_mt) {
+                cur_mt = mt;
+                const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                named_sync(1, 128);     // everyone is done with the previous tables
+                if (tid < cPH) rowsrc[tid] = wg_row_source<STRIDE>(p, ty, tid);
+                if (tid >= 64 && tid - 64 < cPWp) colsrc[tid - 64] = wg_col_source<STRIDE, cPWhalf>(p, tx, tid - 64);
+                named_sync(1, 128);
+#pragma unroll
+                for (int i = 0; i < cNPIX; ++i) {
+                    const int pix = tid + i * 128;
+                    goff[i] = -2;
+                    if (pix < cPPIX) {
+                        const int pr = pix / cPWp;
+                        const int pc = pix - pr * cPWp;
+                        const int r = rowsrc[pr], c = colsrc[pc];
+                        goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * xpix_bytes : -1;
+                    }
+                }
+            }
+            const uint8_t* xt = p.x + (size_t)t * t_stride + (FIRST4 ? 0 : c0);
+            // loads first (all in flight), then wait for the stage, then convert + store
+            uint4 raw[cNPIX][NB / 16];
+#pragma unroll
+            for (int i = 0; i < cNPIX; ++i) {
+#pragma unroll
+                for (int h = 0; h < NB / 16; ++h) raw[i][h] = make_uint4(0u, 0u, 0u, 0u);
+                if (goff[i] >= 0) {
+                    if (FIRST4) {
+                        raw[i][0].x = __ldg(reinterpret_cast<const uint32_t*>(xt + goff[i]));
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < NB / 16; ++h) raw[i][h] = __ldg(reinterpret_cast<const uint4*>(xt + goff[i]) + h);
+                    }
+                }
+            }
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            uint8_t* dst0 = sm + (size_t)stage * cSTAGE + G_TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < cNPIX; ++i) {
+                if (goff[i] != -2) {
+                    const uint32_t off = (uint32_t)(tid + i * 128) * RBX;
+#pragma unroll
+                    for (int h = 0; h < NB / 16; ++h) {
+                        uint4 lo, hi;
+                        cvt16(raw[i][h], lo, hi);
+                        *reinterpret_cast<uint4*>(dst0 + swizzle_off(off + h * 32, swz_mask)) = lo;
+                        *reinterpret_cast<uint4*>(dst0 + swizzle_off(off + h * 32 + 16, swz_mask)) = hi;
+                    }
+                }
+            }
+            fence_proxy_async();        // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            mbar_arrive(bar_full_x + 8 * stage);
+            if (++stage == p.NPS) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        // ================================================================== epilogue: accumulators -> g_w (atomics)
+        if (u1 > u0) {
+            mbar_wait(bar_done, 0);
+            tc_fence_after();
+            const int n = n0 + warp * 32 + lane;          // TMEM lane = output channel
+            const bool n_ok = n < p.Cout;
+            const int Kc = p.cin_real;                    // g_w row = tap * Kc + channel
+            for (int tap = 0; tap < cNTAPS; ++tap) {
+#pragma unroll
+                for (int h = 0; h < NB / 16; ++h) {
+                    int d[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * NB + h * 16), d);
+                    tmem_ld_wait();
+                    if (n_ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int c = c0 + h * 16 + i;
+                            const float v = __int_as_float(d[i]);
+                            if (c < Kc && v != 0.0f) atomicAdd(p.g_w + ((size_t)tap * Kc + c) * p.Cout + n, v);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    } else if (warp < 8) {
+        // ================================================================== g-tile producers (cp.async, zero fill)
+        const int m = threadIdx.x - 128;      // tile pixel: row m >> 3, column m & 7
+        const size_t t_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
+        int stage = 0;
+        uint32_t phase = 0;
+        int cur_mt = -1;
+        long long pix_off = -1;
+        for (int u = u0; u < u1; ++u) {
+            const int mt = u / p.T;
+            const int t = u - mt * p.T;
+            if (mt != cur_mt) {
+                cur_mt = mt;
+                const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                const int so = ty * 16 + (m >> 3);
+                const int b = so / p.HsO;
+                const int oy = so - b * p.HsO;
+                const int ox = tx * 8 + (m & 7);
+                pix_off = (b < p.B && oy < p.Hout && ox < p.Wout) ? ((long long)(b * p.Hout + oy) * p.Wout + ox) * p.Cout : -1;
+            }
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            const uint32_t dst0 = base + (uint32_t)stage * cSTAGE + (uint32_t)m * 128u;
+            const __nv_bfloat16* src = p.g + (size_t)t * t_stride + (pix_off >= 0 ? pix_off : 0) + n0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const bool ok = pix_off >= 0 && n0 + c * 8 < p.Cout;
+                const uint32_t dst = dst0 + (uint32_t)(c >> 3) * 16384u + ((uint32_t)((c & 7) ^ (m & 7)) << 4);
+                cp_async_16(dst, ok ? (const void*)(src + c * 8) : (const void*)p.g, ok ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(bar_full_g + 8 * stage);
+            if (++stage == p.NPS) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (warp == 8) {
+        // ================================================================== MMA issuer
+        if (elect_one()) {
+            // kind::f16: D f32, A and B bf16, both MN-major, M = 128, N = NB
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) |
+                                       ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t b_layout = RBX == 128 ? 2u : (RBX == 64 ? 4u : 6u);
+            constexpr uint32_t b_sbo = (uint32_t)(STRIDE * cPWp * RBX);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = u0; u < u1; ++u) {
+                mbar_wait(bar_full_x + 8 * stage, phase);
+                mbar_wait(bar_full_g + 8 * stage, phase);
+                fence_proxy_async();      // the g tile arrived through cp.async (generic proxy)
+                tc_fence_after();
+                const uint32_t sbase = base + (uint32_t)stage * cSTAGE;
+                const uint64_t a0 = make_desc_mn(sbase, 16384u, 1024u, 2u);
+                const uint64_t b0 = make_desc_mn(sbase + G_TILE_BYTES, 16u, b_sbo, b_layout);
+                const uint32_t first = (u == u0) ? 0u : 1u;
+#pragma unroll 1
+                for (int ks = 0; ks < 8; ++ks) {
+                    // K = 16 pixels = tile rows 2*ks, 2*ks + 1
+                    const uint64_t a = a0 + (uint64_t)((uint32_t)(ks * 2048) >> 4);
+                    const uint64_t bk = b0 + (uint64_t)((uint32_t)(ks * 2 * STRIDE * cPWp * RBX) >> 4);
+                    const uint32_t acc = (ks == 0) ? first : 1u;
+#pragma unroll
+                    for (int tap = 0; tap < cNTAPS; ++tap) {
+                        const int ky = tap / KS, kx = tap - ky * KS;
+                        const int toff = STRIDE == 1 ? ky * cPWp + kx : ky * cPWp + (kx & 1) * cPWhalf + (kx >> 1);
+                        umma_f16(tmem_base + (uint32_t)(tap * NB), a, bk + (uint64_t)((uint32_t)(toff * RBX) >> 4), idesc, acc);
+                    }
+                }
+                umma_commit(bar_empty + 8 * stage);
+                if (++stage == p.NPS) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            if (u1 > u0) umma_commit(bar_done);
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+}  // namespace ss
+
 using namespace ss;
+
 extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const void* g_bf16, float* g_w, void* stream) {
-    set_error("ss_conv_wgrad_bf16: not built yet");
-    return SS_EUNSUPPORTED;
+    if (g == nullptr) {
+        set_error("ss_conv_wgrad_bf16: null descriptor");
+        return SS_EINVAL;
+    }
+    if (g->T == 0 || g->B == 0) return SS_OK;
+    if (x == nullptr || g_bf16 == nullptr || g_w == nullptr) {
+        set_error("ss_conv_wgrad_bf16: null argument");
+        return SS_EINVAL;
+    }
+    const bool first = g->Cin >= 1 && g->Cin <= 4;
+    const bool up = g->upsample != 0;
+    if (g->T < 0 || g->B < 0 || g->Hin <= 0 || g->Win <= 0 || g->Hout <= 0 || g->Wout <= 0 || g->Cout <= 0 || g->Cout % 16 != 0 ||
+        (!first && g->Cin % 16 != 0)) {
+        set_error("ss_conv_wgrad_bf16: bad geometry (Cout %% 16, Cin %% 16 or Cin <= 4)");
+        return SS_EINVAL;
+    }
+    if (!(g->ks == 3 || g->ks == 5) || !(g->stride == 1 || g->stride == 2) || (up && g->stride != 1) ||
+        (g->stride == 2 && (g->pad % 2 != 0 || g->ks != 5)) || (first && (g->ks != 5 || g->stride != 1 || up))) {
+        set_error("ss_conv_wgrad_bf16: unsupported conv shape (ks %d stride %d pad %d upsample %d)", g->ks, g->stride, g->pad,
+                  g->upsample);
+        return SS_EUNSUPPORTED;
+    }
+    WgParams p{};
+    p.T = g->T; p.B = g->B; p.Hin = g->Hin; p.Win = g->Win; p.Cin = g->Cin; p.Hout = g->Hout; p.Wout = g->Wout; p.Cout = g->Cout;
+    p.pad = up ? 0 : g->pad;
+    p.upsample = up ? 1 : 0;
+    p.Hup = g->Hout + g->ks - 1;
+    p.Wup = g->Wout + g->ks - 1;
+    if (up) {
+        p.HsO = p.Hup;
+    } else {
+        const int need = g->Hin + p.pad;
+        const int reach = g->stride * (g->Hout - 1) + g->ks - p.pad;
+        const int span = need > reach ? need : reach;
+        p.HsO = (span + g->stride - 1) / g->stride;
+        if (p.HsO < g->Hout) p.HsO = g->Hout;
+    }
+    const long long rows = (long long)p.HsO * g->B;
+    p.tiles_x = (g->Wout + 7) / 8;
+    p.mtiles = (int)((rows + 15) / 16) * p.tiles_x;
+    const int NB = (g->ks == 3 && !first && g->Cin % 32 == 0) ? 32 : 16;
+    p.nblk = (g->Cout + 127) / 128;
+    p.nchunk = first ? 1 : g->Cin / NB;
+    p.cin_real = g->Cin;
+    const long long U = (long long)p.mtiles * g->T;
+    if (U > 0x7fffffffLL || (long long)g->B * g->Hin * g->Win * g->Cin > 0x7fffffffLL ||
+        (long long)g->B * g->Hout * g->Wout * g->Cout > 0x7fffffffLL) {
+        set_error("ss_conv_wgrad_bf16: problem too large for 32-bit indexing");
+        return SS_EINVAL;
+    }
+    int dev = 0, num_sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+    const int pairs = p.nblk * p.nchunk;
+    long long ns = (num_sms + pairs - 1) / pairs;          // fill the machine at least once
+    if (ns > U) ns = U;
+    if (ns < 1) ns = 1;
+    p.nsplit = (int)ns;
+    p.yscale = up ? (float)g->Hin / (float)p.Hup : 1.0f;
+    p.xscale = up ? (float)g->Win / (float)p.Wup : 1.0f;
+    p.x = reinterpret_cast<const uint8_t*>(x);
+    p.g = reinterpret_cast<const __nv_bfloat16*>(g_bf16);
+    p.g_w = g_w;
+    const int PH = 15 * g->stride + g->ks;
+    const int PWp = g->stride == 1 ? 8 + g->ks - 1 : 2 * (8 + (g->ks - 1) / 2);
+    const int PBX = (PH * PWp * 2 * NB + 1023) / 1024 * 1024;
+    const int stage_bytes = G_TILE_BYTES + PBX;
+    const int tail_bytes = 256 + (3 * WG_MAX_STAGES + 1) * 8 + 64;
+    int nps = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
+    if (nps > WG_MAX_STAGES) nps = WG_MAX_STAGES;
+    if (nps < 2) {
+        set_error("ss_conv_wgrad_bf16: not enough shared memory");
+        return SS_EUNSUPPORTED;
+    }
+    p.NPS = nps;
+    const size_t smem = 1024 + (size_t)nps * stage_bytes + tail_bytes;
+    const unsigned grid = (unsigned)(pairs * p.nsplit);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool launched = false;
+#define SS_TRY_WG(KS_, ST_, NB_, F4_)                                                                                            \
+    if (!launched && g->ks == KS_ && g->stride == ST_ && NB == NB_ && first == F4_) {                                            \
+        static bool attr = false;                                                                                                \
+        if (!attr) {                                                                                                             \
+            cudaFuncSetAttribute(conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                 227 * 1024);                                                                                    \
+            attr = true;                                                                                                         \
+        }                                                                                                                        \
+        conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_><<<grid, WG_THREADS, smem, st>>>(p);                                           \
+        launched = true;                                                                                                         \
+    }
+    SS_TRY_WG(5, 1, 16, false)
+    SS_TRY_WG(5, 2, 16, false)
+    SS_TRY_WG(3, 1, 32, false)
+    SS_TRY_WG(3, 1, 16, false)
+    SS_TRY_WG(5, 1, 16, true)
+#undef SS_TRY_WG
+    if (!launched) {
+        set_error("ss_conv_wgrad_bf16: no kernel instance for ks %d stride %d", g->ks, g->stride);
+        return SS_EUNSUPPORTED;
+    }
+    count_launch();
+    return check_launch("conv_wgrad_umma");
 }

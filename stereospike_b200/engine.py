@@ -4,8 +4,10 @@ feed-forward in depth) and calls one CUDA kernel per block 
 
 Forward : ss_pack_events + ss_conv_i8_fwd (tcgen05 int8 tensor-core kernel) per spiking block -- or ss_conv_neuron_fwd
           (fp32 CUDA cores) when impl='simt' -- then ss_heads_fwd for the four heads + I-neurons.
-Backward: ss_heads_bwd, then per block in reverse order ss_neuron_bwd (surrogate BPTT scan), ss_conv_wgrad,
-          ss_conv_dgrad.  Replaces PyTorch autograd through the reference modules.
+Backward: ss_heads_bwd, then per block in reverse order ss_neuron_bwd_ex (surrogate BPTT scan, bf16 gradient out),
+          ss_conv_wgrad_bf16 and ss_corr_bf16 (tcgen05 bf16 tensor-core kernels; bwd_impl='simt' selects the fp32
+          CUDA-core ss_conv_wgrad / ss_conv_dgrad).  Replaces PyTorch autograd through the reference modules
+          (SURVEY.md section 3(C)).
 """
 import ctypes
 
@@ -25,6 +27,15 @@ class Site:
         self.name, self.out, self.src, self.resid = name, out, src, resid
         self.conv, self.gain_mod, self.node, self.up_size = conv, gain_mod, node, up_size
         self._pack = None
+        self._dgrad = None
+
+    def dgrad_plan(self, geom):
+        """Correlation weights / maps of this block's data gradient (ops.DgradPlan), cached on the weight's version."""
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version, geom.Hin, geom.Win, geom.Hout, geom.Wout, str(w.device))
+        if self._dgrad is None or self._dgrad[0] != key:
+            self._dgrad = (key, ops.DgradPlan(w, geom, w.device))
+        return self._dgrad[1]
 
     def geom(self, Hin, Win):
         c = self.conv
@@ -111,6 +122,7 @@ class Engine:
         self.fold_upsample = False  # NNConvUpsampling blocks as four folded 3x3 convs on the source + band passes (9 taps instead of
         #                             25, bit-identical integers, 3 bits less weight precision); off by default: the full-resolution blocks
         #                             are epilogue-bound, so the saved MMAs do not pay yet (profiles/r1e_fold_launches.txt)
+        self.bwd_impl = 'umma'      # gradients of the convs: 'umma' = bf16 tensor cores (fp32 accumulation), 'simt' = fp32 CUDA cores
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
         #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
 
@@ -182,6 +194,7 @@ class Engine:
             if use_i8:
                 if first and not packed_in:
                     xin = ops.pack_events(x_seq, self.event_status)     # fp32 NCHW counts -> u8 NHWC4
+                    acts['x_packed'] = xin
                 tsum = None
                 if s.out in head_srcs and self.heads_time_sum and 1 < T <= 86:
                     tsum = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=ops.ACT_DTYPE, device=dev)
@@ -287,35 +300,50 @@ class Engine:
             g_out = g.pop(s.out)
             node = s.node
             N = B * gm.Hout * gm.Wout * gm.Cout
-            g_acc = torch.empty_like(g_out)
+            first = s.src == 'x'
+            x_in = acts['x_packed'] if (first and 'x_packed' in acts) else acts[s.src]
+            tc_ok = self.bwd_impl == 'umma' and gm.Cout % 16 == 0 and x_in.dtype == ops.ACT_DTYPE
+            tc_w = tc_ok and (x_in.shape[-1] % 16 == 0 or (first and x_in.shape[-1] == 4 and gm.ks == 5 and gm.stride == 1))
+            tc_d = tc_ok and not first and gm.Cin % 32 == 0
+            need32 = not (tc_w and (tc_d or first))
+            g_acc = torch.empty_like(g_out) if need32 else None
+            g_b16 = torch.empty(g_out.shape, dtype=torch.bfloat16, device=dev) if (tc_w or tc_d) else None
             decay = sv['decay']
             g_decay = torch.zeros((1,), dtype=torch.float32, device=dev) if decay is not None else None
             sf = node.surrogate_function
-            rc = L.ss_neuron_bwd(T, N, node.kind, sf.kind, sf.alpha, s.gain_mod.gain(), node.v_threshold, node.v_reset,
-                                 node._tau_value(), _ptr(decay), _ptr(sv['h_seq']), _ptr(sv['v_in']), _ptr(g_out), None,
-                                 _ptr(g_acc), None, _ptr(g_decay), _stream())
+            rc = L.ss_neuron_bwd_ex(T, N, node.kind, sf.kind, sf.alpha, s.gain_mod.gain(), node.v_threshold, node.v_reset,
+                                    node._tau_value(), _ptr(decay), _ptr(sv['h_seq']), _ptr(sv['v_in']), _ptr(g_out), None,
+                                    _ptr(g_acc), _ptr(g_b16), None, _ptr(g_decay), _stream())
             _lib.check(rc, 'ss_neuron_bwd')
             if s.resid is not None:
                 if s.resid in g:
                     g[s.resid] += g_out
                 else:
                     g[s.resid] = g_out      # donate: the residual branch passes the gradient through unchanged
-            first = s.src == 'x'
             cg = _lib.ConvGeom(T=T, B=B, Hin=gm.Hin, Win=gm.Win, Cin=gm.Cin, Hout=gm.Hout, Wout=gm.Wout, Cout=gm.Cout,
                                ks=gm.ks, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC, neuron=node.kind,
                                reserved0=0, gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0, reserved1=0, reserved2=0)
             ym, xm = gm.maps(dev)
-            g_wkn = torch.zeros((gm.K, gm.Cout), dtype=torch.float32, device=dev)
-            rc = L.ss_conv_wgrad(ctypes.byref(cg), _ptr(acts[s.src]), _ptr(ym), _ptr(xm), _ptr(g_acc), _ptr(g_wkn), _stream())
-            _lib.check(rc, 'ss_conv_wgrad')
+            if tc_w:
+                cin_dev = int(x_in.shape[-1])
+                g_wkn = ops.conv_wgrad_bf16(x_in, g_b16, gm, T, B, cin=cin_dev)
+                if cin_dev != gm.Cin:       # packed first layer: drop the padding channels
+                    g_wkn = g_wkn.view(gm.ks * gm.ks, cin_dev, gm.Cout)[:, :gm.Cin].reshape(gm.K, gm.Cout)
+            else:
+                g_wkn = torch.zeros((gm.K, gm.Cout), dtype=torch.float32, device=dev)
+                rc = L.ss_conv_wgrad(ctypes.byref(cg), _ptr(acts[s.src]), _ptr(ym), _ptr(xm), _ptr(g_acc), _ptr(g_wkn), _stream())
+                _lib.check(rc, 'ss_conv_wgrad')
             grads[2 * i] = ops.kn_to_weight(g_wkn, gm.Cout, gm.Cin, gm.ks)
             if g_decay is not None:
                 grads[2 * i + 1] = g_decay.reshape(params[2 * i + 1].shape)
             if not first:
                 gx = gbuf(s.src)
-                rc = L.ss_conv_dgrad(ctypes.byref(cg), _ptr(ym), _ptr(xm), _ptr(sv['w_kn']), _ptr(g_acc), _ptr(gx), _stream())
-                _lib.check(rc, 'ss_conv_dgrad')
-            del g_acc, g_out
+                if tc_d:
+                    s.dgrad_plan(gm).run(g_b16, gx, T, B)
+                else:
+                    rc = L.ss_conv_dgrad(ctypes.byref(cg), _ptr(ym), _ptr(xm), _ptr(sv['w_kn']), _ptr(g_acc), _ptr(gx), _stream())
+                    _lib.check(rc, 'ss_conv_dgrad')
+            del g_acc, g_b16, g_out
         return grads
 
 

@@ -125,10 +125,12 @@ class _SpikingUNet(NeuromorphicNet):
             object.__setattr__(self, '_engine', Engine(sites, heads, self.Ineurons))
         return self._engine
 
-    def set_kernel_options(self, impl=None, weight_planes=None, keep_state=None, heads_time_sum=None, fold_upsample=None):
+    def set_kernel_options(self, impl=None, weight_planes=None, keep_state=None, heads_time_sum=None, fold_upsample=None,
+                           bwd_impl=None):
         """impl: 'umma' (tcgen05 int8 tensor-core kernel; default) or 'simt' (exact-fp32 CUDA cores).
         weight_planes: int8 digit planes per weight -- 3 = 24-bit fixed point, fp32-class (default);
-        2 = 16-bit (the reduced-precision training configuration); 4 = 32-bit."""
+        2 = 16-bit (the reduced-precision training configuration); 4 = 32-bit.
+        bwd_impl: 'umma' (conv gradients on the bf16 tensor cores, fp32 accumulation; default) or 'simt' (fp32 CUDA cores)."""
         e = self.engine
         if impl is not None:
             assert impl in ('auto', 'umma', 'simt')
@@ -142,6 +144,9 @@ class _SpikingUNet(NeuromorphicNet):
             e.heads_time_sum = bool(heads_time_sum)
         if fold_upsample is not None:
             e.fold_upsample = bool(fold_upsample)
+        if bwd_impl is not None:
+            assert bwd_impl in ('umma', 'simt')
+            e.bwd_impl = bwd_impl
         return self
 
     # ---- forward

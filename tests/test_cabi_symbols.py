@@ -30,7 +30,7 @@ def test_header_matches_binding_and_library(lib):
 
 
 def test_abi_version_and_launch_counter(lib):
-    assert lib.ss_abi_version() == 2
+    assert lib.ss_abi_version() == 3
     assert lib.ss_launch_count() >= 0
     assert isinstance(lib.ss_last_error(), bytes)
 

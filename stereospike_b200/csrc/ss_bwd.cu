@@ -21,6 +21,8 @@ __device__ __forceinline__ float surrogate_grad(int kind, float alpha, float u) 
     return alpha * sg * (1.0f - sg);
 }
 
+// One thread scans VEC consecutive neurons (VEC = 4: 16-byte loads of h and g_s, 8-byte bf16 stores) backwards in time.
+template <int VEC>
 __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int neuron, int surrogate, float alpha,
                                                          float gain, float v_th, float v_reset, float tau,
                                                          const float* __restrict__ decay_p, const float* __restrict__ h_seq,
@@ -28,35 +30,72 @@ __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int
                                                          const float* __restrict__ g_v_last, float* g_acc,
                                                          __nv_bfloat16* __restrict__ g_acc_bf16, float* __restrict__ g_v_init,
                                                          float* __restrict__ g_decay) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     float gd_local = 0.0f;
     if (n < N) {
         float r = 1.0f;
         if (neuron == SS_NEURON_LIF) r = 1.0f / tau;
         if (neuron == SS_NEURON_PLIF) r = __ldg(decay_p);
         const float keep = (neuron == SS_NEURON_IF) ? 1.0f : 1.0f - r;
-        float g_v = (g_v_last != nullptr) ? g_v_last[n] : 0.0f;
-        float h = h_seq[(size_t)(T - 1) * N + n];
+        float g_v[VEC], h[VEC], h_prev[VEC], gs[VEC];
+        auto load = [&](const float* src, float (&dst)[VEC]) {
+            if constexpr (VEC == 4) {
+                const float4 q = *reinterpret_cast<const float4*>(src);
+                dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[VEC - 1] = q.w;
+            } else {
+                dst[0] = *src;
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) g_v[i] = 0.0f;
+        if (g_v_last != nullptr) load(g_v_last + n, g_v);
+        load(h_seq + (size_t)(T - 1) * N + n, h);
         for (int t = T - 1; t >= 0; --t) {
             // potential before this step: reset(h_{t-1}) or the initial state
-            float h_prev = 0.0f, v_prev;
+            float v_prev[VEC];
             if (t > 0) {
-                h_prev = h_seq[(size_t)(t - 1) * N + n];
-                v_prev = (h_prev - v_th >= 0.0f) ? v_reset : h_prev;
+                load(h_seq + (size_t)(t - 1) * N + n, h_prev);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) v_prev[i] = (h_prev[i] - v_th >= 0.0f) ? v_reset : h_prev[i];
             } else {
-                v_prev = (v_init != nullptr) ? v_init[n] : v_reset;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    h_prev[i] = 0.0f;
+                    v_prev[i] = v_reset;
+                }
+                if (v_init != nullptr) load(v_init + n, v_prev);
             }
-            const float u = h - v_th;
-            const float s = (u >= 0.0f) ? 1.0f : 0.0f;
-            const float g_h = g_s[(size_t)t * N + n] * surrogate_grad(surrogate, alpha, u) + g_v * (1.0f - s);
-            const float g_x = (neuron == SS_NEURON_IF) ? g_h : g_h * r;
-            if (g_acc != nullptr) g_acc[(size_t)t * N + n] = g_x * gain;
-            if (g_acc_bf16 != nullptr) g_acc_bf16[(size_t)t * N + n] = __float2bfloat16_rn(g_x * gain);
-            if (neuron == SS_NEURON_PLIF) gd_local += g_h * ((h - v_prev) / r);  // d h / d r = x - (v - v_reset)
-            g_v = g_h * keep;
-            h = h_prev;
+            load(g_s + (size_t)t * N + n, gs);
+            float gx[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float u = h[i] - v_th;
+                const float sp = (u >= 0.0f) ? 1.0f : 0.0f;
+                const float g_h = gs[i] * surrogate_grad(surrogate, alpha, u) + g_v[i] * (1.0f - sp);
+                gx[i] = ((neuron == SS_NEURON_IF) ? g_h : g_h * r) * gain;
+                if (neuron == SS_NEURON_PLIF) gd_local += g_h * ((h[i] - v_prev[i]) / r);  // d h / d r = x - (v - v_reset)
+                g_v[i] = g_h * keep;
+                h[i] = h_prev[i];
+            }
+            if constexpr (VEC == 4) {
+                if (g_acc != nullptr) *reinterpret_cast<float4*>(g_acc + (size_t)t * N + n) = make_float4(gx[0], gx[1], gx[2], gx[VEC - 1]);
+                if (g_acc_bf16 != nullptr) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(gx[0], gx[1]);
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(gx[2], gx[VEC - 1]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(g_acc_bf16 + (size_t)t * N + n) = pk;
+                }
+            } else {
+                if (g_acc != nullptr) g_acc[(size_t)t * N + n] = gx[0];
+                if (g_acc_bf16 != nullptr) g_acc_bf16[(size_t)t * N + n] = __float2bfloat16_rn(gx[0]);
+            }
         }
-        if (g_v_init != nullptr) g_v_init[n] = g_v;
+        if (g_v_init != nullptr) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) g_v_init[n + i] = g_v[i];
+        }
     }
     if (neuron == SS_NEURON_PLIF && g_decay != nullptr) {
 #pragma unroll
@@ -292,7 +331,11 @@ __global__ void __launch_bounds__(256) heads_bin_kernel(const HeadsBwdParams p) 
     }
 }
 
-// step 2: per (t, source pixel): g_act[c] += gain * sum_tap bin[tap] * w[tap][c];  g_w[tap][c] += gain * bin[tap] * act[c]
+// step 2: per source pixel s and 8-channel group:
+//   g_act[t][s][c] += gain * sum_tap bin_cls(t)[s][tap] * w[tap][c]          (cls = 1 for the last timestep, else 0)
+//   g_w[tap][c]    += gain * (bin_0[s][tap] * sum_{t<T-1} act[t][s][c] + bin_1[s][tap] * act[T-1][s][c])
+// A thread owns one channel group and walks a strided set of source pixels with its 9 x 8 weight-gradient partials in
+// registers; they meet in shared memory once per block and reach HBM with 9*C atomics per block.
 __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, int head) {
     extern __shared__ float sh[];  // w [9][C] then g_w accumulators [9][C]
     const int C = p.C[head];
@@ -306,42 +349,77 @@ __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, 
     const int S = p.B * p.Hs[head] * p.Ws[head];
     const size_t plane = (size_t)S * 9;
     const int c8n = C / 8;
-    // one thread handles one (source pixel, 8-channel group); the timestep is blockIdx.y
-    const int t = blockIdx.y;
-    const float* bins = p.bins[head] + ((t == p.T - 1) ? plane : 0);
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < (long long)S * c8n) {
-        const int s = (int)(item / c8n);
-        const int c0 = (int)(item - (long long)s * c8n) * 8;
-        float bn[9];
-        bool any = false;
+    const int cg = threadIdx.x % c8n;            // channel group of this thread
+    const int c0 = cg * 8;
+    const int lanes = blockDim.x / c8n;          // pixels handled concurrently by one block
+    const int pl = threadIdx.x / c8n;
+    const int T = p.T;
+    float acc[9][8];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            bn[k] = __ldg(bins + (size_t)s * 9 + k) * p.gain;
-            any |= bn[k] != 0.0f;
-        }
-        const size_t eo = ((size_t)t * S + s) * C + c0;
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + eo));
-        float a[8];
+    for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            a[e] = (float)((raw.x >> (8 * e)) & 0xFFu);
-            a[4 + e] = (float)((raw.y >> (8 * e)) & 0xFFu);
-        }
-        float ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (any) {
+        for (int e = 0; e < 8; ++e) acc[k][e] = 0.0f;
+    float wr[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wr[k][e] = wsm[k * C + c0 + e];
+    if (pl < lanes) {
+        for (long long s = (long long)blockIdx.x * lanes + pl; s < S; s += (long long)gridDim.x * lanes) {
+            float b0[9], b1[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
+                b0[k] = (T > 1) ? __ldg(p.bins[head] + (size_t)s * 9 + k) * p.gain : 0.0f;
+                b1[k] = __ldg(p.bins[head] + plane + (size_t)s * 9 + k) * p.gain;
+            }
+            float ga0[8], ga1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ga0[e] = ga1[e] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    ga[e] = fmaf(bn[k], wsm[k * C + c0 + e], ga[e]);
-                    if (a[e] != 0.0f && bn[k] != 0.0f) atomicAdd(&gws[k * C + c0 + e], bn[k] * a[e]);
+                    ga0[e] = fmaf(b0[k], wr[k][e], ga0[e]);
+                    ga1[e] = fmaf(b1[k], wr[k][e], ga1[e]);
+                }
+            float asum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int t = 0; t < T; ++t) {
+                const size_t eo = ((size_t)t * S + s) * C + c0;
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + eo));
+                float4* gp = reinterpret_cast<float4*>(p.g_acts[head] + eo);
+                float4 q0 = gp[0], q1 = gp[1];
+                const bool last = t == T - 1;
+                const float* ga = last ? ga1 : ga0;
+                q0.x += ga[0]; q0.y += ga[1]; q0.z += ga[2]; q0.w += ga[3];
+                q1.x += ga[4]; q1.y += ga[5]; q1.z += ga[6]; q1.w += ga[7];
+                gp[0] = q0;
+                gp[1] = q1;
+                float a[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    a[e] = (float)((raw.x >> (8 * e)) & 0xFFu);
+                    a[4 + e] = (float)((raw.y >> (8 * e)) & 0xFFu);
+                }
+                if (!last) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) asum[e] += a[e];      // small integers: exact
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(b1[k], a[e], acc[k][e]);
                 }
             }
-            float* gp = p.g_acts[head] + eo;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) gp[e] += ga[e];
+            for (int k = 0; k < 9; ++k)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(b0[k], asum[e], acc[k][e]);
         }
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (acc[k][e] != 0.0f) atomicAdd(&gws[k * C + c0 + e], acc[k][e]);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < 9 * C; j += blockDim.x)
@@ -380,9 +458,18 @@ extern "C" int ss_neuron_bwd_ex(int32_t T, int64_t N, int32_t neuron, int32_t su
         return SS_EINVAL;
     }
     if (T == 0 || N == 0) return SS_OK;
-    neuron_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
-        reinterpret_cast<__nv_bfloat16*>(g_acc_bf16), g_v_init, g_decay);
+    auto aligned16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (N % 4 == 0 && aligned16(h_seq) && aligned16(g_s) && aligned16(g_acc) && aligned16(g_acc_bf16) && aligned16(v_init) &&
+        aligned16(g_v_last) && aligned16(g_v_init)) {
+        const long long nt = N / 4;
+        neuron_bwd_kernel<4><<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
+            reinterpret_cast<__nv_bfloat16*>(g_acc_bf16), g_v_init, g_decay);
+    } else {
+        neuron_bwd_kernel<1><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
+            reinterpret_cast<__nv_bfloat16*>(g_acc_bf16), g_v_init, g_decay);
+    }
     count_launch();
     return check_launch("neuron_bwd");
 }
@@ -473,10 +560,16 @@ extern "C" int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float
     count_launch();
     if (check_launch("heads_bin") != SS_OK) return SS_ECUDA;
     for (int i = 0; i < 4; ++i) {
-        const long long items = (long long)p.B * p.Hs[i] * p.Ws[i] * (p.C[i] / 8);
+        const int lanes = 256 / (p.C[i] / 8);
+        if (lanes < 1) {
+            set_error("ss_heads_bwd: more than 2048 channels");
+            return SS_EUNSUPPORTED;
+        }
+        const long long S = (long long)p.B * p.Hs[i] * p.Ws[i];
+        long long blocks = (S + lanes - 1) / lanes;
+        if (blocks > 148 * 8) blocks = 148 * 8;
         const size_t smem = (size_t)18 * p.C[i] * sizeof(float);
-        dim3 grid((unsigned)((items + 255) / 256), p.T);
-        heads_src_kernel<<<grid, 256, smem, st>>>(p, i);
+        heads_src_kernel<<<(unsigned)blocks, 256, smem, st>>>(p, i);
         count_launch();
         if (check_launch("heads_src") != SS_OK) return SS_ECUDA;
     }

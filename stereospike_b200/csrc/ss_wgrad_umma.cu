@@ -415,7 +415,8 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
     const int pairs = p.nblk * p.nchunk;
-    long long ns = (num_sms + pairs - 1) / pairs;          // fill the machine at least once
+    long long ns = num_sms / pairs;                        // one wave: every CTA keeps its accumulators for its whole life,
+                                                           // so a second, partial wave would double the kernel's duration
     if (ns > U) ns = U;
     if (ns < 1) ns = 1;
     p.nsplit = (int)ns;

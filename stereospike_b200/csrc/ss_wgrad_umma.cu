@@ -19,6 +19,12 @@
 // A CTA owns one (128-channel block of Cout, N-channel chunk of Cin) pair and a contiguous range of (tile, timestep) units;
 // the accumulators never leave TMEM until the end, when four warps add them into g_w with coalesced atomics.
 //
+// Few output channels (Cout <= 64: the full-resolution blocks, where most pixels are).  M = 128 lanes would be mostly
+// padding, so the A operand is made of SH = 2 / 4 copies of the SAME g patch, copy i starting one pixel after copy i-1
+// (leading-byte-offset = one patch pixel): accumulator rows [i*CH, (i+1)*CH) then hold the tap whose column offset is
+// (SH-1-i)*stride further right, and one MMA produces SH taps -- 15 or 10 MMAs per K step instead of 25.  The g patch gets
+// SH-1 halo columns on the left so that every copy still sees every pixel exactly once across the tiles of a row.
+//
 // Warp roles: 0-3 x-patch producers (LDG u8 -> bf16 -> swizzled STS), 4-7 g-tile producers (cp.async), 8 MMA issuer.
 #include <cuda_bf16.h>
 
@@ -115,19 +121,36 @@ __device__ __forceinline__ void cvt16(const uint4 v, uint4& lo, uint4& hi) {
 
 // NB: input channels per CTA (16 -> 32-byte patch rows, 32 -> 64-byte rows).  FIRST4: x is the packed first-layer input
 // u8 [..][4]; its 4 channels are widened to one 16-channel chunk (channels 4..15 zero).
-template <int KS, int STRIDE, int NB, bool FIRST4>
+// column shifts of the B operand issued per filter row, and how many of them
+template <int KS, int STRIDE, int SH>
+__host__ __device__ constexpr int wg_nshift() {
+    return SH == 1 ? KS : (STRIDE == 1 ? (KS + SH - 1) / SH : 3);
+}
+template <int KS, int STRIDE, int SH>
+__host__ __device__ constexpr int wg_shift(int si) {
+    return SH == 1 ? si : (STRIDE == 1 ? si * SH : si);     // stride 1: {0, SH, 2*SH..};  stride 2, SH 2: {0, 1, 2}
+}
+
+template <int KS, int STRIDE, int NB, bool FIRST4, int SH>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const WgParams p) {
     constexpr int RBX = 2 * NB;
-    constexpr int cNTAPS = KS * KS;
+    constexpr int CH = 128 / SH;                        // output channels per copy of the g patch
+    constexpr int RBG = SH == 1 ? 128 : CH * 2;         // bytes per g-patch pixel (= its swizzle width)
+    constexpr int GPW = 8 + SH - 1;                     // g-patch columns: SH-1 halo columns on the left
+    constexpr int NPIXG = 16 * GPW;
+    constexpr int G_BYTES = SH == 1 ? G_TILE_BYTES : (NPIXG * RBG + 1023) / 1024 * 1024;
+    constexpr int NS = wg_nshift<KS, STRIDE, SH>();
+    constexpr int NACC = KS * NS;                       // accumulators ([128][NB] each)
+    static_assert(SH == 1 || (KS == 5 && (STRIDE == 1 || SH == 2)), "shifted copies: 5x5 only; stride 2 with SH = 2");
     constexpr int cPWhalf = 8 + (KS - 1) / 2;
     constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
     constexpr int cPH = 15 * STRIDE + KS;
     constexpr int cPPIX = cPH * cPWp;
     constexpr int cPBX = (cPPIX * RBX + 1023) / 1024 * 1024;
-    constexpr int cSTAGE = G_TILE_BYTES + cPBX;
+    constexpr int cSTAGE = G_BYTES + cPBX;
     constexpr int cNPIX = (cPPIX + 127) / 128;
     constexpr uint32_t swz_mask = (uint32_t)(RBX >> 4) - 1u;
-    static_assert(cNTAPS * NB <= 512, "accumulators do not fit TMEM");
+    static_assert(NACC * NB <= 512, "accumulators do not fit TMEM");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -222,7 +245,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                 }
             }
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            uint8_t* dst0 = sm + (size_t)stage * cSTAGE + G_TILE_BYTES;
+            uint8_t* dst0 = sm + (size_t)stage * cSTAGE + G_BYTES;
 #pragma unroll
             for (int i = 0; i < cNPIX; ++i) {
                 if (goff[i] != -2) {
@@ -247,16 +270,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
         if (u1 > u0) {
             mbar_wait(bar_done, 0);
             tc_fence_after();
-            const int n = n0 + warp * 32 + lane;          // TMEM lane = output channel
+            const int L = warp * 32 + lane;               // TMEM lane = (copy, output channel)
+            const int copy = L / CH;
+            const int n = n0 + (L - copy * CH);
             const bool n_ok = n < p.Cout;
             const int Kc = p.cin_real;                    // g_w row = tap * Kc + channel
-            for (int tap = 0; tap < cNTAPS; ++tap) {
+            for (int a = 0; a < NACC; ++a) {
+                const int ky = a / NS;
+                const int shift = wg_shift<KS, STRIDE, SH>(a - ky * NS);
+                const int kx = shift + STRIDE * (SH - 1 - copy);
+                const int tap = ky * KS + kx;
+                // stride 2: shift 2 of the un-shifted copy is the same tap as shift 0 of the shifted one -- count it once
+                const bool dup = STRIDE == 2 && SH == 2 && copy == 1 && shift == 2;
 #pragma unroll
                 for (int h = 0; h < NB / 16; ++h) {
                     int d[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * NB + h * 16), d);
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NB + h * 16), d);
                     tmem_ld_wait();
-                    if (n_ok) {
+                    if (n_ok && kx < KS && !dup) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int c = c0 + h * 16 + i;
@@ -270,37 +301,84 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
         }
     } else if (warp < 8) {
         // ================================================================== g-tile producers (cp.async, zero fill)
-        const int m = threadIdx.x - 128;      // tile pixel: row m >> 3, column m & 7
+        const int m = threadIdx.x - 128;
         const size_t t_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
         int stage = 0;
         uint32_t phase = 0;
         int cur_mt = -1;
-        long long pix_off = -1;
-        for (int u = u0; u < u1; ++u) {
-            const int mt = u / p.T;
-            const int t = u - mt * p.T;
-            if (mt != cur_mt) {
-                cur_mt = mt;
-                const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
-                const int so = ty * 16 + (m >> 3);
-                const int b = so / p.HsO;
-                const int oy = so - b * p.HsO;
-                const int ox = tx * 8 + (m & 7);
-                pix_off = (b < p.B && oy < p.Hout && ox < p.Wout) ? ((long long)(b * p.Hout + oy) * p.Wout + ox) * p.Cout : -1;
-            }
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            const uint32_t dst0 = base + (uint32_t)stage * cSTAGE + (uint32_t)m * 128u;
-            const __nv_bfloat16* src = p.g + (size_t)t * t_stride + (pix_off >= 0 ? pix_off : 0) + n0;
+        if constexpr (SH == 1) {
+            // tile pixel m: row m >> 3, column m & 7; 128 channels = 2 blocks of 64 (16 KB apart)
+            long long pix_off = -1;
+            for (int u = u0; u < u1; ++u) {
+                const int mt = u / p.T;
+                const int t = u - mt * p.T;
+                if (mt != cur_mt) {
+                    cur_mt = mt;
+                    const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                    const int so = ty * 16 + (m >> 3);
+                    const int b = so / p.HsO;
+                    const int oy = so - b * p.HsO;
+                    const int ox = tx * 8 + (m & 7);
+                    pix_off = (b < p.B && oy < p.Hout && ox < p.Wout) ? ((long long)(b * p.Hout + oy) * p.Wout + ox) * p.Cout : -1;
+                }
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                const uint32_t dst0 = base + (uint32_t)stage * cSTAGE + (uint32_t)m * 128u;
+                const __nv_bfloat16* src = p.g + (size_t)t * t_stride + (pix_off >= 0 ? pix_off : 0) + n0;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const bool ok = pix_off >= 0 && n0 + c * 8 < p.Cout;
-                const uint32_t dst = dst0 + (uint32_t)(c >> 3) * 16384u + ((uint32_t)((c & 7) ^ (m & 7)) << 4);
-                cp_async_16(dst, ok ? (const void*)(src + c * 8) : (const void*)p.g, ok ? 16u : 0u);
+                for (int c = 0; c < 16; ++c) {
+                    const bool ok = pix_off >= 0 && n0 + c * 8 < p.Cout;
+                    const uint32_t dst = dst0 + (uint32_t)(c >> 3) * 16384u + ((uint32_t)((c & 7) ^ (m & 7)) << 4);
+                    cp_async_16(dst, ok ? (const void*)(src + c * 8) : (const void*)p.g, ok ? 16u : 0u);
+                }
+                cp_async_arrive_noinc(bar_full_g + 8 * stage);
+                if (++stage == p.NPS) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
-            cp_async_arrive_noinc(bar_full_g + 8 * stage);
-            if (++stage == p.NPS) {
-                stage = 0;
-                phase ^= 1u;
+        } else {
+            // g patch: 16 rows x GPW columns (output columns tx*8 - (SH-1) .. tx*8 + 7), CH channels per pixel
+            constexpr int NPT = (NPIXG + 127) / 128;
+            constexpr uint32_t gmask = (uint32_t)(RBG >> 4) - 1u;
+            long long pix_off[NPT];
+            for (int u = u0; u < u1; ++u) {
+                const int mt = u / p.T;
+                const int t = u - mt * p.T;
+                if (mt != cur_mt) {
+                    cur_mt = mt;
+                    const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+#pragma unroll
+                    for (int i = 0; i < NPT; ++i) {
+                        const int pix = m + i * 128;
+                        const int r = pix / GPW, cc = pix - r * GPW;
+                        const int so = ty * 16 + r;
+                        const int b = so / p.HsO;
+                        const int oy = so - b * p.HsO;
+                        const int ox = tx * 8 - (SH - 1) + cc;
+                        pix_off[i] = (pix < NPIXG && b < p.B && oy < p.Hout && ox >= 0 && ox < p.Wout)
+                                         ? ((long long)(b * p.Hout + oy) * p.Wout + ox) * p.Cout : -1;
+                    }
+                }
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                const uint32_t dst0 = base + (uint32_t)stage * cSTAGE;
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) {
+                    const int pix = m + i * 128;
+                    if (pix < NPIXG) {
+                        const __nv_bfloat16* src = p.g + (size_t)t * t_stride + (pix_off[i] >= 0 ? pix_off[i] : 0);
+#pragma unroll
+                        for (int c = 0; c < RBG / 16; ++c) {
+                            const bool ok = pix_off[i] >= 0 && c * 8 < p.Cout;
+                            cp_async_16(dst0 + swizzle_off((uint32_t)pix * RBG + c * 16, gmask), ok ? (const void*)(src + c * 8) : (const void*)p.g,
+                                        ok ? 16u : 0u);
+                        }
+                    }
+                }
+                cp_async_arrive_noinc(bar_full_g + 8 * stage);
+                if (++stage == p.NPS) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
         }
     } else if (warp == 8) {
@@ -319,20 +397,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                 fence_proxy_async();      // the g tile arrived through cp.async (generic proxy)
                 tc_fence_after();
                 const uint32_t sbase = base + (uint32_t)stage * cSTAGE;
-                const uint64_t a0 = make_desc_mn(sbase, 16384u, 1024u, 2u);
-                const uint64_t b0 = make_desc_mn(sbase + G_TILE_BYTES, 16u, b_sbo, b_layout);
+                // A: SH == 1: two 64-channel blocks 16 KB apart, 8-pixel groups 1 KB apart;
+                //    SH  > 1: SH copies one pixel apart, 8-pixel groups one patch row apart
+                constexpr uint32_t a_layout = RBG == 128 ? 2u : 4u;
+                constexpr uint32_t a_kstep = SH == 1 ? 2048u : (uint32_t)(2 * GPW * RBG);
+                const uint64_t a0 = SH == 1 ? make_desc_mn(sbase, 16384u, 1024u, 2u)
+                                            : make_desc_mn(sbase, (uint32_t)RBG, (uint32_t)(GPW * RBG), a_layout);
+                const uint64_t b0 = make_desc_mn(sbase + G_BYTES, 16u, b_sbo, b_layout);
                 const uint32_t first = (u == u0) ? 0u : 1u;
 #pragma unroll 1
                 for (int ks = 0; ks < 8; ++ks) {
                     // K = 16 pixels = tile rows 2*ks, 2*ks + 1
-                    const uint64_t a = a0 + (uint64_t)((uint32_t)(ks * 2048) >> 4);
+                    const uint64_t a = a0 + (uint64_t)(((uint32_t)ks * a_kstep) >> 4);
                     const uint64_t bk = b0 + (uint64_t)((uint32_t)(ks * 2 * STRIDE * cPWp * RBX) >> 4);
                     const uint32_t acc = (ks == 0) ? first : 1u;
 #pragma unroll
-                    for (int tap = 0; tap < cNTAPS; ++tap) {
-                        const int ky = tap / KS, kx = tap - ky * KS;
+                    for (int ai = 0; ai < NACC; ++ai) {
+                        const int ky = ai / NS;
+                        const int kx = wg_shift<KS, STRIDE, SH>(ai - ky * NS);
                         const int toff = STRIDE == 1 ? ky * cPWp + kx : ky * cPWp + (kx & 1) * cPWhalf + (kx >> 1);
-                        umma_f16(tmem_base + (uint32_t)(tap * NB), a, bk + (uint64_t)((uint32_t)(toff * RBX) >> 4), idesc, acc);
+                        umma_f16(tmem_base + (uint32_t)(ai * NB), a, bk + (uint64_t)((uint32_t)(toff * RBX) >> 4), idesc, acc);
                     }
                 }
                 umma_commit(bar_empty + 8 * stage);
@@ -398,10 +482,12 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
         if (p.HsO < g->Hout) p.HsO = g->Hout;
     }
     const long long rows = (long long)p.HsO * g->B;
-    p.tiles_x = (g->Wout + 7) / 8;
+    // copies of the g patch per MMA (see the kernel header): only where 128 accumulator rows would be mostly padding
+    const int SH = (g->ks == 5 && g->Cout <= 32 && g->stride == 1) ? 4 : ((g->ks == 5 && g->Cout <= 64) ? 2 : 1);
+    p.tiles_x = (g->Wout + (SH - 1) + 7) / 8;
     p.mtiles = (int)((rows + 15) / 16) * p.tiles_x;
     const int NB = (g->ks == 3 && !first && g->Cin % 32 == 0) ? 32 : 16;
-    p.nblk = (g->Cout + 127) / 128;
+    p.nblk = SH > 1 ? 1 : (g->Cout + 127) / 128;
     p.nchunk = first ? 1 : g->Cin / NB;
     p.cin_real = g->Cin;
     const long long U = (long long)p.mtiles * g->T;
@@ -428,7 +514,8 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     const int PH = 15 * g->stride + g->ks;
     const int PWp = g->stride == 1 ? 8 + g->ks - 1 : 2 * (8 + (g->ks - 1) / 2);
     const int PBX = (PH * PWp * 2 * NB + 1023) / 1024 * 1024;
-    const int stage_bytes = G_TILE_BYTES + PBX;
+    const int g_bytes = SH == 1 ? G_TILE_BYTES : (16 * (8 + SH - 1) * (256 / SH) + 1023) / 1024 * 1024;
+    const int stage_bytes = g_bytes + PBX;
     const int tail_bytes = 256 + (3 * WG_MAX_STAGES + 1) * 8 + 64;
     int nps = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
     if (nps > WG_MAX_STAGES) nps = WG_MAX_STAGES;
@@ -441,22 +528,27 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     const unsigned grid = (unsigned)(pairs * p.nsplit);
     cudaStream_t st = (cudaStream_t)stream;
     bool launched = false;
-#define SS_TRY_WG(KS_, ST_, NB_, F4_)                                                                                            \
-    if (!launched && g->ks == KS_ && g->stride == ST_ && NB == NB_ && first == F4_) {                                            \
+#define SS_TRY_WG(KS_, ST_, NB_, F4_, SH_)                                                                                       \
+    if (!launched && g->ks == KS_ && g->stride == ST_ && NB == NB_ && first == F4_ && SH == SH_) {                               \
         static bool attr = false;                                                                                                \
         if (!attr) {                                                                                                             \
-            cudaFuncSetAttribute(conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+            cudaFuncSetAttribute(conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_, SH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  227 * 1024);                                                                                    \
             attr = true;                                                                                                         \
         }                                                                                                                        \
-        conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_><<<grid, WG_THREADS, smem, st>>>(p);                                           \
+        conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_, SH_><<<grid, WG_THREADS, smem, st>>>(p);                                      \
         launched = true;                                                                                                         \
     }
-    SS_TRY_WG(5, 1, 16, false)
-    SS_TRY_WG(5, 2, 16, false)
-    SS_TRY_WG(3, 1, 32, false)
-    SS_TRY_WG(3, 1, 16, false)
-    SS_TRY_WG(5, 1, 16, true)
+    SS_TRY_WG(5, 1, 16, false, 1)
+    SS_TRY_WG(5, 1, 16, false, 2)
+    SS_TRY_WG(5, 1, 16, false, 4)
+    SS_TRY_WG(5, 2, 16, false, 1)
+    SS_TRY_WG(5, 2, 16, false, 2)
+    SS_TRY_WG(3, 1, 32, false, 1)
+    SS_TRY_WG(3, 1, 16, false, 1)
+    SS_TRY_WG(5, 1, 16, true, 1)
+    SS_TRY_WG(5, 1, 16, true, 2)
+    SS_TRY_WG(5, 1, 16, true, 4)
 #undef SS_TRY_WG
     if (!launched) {
         set_error("ss_conv_wgrad_bf16: no kernel instance for ks %d stride %d", g->ks, g->stride);

@@ -14,7 +14,8 @@
 //
 //   A = g tile      [K = 16 pixels (2 tile rows x 8)][M = 128 output channels]   bf16, SWIZZLE_128B, 2 channel blocks (LBO)
 //   B = x patch     [K = 16 pixels, shifted by tap  ][N = 16 / 32 input channels] u8 spikes converted to bf16 by the producer
-//   D = one fp32 accumulator [128][N] PER TAP in TMEM (25 x 16 or 9 x 32 columns), alive for the whole CTA
+//   D = one fp32 accumulator [128][N] PER TAP in TMEM, alive for the whole CTA.  512 columns hold 16 accumulators of N = 32:
+//       a 5x5 filter is split into two groups of filter rows (3 + 2) handled by different CTAs
 //
 // A CTA owns one (128-channel block of Cout, N-channel chunk of Cin) pair and a contiguous range of (tile, timestep) units;
 // the accumulators never leave TMEM until the end, when four warps add them into g_w with coalesced atomics.
@@ -140,7 +141,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
     constexpr int NPIXG = 16 * GPW;
     constexpr int G_BYTES = SH == 1 ? G_TILE_BYTES : (NPIXG * RBG + 1023) / 1024 * 1024;
     constexpr int NS = wg_nshift<KS, STRIDE, SH>();
-    constexpr int NACC = KS * NS;                       // accumulators ([128][NB] each)
+    constexpr int GK = (512 / NB) / NS < KS ? (512 / NB) / NS : KS;   // filter rows per CTA (TMEM: 512 columns)
+    constexpr int NGRP = (KS + GK - 1) / GK;            // groups of filter rows
+    constexpr int NACC = GK * NS;                       // accumulators ([128][NB] each)
     static_assert(SH == 1 || (KS == 5 && (STRIDE == 1 || SH == 2)), "shifted copies: 5x5 only; stride 2 with SH = 2");
     constexpr int cPWhalf = 8 + (KS - 1) / 2;
     constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
@@ -188,6 +191,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
 
     // this CTA's (output-channel block, input-channel chunk, unit range)
     int item = blockIdx.x;
+    const int grp = item % NGRP; item /= NGRP;
+    const int ky0 = grp * GK;
+    const int nky = min(GK, KS - ky0);
     const int split = item % p.nsplit; item /= p.nsplit;
     const int chunk = item % p.nchunk;
     const int nblk = item / p.nchunk;
@@ -275,9 +281,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             const int n = n0 + (L - copy * CH);
             const bool n_ok = n < p.Cout;
             const int Kc = p.cin_real;                    // g_w row = tap * Kc + channel
-            for (int a = 0; a < NACC; ++a) {
-                const int ky = a / NS;
-                const int shift = wg_shift<KS, STRIDE, SH>(a - ky * NS);
+            for (int a = 0; a < nky * NS; ++a) {
+                const int ky = ky0 + a / NS;
+                const int shift = wg_shift<KS, STRIDE, SH>(a % NS);
                 const int kx = shift + STRIDE * (SH - 1 - copy);
                 const int tap = ky * KS + kx;
                 // stride 2: shift 2 of the un-shifted copy is the same tap as shift 0 of the shifted one -- count it once
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                 constexpr uint32_t a_kstep = SH == 1 ? 2048u : (uint32_t)(2 * GPW * RBG);
                 const uint64_t a0 = SH == 1 ? make_desc_mn(sbase, 16384u, 1024u, 2u)
                                             : make_desc_mn(sbase, (uint32_t)RBG, (uint32_t)(GPW * RBG), a_layout);
-                const uint64_t b0 = make_desc_mn(sbase + G_BYTES, 16u, b_sbo, b_layout);
+                const uint64_t b0 = make_desc_mn(sbase + G_BYTES + (uint32_t)(ky0 * cPWp * RBX), 16u, b_sbo, b_layout);
                 const uint32_t first = (u == u0) ? 0u : 1u;
 #pragma unroll 1
                 for (int ks = 0; ks < 8; ++ks) {
@@ -413,10 +419,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                     const uint32_t acc = (ks == 0) ? first : 1u;
 #pragma unroll
                     for (int ai = 0; ai < NACC; ++ai) {
-                        const int ky = ai / NS;
+                        const int ky = ai / NS;       // relative to this CTA's first filter row
                         const int kx = wg_shift<KS, STRIDE, SH>(ai - ky * NS);
                         const int toff = STRIDE == 1 ? ky * cPWp + kx : ky * cPWp + (kx & 1) * cPWhalf + (kx >> 1);
-                        umma_f16(tmem_base + (uint32_t)(ai * NB), a, bk + (uint64_t)((uint32_t)(toff * RBX) >> 4), idesc, acc);
+                        if (ky < nky)
+                            umma_f16(tmem_base + (uint32_t)(ai * NB), a, bk + (uint64_t)((uint32_t)(toff * RBX) >> 4), idesc, acc);
                     }
                 }
                 umma_commit(bar_empty + 8 * stage);
@@ -486,7 +493,12 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     const int SH = (g->ks == 5 && g->Cout <= 32 && g->stride == 1) ? 4 : ((g->ks == 5 && g->Cout <= 64) ? 2 : 1);
     p.tiles_x = (g->Wout + (SH - 1) + 7) / 8;
     p.mtiles = (int)((rows + 15) / 16) * p.tiles_x;
-    const int NB = (g->ks == 3 && !first && g->Cin % 32 == 0) ? 32 : 16;
+    // input channels per CTA: 32 where the patch still leaves room for >= 3 pipeline stages (not the strided 5x5 patch)
+    const int NB = (!first && g->Cin % 32 == 0 && g->stride == 1) ? 32 : 16;
+    const int NS = SH == 1 ? g->ks : (g->stride == 1 ? (g->ks + SH - 1) / SH : 3);
+    int GK = (512 / NB) / NS;
+    if (GK > g->ks) GK = g->ks;
+    const int NGRP = (g->ks + GK - 1) / GK;
     p.nblk = SH > 1 ? 1 : (g->Cout + 127) / 128;
     p.nchunk = first ? 1 : g->Cin / NB;
     p.cin_real = g->Cin;
@@ -500,7 +512,7 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
-    const int pairs = p.nblk * p.nchunk;
+    const int pairs = p.nblk * p.nchunk * NGRP;
     long long ns = num_sms / pairs;                        // one wave: every CTA keeps its accumulators for its whole life,
                                                            // so a second, partial wave would double the kernel's duration
     if (ns > U) ns = U;
@@ -539,6 +551,9 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
         conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_, SH_><<<grid, WG_THREADS, smem, st>>>(p);                                      \
         launched = true;                                                                                                         \
     }
+    SS_TRY_WG(5, 1, 32, false, 1)
+    SS_TRY_WG(5, 1, 32, false, 2)
+    SS_TRY_WG(5, 1, 32, false, 4)
     SS_TRY_WG(5, 1, 16, false, 1)
     SS_TRY_WG(5, 1, 16, false, 2)
     SS_TRY_WG(5, 1, 16, false, 4)

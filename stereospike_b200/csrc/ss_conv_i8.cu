@@ -519,6 +519,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 for (int t0 = 0; t0 < p.T; t0 += cTC) {
                     const int tc = min(cTC, p.T - t0);
                     for (int s = 0; s < tc; ++s) {
+                        float* dst = p.g_dst + (size_t)(t0 + s) * t_out + o0;
+                        // accumulate mode: fetch the destination BEFORE blocking on the accumulator, so the round trip to
+                        // HBM overlaps the MMAs of this slot instead of stalling the adds behind it
+                        float4 oldv[NCH * 4];
+                        if (live && p.g_mode == SS_CORR_ACCUMULATE) {
+#pragma unroll
+                            for (int q = 0; q < NCH * 4; ++q) oldv[q] = *reinterpret_cast<const float4*>(dst + q * 4);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < NCH * 4; ++q) oldv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                         mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
                         slot_phase ^= 1u << s;
                         tc_fence_after();
@@ -530,7 +541,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         tc_fence_before();
                         mbar_arrive(bar_empty_a + 8 * s);
                         if (!live) continue;
-                        float* dst = p.g_dst + (size_t)(t0 + s) * t_out + o0;
 #pragma unroll
                         for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -542,10 +552,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                                                  : "memory");
                                 } else {
-                                    if (p.g_mode == SS_CORR_ACCUMULATE) {
-                                        const float4 old = *dp;
-                                        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-                                    }
+                                    const float4 old = oldv[c * 4 + q];       // zeros in store mode
+                                    v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
                                     *dp = v;
                                 }
                             }

@@ -294,6 +294,20 @@ int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const void* g_bf16
 int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float* const* g_acts, float* const* g_w,
                  float* const* g_bias, float* const* bins, void* stream);
 
+/* ---- loss + metric (first "next" row of the scope table: the step right after the path in the training loop) ----
+ * Replaces network/loss.py:7-135 (Total_Loss = multi-scale scale-invariant loss + alpha * multi-scale Sobel gradient-matching
+ * loss on the NaN-masked residual) and network/metrics.py:83-95 (MeanDepthError), train.py:238,257.
+ *   pred[k] fp32 [B][H][W], k < nscale <= 4 (the four depth maps, all at full resolution); gt fp32 [B][H][W], NaN = invalid
+ *   sums   device fp64 [nscale][5], zero-filled by the caller: n, sum r, sum r^2, sum(|gx| + |gy|), sum |r|   (r = pred - gt)
+ *          => SI_k = S2/n - (S1/n)^2,  GM_k = G/n,  MDE_k = A/n
+ *   signs  device u8 [nscale][B*H*W] written by the forward pass (signs of the Sobel responses), read by the backward pass
+ *   coef_si / coef_gm  device fp32 [nscale] = weight of SI_k / GM_k in the total * upstream gradient;
+ *   g_pred[k] fp32 [B][H][W] = d loss / d pred[k] */
+int ss_loss_fwd(int32_t nscale, int32_t B, int32_t H, int32_t W, const float* const* pred, const float* gt, double* sums,
+                void* signs, void* stream);
+int ss_loss_bwd(int32_t nscale, int32_t B, int32_t H, int32_t W, const float* const* pred, const float* gt, const double* sums,
+                const void* signs, const float* coef_si, const float* coef_gm, float* const* g_pred, void* stream);
+
 int ss_abi_version(void);
 const char* ss_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */

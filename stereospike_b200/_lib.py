@@ -17,7 +17,7 @@ SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
 SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
            'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_neuron_bwd_ex', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
-           'ss_pack_weights_bf16', 'ss_corr_bf16', 'ss_conv_wgrad_bf16',
+           'ss_pack_weights_bf16', 'ss_corr_bf16', 'ss_conv_wgrad_bf16', 'ss_loss_fwd', 'ss_loss_bwd',
            'ss_abi_version', 'ss_last_error', 'ss_launch_count')
 
 
@@ -120,6 +120,10 @@ def lib():
     L.ss_corr_bf16.restype = ctypes.c_int
     L.ss_conv_wgrad_bf16.argtypes = [ctypes.POINTER(BlockDesc)] + [vp] * 4
     L.ss_conv_wgrad_bf16.restype = ctypes.c_int
+    L.ss_loss_fwd.argtypes = [i32, i32, i32, i32, vp * 4, vp, vp, vp, vp]
+    L.ss_loss_fwd.restype = ctypes.c_int
+    L.ss_loss_bwd.argtypes = [i32, i32, i32, i32, vp * 4, vp, vp, vp, vp, vp, vp * 4, vp]
+    L.ss_loss_bwd.restype = ctypes.c_int
     L.ss_conv_dgrad.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 6
     L.ss_conv_dgrad.restype = ctypes.c_int
     L.ss_conv_wgrad.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 6

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'lib', 'libstereospike_b200.so')
-SOURCES = ('ss_api.cu', 'ss_simt.cu', 'ss_heads.cu', 'ss_conv_i8.cu', 'ss_bwd.cu', 'ss_events.cu', 'ss_wgrad_umma.cu')
+SOURCES = ('ss_api.cu', 'ss_simt.cu', 'ss_heads.cu', 'ss_conv_i8.cu', 'ss_bwd.cu', 'ss_events.cu', 'ss_wgrad_umma.cu', 'ss_loss.cu')
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17', '--threads', '0', '-I' + os.path.join(ROOT, 'include')]
 

@@ -288,11 +288,13 @@ int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const void* g_bf16
 
 /* Backward of ss_heads_fwd (autograd through predict_depthK + the I-neuron running sum).
  *   g_depths fp32 [4][B][H][W]: gradient w.r.t. the four returned depth maps (execution order)
- *   g_acts[i] fp32 [T][B][Hs][Ws][C] accumulated (acts u8 as in ss_heads_fwd; taps unused); g_w[i] fp32 [9][C] accumulated; g_bias[i] scalar accumulated
+ *   g_acts[i] fp32 [T][B][Hs][Ws][C]: accumulated into, or (store_g_acts != 0) every element written -- the heads are the first
+ *   consumer visited in the backward pass, so the caller can hand in uninitialised buffers (acts u8 as in ss_heads_fwd; taps unused);
+ *   g_w[i] fp32 [9][C] accumulated; g_bias[i] scalar accumulated
  *   bins[i]   fp32 [2][B][Hs][Ws][9] zero-filled workspace
  */
 int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float* const* g_acts, float* const* g_w,
-                 float* const* g_bias, float* const* bins, void* stream);
+                 float* const* g_bias, float* const* bins, int32_t store_g_acts, void* stream);
 
 /* ---- loss + metric (first "next" row of the scope table: the step right after the path in the training loop) ----
  * Replaces network/loss.py:7-135 (Total_Loss = multi-scale scale-invariant loss + alpha * multi-scale Sobel gradient-matching

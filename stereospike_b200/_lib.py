@@ -106,7 +106,7 @@ def lib():
     L.ss_conv_neuron_fwd.restype = ctypes.c_int
     L.ss_heads_fwd.argtypes = [ctypes.POINTER(HeadsArgs), vp, vp, vp]
     L.ss_heads_fwd.restype = ctypes.c_int
-    L.ss_heads_bwd.argtypes = [ctypes.POINTER(HeadsArgs), vp, vp * 4, vp * 4, vp * 4, vp * 4, vp]
+    L.ss_heads_bwd.argtypes = [ctypes.POINTER(HeadsArgs), vp, vp * 4, vp * 4, vp * 4, vp * 4, i32, vp]
     L.ss_heads_bwd.restype = ctypes.c_int
     L.ss_neuron_fwd.argtypes = [i32, i64, i32, f32, f32, f32] + [vp] * 6
     L.ss_neuron_fwd.restype = ctypes.c_int

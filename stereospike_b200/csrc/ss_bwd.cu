@@ -281,6 +281,7 @@ struct HeadsBwdParams {
     float* g_w[4];
     float* g_bias[4];
     float* bins[4];
+    int store;          // 1: g_acts is written (first writer of a fresh buffer), 0: accumulated into
 };
 
 // step 1: bin the per-pixel head gradients onto (source pixel, tap).  Class 0 = timesteps before the last
@@ -387,7 +388,11 @@ __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, 
                 const size_t eo = ((size_t)t * S + s) * C + c0;
                 const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + eo));
                 float4* gp = reinterpret_cast<float4*>(p.g_acts[head] + eo);
-                float4 q0 = gp[0], q1 = gp[1];
+                float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+                if (!p.store) {
+                    q0 = gp[0];
+                    q1 = gp[1];
+                }
                 const bool last = t == T - 1;
                 const float* ga = last ? ga1 : ga0;
                 q0.x += ga[0]; q0.y += ga[1]; q0.z += ga[2]; q0.w += ga[3];
@@ -535,7 +540,7 @@ extern "C" int ss_conv_wgrad(const ss_conv_geom* g, const void* x, const int32_t
 }
 
 extern "C" int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float* const* g_acts, float* const* g_w,
-                            float* const* g_bias, float* const* bins, void* stream) {
+                            float* const* g_bias, float* const* bins, int32_t store_g_acts, void* stream) {
     if (a == nullptr || g_depths == nullptr || g_acts == nullptr || g_w == nullptr || g_bias == nullptr || bins == nullptr) {
         set_error("ss_heads_bwd: null argument");
         return SS_EINVAL;
@@ -553,6 +558,7 @@ extern "C" int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float
         p.g_acts[i] = g_acts[i]; p.g_w[i] = g_w[i]; p.g_bias[i] = g_bias[i]; p.bins[i] = bins[i];
     }
     p.g_depths = g_depths;
+    p.store = store_g_acts ? 1 : 0;
     const long long npix = (long long)p.B * p.H * p.W;
     if (npix == 0 || p.T == 0) return SS_OK;
     cudaStream_t st = (cudaStream_t)stream;

@@ -258,9 +258,10 @@ class Engine:
         grads = [None] * len(params)
         g = {}
 
-        def gbuf(name):
+        def gbuf(name, fresh_ok=False):
             if name not in g:
-                g[name] = torch.zeros(acts[name].shape, dtype=torch.float32, device=dev)
+                alloc = torch.empty if fresh_ok else torch.zeros      # fresh_ok: the caller writes every element
+                g[name] = alloc(acts[name].shape, dtype=torch.float32, device=dev)
             return g[name]
 
         # ---- heads
@@ -270,6 +271,7 @@ class Engine:
         vp4 = ctypes.c_void_p * 4
         g_acts, g_w, g_b, bins = vp4(), vp4(), vp4(), vp4()
         gw_t, gb_t = [], []
+        store_heads = len({h.src for h in self.heads}) == len(self.heads)     # distinct sources: each buffer has one writer here
         for j, h in enumerate(self.heads):
             gm = saved['hg'][j]
             ym, xm = gm.maps(dev)
@@ -277,7 +279,7 @@ class Engine:
             a.acts[j] = saved['hacts'][j].data_ptr()
             a.w[j] = saved['hw'][j].data_ptr()
             a.ymap[j], a.xmap[j] = ym.data_ptr(), xm.data_ptr()
-            ga = gbuf(h.src)
+            ga = gbuf(h.src, fresh_ok=store_heads)
             gw = torch.zeros((9, gm.Cin), dtype=torch.float32, device=dev)
             gb = torch.zeros((1,), dtype=torch.float32, device=dev)
             bn = torch.zeros((2, B, gm.Hin, gm.Win, 9), dtype=torch.float32, device=dev)
@@ -285,7 +287,8 @@ class Engine:
             gw_t.append(gw)
             gb_t.append(gb)
             g_acts[j], g_w[j], g_b[j], bins[j] = ga.data_ptr(), gw.data_ptr(), gb.data_ptr(), bn.data_ptr()
-        _lib.check(L.ss_heads_bwd(ctypes.byref(a), _ptr(g_depths), g_acts, g_w, g_b, bins, _stream()), 'ss_heads_bwd')
+        _lib.check(L.ss_heads_bwd(ctypes.byref(a), _ptr(g_depths), g_acts, g_w, g_b, bins, 1 if store_heads else 0, _stream()),
+                   'ss_heads_bwd')
         for j, h in enumerate(self.heads):
             C = saved['hg'][j].Cin
             grads[n_site + 2 * j] = gw_t[j].reshape(3, 3, C).permute(2, 0, 1).reshape(1, C, 3, 3).contiguous()

@@ -382,18 +382,13 @@ class DgradPlan:
             # input row y = 2i + py receives  sum_dy g[i - 1 + dy] * W[2*(2 - dy) + py]  (dy = 0..2; tap index > 4 -> absent)
             self.ks, self.pad, self.nclass, self.mode = 3, 1, 4, _lib.SS_CORR_ACCUMULATE
             self.Hv, self.Wv = (g.Hin + 1) // 2, (g.Win + 1) // 2
-            sets = []
-            for py in (0, 1):
-                for px in (0, 1):
-                    f = w.new_zeros(ci, co, 3, 3)
-                    for dy in range(3):
-                        for dx in range(3):
-                            ky, kx = 2 * (2 - dy) + py, 2 * (2 - dx) + px
-                            if ky <= 4 and kx <= 4:
-                                f[:, :, dy, dx] = w[:, :, ky, kx].transpose(0, 1)
-                    sets.append(f)
+            # one gather instead of 36 slice copies: tap index 5 = an appended zero tap
+            wp = torch.nn.functional.pad(w, (0, 1, 0, 1))
+            kidx = torch.tensor([[2 * (2 - d) + par for d in range(3)] for par in (0, 1)], device=w.device).clamp_(max=5)   # [parity][d]
+            f = wp[:, :, kidx[:, :, None, None], kidx[None, None, :, :]]          # [co][ci][py][dy][px][dx]
             nt = self.ntile
-            w_eff = torch.stack(sets, 0).view(4, ci // nt, nt, co, 3, 3).permute(1, 0, 2, 3, 4, 5).reshape(4 * ci, co, 3, 3)
+            # -> [ci-tile][class = 2*py + px][nt][co][dy][dx]
+            w_eff = f.permute(1, 2, 4, 0, 3, 5).reshape(ci // nt, nt, 4, co, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(4 * ci, co, 3, 3)
             ym = np.full((2, self.Hv), -1, dtype=np.int32)
             xm = np.full((2, self.Wv), -1, dtype=np.int32)
             for par in (0, 1):

@@ -92,21 +92,31 @@ def _node_v_in(node, shape_bhwc, device):
 
 
 class _NetFunction(torch.autograd.Function):
-    """Whole-network autograd node: inputs are the parameter tensors, output is the depth stack [4,B,H,W]."""
+    """Whole-network autograd node: inputs are the parameter tensors, outputs are the depth stack [4,B,H,W] and, when
+    asked for (side['spike_outputs']), the last-timestep spike maps of the named layers as fp32 NCHW tensors -- so that a
+    loss on the spikes (the reference's SpikePenalization_Loss, loss.py:96-107) back-propagates through the surrogates."""
 
     @staticmethod
     def forward(ctx, eng, x_seq, side, n_site_params, *params):
         need_grad = side['need_grad']
         res = eng._run_forward(x_seq, params, n_site_params, side, want_h=need_grad)
+        names = side.get('spike_outputs') or ()
+        spks = tuple(side['acts'][k][-1].permute(0, 3, 1, 2).float() for k in names) if need_grad else ()
         if need_grad:
             ctx.eng, ctx.side, ctx.n_site_params = eng, side, n_site_params
             ctx.params = params
             ctx.saved = res
-        return res['depths']
+            ctx.spk_names = names
+        side['spikes_fp32'] = spks
+        return (res['depths'],) + spks
 
     @staticmethod
-    def backward(ctx, g_depths):
-        grads = ctx.eng._run_backward(ctx.saved, ctx.params, ctx.n_site_params, g_depths.contiguous().float())
+    def backward(ctx, g_depths, *g_spks):
+        saved = ctx.saved
+        if g_depths is None:
+            g_depths = torch.zeros_like(saved['depths'])
+        inject = {k: gs for k, gs in zip(ctx.spk_names, g_spks) if gs is not None}
+        grads = ctx.eng._run_backward(saved, ctx.params, ctx.n_site_params, g_depths.contiguous().float(), inject)
         ctx.saved = None
         return (None, None, None, None) + tuple(grads)
 
@@ -139,8 +149,9 @@ class Engine:
         return ps, n_site
 
     # ------------------------------------------------------------------ public entry
-    def run(self, x_seq, return_layers=False):
-        """x_seq fp32 [B,T,C,H,W] on CUDA.  Returns (depth stack [4,B,H,W] in execution order, side dict)."""
+    def run(self, x_seq, return_layers=False, spike_outputs=None):
+        """x_seq fp32 [B,T,C,H,W] on CUDA.  Returns (depth stack [4,B,H,W] in execution order, side dict).
+        ``spike_outputs``: layer names whose last-timestep spike maps should be differentiable outputs (side['spikes_fp32'])."""
         ops._require_cuda(x_seq, 'x')
         if x_seq.dim() != 5:
             raise ValueError('expected x of shape [B, T, C, H, W]')
@@ -155,9 +166,10 @@ class Engine:
         need_grad = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params)
         if need_grad and x_seq.dtype == torch.uint8:
             raise NotImplementedError('packed u8 input is forward-only (the first layer\'s weight gradient reads the fp32 frames)')
-        side = {'need_grad': need_grad, 'return_layers': return_layers}
-        depths = _NetFunction.apply(self, x_seq, side, n_site, *params)
-        return depths, side
+        side = {'need_grad': need_grad, 'return_layers': return_layers, 'spike_outputs': tuple(spike_outputs or ())}
+        outs = _NetFunction.apply(self, x_seq, side, n_site, *params)
+        side['spikes_fp32'] = outs[1:]
+        return outs[0], side
 
     # ------------------------------------------------------------------ forward
     def _run_forward(self, x_seq, params, n_site, side, want_h):
@@ -250,7 +262,7 @@ class Engine:
         return saved
 
     # ------------------------------------------------------------------ backward
-    def _run_backward(self, saved, params, n_site, g_depths):
+    def _run_backward(self, saved, params, n_site, g_depths, inject=None):
         L = _lib.lib()
         B, T, H, W = saved['B'], saved['T'], saved['H'], saved['W']
         acts = saved['acts']
@@ -293,6 +305,11 @@ class Engine:
             C = saved['hg'][j].Cin
             grads[n_site + 2 * j] = gw_t[j].reshape(3, 3, C).permute(2, 0, 1).reshape(1, C, 3, 3).contiguous()
             grads[n_site + 2 * j + 1] = gb_t[j]
+
+        # ---- gradients arriving on the returned spike maps (last timestep, NCHW) join the buffers the heads just created
+        for name, gs in (inject or {}).items():
+            buf = gbuf(name)
+            buf[T - 1] += gs.permute(0, 2, 3, 1).to(torch.float32)
 
         # ---- spiking blocks, reverse order
         for i in range(len(self.sites) - 1, -1, -1):

@@ -112,8 +112,8 @@ def MultiScale_GradientMatching_Loss(predicted, groundtruth, factors=(1., 1., 1.
 
 
 def SpikePenalization_Loss(intermediary_spike_tensors):
-    """loss.py:96-107.  Value only: the fused engine returns spike maps without an autograd graph, so no gradient flows
-    through this term (the reference back-propagates it through the surrogate)."""
+    """loss.py:96-107.  The spike maps returned by ``forward`` / ``forward_seq(spikes_fp32=True)`` are outputs of the
+    network's autograd node, so this term back-propagates through the surrogates like in the reference."""
     loss = 0.0
     for s in intermediary_spike_tensors:
         s = s.float()

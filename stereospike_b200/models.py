@@ -150,29 +150,36 @@ class _SpikingUNet(NeuromorphicNet):
         return self
 
     # ---- forward
+    _SPIKE_OUTPUTS = ('out_rconv', 'out_add4', 'out_add3', 'out_add2', 'out_add1')
+
     def _package(self, depths, side, spikes_fp32):
         d = [depths[3].unsqueeze(1), depths[2].unsqueeze(1), depths[1].unsqueeze(1), depths[0].unsqueeze(1)]
         if not self._returns_spikes:
             return d
+        if spikes_fp32 and len(side.get('spikes_fp32', ())) == len(self._SPIKE_OUTPUTS):
+            return d, list(side['spikes_fp32'])    # differentiable: a loss on them reaches the weights through the surrogates
         acts = side['acts']
         spks = []
-        for k in ('out_rconv', 'out_add4', 'out_add3', 'out_add2', 'out_add1'):
+        for k in self._SPIKE_OUTPUTS:
             s = acts[k][-1].permute(0, 3, 1, 2)        # last timestep, NCHW-shaped view of the u8 NHWC buffer
             spks.append(s.float() if spikes_fp32 else s)
         return d, spks
 
+    def _run(self, x, spikes_fp32):
+        want = self._SPIKE_OUTPUTS if (spikes_fp32 and self._returns_spikes) else None
+        depths, side = self.engine.run(x, spike_outputs=want)
+        return self._package(depths, side, spikes_fp32)
+
     def forward(self, x):
         """Reference contract (SNN_models.py:152-192): reads frame 0 of ``x``; stateful across calls."""
-        depths, side = self.engine.run(x[:, 0:1])
-        return self._package(depths, side, spikes_fp32=True)
+        return self._run(x[:, 0:1], True)
 
     def forward_seq(self, x_seq, spikes_fp32=False):
         """T-loop over ``x_seq[:, t]`` without reset, fused: one kernel per block for all T timesteps.
         ``x_seq`` is the reference's fp32 ``[B, T, C, H, W]`` or the packed u8 ``[T, B, H, W, 4]`` of ``stereospike_b200.events``.
         Returns what the LAST ``forward`` call of the equivalent loop would return.  Spike tensors are
-        NCHW-shaped u8 views unless ``spikes_fp32``."""
-        depths, side = self.engine.run(x_seq)
-        return self._package(depths, side, spikes_fp32)
+        NCHW-shaped u8 views unless ``spikes_fp32`` (then fp32, and differentiable when gradients are enabled)."""
+        return self._run(x_seq, spikes_fp32)
 
     def set_init_depths_potentials(self, depth_prior):
         self.Ineurons.v = depth_prior

@@ -80,3 +80,38 @@ def test_training_step_with_fused_loss_matches_oracle_loss():
         grads.append([p.grad.clone() for p in net.parameters()])
     for a, b in zip(*grads):
         assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-10
+
+
+def test_spike_penalisation_back_propagates_like_the_oracle():
+    """Total_Loss(penalize_spikes=True) (loss.py:96-135): the penalty on the returned spike maps reaches the weights through
+    the surrogate gradients.  Parameter gradients against autograd through the oracle (cosine >= 0.999, as for the depth
+    loss), and the penalty must actually change them."""
+    import stereospike_b200 as sb
+    from oracle import loss_ref, ref_model as rm, sj_compat as sj
+    from stereospike_b200 import loss as sl
+    torch.manual_seed(5)     # a configuration on which the fp32 oracle and the exact-integer forward agree spike for spike
+    oracle = rm.SpikingUNet('lif', tau=3.0, multiply_factor=15.0)
+    net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=False, tau=3.0, multiply_factor=15.0)
+    net.load_state_dict(oracle.state_dict())
+    net = net.cuda()
+    x = rm.synthetic_inputs(1, 2, 4, seed=6)
+    label = rm.synthetic_label(1, seed=7)
+    beta = 50.0
+    sj.reset_net(oracle)
+    d_ref, s_ref = oracle.forward_seq(x)
+    loss_ref.total_loss(d_ref, label, spikes=s_ref, beta=beta).backward()
+    got = {}
+    for penal in (True, False):
+        net.zero_grad()
+        sb.functional.reset_net(net)
+        d, s = net.forward_seq(x.cuda(), spikes_fp32=True)
+        sl.Total_Loss(penalize_spikes=penal, beta=beta)(d, label.cuda(), s).backward()
+        got[penal] = {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}
+    ref = dict(oracle.named_parameters())
+    changed = 0
+    for k, g in got[True].items():
+        a, b = ref[k].grad.flatten().double(), g.flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        assert cos >= 0.999, (k, cos)
+        changed += int(float((g - got[False][k]).abs().max()) > 1e-3 * float(g.abs().max()))
+    assert changed >= 10, changed

@@ -191,7 +191,8 @@ class Engine:
             use_i8 = impl != SS_IMPL_SIMT
             fold = use_i8 and self.fold_upsample and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
                 min(g.Hin, g.Win) >= 8 and abs(g.Hout + 4 - 2 * g.Hin) <= g.Hin // 8 and abs(g.Wout + 4 - 2 * g.Win) <= g.Win // 8
-            w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=want_h or not use_i8, fold=fold)
+            # the fp32 [K][Cout] copy is only read by the CUDA-core kernels (forward impl='simt', backward bwd_impl='simt')
+            w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=(want_h and self.bwd_impl == 'simt') or not use_i8, fold=fold)
             decay = params[2 * i + 1]
             if decay is not None:
                 decay = decay.detach().contiguous()
@@ -361,7 +362,8 @@ class Engine:
                 if tc_d:
                     s.dgrad_plan(gm).run(g_b16, gx, T, B)
                 else:
-                    rc = L.ss_conv_dgrad(ctypes.byref(cg), _ptr(ym), _ptr(xm), _ptr(sv['w_kn']), _ptr(g_acc), _ptr(gx), _stream())
+                    w_kn = sv['w_kn'] if sv['w_kn'] is not None else ops.weight_to_kn(s.conv.weight)
+                    rc = L.ss_conv_dgrad(ctypes.byref(cg), _ptr(ym), _ptr(xm), _ptr(w_kn), _ptr(g_acc), _ptr(gx), _stream())
                     _lib.check(rc, 'ss_conv_dgrad')
             del g_acc, g_b16, g_out
         return grads

@@ -358,6 +358,32 @@ def _pack_bf16(w_eff, ks, ntile):
     return img
 
 
+@functools.lru_cache(maxsize=None)
+def _dgrad_tables(kind, stride, ks, Hin, Win, Hout, Wout, device):
+    """Geometry-only device tables of a block's data gradient (cached: building them is a blocking host-to-device copy)."""
+    dev = torch.device(device)
+    t = lambda a: torch.tensor(a, dtype=torch.int32, device=dev).contiguous()
+    if kind == 'conv' and stride == 1:
+        return None, None, None
+    if kind == 'conv':
+        Hv, Wv = (Hin + 1) // 2, (Win + 1) // 2
+        ym = np.full((2, Hv), -1, dtype=np.int32)
+        xm = np.full((2, Wv), -1, dtype=np.int32)
+        for par in (0, 1):
+            yy = 2 * np.arange(Hv) + par
+            xx = 2 * np.arange(Wv) + par
+            ym[par] = np.where(yy < Hin, yy, -1)
+            xm[par] = np.where(xx < Win, xx, -1)
+        # filter tap read by correlation offset d of parity class par: 2*(2 - d) + par; 5 = the appended zero tap
+        kidx = torch.tensor([[min(2 * (2 - d) + par, 5) for d in range(3)] for par in (0, 1)], device=dev)
+        return t(ym), t(xm), kidx
+
+    def src(n_in, n_up):
+        scale = np.float32(n_in) / np.float32(n_up)
+        return np.minimum(np.floor(np.arange(n_up, dtype=np.float32) * scale).astype(np.int64), n_in - 1).astype(np.int32)
+    return t(src(Hin, Hout + ks - 1)), t(src(Win, Wout + ks - 1)), None
+
+
 class DgradPlan:
     """Data gradient of one fused block as a single ss_corr_bf16 call (include/stereospike_b200.h): correlation weights
     derived from the block's OIHW weight, virtual grid, output maps.  ``geom`` is the block's forward BlockGeom."""
@@ -368,10 +394,8 @@ class DgradPlan:
         co, ci, ks, _ = w.shape
         self.ntile = 64 if ci % 64 == 0 else 32
         assert ci % 32 == 0 and co % 16 == 0
-        dev = torch.device(device)
-        t = lambda a: torch.tensor(a, dtype=torch.int32, device=dev).contiguous()
+        self.ymap, self.xmap, kidx = _dgrad_tables(g.kind, g.stride, ks, g.Hin, g.Win, g.Hout, g.Wout, str(device))
         wt = w.flip(2, 3).transpose(0, 1)                       # [Cin][Cout][ks][ks]: correlation form of the transposed conv
-        self.ymap = self.xmap = None
         if g.kind == 'conv' and g.stride == 1:
             assert 2 * g.pad == ks - 1
             self.ks, self.pad, self.nclass, self.mode = ks, ks - 1 - g.pad, 1, _lib.SS_CORR_ACCUMULATE
@@ -382,30 +406,15 @@ class DgradPlan:
             # input row y = 2i + py receives  sum_dy g[i - 1 + dy] * W[2*(2 - dy) + py]  (dy = 0..2; tap index > 4 -> absent)
             self.ks, self.pad, self.nclass, self.mode = 3, 1, 4, _lib.SS_CORR_ACCUMULATE
             self.Hv, self.Wv = (g.Hin + 1) // 2, (g.Win + 1) // 2
-            # one gather instead of 36 slice copies: tap index 5 = an appended zero tap
-            wp = torch.nn.functional.pad(w, (0, 1, 0, 1))
-            kidx = torch.tensor([[2 * (2 - d) + par for d in range(3)] for par in (0, 1)], device=w.device).clamp_(max=5)   # [parity][d]
+            wp = torch.nn.functional.pad(w, (0, 1, 0, 1))      # one gather instead of 36 slice copies
             f = wp[:, :, kidx[:, :, None, None], kidx[None, None, :, :]]          # [co][ci][py][dy][px][dx]
             nt = self.ntile
             # -> [ci-tile][class = 2*py + px][nt][co][dy][dx]
             w_eff = f.permute(1, 2, 4, 0, 3, 5).reshape(ci // nt, nt, 4, co, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(4 * ci, co, 3, 3)
-            ym = np.full((2, self.Hv), -1, dtype=np.int32)
-            xm = np.full((2, self.Wv), -1, dtype=np.int32)
-            for par in (0, 1):
-                yy = 2 * np.arange(self.Hv) + par
-                xx = 2 * np.arange(self.Wv) + par
-                ym[par] = np.where(yy < g.Hin, yy, -1)
-                xm[par] = np.where(xx < g.Win, xx, -1)
-            self.ymap, self.xmap = t(ym), t(xm)
         else:
             # NNConvUpsampling: gradient w.r.t. the virtual upsampled image, routed to its nearest-neighbour source pixel
             self.ks, self.pad, self.nclass, self.mode = ks, ks - 1, 1, _lib.SS_CORR_ATOMIC
             self.Hv, self.Wv = g.Hout + ks - 1, g.Wout + ks - 1
-
-            def src(n_in, n_up):
-                scale = np.float32(n_in) / np.float32(n_up)
-                return np.minimum(np.floor(np.arange(n_up, dtype=np.float32) * scale).astype(np.int64), n_in - 1).astype(np.int32)
-            self.ymap, self.xmap = t(src(g.Hin, self.Hv)), t(src(g.Win, self.Wv))
             w_eff = wt
         self.w_img = _pack_bf16(w_eff, self.ks, self.ntile)
         self.geom = g

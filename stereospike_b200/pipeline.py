@@ -49,3 +49,49 @@ class HostPipeline:
 
     def sync(self):
         torch.cuda.synchronize(self.device)
+
+
+class GraphedInference:
+    """Stateless sequence inference (``reset_net`` + ``forward_seq``, what test.py does per sample) captured once in a
+    CUDA graph and replayed: one graph launch instead of ~20 kernel launches and their Python dispatch, which is what
+    bounds small batches (B = 1, T = 1: the live event-camera case).
+
+        run = GraphedInference(net, batch_shape=(1, 5, 4, 260, 346))
+        depths = run(x)          # list [depth1..depth4] of static fp32 [B,1,H,W] tensors, overwritten by the next call
+
+    The weights are baked into the captured launches' packed images: re-create the object after changing them.
+    """
+
+    def __init__(self, net, batch_shape, dtype=torch.float32, device=None, warmup=2):
+        self.net = net
+        self.device = torch.device(device) if device is not None else next(net.parameters()).device
+        self.x = torch.zeros(batch_shape, dtype=dtype, device=self.device)
+        self.stream = torch.cuda.Stream(self.device)
+        eng = net.engine
+        keep = eng.keep_state
+        eng.keep_state = False            # nothing reads the final potentials of a stateless run: skip writing them
+        try:
+            cur = torch.cuda.current_stream(self.device)
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                for _ in range(warmup):   # lazy one-time work (weight images, geometry tables, function attributes) stays outside
+                    self._eager()
+            cur.wait_stream(self.stream)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.out = self._eager()
+        finally:
+            eng.keep_state = keep
+        functional.reset_net(net)         # the captured run left graph-owned tensors in the neuron modules
+
+    def _eager(self):
+        functional.reset_net(self.net)
+        with torch.no_grad():
+            out = self.net.forward_seq(self.x)
+        return list(out[0]) if isinstance(out, tuple) else list(out)
+
+    def __call__(self, x):
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out

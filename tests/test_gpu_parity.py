@@ -411,3 +411,25 @@ def test_standalone_blocks():
     node(torch.ones(3, device='cuda'))
     node(torch.ones(3, device='cuda') * 2)
     assert torch.equal(node.v.cpu(), torch.full((3,), 3.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,T', [(1, 1), (2, 3)])
+def test_graphed_inference_equals_eager(B, T):
+    """CUDA-graph replay of reset + forward_seq (stereospike_b200.pipeline.GraphedInference) is bit-identical to the eager
+    calls, for inputs different from the one it was captured with, replay after replay."""
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm
+    from stereospike_b200.pipeline import GraphedInference
+    torch.manual_seed(2)
+    net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=False, tau=3.0, multiply_factor=15.0).cuda()
+    run = GraphedInference(net, (B, T, 4, 260, 346))
+    for seed in (21, 22, 21):
+        x = rm.synthetic_inputs(B, T, 4, seed=seed).cuda()
+        got = [d.clone() for d in run(x)]
+        sb.functional.reset_net(net)
+        with torch.no_grad():
+            want, _ = net.forward_seq(x)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    assert float(got[0].abs().sum()) > 0

@@ -333,10 +333,12 @@ __global__ void __launch_bounds__(256) heads_bin_kernel(const HeadsBwdParams p) 
 }
 
 // step 2: per source pixel s and 8-channel group:
-//   g_act[t][s][c] += gain * sum_tap bin_cls(t)[s][tap] * w[tap][c]          (cls = 1 for the last timestep, else 0)
-//   g_w[tap][c]    += gain * (bin_0[s][tap] * sum_{t<T-1} act[t][s][c] + bin_1[s][tap] * act[T-1][s][c])
-// A thread owns one channel group and walks a strided set of source pixels with its 9 x 8 weight-gradient partials in
-// registers; they meet in shared memory once per block and reach HBM with 9*C atomics per block.
+//   GACT: g_act[t][s][c] (+)= gain * sum_tap bin_cls(t)[s][tap] * w[tap][c]          (cls = 1 for the last timestep, else 0)
+//   GW  : g_w[tap][c]    += gain * (bin_0[s][tap] * sum_{t<T-1} act[t][s][c] + bin_1[s][tap] * act[T-1][s][c])
+// Two instantiations: the activation-gradient writer is a pure streaming kernel that wants many resident warps; the
+// weight-gradient one keeps 9 x 8 partials per thread in registers (they meet in shared memory once per block and reach
+// HBM with 9*C atomics per block) and only reads the u8 activations.
+template <bool GACT, bool GW>
 __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, int head) {
     extern __shared__ float sh[];  // w [9][C] then g_w accumulators [9][C]
     const int C = p.C[head];
@@ -355,16 +357,13 @@ __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, 
     const int lanes = blockDim.x / c8n;          // pixels handled concurrently by one block
     const int pl = threadIdx.x / c8n;
     const int T = p.T;
-    float acc[9][8];
+    float acc[GW ? 9 : 1][8];
+    if (GW) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
+        for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[k][e] = 0.0f;
-    float wr[9][8];
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) wr[k][e] = wsm[k * C + c0 + e];
+            for (int e = 0; e < 8; ++e) acc[GW ? k : 0][e] = 0.0f;
+    }
     if (pl < lanes) {
         for (long long s = (long long)blockIdx.x * lanes + pl; s < S; s += (long long)gridDim.x * lanes) {
             float b0[9], b1[9];
@@ -373,62 +372,73 @@ __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, 
                 b0[k] = (T > 1) ? __ldg(p.bins[head] + (size_t)s * 9 + k) * p.gain : 0.0f;
                 b1[k] = __ldg(p.bins[head] + plane + (size_t)s * 9 + k) * p.gain;
             }
-            float ga0[8], ga1[8];
+            if (GACT) {
+                float ga0[8], ga1[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ga0[e] = ga1[e] = 0.0f;
+                for (int e = 0; e < 8; ++e) ga0[e] = ga1[e] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 9; ++k)
+                for (int k = 0; k < 9; ++k)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    ga0[e] = fmaf(b0[k], wr[k][e], ga0[e]);
-                    ga1[e] = fmaf(b1[k], wr[k][e], ga1[e]);
-                }
-            float asum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int t = 0; t < T; ++t) {
-                const size_t eo = ((size_t)t * S + s) * C + c0;
-                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + eo));
-                float4* gp = reinterpret_cast<float4*>(p.g_acts[head] + eo);
-                float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-                if (!p.store) {
-                    q0 = gp[0];
-                    q1 = gp[1];
-                }
-                const bool last = t == T - 1;
-                const float* ga = last ? ga1 : ga0;
-                q0.x += ga[0]; q0.y += ga[1]; q0.z += ga[2]; q0.w += ga[3];
-                q1.x += ga[4]; q1.y += ga[5]; q1.z += ga[6]; q1.w += ga[7];
-                gp[0] = q0;
-                gp[1] = q1;
-                float a[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    a[e] = (float)((raw.x >> (8 * e)) & 0xFFu);
-                    a[4 + e] = (float)((raw.y >> (8 * e)) & 0xFFu);
-                }
-                if (!last) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) asum[e] += a[e];      // small integers: exact
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k)
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(b1[k], a[e], acc[k][e]);
+                    for (int e = 0; e < 8; ++e) {
+                        const float wv = wsm[k * C + c0 + e];
+                        ga0[e] = fmaf(b0[k], wv, ga0[e]);
+                        ga1[e] = fmaf(b1[k], wv, ga1[e]);
+                    }
+                for (int t = 0; t < T; ++t) {
+                    float4* gp = reinterpret_cast<float4*>(p.g_acts[head] + ((size_t)t * S + s) * C + c0);
+                    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+                    if (!p.store) {
+                        q0 = gp[0];
+                        q1 = gp[1];
+                    }
+                    const bool last = t == T - 1;
+                    q0.x += last ? ga1[0] : ga0[0]; q0.y += last ? ga1[1] : ga0[1];
+                    q0.z += last ? ga1[2] : ga0[2]; q0.w += last ? ga1[3] : ga0[3];
+                    q1.x += last ? ga1[4] : ga0[4]; q1.y += last ? ga1[5] : ga0[5];
+                    q1.z += last ? ga1[6] : ga0[6]; q1.w += last ? ga1[7] : ga0[7];
+                    gp[0] = q0;
+                    gp[1] = q1;
                 }
             }
+            if (GW) {
+                float asum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int t = 0; t < T; ++t) {
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + ((size_t)t * S + s) * C + c0));
+                    float a[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a[e] = (float)((raw.x >> (8 * e)) & 0xFFu);
+                        a[4 + e] = (float)((raw.y >> (8 * e)) & 0xFFu);
+                    }
+                    if (t != T - 1) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) asum[e] += a[e];      // small integers: exact
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[GW ? k : 0][e] = fmaf(b1[k], a[e], acc[GW ? k : 0][e]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[GW ? k : 0][e] = fmaf(b0[k], asum[e], acc[GW ? k : 0][e]);
+            }
+        }
+        if (GW) {
 #pragma unroll
             for (int k = 0; k < 9; ++k)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(b0[k], asum[e], acc[k][e]);
+                for (int e = 0; e < 8; ++e)
+                    if (acc[GW ? k : 0][e] != 0.0f) atomicAdd(&gws[k * C + c0 + e], acc[GW ? k : 0][e]);
         }
-#pragma unroll
-        for (int k = 0; k < 9; ++k)
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (acc[k][e] != 0.0f) atomicAdd(&gws[k * C + c0 + e], acc[k][e]);
     }
-    __syncthreads();
-    for (int j = threadIdx.x; j < 9 * C; j += blockDim.x)
-        if (gws[j] != 0.0f) atomicAdd(p.g_w[head] + j, gws[j]);
+    if (GW) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < 9 * C; j += blockDim.x)
+            if (gws[j] != 0.0f) atomicAdd(p.g_w[head] + j, gws[j]);
+    }
 }
 
 int fill_params(const ss_conv_geom* g, ConvParams& p) {
@@ -575,8 +585,11 @@ extern "C" int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float
         long long blocks = (S + lanes - 1) / lanes;
         if (blocks > 148 * 8) blocks = 148 * 8;
         const size_t smem = (size_t)18 * p.C[i] * sizeof(float);
-        heads_src_kernel<<<(unsigned)blocks, 256, smem, st>>>(p, i);
-        count_launch();
+        long long blocks_a = (S + lanes - 1) / lanes;
+        if (blocks_a > 148 * 32) blocks_a = 148 * 32;
+        heads_src_kernel<true, false><<<(unsigned)blocks_a, 256, smem, st>>>(p, i);
+        heads_src_kernel<false, true><<<(unsigned)blocks, 256, smem, st>>>(p, i);
+        count_launch(2);
         if (check_launch("heads_src") != SS_OK) return SS_ECUDA;
     }
     return SS_OK;

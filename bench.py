@@ -340,7 +340,8 @@ def run_ours(args):
         ach = conv_gflop / conv_ms if conv_ms > 0 else 0.0      # GFLOP/ms == TFLOP/s
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.isfile(tp):
+        # the ncu capture behind traffic.json is of the headline configuration only (B=8 per GPU, T=5, 3 planes, inference)
+        if os.path.isfile(tp) and B == 8 and T == 5 and args.planes == 3 and args.mode == 'infer':
             traffic = json.load(open(tp)).get('conv_i8_dram_bytes_per_step')
         line = {
             'metric': 'event-frames/sec', 'value': value, 'unit': 'event-frames/s', 'n_gpus': world, 'steps': args.steps,

@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             int loaded_ntile = -1;
             uint32_t w_pending = 0;    // resident: bit cb set while full_w[cb] has not been observed for the current load
             uint32_t g = 0;            // global stage counter
+            uint32_t sbase = 0;        // running accumulator-slot count
             uint32_t mine = 0;         // stages issued by this thread so far
             const uint32_t tok_wait = bar_tok + 8 * (role ^ 1u);   // predecessor's "issued" token
             const uint32_t tok_post = bar_tok + 8 * role;
@@ -405,8 +406,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 }
                 for (int t0 = 0; t0 < p.T; t0 += cTC) {
                     const int tc = min(cTC, p.T - t0);
+                    // Accumulator slots rotate across items (slot = running count mod cTC) instead of restarting at 0: with a
+                    // short sequence (T = 1: the reference's forward() contract) the next tile's MMAs then run into a free slot
+                    // while the epilogue is still busy with the previous one.  T == cTC: every item uses slots 0..T-1 as before.
                     if (p.resident) {
-                        for (int s = 0; s < tc; ++s) {
+                        for (int s0 = 0; s0 < tc; ++s0) {
+                            const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);
                             // BOTH threads wait for every slot hand-back (and every weight fill below), not only the thread that
                             // issues into it: a parity wait is only meaningful if the waiter is at most one phase behind.
                             mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
@@ -424,7 +429,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             const int buf = (int)(wu % NWB);
                             mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
                             bool last_own = false;
-                            for (int s = 0; s < tc; ++s) {
+                            for (int s0 = 0; s0 < tc; ++s0) {
+                                const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);
                                 if (cb == 0) {
                                     mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
                                     slot_phase ^= 1u << s;
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             ++wu;
                         }
                     }
+                    sbase += (uint32_t)tc;
                 }
                 if (p.resident) {
                     const int nxt = it + gridDim.x;
@@ -498,6 +505,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             constexpr int NCH = HALF / 16;
             const size_t t_out = (size_t)M * p.Cout;
             uint32_t slot_phase = 0;
+            uint32_t sbase = 0;
             for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
                 const int wset = it / p.mtiles;
                 const int mt = it - wset * p.mtiles;
@@ -518,8 +526,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 const size_t o0 = live ? ((size_t)(b * p.Hout + oy) * p.Wout + ox) * p.Cout + nb : 0;
                 for (int t0 = 0; t0 < p.T; t0 += cTC) {
                     const int tc = min(cTC, p.T - t0);
-                    for (int s = 0; s < tc; ++s) {
-                        float* dst = p.g_dst + (size_t)(t0 + s) * t_out + o0;
+                    for (int s0 = 0; s0 < tc; ++s0) {
+                        const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);      // rotating slot, as in the MMA role
+                        float* dst = p.g_dst + (size_t)(t0 + s0) * t_out + o0;
                         // accumulate mode: fetch the destination BEFORE blocking on the accumulator, so the round trip to
                         // HBM overlaps the MMAs of this slot instead of stalling the adds behind it
                         float4 oldv[NCH * 4];
@@ -558,6 +567,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                                 }
                             }
                     }
+                    sbase += (uint32_t)tc;
                 }
             }
         } else {
@@ -567,6 +577,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         nc.decay = (p.neuron == SS_NEURON_PLIF) ? __ldg(p.decay) : 0.0f;
         const size_t t_out = (size_t)M * p.Cout;
         uint32_t slot_phase = 0;
+        uint32_t sbase = 0;           // running accumulator-slot count (same sequence as in the MMA role)
         int sc_ntile = -1;
         float sc[16];                 // wscale * gain (wscale is a power of two, so this product is exact)
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
@@ -624,8 +635,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             }
             for (int t0 = 0; t0 < p.T; t0 += cTC) {
                 const int tc = min(cTC, p.T - t0);
-                for (int s = 0; s < tc; ++s) {
-                    const int t = t0 + s;
+                for (int s0 = 0; s0 < tc; ++s0) {
+                    const int t = t0 + s0;
+                    const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);
                     // residual of this step was requested one step ago; request the next one before blocking
                     const uint4 rs_cur = rs_next;
                     if (use_resid && t + 1 < p.T) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + (size_t)(t + 1) * t_out + o0));
@@ -686,6 +698,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         for (int i = 0; i < 4; ++i) hp[i] = make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]);
                     }
                 }
+                sbase += (uint32_t)tc;
             }
             if (p.tsum != nullptr && live) *reinterpret_cast<uint4*>(p.tsum + o0) = make_uint4(ts[0], ts[1], ts[2], ts[3]);
             if (p.v_out != nullptr && live) {

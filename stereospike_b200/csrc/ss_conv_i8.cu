@@ -87,6 +87,27 @@ struct I8Params {
 constexpr int MODE_I8 = 0;     // forward block: u8 activations x int8 weight digit planes -> s32, neuron epilogue
 constexpr int MODE_BF16 = 1;   // gradient-side correlation: bf16 gradients x bf16 weights -> f32, store / accumulate / atomic epilogue
 
+
+// Optional instrumentation build (-DSS_ROLE_TIMING, see tools/role_timing.py): per CTA and role, cycles spent waiting on
+// each barrier class vs working, accumulated with clock64() and dumped through ss_debug_read().  Not part of the product .so.
+#ifdef SS_ROLE_TIMING
+__device__ unsigned long long ss_dbg[148 * 4 * 8];
+#define SS_T0() const long long _t0 = clock64()
+#define SS_ACC(role, slot) ss_acc[slot] += (unsigned long long)(clock64() - _t0)
+#define SS_DECL() unsigned long long ss_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long _tstart = clock64()
+#define SS_DUMP(role)                                                                              \
+    do {                                                                                           \
+        ss_acc[7] = (unsigned long long)(clock64() - _tstart);                                     \
+        if (blockIdx.x < 148)                                                                      \
+            for (int _i = 0; _i < 8; ++_i) ss_dbg[(blockIdx.x * 4 + (role)) * 8 + _i] = ss_acc[_i]; \
+    } while (0)
+#else
+#define SS_T0()
+#define SS_ACC(role, slot)
+#define SS_DECL()
+#define SS_DUMP(role)
+#endif
+
 // ------------------------------------------------------------------------------------------------ geometry
 // Source row (b*Hin + iy) read by patch row `pr` of tile row `ty`, or -1 (zero padding / gap between stacked images).
 template <int STRIDE>
@@ -282,13 +303,33 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         }
     } else if (warp < 4) {
         // ================================================================== patch producers
+        // Work unit = one 16-byte chunk of one patch pixel.  Consecutive lanes take consecutive chunks of consecutive INPUT
+        // pixels (for the parity-split stride-2 rows: alternating planes), so one warp-level cp.async reads a contiguous
+        // 512-byte run of the NHWC tensor instead of 32 separate half-sectors.
         const int tid = threadIdx.x;
         const size_t t_stride = (size_t)p.B * p.Hin * p.Win * p.Cin;
         constexpr int chunks = RB >> 4;
+        constexpr int cUNITS = cPPIX * chunks;
+        constexpr int cNU = (cUNITS + 127) / 128;     // units per producer thread
         int stage = 0;
         uint32_t phase = 0;
         int itcount = 0;
+        // loop-invariant part of every unit: its patch row / column and its swizzled shared-memory offset
+        int urc[cNU];            // patch row * 32 + patch column, or -1 past the end of the patch
+        uint32_t soff[cNU];
+#pragma unroll
+        for (int i = 0; i < cNU; ++i) {
+            const int u = tid + i * 128;
+            const int pixl = u / chunks, ch = u - pixl * chunks;
+            int pr = pixl / cPWp;
+            int pc = pixl - pr * cPWp;
+            if (STRIDE == 2) pc = (pc & 1) * cPWhalf + (pc >> 1);      // neighbours in memory = alternating parity planes
+            soff[i] = swizzle_off((uint32_t)((pr * cPWp + pc) * RB + ch * 16), swz_mask);
+            urc[i] = u < cUNITS ? pr * 32 + pc : -1;
+        }
+        SS_DECL();
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x, ++itcount) {
+            SS_T0();
             const int ntile = it / p.mtiles;
             const int mt = it - ntile * p.mtiles;
             const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
@@ -297,18 +338,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             if (tid < cPH) rs[tid] = row_source<STRIDE>(p, ty, tid);
             if (tid >= 64 && tid - 64 < cPWp) cs[tid - 64] = col_source<STRIDE, cPWhalf>(p, tx, tid - 64);
             named_sync(1, 128);
-            int goff[cNPIX];
+            int goff[cNU];
 #pragma unroll
-            for (int i = 0; i < cNPIX; ++i) {
-                const int pix = tid + i * 128;
+            for (int i = 0; i < cNU; ++i) {
                 goff[i] = -2;
-                if (pix < cPPIX) {
-                    const int pr = pix / cPWp;
-                    const int pc = pix - pr * cPWp;
-                    const int r = rs[pr], c = cs[pc];
-                    goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * p.Cin : -1;
+                if (urc[i] >= 0) {
+                    const int r = rs[urc[i] >> 5], c = cs[urc[i] & 31];
+                    const int ch = (tid + i * 128) % chunks;
+                    goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * p.Cin + ch * 16 : -1;
                 }
             }
+            SS_ACC(0, 0);     // geometry
             for (int t0 = 0; t0 < p.T; t0 += cTC) {
                 const int tc = min(cTC, p.T - t0);
                 const int n_outer = p.resident ? tc : p.ncb;
@@ -317,22 +357,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     for (int in = 0; in < n_inner; ++in) {
                         const int cb = p.resident ? in : o;
                         const int t = t0 + (p.resident ? o : in);
-                        mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
+                        {
+                            SS_T0();
+                            mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
+                            SS_ACC(0, 1);     // wait for a free patch stage
+                        }
+                        SS_T0();
                         const uint8_t* xt = p.x + (size_t)t * t_stride + cb * RB;
                         const uint32_t dst0 = patch_base + (uint32_t)stage * cPB;
 #pragma unroll
-                        for (int i = 0; i < cNPIX; ++i) {
+                        for (int i = 0; i < cNU; ++i) {
                             if (goff[i] != -2) {
-                                const uint32_t off = (uint32_t)(tid + i * 128) * RB;
                                 const bool ok = goff[i] >= 0;
-                                const uint8_t* src = ok ? xt + goff[i] : p.x;
-#pragma unroll
-                                for (int c = 0; c < chunks; ++c)
-                                    cp_async_16(dst0 + swizzle_off(off + c * 16, swz_mask), ok ? src + c * 16 : src, ok ? 16u : 0u);
+                                cp_async_16(dst0 + soff[i], ok ? xt + goff[i] : p.x, ok ? 16u : 0u);
                             }
                         }
                         // the barrier arrival fires when this thread's copies have landed; nobody blocks here
                         cp_async_arrive_noinc(bar_full_p + 8 * stage);
+                        SS_ACC(0, 2);         // copy issue
                         if (++stage == p.NPS) {
                             stage = 0;
                             phase ^= 1u;
@@ -341,6 +383,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 }
             }
         }
+        if (threadIdx.x == 0) SS_DUMP(0);
     } else if (warp == 4 || warp == 6) {
         // ================================================================== MMA issuers: two elected threads (warps 4 and 6) ping-pong
         // The tensor pipe's issue queue is only ~3 MMAs deep and the bookkeeping between two stages (barrier waits, proxy
@@ -364,6 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             uint32_t w_pending = 0;    // resident: bit cb set while full_w[cb] has not been observed for the current load
             uint32_t g = 0;            // global stage counter
             uint32_t sbase = 0;        // running accumulator-slot count
+            SS_DECL();
             uint32_t mine = 0;         // stages issued by this thread so far
             const uint32_t tok_wait = bar_tok + 8 * (role ^ 1u);   // predecessor's "issued" token
             const uint32_t tok_post = bar_tok + 8 * role;
@@ -375,20 +419,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 const bool own = (g & 1u) == role;
                 ++g;
                 if (own) {
-                    mbar_wait(bar_full_p + 8 * stage, phase);
+                    {
+                        SS_T0();
+                        mbar_wait(bar_full_p + 8 * stage, phase);
+                        SS_ACC(1, 0);         // wait for the patch
+                    }
                     fence_proxy_async();   // cp.async wrote the patch through the generic proxy; the MMA reads it through the async proxy
                     const uint64_t a0 = a_stage0 + (uint64_t)((uint32_t)stage * (uint32_t)(cPB >> 4));
                     const uint64_t b0 = b_buf0 + (uint64_t)((uint32_t)wbuf * (uint32_t)(cWB >> 4));
                     const uint32_t d = tmem_base + (uint32_t)(slot * cN);
                     // everything is ready: wait until the other thread has issued the previous stage
-                    mbar_wait(tok_wait, role == 0 ? ((mine & 1u) ^ 1u) : (mine & 1u));
+                    {
+                        SS_T0();
+                        mbar_wait(tok_wait, role == 0 ? ((mine & 1u) ^ 1u) : (mine & 1u));
+                        SS_ACC(1, 1);         // wait for the other issuer's token
+                    }
                     ++mine;
+                    SS_T0();
                     tc_fence_after();
                     umma_i8<MODE>(d, a0, b0, idesc, first ? 0u : 1u);
                     issue_taps<MODE, KS, STRIDE, RB, cN, cPWp, cPWhalf>(d, a0, b0, idesc);
                     tc_fence_before();
                     mbar_arrive(tok_post);
                     umma_commit(bar_empty_p + 8 * stage);
+                    SS_ACC(1, 2);             // issue
                 }
                 if (++stage == p.NPS) {
                     stage = 0;
@@ -414,7 +468,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);
                             // BOTH threads wait for every slot hand-back (and every weight fill below), not only the thread that
                             // issues into it: a parity wait is only meaningful if the waiter is at most one phase behind.
-                            mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                            {
+                                SS_T0();
+                                mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                                SS_ACC(1, 3);     // wait for a free accumulator slot
+                            }
                             slot_phase ^= 1u << s;
                             bool last_own = false;
                             for (int cb = 0; cb < p.ncb; ++cb) {
@@ -427,12 +485,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     } else {
                         for (int cb = 0; cb < p.ncb; ++cb) {
                             const int buf = (int)(wu % NWB);
-                            mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+                            {
+                                SS_T0();
+                                mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+                                SS_ACC(1, 4);     // wait for streamed weights
+                            }
                             bool last_own = false;
                             for (int s0 = 0; s0 < tc; ++s0) {
                                 const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);
                                 if (cb == 0) {
+                                    SS_T0();
                                     mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                                    SS_ACC(1, 3);
                                     slot_phase ^= 1u << s;
                                 }
                                 last_own = do_stage(buf, s, cb == 0);
@@ -451,6 +515,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         for (int cb = 0; cb < p.ncb; ++cb) umma_commit(bar_empty_w + 8 * cb);
                 }
             }
+            SS_DUMP(1 + (int)role);
         }
         __syncwarp();
     } else if (warp == 5) {
@@ -578,6 +643,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         const size_t t_out = (size_t)M * p.Cout;
         uint32_t slot_phase = 0;
         uint32_t sbase = 0;           // running accumulator-slot count (same sequence as in the MMA role)
+        SS_DECL();
         int sc_ntile = -1;
         float sc[16];                 // wscale * gain (wscale is a power of two, so this product is exact)
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
@@ -641,7 +707,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     // residual of this step was requested one step ago; request the next one before blocking
                     const uint4 rs_cur = rs_next;
                     if (use_resid && t + 1 < p.T) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + (size_t)(t + 1) * t_out + o0));
-                    mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
+                    {
+                        SS_T0();
+                        mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
+                        SS_ACC(3, 0);         // wait for the accumulator
+                    }
                     slot_phase ^= 1u << s;
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * cN + hf * 16);
@@ -707,6 +777,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 for (int i = 0; i < 4; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
         }
+        if (threadIdx.x == 256) SS_DUMP(3);
         }   // MODE_I8
     }
 
@@ -1300,3 +1371,9 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
     count_launch();
     return check_launch("corr_bf16");
 }
+
+#ifdef SS_ROLE_TIMING
+extern "C" int ss_debug_read(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, ss::ss_dbg, sizeof(unsigned long long) * 148 * 4 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif

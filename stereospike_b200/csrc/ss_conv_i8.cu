@@ -56,6 +56,7 @@ struct I8Params {
     int PH, PWp, PWhalf, ppix;
     int HsO, Hup, Wup;
     int tiles_x, mtiles, nitems;
+    uint32_t m_mtiles, m_tiles_x, m_per, m_hso;   // ceil(2^32 / d): exact unsigned division by multiply-high while n * d < 2^32 (0 = use '/')
     int Hv, Wv;            // iteration space of the tiles (== Hout, Wout except for the folded / band passes of an upsampled conv)
     int mode;              // SS_TILES_*
     int nclass;            // weight sets per output-channel tile (folded pass: 4 = {L,M} x {L,M}), else 1
@@ -108,13 +109,24 @@ __device__ unsigned long long ss_dbg[148 * 4 * 8];
 #define SS_DUMP(role)
 #endif
 
+// n / d for a loop-invariant divisor: one multiply-high instead of the ~35-instruction software division (the tile
+// decoding sits on the producers' and the epilogue's per-item critical path, which is what bounds single-step calls)
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+    return magic != 0u ? (int)__umulhi((uint32_t)n, magic) : n / d;
+}
+__host__ inline uint32_t div_magic(long long d, long long n_max) {
+    // valid while n_max * d < 2^32 (error term n * (magic * d - 2^32) < 2^32)
+    if (d <= 1 || n_max * d >= (1LL << 32)) return 0u;
+    return (uint32_t)(((1ULL << 32) + (unsigned long long)d - 1ULL) / (unsigned long long)d);
+}
+
 // ------------------------------------------------------------------------------------------------ geometry
 // Source row (b*Hin + iy) read by patch row `pr` of tile row `ty`, or -1 (zero padding / gap between stacked images).
 template <int STRIDE>
 __device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr) {
     const int gi = ty * 16 * STRIDE + pr;
     const int per = STRIDE * p.HsO;
-    int b = gi / per;
+    int b = fast_div(gi, per, p.m_per);
     int local = gi - b * per;
     if (p.mode == SS_TILES_ROW_BANDS) {
         // stacked mini-images: (sample, band); `local` indexes the upsampled rows band_start .. band_start + band_rows + ks - 2
@@ -267,9 +279,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         const uint32_t row_base = patch_base + (uint32_t)r * 128u;
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
             const int mt = it % p.mtiles;
-            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
             const int so = ty * 16 + (r >> 3);
-            const int b = so / p.HsO;
+            const int b = fast_div(so, p.HsO, p.m_hso);
             const int oy = so - b * p.HsO;
             const int ox = tx * 8 + (r & 7);
             uint32_t vmask = 0;
@@ -330,9 +342,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         SS_DECL();
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x, ++itcount) {
             SS_T0();
-            const int ntile = it / p.mtiles;
+            const int ntile = fast_div(it, p.mtiles, p.m_mtiles);
             const int mt = it - ntile * p.mtiles;
-            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
             int* rs = rowsrc + (itcount & 1) * 40;
             int* cs = colsrc + (itcount & 1) * 24;
             if (tid < cPH) rs[tid] = row_source<STRIDE>(p, ty, tid);
@@ -452,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             };
 
             for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-                const int ntile = it / p.mtiles;   // weight-set index: (output-channel tile, class)
+                const int ntile = fast_div(it, p.mtiles, p.m_mtiles);   // weight-set index: (output-channel tile, class)
                 if (p.resident && ntile != loaded_ntile) {
                     loaded_ntile = ntile;
                     w_pending = (1u << p.ncb) - 1u;
@@ -531,7 +543,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 for (int o = 0; o < cWB; o += 16384) bulk_load(dst + o, src + o, (uint32_t)min(16384, cWB - o), full);
             };
             for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-                const int ntile = it / p.mtiles;
+                const int ntile = fast_div(it, p.mtiles, p.m_mtiles);
                 if (p.resident) {
                     if (ntile != loaded_ntile) {
                         for (int cb = 0; cb < p.ncb; ++cb) {
@@ -572,12 +584,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             uint32_t slot_phase = 0;
             uint32_t sbase = 0;
             for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-                const int wset = it / p.mtiles;
+                const int wset = fast_div(it, p.mtiles, p.m_mtiles);
                 const int mt = it - wset * p.mtiles;
-                const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+                const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
                 const int cls = wset % p.nclass;
                 const int so = ty * 16 + g;
-                const int b = so / p.HsO;
+                const int b = fast_div(so, p.HsO, p.m_hso);
                 int oy = so - b * p.HsO;
                 int ox = tx * 8 + j;
                 bool live = oy < p.Hv && ox < p.Wv && b < p.B;
@@ -647,13 +659,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         int sc_ntile = -1;
         float sc[16];                 // wscale * gain (wscale is a power of two, so this product is exact)
         for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-            const int ntile = it / p.mtiles;
+            const int ntile = fast_div(it, p.mtiles, p.m_mtiles);
             const int mt = it - ntile * p.mtiles;
-            const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+            const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
             const int wset = ntile;                       // it / mtiles: (output-channel tile, class)
             const int cls = wset % p.nclass;
             const int so = ty * 16 + g;
-            int b = so / p.HsO;
+            int b = fast_div(so, p.HsO, p.m_hso);
             int oy = so - b * p.HsO;
             int ox = tx * 8 + j;
             bool live = oy < p.Hv && ox < p.Wv;
@@ -1120,6 +1132,10 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         return SS_EINVAL;
     }
     p.nitems = (int)nitems;
+    p.m_mtiles = div_magic(p.mtiles, nitems);
+    p.m_tiles_x = div_magic(p.tiles_x, p.mtiles);
+    p.m_per = div_magic((long long)p.stride * p.HsO, (long long)p.stride * (rows + 64));
+    p.m_hso = div_magic(p.HsO, rows + 64);
     p.TC = 512 / p.N;
     if (p.TC > MAX_SLOTS) p.TC = MAX_SLOTS;
     p.WB = p.ntaps * p.N * p.RB;
@@ -1308,6 +1324,10 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
         return SS_EINVAL;
     }
     p.nitems = (int)nitems;
+    p.m_mtiles = div_magic(p.mtiles, nitems);
+    p.m_tiles_x = div_magic(p.tiles_x, p.mtiles);
+    p.m_per = div_magic((long long)p.stride * p.HsO, (long long)p.stride * (rows + 64));
+    p.m_hso = div_magic(p.HsO, rows + 64);
     p.TC = 512 / p.N;
     if (p.TC > MAX_SLOTS) p.TC = MAX_SLOTS;
     p.WB = p.ntaps * p.N * p.RB;

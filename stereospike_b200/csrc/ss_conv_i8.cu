@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     int* colsrc = rowsrc + 80;                               // [2][24]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
     // bars: full_p[8], empty_p[8], full_w[2], empty_w[2], full_a[8], empty_a[8], tok[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+    // (+ raw_full[2], raw_empty[2] of the first-layer producers at bars + 38)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
-            mbar_init(bar_full_p + 8 * s, 128);
+            mbar_init(bar_full_p + 8 * s, FIRST ? 64 : 128);
             mbar_init(bar_empty_p + 8 * s, 1);
         }
         for (int s = 0; s < NWB; ++s) {
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         }
         mbar_init(bar_tok, 1);
         mbar_init(bar_tok + 8, 1);
+        for (int s = 0; s < 4; ++s) mbar_init(smem_u32(bars + 38 + s), 64);
         fence_barrier_init();
     }
     if (warp == 4) {
@@ -260,56 +262,102 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     constexpr uint32_t swz_mask = (uint32_t)(RB >> 4) - 1u;  // 32 -> 1, 64 -> 3, 128 -> 7
 
     if (warp < 4 && FIRST) {
-        // ================================================================== first-layer im2col producers
-        // Thread r owns tile row r (one output pixel): 25 asynchronous 4-byte copies (one per tap, zero-filled outside the
-        // image) straight into the swizzled 128-byte im2col row; bytes 100..127 of every row are zeroed once.  No register
-        // staging and no producer-side fence, so nothing in this loop waits for memory.
-        const int r = threadIdx.x;
+        // ================================================================== first-layer im2col producers (two steps)
+        // The im2col row of a pixel is 25 four-byte taps; copying them one by one (25 cp.async per pixel and timestep) made
+        // this layer producer-bound.  Instead warps 0-1 stage the tile's raw 20 x 12-pixel halo patch (960 B) with 8-byte
+        // copies into a small double buffer, and warps 2-3 expand it into the swizzled 128-byte im2col rows with ordinary
+        // shared-memory loads / 16-byte stores (bytes 100..127 = 0).  Only the expanding warps fence towards the async proxy,
+        // and they never have global loads in flight, so the fence does not wait for memory.
+        constexpr int PH5 = 20, PW5 = 12;            // halo patch of the real 5x5 filter (the template's KS is the single im2col "tap")
+        uint8_t* raw = tail + 1024;                  // [2][1024]
+        const uint32_t bar_raw_full = smem_u32(bars + 38);
+        const uint32_t bar_raw_empty = smem_u32(bars + 40);
         const size_t t_stride = (size_t)p.B * p.Hin * p.Win * 4;
-        constexpr int ks = 5;                    // real filter (the template's KS is the single im2col "tap")
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int st = 0; st < p.NPS; ++st) {
-            uint8_t* row = sm + (size_t)p.nwb * cWB + (size_t)st * cPB + (size_t)r * 128;
-            *reinterpret_cast<uint4*>(row + ((6 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // bytes 96..111 (tap 24 lands in 96..99)
-            *reinterpret_cast<uint4*>(row + ((7 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // bytes 112..127
-        }
-        fence_proxy_async();
-        named_sync(1, 128);
-        const uint32_t row_base = patch_base + (uint32_t)r * 128u;
-        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-            const int mt = it % p.mtiles;
-            const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
-            const int so = ty * 16 + (r >> 3);
-            const int b = fast_div(so, p.HsO, p.m_hso);
-            const int oy = so - b * p.HsO;
-            const int ox = tx * 8 + (r & 7);
-            uint32_t vmask = 0;
-            if (b < p.B && oy < p.Hout && ox < p.Wout) {
-                for (int ky = 0; ky < ks; ++ky)
-                    for (int kx = 0; kx < ks; ++kx) {
-                        const int iy = oy + ky - p.pad, ix = ox + kx - p.pad;
-                        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) vmask |= 1u << (ky * ks + kx);
-                    }
+        if (warp < 2) {
+            const int tid = threadIdx.x;             // 0..63
+            // two pixels per copy when every pair stays 8-byte aligned and on one side of the image border
+            const bool pair = (p.Win & 1) == 0 && (p.pad & 1) == 0;
+            const int upr = pair ? PW5 / 2 : PW5;    // copies per patch row
+            const int nunits = PH5 * upr;
+            int urow[4], useg[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int u = tid + i * 64;
+                urow[i] = u < nunits ? u / upr : -1;
+                useg[i] = u - (u / upr) * upr;
             }
-            const long long o00 = ((long long)(b * p.Hin + oy - p.pad) * p.Win + (ox - p.pad)) * 4;
-            for (int t = 0; t < p.T; ++t) {
-                mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
-                const uint8_t* xt = p.x + (size_t)t * t_stride + o00;
-                const uint32_t dst = row_base + (uint32_t)stage * cPB;
+            int rb = 0, itcount = 0;
+            uint32_t rphase = 0;
+            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x, ++itcount) {
+                const int mt = it % p.mtiles;
+                const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
+                int* rs = rowsrc + (itcount & 1) * 40;
+                int* cs = colsrc + (itcount & 1) * 24;
+                if (tid < PH5) rs[tid] = row_source<1>(p, ty, tid);
+                if (tid >= 32 && tid - 32 < PW5) cs[tid - 32] = col_source<1, 10>(p, tx, tid - 32);
+                named_sync(1, 64);
+                int goff[4];
 #pragma unroll
-                for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 5; ++kx) {
-                        const int tap = ky * 5 + kx;
-                        const bool ok = (vmask >> tap) & 1u;
-                        const uint32_t d = dst + ((((uint32_t)tap >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)tap & 3u) * 4u;
-                        cp_async_4(d, ok ? xt + ((long long)ky * p.Win + kx) * 4 : p.x, ok ? 4u : 0u);
+                for (int i = 0; i < 4; ++i) {
+                    goff[i] = -2;
+                    if (urow[i] >= 0) {
+                        const int r = rs[urow[i]], c = cs[pair ? 2 * useg[i] : useg[i]];
+                        goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * 4 : -1;
                     }
-                cp_async_arrive_noinc(bar_full_p + 8 * stage);
-                if (++stage == p.NPS) {
-                    stage = 0;
-                    phase ^= 1u;
+                }
+                for (int t = 0; t < p.T; ++t) {
+                    mbar_wait(bar_raw_empty + 8 * rb, rphase ^ 1u);
+                    const uint8_t* xt = p.x + (size_t)t * t_stride;
+                    const uint32_t dst = smem_u32(raw) + (uint32_t)rb * 1024u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (goff[i] != -2) {
+                            const bool ok = goff[i] >= 0;
+                            const uint32_t d = dst + (uint32_t)(urow[i] * (PW5 * 4) + useg[i] * (pair ? 8 : 4));
+                            if (pair) cp_async_8(d, ok ? xt + goff[i] : p.x, ok ? 8u : 0u);
+                            else cp_async_4(d, ok ? xt + goff[i] : p.x, ok ? 4u : 0u);
+                        }
+                    }
+                    cp_async_arrive_noinc(bar_raw_full + 8 * rb);
+                    rb ^= 1;
+                    if (rb == 0) rphase ^= 1u;
+                }
+            }
+        } else {
+            const int bt = threadIdx.x - 64;         // 0..63: expands tile pixels bt and bt + 64
+            int stage = 0, rb = 0;
+            uint32_t phase = 0, rphase = 0;
+            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+                for (int t = 0; t < p.T; ++t) {
+                    mbar_wait(bar_raw_full + 8 * rb, rphase);
+                    mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
+                    const uint8_t* rw = raw + rb * 1024;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = bt + h * 64;
+                        const int g = r >> 3, j = r & 7;
+                        uint32_t w[32];
+#pragma unroll
+                        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 5; ++kx)
+                                w[ky * 5 + kx] = *reinterpret_cast<const uint32_t*>(rw + ((g + ky) * PW5 + j + kx) * 4);
+#pragma unroll
+                        for (int k = 25; k < 32; ++k) w[k] = 0u;
+                        uint8_t* row = sm + (size_t)p.nwb * cWB + (size_t)stage * cPB + (size_t)r * 128;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                    }
+                    fence_proxy_async();      // generic-proxy stores -> visible to the MMA's async-proxy reads
+                    mbar_arrive(bar_full_p + 8 * stage);
+                    mbar_arrive(bar_raw_empty + 8 * rb);
+                    if (++stage == p.NPS) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                    rb ^= 1;
+                    if (rb == 0) rphase ^= 1u;
                 }
             }
         }
@@ -1105,8 +1153,6 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         p.HsO = tm->band_rows + g->ks - 1;    // one stacked mini-image per (sample, band)
     } else if (up) {
         p.HsO = p.Hup;
-    } else if (first) {
-        p.HsO = g->Hout;   // explicit im2col rows: no halo shared between rows, so no gap rows between stacked images
     } else {
         // Stacked output rows per image.  Rows of the next image start stride*HsO input rows later; that must be
         // past this image's real rows (Hin + pad) and far enough that a tap reaching below the last output row
@@ -1146,7 +1192,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         set_error("ss_conv_i8_fwd: patch too large");
         return SS_EUNSUPPORTED;
     }
-    const int tail_bytes = 512 + 40 * 8 + 64;
+    const int tail_bytes = 1024 + 2048 + 64;   // tables + barriers, first-layer raw patch double buffer
     const int budget = 227 * 1024 - 1024 - tail_bytes - p.nwb * p.WB;
     int nps = budget / p.PB;
     if (nps > MAX_STAGES) nps = MAX_STAGES;
@@ -1334,7 +1380,7 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
     p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
     p.resident = p.ncb <= NWB ? 1 : 0;
     p.nwb = p.ncb < NWB ? p.ncb : NWB;
-    const int tail_bytes = 512 + 40 * 8 + 64;
+    const int tail_bytes = 1024 + 2048 + 64;   // tables + barriers, first-layer raw patch double buffer
     const int budget = 227 * 1024 - 1024 - tail_bytes - p.nwb * p.WB;
     int nps = budget / p.PB;
     if (nps > MAX_STAGES) nps = MAX_STAGES;

@@ -493,8 +493,8 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     const int SH = (g->ks == 5 && g->Cout <= 32 && g->stride == 1) ? 4 : ((g->ks == 5 && g->Cout <= 64) ? 2 : 1);
     p.tiles_x = (g->Wout + (SH - 1) + 7) / 8;
     p.mtiles = (int)((rows + 15) / 16) * p.tiles_x;
-    // input channels per CTA: 32 where the patch still leaves room for >= 3 pipeline stages (not the strided 5x5 patch)
-    const int NB = (!first && g->Cin % 32 == 0 && g->stride == 1) ? 32 : 16;
+    // input channels per CTA
+    const int NB = (!first && g->Cin % 32 == 0) ? 32 : 16;
     const int NS = SH == 1 ? g->ks : (g->stride == 1 ? (g->ks + SH - 1) / SH : 3);
     int GK = (512 / NB) / NS;
     if (GK > g->ks) GK = g->ks;
@@ -557,6 +557,8 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     SS_TRY_WG(5, 1, 16, false, 1)
     SS_TRY_WG(5, 1, 16, false, 2)
     SS_TRY_WG(5, 1, 16, false, 4)
+    SS_TRY_WG(5, 2, 32, false, 1)
+    SS_TRY_WG(5, 2, 32, false, 2)
     SS_TRY_WG(5, 2, 16, false, 1)
     SS_TRY_WG(5, 2, 16, false, 2)
     SS_TRY_WG(3, 1, 32, false, 1)

@@ -24,9 +24,10 @@ def run(name, kind, Cin, Cout, ks, Hin, Win, stride, pad, up, T, B):
         geom = ops.BlockGeom('upconv', Cin, Cout, ks, Hin, Win, up[0], up[1])
     x = (torch.rand(T, B, Hin, Win, Cin, device=dev) < 0.1).to(torch.uint8)
     w = (torch.rand(Cout, Cin, ks, ks, device=dev) * 2 - 1) / (Cin * ks * ks) ** 0.5
-    q, sc, _ = ops.pack_weights_i8(w, 3)
+    q, sc, _ = ops.pack_weights_i8(w, 3, cin_pad=4 if Cin <= 4 else None)
     for _ in range(2):
-        ops.conv_i8_fwd(x, geom, q, sc, T=T, B=B, neuron=1, gain=15.0, v_th=1.0, v_reset=0.0, tau=3.0, want_v_out=True)
+        ops.conv_i8_fwd(x, geom, q, sc, T=T, B=B, neuron=1, gain=15.0, v_th=1.0, v_reset=0.0, tau=3.0, want_v_out=True,
+                        cin=Cin)
     torch.cuda.synchronize()
     buf = np.zeros(148 * 4 * 8, dtype=np.uint64)
     assert L.ss_debug_read(buf.ctypes.data) == 0
@@ -40,6 +41,7 @@ def run(name, kind, Cin, Cout, ks, Hin, Win, stride, pad, up, T, B):
 
 
 for T in (1, 5):
+    run('bottom', 'conv', 4, 32, 5, 260, 346, 1, 2, None, T, 16)
     run('conv1', 'conv', 32, 64, 5, 260, 346, 2, 2, None, T, 16)
     run('conv3', 'conv', 128, 256, 5, 65, 87, 2, 2, None, T, 16)
     run('deconv1', 'upconv', 64, 32, 5, 130, 173, 1, 0, (260, 346), T, 16)

@@ -346,7 +346,8 @@ def run_ours(args):
         line = {
             'metric': 'event-frames/sec', 'value': value, 'unit': 'event-frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'u8 x s8 -> s32 (tcgen05 kind::i8, %d weight digit planes), fp32 neuron state' % args.planes,
+            'vs_baseline': None, 'dtype': 'u8 x s8 -> s32 (tcgen05 kind::i8, %d weight digit planes), fp32 neuron state' % args.planes +
+                                           ('; backward bf16 x bf16 -> f32 (tcgen05 kind::f16), fp32 surrogate scan' if args.mode == 'train' else ''),
             'data': 'synthetic', 'config': workload_config(args, B),
             'e2e': {'value': e2e_val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': xs_host[0].numel() * 4,
                     'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': ms_e2e / args.steps,

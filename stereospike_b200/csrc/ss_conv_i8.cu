@@ -201,8 +201,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     constexpr int cWB = cNTAPS * cN * RB;
     constexpr int cPB = (cPPIX * RB + 1023) / 1024 * 1024;
     constexpr int cTC = (512 / cN) < MAX_SLOTS ? (512 / cN) : MAX_SLOTS;
-    constexpr int cKSTEPS = RB / 32;
-    constexpr int cNPIX = (cPPIX + 127) / 128;   // patch pixels per producer thread
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;

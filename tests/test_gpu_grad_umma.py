@@ -13,7 +13,7 @@ CASES = [
     # kind, Cin, Cout, ks, Hin, Win, stride, pad, up, T, B
     ('conv', 64, 64, 3, 17, 22, 1, 1, None, 2, 3),       # bottleneck geometry
     ('conv', 32, 64, 5, 37, 45, 2, 2, None, 2, 2),       # strided encoder conv (odd sizes)
-    ('conv', 64, 32, 5, 40, 30, 2, 2, None, 3, 1),       # even sizes, 32 -> ntile 32? (Cin 64 -> ntile 64)
+    ('conv', 64, 32, 5, 40, 30, 2, 2, None, 3, 1),       # strided, even sizes, 32 output channels (4 shifted copies in wgrad)
     ('conv', 32, 32, 5, 21, 19, 2, 2, None, 1, 2),       # destination 32 channels (ntile 32)
     ('upconv', 64, 32, 5, 17, 22, 1, 0, (33, 44), 2, 2),  # decoder geometry
     ('upconv', 128, 64, 5, 9, 12, 1, 0, (20, 23), 5, 1),

@@ -15,3 +15,11 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_sessionstart(session):
+    """A fresh checkout has no in-tree library (*.so is git-ignored): build it once instead of failing every test.
+    An existing library is left alone (the GPU box receives the one built here)."""
+    from stereospike_b200 import _lib, build
+    if not os.path.isfile(_lib.LIB_PATH) and os.path.isfile(os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')):
+        build.build()

@@ -34,6 +34,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ss_common.cuh"
 #include "ss_umma.cuh"
@@ -56,6 +57,8 @@ struct I8Params {
     int PH, PWp, PWhalf, ppix;
     int HsO, Hup, Wup;
     int tiles_x, mtiles, nitems;
+    int mtiles2, nitems2;                          // CTA pairs: pairs of m-tiles per weight set, items per pair walk
+    uint32_t m_mtiles2;
     uint32_t m_mtiles, m_tiles_x, m_per, m_hso;   // ceil(2^32 / d): exact unsigned division by multiply-high while n * d < 2^32 (0 = use '/')
     int Hv, Wv;            // iteration space of the tiles (== Hout, Wout except for the folded / band passes of an upsampled conv)
     int mode;              // SS_TILES_*
@@ -189,7 +192,10 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // FIRST: the first layer (Cin <= 4, event-count frames u8 [T][B][H][W][4]).  Its K = ks*ks*4 <= 128 is one swizzle row,
 // so the producers assemble an explicit im2col tile (KS = 1 "tap", RB = 128: row = output pixel, byte = tap*4 + c) with
 // L1-cached 4-byte loads instead of a halo patch -- 4 MMAs per tile instead of ks*ks*(32-channel padded blocks).
-template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8>
+// PAIR: two CTAs of a 2-cluster process two m-tiles against the same weight set with one tcgen05.mma.cta_group::2 (M = 256):
+// each CTA stages its own patch and HALF of the weight rows, so the shared-memory operand feed per MMA drops from 7 KB to
+// 5.5 KB per SM (N = 96) and the MMA leaves the feed-bound regime.  Rank 0 issues; rank 1 relays its producers' barriers.
+template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
@@ -198,7 +204,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
     constexpr int cPH = 15 * STRIDE + KS;
     constexpr int cPPIX = cPH * cPWp;
-    constexpr int cWB = cNTAPS * cN * RB;
+    constexpr int cNB = PAIR ? cN / 2 : cN;                 // weight rows (of the MMA's N) held by this CTA
+    constexpr int cWB = cNTAPS * cNB * RB;
+    constexpr int MMA_MODE = PAIR ? 2 : MODE;
+    static_assert(!PAIR || (MODE == MODE_I8 && !FIRST && cN % 16 == 0), "CTA pairs: int8 forward blocks only");
     constexpr int cPB = (cPPIX * RB + 1023) / 1024 * 1024;
     constexpr int cTC = (512 / cN) < MAX_SLOTS ? (512 / cN) : MAX_SLOTS;
     extern __shared__ uint8_t smem_raw[];
@@ -214,7 +223,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
     // bars: full_p[8], empty_p[8], full_w[2], empty_w[2], full_a[8], empty_a[8], tok[2]
     // (+ raw_full[2], raw_empty[2] of the first-layer producers at bars + 38)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+    // (+ CTA pairs: peer_full_p[8] at bars + 42, peer_full_w[2] at bars + 50: the peer CTA's producers, relayed to rank 0)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -225,6 +235,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     const uint32_t bar_full_a = smem_u32(bars + 20);
     const uint32_t bar_empty_a = smem_u32(bars + 28);
     const uint32_t bar_tok = smem_u32(bars + 36);
+    const uint32_t bar_peer_p = smem_u32(bars + 42);
+    const uint32_t bar_peer_w = smem_u32(bars + 50);
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    // item walk: a pair shares the weight set and takes m-tiles 2q, 2q+1
+    const int it0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int its = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int mt_per = PAIR ? p.mtiles2 : p.mtiles;            // items per weight set
+    const uint32_t m_mt_per = PAIR ? p.m_mtiles2 : p.m_mtiles;
+    const int nit = PAIR ? p.nitems2 : p.nitems;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
@@ -237,20 +256,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         }
         for (int s = 0; s < MAX_SLOTS; ++s) {
             mbar_init(bar_full_a + 8 * s, 1);
-            mbar_init(bar_empty_a + 8 * s, 256);
+            mbar_init(bar_empty_a + 8 * s, PAIR ? 512 : 256);
         }
         mbar_init(bar_tok, 1);
         mbar_init(bar_tok + 8, 1);
         for (int s = 0; s < 4; ++s) mbar_init(smem_u32(bars + 38 + s), 64);
+        for (int s = 0; s < 10; ++s) mbar_init(bar_peer_p + 8 * s, 1);
         fence_barrier_init();
     }
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anybody arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the previous
@@ -286,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             }
             int rb = 0, itcount = 0;
             uint32_t rphase = 0;
-            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x, ++itcount) {
+            for (int it = it0; it < nit; it += its, ++itcount) {
                 const int mt = it % p.mtiles;
                 const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
                 int* rs = rowsrc + (itcount & 1) * 40;
@@ -325,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const int bt = threadIdx.x - 64;         // 0..63: expands tile pixels bt and bt + 64
             int stage = 0, rb = 0;
             uint32_t phase = 0, rphase = 0;
-            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+            for (int it = it0; it < nit; it += its) {
                 for (int t = 0; t < p.T; ++t) {
                     mbar_wait(bar_raw_full + 8 * rb, rphase);
                     mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
@@ -386,10 +413,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             urc[i] = u < cUNITS ? pr * 32 + pc : -1;
         }
         SS_DECL();
-        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x, ++itcount) {
+        for (int it = it0; it < nit; it += its, ++itcount) {
             SS_T0();
-            const int ntile = fast_div(it, p.mtiles, p.m_mtiles);
-            const int mt = it - ntile * p.mtiles;
+            const int ntile = fast_div(it, mt_per, m_mt_per);
+            const int mt = PAIR ? 2 * (it - ntile * mt_per) + (int)crank : it - ntile * mt_per;   // (an odd tail tile is all padding)
             const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
             int* rs = rowsrc + (itcount & 1) * 40;
             int* cs = colsrc + (itcount & 1) * 24;
@@ -449,11 +476,55 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         // issuing thread (measured with the SS_MMA_TIMING build).  So stage g is issued by thread g & 1: while one thread's
         // 25 MMAs drain, the other has already waited for its patch, fenced and built its descriptors, and only waits for the
         // "issued" token of its predecessor.  Both threads walk the same loop nest and keep identical phase bookkeeping.
-        if (elect_one()) {
+        if (PAIR && crank != 0u) {
+            // ---------------------------------------------------------- peer CTA of a pair: no MMA issue here.  One thread of
+            // warp 4 forwards "patch stage filled", one of warp 6 "weight half loaded" to rank 0, in the producers' order.
+            if (elect_one()) {
+                if (warp == 4) {
+                    int stage = 0;
+                    uint32_t phase = 0;
+                    for (int it = it0; it < nit; it += its)
+                        for (int k = 0; k < p.T * p.ncb; ++k) {
+                            mbar_wait(bar_full_p + 8 * stage, phase);
+                            fence_proxy_async();     // our cp.async writes -> the tensor core's async-proxy reads of OUR shared memory
+                            mbar_arrive_cluster(mapa_u32(bar_peer_p + 8 * stage, 0u));
+                            if (++stage == p.NPS) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                } else {
+                    uint32_t wu = 0;
+                    int loaded_ntile = -1;
+                    for (int it = it0; it < nit; it += its) {
+                        const int ntile = fast_div(it, mt_per, m_mt_per);
+                        if (p.resident) {
+                            if (ntile != loaded_ntile) {
+                                loaded_ntile = ntile;
+                                ++wu;
+                                for (int cb = 0; cb < p.ncb; ++cb) {
+                                    mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
+                                    mbar_arrive_cluster(mapa_u32(bar_peer_w + 8 * cb, 0u));
+                                }
+                            }
+                        } else {
+                            for (int t0 = 0; t0 < p.T; t0 += cTC)
+                                for (int cb = 0; cb < p.ncb; ++cb) {
+                                    const int buf = (int)(wu % NWB);
+                                    mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+                                    mbar_arrive_cluster(mapa_u32(bar_peer_w + 8 * buf, 0u));
+                                    ++wu;
+                                }
+                        }
+                    }
+                }
+            }
+        } else if (elect_one()) {
             const uint32_t role = warp == 4 ? 0u : 1u;
-            // instruction descriptor: i8 = s32 accumulate, A u8, B s8;  bf16 = f32 accumulate, A and B bf16; both operands K-major
+            // instruction descriptor: i8 = s32 accumulate, A u8, B s8;  bf16 = f32 accumulate, A and B bf16; both operands K-major;
+            // a CTA pair runs M = 256 (128 rows per CTA)
             constexpr uint32_t idesc = (MODE == MODE_I8 ? ((2u << 4) | (0u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
-                                       ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                       ((uint32_t)(cN >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
             constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
             constexpr uint32_t a_sbo = (uint32_t)(STRIDE * cPWp * RB);
             constexpr uint32_t b_sbo = (uint32_t)(8 * RB);
@@ -472,6 +543,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const uint64_t a_stage0 = make_desc(patch_base, a_sbo, layout);
             const uint64_t b_buf0 = make_desc(w_base, b_sbo, layout);
 
+            // completion of everything issued so far -> a barrier (of both CTAs of a pair, at the same shared-memory offset)
+            auto commit = [&](uint32_t bar) {
+                if constexpr (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
+            // hand-backs from the epilogue warps arrive from both CTAs of a pair
+            auto wait_slot = [&](uint32_t bar, uint32_t parity) {
+                if constexpr (PAIR) mbar_wait_cluster(bar, parity);
+                else mbar_wait(bar, parity);
+            };
             // returns true when this thread issued the stage
             auto do_stage = [&](int wbuf, int slot, bool first) -> bool {
                 const bool own = (g & 1u) == role;
@@ -480,6 +561,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     {
                         SS_T0();
                         mbar_wait(bar_full_p + 8 * stage, phase);
+                        if constexpr (PAIR) mbar_wait_cluster(bar_peer_p + 8 * stage, phase);   // ... and for the peer's
                         SS_ACC(1, 0);         // wait for the patch
                     }
                     fence_proxy_async();   // cp.async wrote the patch through the generic proxy; the MMA reads it through the async proxy
@@ -495,11 +577,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     ++mine;
                     SS_T0();
                     tc_fence_after();
-                    umma_i8<MODE>(d, a0, b0, idesc, first ? 0u : 1u);
-                    issue_taps<MODE, KS, STRIDE, RB, cN, cPWp, cPWhalf>(d, a0, b0, idesc);
+                    umma_i8<MMA_MODE>(d, a0, b0, idesc, first ? 0u : 1u);
+                    issue_taps<MMA_MODE, KS, STRIDE, RB, cNB, cPWp, cPWhalf>(d, a0, b0, idesc);
                     tc_fence_before();
                     mbar_arrive(tok_post);
-                    umma_commit(bar_empty_p + 8 * stage);
+                    commit(bar_empty_p + 8 * stage);
                     SS_ACC(1, 2);             // issue
                 }
                 if (++stage == p.NPS) {
@@ -509,8 +591,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 return own;
             };
 
-            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-                const int ntile = fast_div(it, p.mtiles, p.m_mtiles);   // weight-set index: (output-channel tile, class)
+            for (int it = it0; it < nit; it += its) {
+                const int ntile = fast_div(it, mt_per, m_mt_per);   // weight-set index: (output-channel tile, class)
                 if (p.resident && ntile != loaded_ntile) {
                     loaded_ntile = ntile;
                     w_pending = (1u << p.ncb) - 1u;
@@ -528,17 +610,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             // issues into it: a parity wait is only meaningful if the waiter is at most one phase behind.
                             {
                                 SS_T0();
-                                mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                                wait_slot(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
                                 SS_ACC(1, 3);     // wait for a free accumulator slot
                             }
                             slot_phase ^= 1u << s;
                             bool last_own = false;
                             for (int cb = 0; cb < p.ncb; ++cb) {
-                                if (w_pending & (1u << cb)) mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
+                                if (w_pending & (1u << cb)) {
+                                    mbar_wait(bar_full_w + 8 * cb, (wu - 1u) & 1u);
+                                    if constexpr (PAIR) mbar_wait_cluster(bar_peer_w + 8 * cb, (wu - 1u) & 1u);
+                                }
                                 w_pending &= ~(1u << cb);
                                 last_own = do_stage(cb, s, cb == 0);
                             }
-                            if (last_own) umma_commit(bar_full_a + 8 * s);
+                            if (last_own) commit(bar_full_a + 8 * s);
                         }
                     } else {
                         for (int cb = 0; cb < p.ncb; ++cb) {
@@ -546,6 +631,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                             {
                                 SS_T0();
                                 mbar_wait(bar_full_w + 8 * buf, (wu / NWB) & 1u);
+                                if constexpr (PAIR) mbar_wait_cluster(bar_peer_w + 8 * buf, (wu / NWB) & 1u);
                                 SS_ACC(1, 4);     // wait for streamed weights
                             }
                             bool last_own = false;
@@ -553,24 +639,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                                 const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);
                                 if (cb == 0) {
                                     SS_T0();
-                                    mbar_wait(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
+                                    wait_slot(bar_empty_a + 8 * s, ((slot_phase >> s) & 1u) ^ 1u);
                                     SS_ACC(1, 3);
                                     slot_phase ^= 1u << s;
                                 }
                                 last_own = do_stage(buf, s, cb == 0);
-                                if (cb == p.ncb - 1 && last_own) umma_commit(bar_full_a + 8 * s);
+                                if (cb == p.ncb - 1 && last_own) commit(bar_full_a + 8 * s);
                             }
-                            if (last_own) umma_commit(bar_empty_w + 8 * buf);
+                            if (last_own) commit(bar_empty_w + 8 * buf);
                             ++wu;
                         }
                     }
                     sbase += (uint32_t)tc;
                 }
                 if (p.resident) {
-                    const int nxt = it + gridDim.x;
+                    const int nxt = it + its;
                     // the thread that issued the last stage releases the resident weight buffers before a reload
-                    if (nxt < p.nitems && nxt / p.mtiles != ntile && ((g - 1u) & 1u) == role)
-                        for (int cb = 0; cb < p.ncb; ++cb) umma_commit(bar_empty_w + 8 * cb);
+                    if (nxt < nit && nxt / mt_per != ntile && ((g - 1u) & 1u) == role)
+                        for (int cb = 0; cb < p.ncb; ++cb) commit(bar_empty_w + 8 * cb);
                 }
             }
             SS_DUMP(1 + (int)role);
@@ -584,12 +670,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             auto load = [&](int buf, int ntile, int cb) {
                 const uint32_t full = bar_full_w + 8 * buf;
                 mbar_arrive_expect_tx(full, (uint32_t)cWB);
-                const int8_t* src = p.w + (size_t)(ntile * p.ncb + cb) * cWB;
                 const uint32_t dst = w_base + (uint32_t)buf * cWB;
-                for (int o = 0; o < cWB; o += 16384) bulk_load(dst + o, src + o, (uint32_t)min(16384, cWB - o), full);
+                if constexpr (PAIR) {
+                    // this CTA's half of the N rows of every tap (the packed image is [tap][cN rows][RB]; the swizzle of a row
+                    // only depends on row mod 8 groups, which the 48-row split preserves)
+                    const int8_t* src = p.w + (size_t)(ntile * p.ncb + cb) * (size_t)(cNTAPS * cN * RB) + (size_t)crank * (cNB * RB);
+                    for (int tap = 0; tap < cNTAPS; ++tap)
+                        bulk_load(dst + (uint32_t)(tap * cNB * RB), src + (size_t)tap * (cN * RB), (uint32_t)(cNB * RB), full);
+                } else {
+                    const int8_t* src = p.w + (size_t)(ntile * p.ncb + cb) * cWB;
+                    for (int o = 0; o < cWB; o += 16384) bulk_load(dst + o, src + o, (uint32_t)min(16384, cWB - o), full);
+                }
             };
-            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-                const int ntile = fast_div(it, p.mtiles, p.m_mtiles);
+            for (int it = it0; it < nit; it += its) {
+                const int ntile = fast_div(it, mt_per, m_mt_per);
                 if (p.resident) {
                     if (ntile != loaded_ntile) {
                         for (int cb = 0; cb < p.ncb; ++cb) {
@@ -629,7 +723,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const size_t t_out = (size_t)M * p.Cout;
             uint32_t slot_phase = 0;
             uint32_t sbase = 0;
-            for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
+            for (int it = it0; it < nit; it += its) {
                 const int wset = fast_div(it, p.mtiles, p.m_mtiles);
                 const int mt = it - wset * p.mtiles;
                 const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
@@ -701,14 +795,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         const size_t t_out = (size_t)M * p.Cout;
         uint32_t slot_phase = 0;
         uint32_t sbase = 0;           // running accumulator-slot count (same sequence as in the MMA role)
+        const uint32_t empty_a_remote = PAIR ? mapa_u32(bar_empty_a, 0u) : 0u;
         SS_DECL();
         int sc_ntile = -1;
         float sc[16];                 // wscale * gain (wscale is a power of two, so this product is exact)
-        for (int it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-            const int ntile = fast_div(it, p.mtiles, p.m_mtiles);
-            const int mt = it - ntile * p.mtiles;
+        for (int it = it0; it < nit; it += its) {
+            const int ntile = fast_div(it, mt_per, m_mt_per);
+            const int mt = PAIR ? 2 * (it - ntile * mt_per) + (int)crank : it - ntile * mt_per;
             const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
-            const int wset = ntile;                       // it / mtiles: (output-channel tile, class)
+            const int wset = ntile;                       // (output-channel tile, class)
             const int cls = wset % p.nclass;
             const int so = ty * 16 + g;
             int b = fast_div(so, p.HsO, p.m_hso);
@@ -778,7 +873,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(taddr + pl * 32, d[pl]);
                     tmem_ld_wait();
                     tc_fence_before();
-                    mbar_arrive(bar_empty_a + 8 * s);   // the slot is in registers now: hand it back to the MMA warp
+                    // the slot is in registers now: hand it back to the MMA threads (rank 0's barrier for a CTA pair)
+                    if constexpr (PAIR) mbar_arrive_cluster(empty_a_remote + 8 * s);
+                    else mbar_arrive(bar_empty_a + 8 * s);
                     if (!live) continue;
                     float x[16];
 #pragma unroll
@@ -841,9 +938,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // rank 0's MMAs read the peer's shared memory and write its TMEM until the very end
     if (warp == 4) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1180,9 +1279,34 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.m_tiles_x = div_magic(p.tiles_x, p.mtiles);
     p.m_per = div_magic((long long)p.stride * p.HsO, (long long)p.stride * (rows + 64));
     p.m_hso = div_magic(p.HsO, rows + 64);
+    // CTA pairs (cta_group::2): two m-tiles per MMA, each CTA holds half of the weight rows.  Measured (r1h): the MMA-bound
+    // deep decoder blocks gain ~5 %, everything else loses to the coarser item granularity (a pair walks items in lock
+    // step), so pairs are used where the weights are streamed in >= 8 channel blocks and the number of rounds over the
+    // machine does not grow.  SS_PAIR=0 never, SS_PAIR=2 wherever possible (tests), default = the rule above.
+    static int pair_env = -1;
+    if (pair_env < 0) {
+        const char* e = getenv("SS_PAIR");
+        pair_env = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    }
+    p.mtiles2 = (p.mtiles + 1) / 2;
+    p.nitems2 = p.mtiles2 * ntiles * p.nclass;
+    p.m_mtiles2 = div_magic(p.mtiles2, p.nitems2);
+    int sms = 0;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    bool pair = pair_env != 0 && !first && mode == SS_TILES_PLAIN && (g->planes * 32) % 16 == 0 && p.mtiles >= 2 && sms >= 2;
+    if (pair && pair_env == 1) {
+        const long long rounds1 = (nitems + sms - 1) / sms;
+        const long long rounds2 = ((long long)p.nitems2 + sms / 2 - 1) / (sms / 2);
+        pair = g->Cin / rowbytes_for(g->Cin, g->ks) >= 8 && rounds2 <= rounds1;
+    }
     p.TC = 512 / p.N;
     if (p.TC > MAX_SLOTS) p.TC = MAX_SLOTS;
-    p.WB = p.ntaps * p.N * p.RB;
+    p.WB = p.ntaps * (pair ? p.N / 2 : p.N) * p.RB;       // per CTA
     p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
     p.resident = p.ncb <= NWB ? 1 : 0;
     p.nwb = p.ncb < NWB ? p.ncb : NWB;
@@ -1218,7 +1342,10 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
     }
-    const int grid = p.nitems < num_sms ? p.nitems : num_sms;
+    int grid = p.nitems < num_sms ? p.nitems : num_sms;
+    if (pair) {
+        grid = 2 * p.nitems2 < num_sms ? 2 * p.nitems2 : (num_sms & ~1);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     bool launched = false;
     cudaLaunchConfig_t cfg{};
@@ -1226,12 +1353,28 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: our prologue may overlap the previous kernel's tail
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;                  // CTA pairs
+    attrs[1].val.clusterDim.x = 2;
+    attrs[1].val.clusterDim.y = 1;
+    attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pair ? 2 : 1;
+#define SS_TRY_PAIR(PL, KS_, ST_, RB_)                                                                                     \
+    if (!launched && pair && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {                         \
+        static bool attr = false;                                                                                          \
+        if (!attr) {                                                                                                       \
+            cudaFuncSetAttribute(conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, true>,                                  \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                                 \
+            attr = true;                                                                                                   \
+        }                                                                                                                  \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, true>, p);                              \
+        launched = true;                                                                                                   \
+    }
 #define SS_TRY(PL, KS_, ST_, RB_)                                                                                          \
+    SS_TRY_PAIR(PL, KS_, ST_, RB_)                                                                                         \
     if (!launched && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {                                 \
         static bool attr = false;                                                                                          \
         if (!attr) {                                                                                                       \
@@ -1258,6 +1401,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
 #undef SS_TRY_PL
 #undef SS_TRY_FIRST
 #undef SS_TRY
+#undef SS_TRY_PAIR
     if (!launched) {
         set_error("ss_conv_i8_fwd: no kernel instance for planes %d ks %d stride %d rowbytes %d", g->planes, g->ks, g->stride, p.RB);
         return SS_EUNSUPPORTED;

@@ -67,11 +67,18 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
-    } else {
+    } else if constexpr (MODE == 1) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {   // 2: int8, CTA pair
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
     }
@@ -88,7 +95,7 @@ __device__ __forceinline__ void umma_i8_off(uint32_t tmem_d, uint64_t adesc, uin
             "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, 1;\n\t}" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "n"(AOFF), "n"(BOFF)
             : "memory");
-    } else {
+    } else if constexpr (MODE == 1) {
         asm volatile(
             "{\n\t.reg .b64 da, db;\n\t"
             "add.s64 da, %1, %4;\n\t"
@@ -96,7 +103,57 @@ __device__ __forceinline__ void umma_i8_off(uint32_t tmem_d, uint64_t adesc, uin
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t}" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "n"(AOFF), "n"(BOFF)
             : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t"
+            "add.s64 da, %1, %4;\n\t"
+            "add.s64 db, %2, %5;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, 1;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "n"(AOFF), "n"(BOFF)
+            : "memory");
     }
+}
+// ---- CTA pairs (tcgen05 cta_group::2): the two CTAs of a 2-cluster run one MMA of M = 256, each feeding its own A tile and
+//      half of the B operand from its own shared memory; only rank 0 issues, completion is multicast to both CTAs' barriers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait on a barrier that receives arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

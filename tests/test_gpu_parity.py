@@ -18,6 +18,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 TOL_H = 2e-5      # abs+rel tolerance on the fp32 pre-reset potential (|h| up to ~10)
 BAND = 1e-4       # spikes must agree outside this band around the threshold
 TOL_MDE = 1e-3    # north_star: MDE within 1e-3 of the reference on identical inputs
@@ -433,3 +435,45 @@ def test_graphed_inference_equals_eager(B, T):
         for a, b in zip(got, want):
             assert torch.equal(a, b)
     assert float(got[0].abs().sum()) > 0
+
+
+@pytest.mark.gpu
+def test_cta_pair_kernels_are_bit_identical():
+    """The cta_group::2 variant of the block kernel (two m-tiles per MMA, weights split between the CTAs of a 2-cluster) must
+    produce exactly the single-CTA results.  The choice is made once per process from SS_PAIR, so each setting runs in its
+    own interpreter: SS_PAIR=2 forces pairs wherever they are possible, SS_PAIR=0 forbids them."""
+    import subprocess
+    import sys
+    code = r'''
+import hashlib, torch
+from stereospike_b200 import ops
+dev = torch.device('cuda')
+h = hashlib.sha256()
+for (kind, Cin, Cout, ks, Hin, Win, stride, pad, up, T, B) in [
+        ('conv', 64, 64, 3, 17, 22, 1, 1, None, 5, 3), ('conv', 32, 64, 5, 37, 45, 2, 2, None, 2, 2),
+        ('upconv', 64, 32, 5, 17, 22, 1, 0, (33, 44), 5, 2), ('upconv', 512, 256, 5, 17, 22, 1, 0, (33, 44), 5, 2),
+        ('conv', 256, 512, 5, 33, 44, 2, 2, None, 7, 1), ('conv', 512, 512, 3, 17, 22, 1, 1, None, 1, 3)]:
+    g = torch.Generator().manual_seed(3)
+    if kind == 'conv':
+        Hout, Wout = ops.conv_out_size(Hin, ks, stride, pad), ops.conv_out_size(Win, ks, stride, pad)
+        geom = ops.BlockGeom('conv', Cin, Cout, ks, Hin, Win, Hout, Wout, stride, pad)
+    else:
+        geom = ops.BlockGeom('upconv', Cin, Cout, ks, Hin, Win, up[0], up[1])
+    x = (torch.rand(T, B, Hin, Win, Cin, generator=g) < 0.15).to(torch.uint8).to(dev)
+    w = ((torch.rand(Cout, Cin, ks, ks, generator=g) * 2 - 1) / (Cin * ks * ks) ** 0.5).to(dev)
+    q, sc, _ = ops.pack_weights_i8(w, 3)
+    out, v, hs = ops.conv_i8_fwd(x, geom, q, sc, T=T, B=B, neuron=1, gain=12.0, v_th=1.0, v_reset=0.0, tau=3.0,
+                                 want_v_out=True, want_h=True)
+    torch.cuda.synchronize()
+    for t in (out, v, hs):
+        h.update(t.cpu().numpy().tobytes())
+    assert 0.01 < float(out.float().mean()) < 0.9
+print(h.hexdigest())
+'''
+    digests = []
+    for mode in ('0', '2'):
+        env = dict(os.environ, SS_PAIR=mode, PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1], digests

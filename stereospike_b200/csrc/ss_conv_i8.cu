@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         }
         for (int s = 0; s < MAX_SLOTS; ++s) {
             mbar_init(bar_full_a + 8 * s, 1);
-            mbar_init(bar_empty_a + 8 * s, PAIR ? 512 : 256);
+            mbar_init(bar_empty_a + 8 * s, PAIR ? 16 : 8);      // one arrival per epilogue warp (of both CTAs of a pair)
         }
         mbar_init(bar_tok, 1);
         mbar_init(bar_tok + 8, 1);
@@ -765,7 +765,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         for (int c = 0; c < NCH; ++c) tmem_ld16(taddr + c * 16, d[c]);
                         tmem_ld_wait();
                         tc_fence_before();
-                        mbar_arrive(bar_empty_a + 8 * s);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty_a + 8 * s);
                         if (!live) continue;
 #pragma unroll
                         for (int c = 0; c < NCH; ++c)
@@ -873,9 +874,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(taddr + pl * 32, d[pl]);
                     tmem_ld_wait();
                     tc_fence_before();
-                    // the slot is in registers now: hand it back to the MMA threads (rank 0's barrier for a CTA pair)
-                    if constexpr (PAIR) mbar_arrive_cluster(empty_a_remote + 8 * s);
-                    else mbar_arrive(bar_empty_a + 8 * s);
+                    // the slot is in every lane's registers now: one lane hands it back to the MMA threads (rank 0's barrier for a
+                    // CTA pair -- a remote arrival per thread made the paired epilogue slower than the single-CTA one)
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (PAIR) mbar_arrive_cluster(empty_a_remote + 8 * s);
+                        else mbar_arrive(bar_empty_a + 8 * s);
+                    }
                     if (!live) continue;
                     float x[16];
 #pragma unroll

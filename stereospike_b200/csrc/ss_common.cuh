@@ -69,7 +69,9 @@ __device__ __forceinline__ float neuron_step_t(float x, float& v, const NeuronCo
         h = __fadd_rn(v, __fmul_rn(dv, c.decay));
     }
     h_out = h;
-    const bool fire = __fsub_rn(h, c.v_th) >= 0.0f;
+    // heaviside(h - v_th): with gradual underflow h - v_th is zero only for h == v_th and has the sign of the exact
+    // difference otherwise, so the comparison needs no subtraction
+    const bool fire = h >= c.v_th;
     v = fire ? c.v_reset : h;
     return fire ? 1.0f : 0.0f;
 }

@@ -898,24 +898,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                         x[i] = __fmul_rn(conv, sc[i]);   // == (conv * wscale) * gain: the first product is exact
                     }
                     float hbuf[16];
-                    uint32_t fired = 0;
+                    uint32_t sb[16];      // spike of each channel as 0 / 1
                     if (p.neuron == SS_NEURON_IF) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) fired |= (neuron_step_t<SS_NEURON_IF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u) << i;
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<SS_NEURON_IF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     } else if (p.neuron == SS_NEURON_LIF) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) fired |= (neuron_step_t<SS_NEURON_LIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u) << i;
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<SS_NEURON_LIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) fired |= (neuron_step_t<SS_NEURON_PLIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u) << i;
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<SS_NEURON_PLIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     }
-                    // 16 spike bits -> 16 bytes (+ residual bytes; sums stay <= 3, no carry between bytes)
+                    // 16 spikes -> 16 bytes (+ residual bytes; sums stay <= 3, no carry between bytes)
                     uint32_t pk[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t nib = (fired >> (4 * q)) & 0xFu;
-                        pk[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        pk[q] = sb[4 * q] | (sb[4 * q + 1] << 8) | (sb[4 * q + 2] << 16) | (sb[4 * q + 3] << 24);
                     const size_t o = (size_t)t * t_out + o0;
                     pk[0] += rs_cur.x; pk[1] += rs_cur.y; pk[2] += rs_cur.z; pk[3] += rs_cur.w;
                     *reinterpret_cast<uint4*>(p.out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -8,10 +8,14 @@
 A "step" is one forward pass of the whole path over one batch of synthetic event frames: B*T event-frames.
 Rank 0 prints ONE JSON line (contract in the task statement / DESIGN.md section "Measurement").
   value      device-timed throughput, inputs resident in HBM (rotating input sets larger than L2)
-  e2e        same metric through the public nn.Module call with pinned-HOST inputs: H2D of the step's frames and
-             D2H of the finest depth map inside the timed region
-  roofline   tcgen05 conv+neuron kernel: algorithmic FLOPs / CUDA-event time of those launches vs the measured
-             sustained bf16 peak (MEASURED_PEAKS.json)
+  e2e        same metric through the public API (pipeline.HostPipeline.step) with pinned-HOST inputs: H2D of the step's
+             frames and D2H of the finest depth map inside the timed region
+  roofline   tcgen05 conv+neuron kernel: algorithmic FLOPs / CUDA-event time of those launches vs the measured BURST
+             bf16 peak (MEASURED_PEAKS.json; the sustained figure is printed beside it)
+  parity     (N=1) the CUDA path against the oracle on a B=1 slice of the same configuration, outside the timed region:
+             |dMDE|, the oracle's own fp32-vs-float64 sensitivity, worst per-layer spike mismatch, teacher-forced max |dh|
+  train      the training step of BASELINE.json configs[2]/[3] (B=16 per GPU, T=5: forward + surrogate backward + NCCL
+             gradient all-reduce overlapped with the backward + Adam), a short run after the inference measurement
   cpu_baseline  the oracle (pure-PyTorch restatement of the reference, oracle/ref_model.py) on the host cores,
              bounded sample
 `--impl reference` times that CPU oracle alone (the reference cannot be pip-installed: it has no packaging and its
@@ -36,6 +40,7 @@ MFLOP_PER_FRAME = {'bottom': 575.7, 'conv1': 2303.0, 'conv2': 2316.3, 'conv3': 2
                    'bottleneck.1.conv2': 1764.8, 'deconv4': 9515.8, 'deconv3': 9265.2, 'deconv2': 9211.9,
                    'deconv1': 9211.9, 'heads': 777.2}
 TOTAL_GFLOP_PER_FRAME = sum(MFLOP_PER_FRAME.values()) / 1e3
+FOLD_DEFAULT = 0      # decoder blocks folded to 3x3 convs on the source by default?
 
 
 def measured_peaks():
@@ -128,14 +133,13 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    t_all = time.perf_counter()
     import torch
     from oracle import ref_model as rm, sj_compat as sj
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     net = build_oracle(args.neuron, args.gain, args.tau)
     on_gpu = args.reference_device == 'cuda'
-    sample_B = args.batch if on_gpu else 1
+    sample_B = args.batch                  # the batch the config declares (the arm ran B=1 while printing batch 8)
     x = rm.synthetic_inputs(sample_B, args.T, 4, seed=0)
     label = rm.synthetic_label(sample_B, seed=1)
     if on_gpu:
@@ -175,9 +179,10 @@ def run_reference(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, per_gpu_B=args.batch),
         'cpu_baseline': {'value': val, 'unit': 'event-frames/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'each step = B={sample_B} sample x T={args.T} frames of the same workload, {args.mode}, '
+                         'sample': f'each step = the full B={sample_B} x T={args.T} batch of the same workload, {args.mode}, '
                                    f'torch {torch.__version__} ' + ('CUDA eager (cuDNN fp32, allow_tf32=False) -- the reference\'s own GPU '
-                                   'execution model, NOT the CPU arm' if on_gpu else f'CPU fp32, {cores} threads')},
+                                   'execution model, NOT the CPU arm' if on_gpu else f'CPU fp32, {cores} threads') +
+                                   '; one process whatever --gpus says (the reference has no distributed code)'},
         'reference_device': args.reference_device,
         'e2e': {'value': val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -204,8 +209,77 @@ def workload_config(args, per_gpu_B):
                         f'(u8 spikes x {args.planes} int8 weight digit planes on the int8 tensor cores, exact s32 accumulate, one fp32 rounding)',
             'mode': args.mode, 'neuron': args.neuron, 'T': args.T, 'batch_per_gpu': per_gpu_B, 'global_batch': per_gpu_B * args.gpus,
             'weight_planes': args.planes, 'multiply_factor': args.gain, 'tau': args.tau,
+            'state': 'reset before every step (test.py per-sample protocol); final membrane potentials ' +
+                     ('kept (keep_state)' if args.keep_state else 'not written back (stateless serving, keep_state=False)'),
+            'fold_upsample': bool(args.fold),
             'l2': f'rotating {args.input_sets} input sets per step; per-step activation stream (~2 GB) exceeds the 126 MB L2',
-            'parallelism': f'replicas x{args.gpus} (batch shards, no data-path collective)'}
+            'parallelism': f'replicas x{args.gpus} (batch shards, no data-path collective)' if args.mode == 'infer' else
+                           f'dp{args.gpus} (batch shards, NCCL gradient all-reduce issued per block inside the backward)'}
+
+
+def make_net(args, dev):
+    import torch
+    import stereospike_b200 as sb
+    torch.manual_seed(0)
+    if args.neuron == 'if':
+        net = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), multiply_factor=args.gain)
+    else:
+        net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=args.neuron == 'plif', tau=args.tau,
+                                                                              multiply_factor=args.gain)
+    net = net.to(dev)
+    net.set_kernel_options(impl=args.kernel, weight_planes=args.planes, fold_upsample=bool(args.fold))
+    return net
+
+
+def time_training(args, dev, world, rank, B, steps, warmup, barrier):
+    """One training configuration (BASELINE.json configs[2] at N=1, configs[3] at N=8): forward + fused loss + surrogate
+    backward with the per-block gradient all-reduce overlapped (parallel.OverlappedGradientSync) + Adam.  Returns
+    (ms per step with the all-reduce, ms per step with the all-reduce switched off, collectives per step, launches per step)."""
+    import torch
+    import stereospike_b200 as sb
+    from stereospike_b200 import _lib
+    from oracle import ref_model as rm          # synthetic-input recipe only
+    net = make_net(args, dev)
+    T = args.T
+    xs = [rm.synthetic_inputs(B, T, 4, seed=500 + rank * 16 + i).to(dev) for i in range(2)]
+    label = rm.synthetic_label(B, seed=1).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+    crit = sb.loss.Total_Loss()
+    sync = sb.parallel.OverlappedGradientSync(net)
+    sync.set_batch(local_samples=B, global_samples=B * world)
+
+    def step(x):
+        sb.functional.reset_net(net)
+        out = net.forward_seq(x)
+        crit(out[0], label).backward()          # the all-reduces are issued from inside this backward, block by block
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    res = []
+    for use_sync in (True, False):
+        if use_sync and world > 1:
+            sync.attach()
+        else:
+            sync.detach()
+        for i in range(warmup):
+            step(xs[i % 2])
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(xs[i % 2])
+        e1.record()
+        barrier()
+        res.append((e0.elapsed_time(e1) / steps, (_lib.launch_count() - l0) / steps))
+        if world == 1:
+            res.append(res[0])
+            break
+    sync.detach()
+    ncoll = sync.collectives
+    del net, opt, xs
+    torch.cuda.empty_cache()
+    return res[0][0], res[1][0], ncoll, res[0][1]
 
 
 def run_ours(args):
@@ -213,6 +287,7 @@ def run_ours(args):
     import torch.distributed as dist
     import stereospike_b200 as sb
     from stereospike_b200 import _lib
+    from stereospike_b200.pipeline import pack_events_host
     from oracle import ref_model as rm          # synthetic-input recipe only (shared with the CPU arm)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -227,41 +302,44 @@ def run_ours(args):
     _lib.lib()   # fail loudly if the extension is missing
     sampler = ClockSampler(local) if rank == 0 else None      # started early so that it has samples under load
 
-    torch.manual_seed(0)
-    if args.neuron == 'if':
-        net = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), multiply_factor=args.gain)
-    else:
-        net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=args.neuron == 'plif', tau=args.tau,
-                                                                              multiply_factor=args.gain)
-    net = net.to(dev)
-    net.set_kernel_options(impl=args.kernel, weight_planes=args.planes)
-    B, T = args.batch, args.T
-    xs_host = [rm.synthetic_inputs(B, T, 4, seed=100 + rank * 16 + i).pin_memory() for i in range(args.input_sets)]
-    xs = [x.to(dev) for x in xs_host]
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     train = args.mode == 'train'
+    net = make_net(args, dev)
+    net.set_kernel_options(keep_state=bool(args.keep_state) or train)
+    B, T = args.batch, args.T
+    xs_f32 = [rm.synthetic_inputs(B, T, 4, seed=100 + rank * 16 + i) for i in range(args.input_sets)]
+    # host frames as the data loader hands them over: packed u8 counts [T,B,H,W,4] (14.4 MB per batch) by default,
+    # the reference's fp32 [B,T,4,H,W] tensors (57.6 MB) with --host-frames f32
+    if args.host_frames == 'u8' and not train:
+        xs_host = [pack_events_host(x).pin_memory() for x in xs_f32]
+    else:
+        xs_host = [x.pin_memory() for x in xs_f32]
+    xs = [x.to(dev) for x in xs_f32]            # device-resident arm: the reference's fp32 frames, packed by ss_pack_events each step
+    del xs_f32
+
     if train:
         label = rm.synthetic_label(B, seed=1).to(dev)
         opt = torch.optim.Adam(net.parameters(), lr=2e-4)
-        sync = sb.parallel.GradientSynchronizer(net.parameters()) if world > 1 else None
+        crit = sb.loss.Total_Loss()
+        gsync = sb.parallel.OverlappedGradientSync(net)
+        gsync.set_batch(local_samples=B, global_samples=B * world)
+        if world > 1:
+            gsync.attach()
 
     def step(x):
         sb.functional.reset_net(net)
         if train:
             out = net.forward_seq(x)
-            masked_l1(out[0], label).backward()
-            if sync is not None:
-                sync.sync(local_samples=B, global_samples=B * world)     # NCCL all-reduce of the gradients
+            crit(out[0], label).backward()      # NCCL all-reduce of each block's gradient is issued inside the backward
             opt.step()
             opt.zero_grad(set_to_none=True)
             return out
         with torch.no_grad():
             return net.forward_seq(x)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for i in range(args.warmup):
         step(xs[i % len(xs)])
@@ -286,8 +364,6 @@ def run_ours(args):
     #      second stream), finest depth map back to pinned host memory, every step
     if train:
         loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-        # two static device buffers filled on a copy stream (as pipeline.HostPipeline does for inference): the transfer of
-        # step i+1 overlaps the kernels of step i and no 115 MB tensor is allocated per step
         bufs = [torch.empty_like(xs[0]) for _ in range(2)]
         copy_stream = torch.cuda.Stream(dev)
         ready = [torch.cuda.Event() for _ in range(2)]
@@ -307,13 +383,12 @@ def run_ours(args):
             main.wait_event(ready[k])
             out = step(bufs[k])
             free[k].record(main)
-            depth_host = out[0][0]
             loss_host.copy_(out[0][0].mean(), non_blocking=True)
         e3.record()
         barrier()
         d2h_bytes = 4
     else:
-        pipe = sb.pipeline.HostPipeline(net, tuple(xs_host[0].shape), dev)
+        pipe = sb.pipeline.HostPipeline(net, tuple(xs_host[0].shape), dev, dtype=xs_host[0].dtype, stateless=not args.keep_state)
         for i in range(2):
             pipe.step(xs_host[i % len(xs_host)])
         barrier()
@@ -325,6 +400,7 @@ def run_ours(args):
         barrier()
         d2h_bytes = depth_host.numel() * 4
     ms_e2e = e2.elapsed_time(e3)
+    h2d_bytes = xs_host[0].numel() * xs_host[0].element_size()
 
     # ---- per-kernel timing of the tensor-core blocks (roofline)
     eng = net.engine
@@ -338,11 +414,49 @@ def run_ours(args):
     for name, a, b in eng.timing:
         per_site.setdefault(name, []).append(a.elapsed_time(b))
     eng.timing = None
+    flop_scale = dict(getattr(eng, 'flop_scale', {}))      # folded decoder blocks execute (and are credited with) fewer taps
+
+    # ---- the same loop with the other state policy, a few steps (reported beside the main number)
+    alt_ms = None
+    if not train:
+        net.set_kernel_options(keep_state=not args.keep_state)
+        for i in range(3):
+            step(xs[i % len(xs)])
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(min(args.steps, 10)):
+            step(xs[i % len(xs)])
+        a1.record()
+        torch.cuda.synchronize()
+        alt_ms = a0.elapsed_time(a1) / min(args.steps, 10)
+        net.set_kernel_options(keep_state=bool(args.keep_state))
 
     t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
+
+    # ---- training sub-record (configs[2]/[3]) on the same ranks
+    train_rec = None
+    if not train and not args.no_train:
+        del xs, pipe
+        torch.cuda.empty_cache()
+        tsteps, twarm = min(args.steps, 10), 3
+        ms_sync, ms_nosync, ncoll, tl = time_training(args, dev, world, rank, args.train_batch, tsteps, twarm, barrier)
+        tt = torch.tensor([ms_sync, ms_nosync], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_sync, ms_nosync = float(tt[0]), float(tt[1])
+        train_rec = {'metric': 'event-frames/sec', 'value': args.train_batch * T * world / (ms_sync / 1e3), 'unit': 'event-frames/s',
+                     'n_gpus': world, 'steps': tsteps, 'warmup': twarm, 'ms_per_step': ms_sync, 'batch_per_gpu': args.train_batch,
+                     'global_batch': args.train_batch * world, 'T': T,
+                     'step': 'reset_net + forward_seq + Total_Loss (fused) + backward (surrogate BPTT, bf16 tensor-core dgrad/wgrad) + Adam',
+                     'allreduce': {'bytes': 18148708 * 4, 'collectives_per_step': ncoll,
+                                   'ms_per_step_without_allreduce': ms_nosync, 'exposed_ms': max(0.0, ms_sync - ms_nosync),
+                                   'how': 'in-place NCCL all-reduce per block gradient issued inside the backward (reverse layer order), '
+                                          'overlapped with the remaining dgrad/wgrad kernels; exposed = step time with - without it, max over ranks'},
+                     'gpu_launches_per_step': tl}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -351,37 +465,56 @@ def run_ours(args):
         e2e_val = frames * args.steps / (ms_e2e / 1e3)
         conv_sites = [k for k in per_site if k != 'heads']
         conv_ms = sum(statistics.mean(per_site[k]) for k in conv_sites)
-        conv_gflop = sum(MFLOP_PER_FRAME[k] for k in conv_sites) / 1e3 * B * T
+        site_gflop = {k: MFLOP_PER_FRAME[k] * flop_scale.get(k, 1.0) / 1e3 * B * T for k in per_site if k in MFLOP_PER_FRAME}
+        conv_gflop = sum(site_gflop[k] for k in conv_sites)
         ach = conv_gflop / conv_ms if conv_ms > 0 else 0.0      # GFLOP/ms == TFLOP/s
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
-        # the ncu capture behind traffic.json is of the headline configuration only (B=8 per GPU, T=5, 3 planes, inference)
+        # the ncu captures behind traffic.json are of the headline configuration only (B=8 per GPU, T=5, 3 planes, inference)
         if os.path.isfile(tp) and B == 8 and T == 5 and args.planes == 3 and args.mode == 'infer':
-            traffic = json.load(open(tp)).get('conv_i8_dram_bytes_per_step')
+            tj = json.load(open(tp))
+            key = 'conv_i8_dram_bytes_per_step' + ('' if args.keep_state else '_stateless') + ('_fold' if args.fold else '')
+            traffic = tj.get(key)
         line = {
             'metric': 'event-frames/sec', 'value': value, 'unit': 'event-frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8 x s8 -> s32 (tcgen05 kind::i8, %d weight digit planes), fp32 neuron state' % args.planes +
                                            ('; backward bf16 x bf16 -> f32 (tcgen05 kind::f16), fp32 surrogate scan' if args.mode == 'train' else ''),
             'data': 'synthetic', 'config': workload_config(args, B),
-            'e2e': {'value': e2e_val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': xs_host[0].numel() * 4,
+            'e2e': {'value': e2e_val, 'unit': 'event-frames/s', 'h2d_bytes_per_step': h2d_bytes,
                     'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': ms_e2e / args.steps,
-                    'api': ('forward_seq + backward + Adam on frames copied from pinned host memory on a second stream, loss scalar back to pinned memory' if train else 'stereospike_b200.pipeline.HostPipeline.step (pinned fp32 frames -> forward_seq -> pinned depth map)')},
+                    'host_frames': str(xs_host[0].dtype).replace('torch.', '') + ' ' + 'x'.join(str(int(v)) for v in xs_host[0].shape),
+                    'api': ('forward_seq + backward + Adam on frames copied from pinned host memory on a second stream, loss scalar back to pinned memory' if train else
+                            'stereospike_b200.pipeline.HostPipeline.step (pinned host frames -> H2D on a copy stream -> forward_seq -> pinned depth map)')},
             'gpu_launches': launches,
             'clocks': clocks,
-            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
-                         'frac': ach / peaks['bf16_sustained'], 'traffic': traffic,
-                         'kernel': 'conv_i8_kernel (13 launches/step: bottom, conv1-4, bottleneck x4, deconv4-1); achieved, '
-                                   'traffic and algorithmic work are summed over those 13 launches',
-                         'peak_source': peaks['source'] + ' sustained dense bf16 (MEASURED_PEAKS.json; the kernel runs int8 MMAs, '
-                                        '3 digit planes = 1.5 bf16-equivalents per algorithmic FLOP)',
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_burst'], 'unit': 'TFLOP/s',
+                         'frac': ach / peaks['bf16_burst'], 'traffic': traffic,
+                         'frac_of_sustained_peak': ach / peaks['bf16_sustained'], 'peak_sustained': peaks['bf16_sustained'],
+                         'kernel': 'conv_i8_kernel (all launches of the 13 fused blocks: bottom, conv1-4, bottleneck x4, deconv4-1); achieved, '
+                                   'traffic and algorithmic work are summed over those launches',
+                         'peak_source': peaks['source'] + ' BURST dense bf16 (MEASURED_PEAKS.json bf16_tflops: the kernels are timed one by one and the '
+                                        'SM clock stays at its maximum); the kernel runs int8 MMAs, 3 digit planes = 1.5 bf16-equivalents per '
+                                        'algorithmic FLOP, so 0.67 is the ceiling of this formulation at equal clocks',
                          'algorithmic_gflop_per_step': conv_gflop, 'kernel_ms_per_step': conv_ms,
+                         'flops_basis': 'dense 2*M*N*K at reference geometry (SURVEY.md 8(a) row 5)' +
+                                        ('; folded NNConvUpsampling blocks are credited with the taps they execute (flop_scale)' if flop_scale else ''),
+                         'flop_scale': flop_scale or None,
                          'executed_int8_mac_factor': args.planes,
                          'per_block_ms': {k: round(statistics.mean(v), 4) for k, v in per_site.items()},
-                         'per_block_tflops': {k: round(MFLOP_PER_FRAME[k] / 1e3 * B * T / statistics.mean(v), 1)
-                                              for k, v in per_site.items() if k in MFLOP_PER_FRAME}},
+                         'per_block_tflops': {k: round(site_gflop[k] / statistics.mean(per_site[k]), 1) for k in site_gflop},
+                         'per_block_frac': {k: round(site_gflop[k] / statistics.mean(per_site[k]) / peaks['bf16_burst'], 3) for k in site_gflop}},
             'model_gflop_per_frame': TOTAL_GFLOP_PER_FRAME,
         }
+        if alt_ms is not None:
+            line['other_state_policy'] = {'keep_state': (not args.keep_state), 'ms_per_step': alt_ms,
+                                          'value': B * T * world / (alt_ms / 1e3)}
+        if train_rec is not None:
+            line['train'] = train_rec
+        if world == 1 and not args.no_parity and not train:
+            from tests._cases import parity_summary          # the oracle as the checker, outside every timed region
+            line['parity'] = parity_summary(args.neuron, args.gain, args.tau, T=T, B=1, seed=0, planes=args.planes,
+                                            fold=bool(args.fold))
         if world == 1 and not args.no_cpu_baseline:
             v, cores, dt = cpu_oracle_rate(args.neuron, args.gain, args.tau, T, 1, 8)
             line['cpu_baseline'] = {'value': v, 'unit': 'event-frames/s', 'cores': cores, 'kind': 'port',
@@ -389,6 +522,7 @@ def run_ours(args):
                                               f'({dt:.2f} s each), torch CPU fp32, {cores} threads'}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -399,6 +533,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='samples per GPU')
+    ap.add_argument('--train-batch', type=int, default=16, help='samples per GPU of the training sub-record (configs[2]/[3])')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'])
     ap.add_argument('--reference-device', default='cpu', choices=['cpu', 'cuda'],
                     help='--impl reference only: cuda = the oracle in PyTorch eager on the GPU (extra comparison point)')
@@ -409,7 +544,14 @@ def main():
     ap.add_argument('--planes', type=int, default=3)
     ap.add_argument('--kernel', default='umma', choices=['umma', 'simt'])
     ap.add_argument('--input-sets', type=int, default=4)
+    ap.add_argument('--host-frames', default='u8', choices=['u8', 'f32'],
+                    help='e2e arm: packed u8 count frames [T,B,H,W,4] (default) or the reference\'s fp32 [B,T,4,H,W] frames')
+    ap.add_argument('--keep-state', type=int, default=0,
+                    help='1 = write the final membrane potentials back after every step (stateful streaming); 0 = stateless serving')
+    ap.add_argument('--fold', type=int, default=FOLD_DEFAULT, help='NNConvUpsampling blocks as folded 3x3 convs (fewer taps)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-train', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -31,6 +31,10 @@ class MultiplyBy(nn.Module):
         return torch.mul(x, self.scale_value)
 
     def gain(self):
+        if isinstance(self.scale_value, nn.Parameter) and self.scale_value.requires_grad and torch.is_grad_enabled():
+            # the fused kernels take the gain as a launch constant: a learnable gain would silently get no gradient
+            raise NotImplementedError('MultiplyBy(learnable=True) cannot be trained inside the fused blocks (no call site of the '
+                                      'reference sets it); freeze it (requires_grad_(False)) or run under torch.no_grad()')
         return float(self.scale_value)
 
 

@@ -29,6 +29,33 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);
 
+// Per-DEVICE launch state.  cudaFuncSetAttribute and the SM count belong to a device, not to the process: a caller that drives two
+// GPUs from one process must get MaxDynamicSharedMemorySize set on each of them (`static bool attr` cached it once).
+constexpr int SS_MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < SS_MAX_DEVICES) ? dev : 0;
+}
+inline int device_sm_count(int dev) {
+    static int sms[SS_MAX_DEVICES] = {};
+    if (sms[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
+}
+// once per (kernel instance = call site, device): opt in to the large dynamic shared memory carve-out
+#define SS_ENSURE_SMEM(kernel, dev, bytes)                                                       \
+    do {                                                                                         \
+        static bool ss_attr_done[ss::SS_MAX_DEVICES] = {};                                       \
+        if (!ss_attr_done[dev]) {                                                                \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes));  \
+            ss_attr_done[dev] = true;                                                            \
+        }                                                                                        \
+    } while (0)
+
 int launch_conv_neuron_simt(const ConvParams& p, int in_layout, cudaStream_t st);
 
 // Correctly rounded a / b for a loop-invariant divisor b:  y = refined reciprocal of b (div_const_prepare), two

@@ -1294,13 +1294,8 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.mtiles2 = (p.mtiles + 1) / 2;
     p.nitems2 = p.mtiles2 * ntiles * p.nclass;
     p.m_mtiles2 = div_magic(p.mtiles2, p.nitems2);
-    int sms = 0;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
+    const int dev = current_device();
+    const int sms = device_sm_count(dev);
     bool pair = pair_env != 0 && !first && mode == SS_TILES_PLAIN && (g->planes * 32) % 16 == 0 && p.mtiles >= 2 && sms >= 2;
     if (pair && pair_env == 1) {
         const long long rounds1 = (nitems + sms - 1) / sms;
@@ -1338,13 +1333,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.tsum = reinterpret_cast<uint8_t*>(tsum);
 
     const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = sms;
     int grid = p.nitems < num_sms ? p.nitems : num_sms;
     if (pair) {
         grid = 2 * p.nitems2 < num_sms ? 2 * p.nitems2 : (num_sms & ~1);
@@ -1367,33 +1356,20 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     cfg.numAttrs = pair ? 2 : 1;
 #define SS_TRY_PAIR(PL, KS_, ST_, RB_)                                                                                     \
     if (!launched && pair && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {                         \
-        static bool attr = false;                                                                                          \
-        if (!attr) {                                                                                                       \
-            cudaFuncSetAttribute(conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, true>,                                  \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                                 \
-            attr = true;                                                                                                   \
-        }                                                                                                                  \
+        SS_ENSURE_SMEM((conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, true>), dev, 227 * 1024);                        \
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, true>, p);                              \
         launched = true;                                                                                                   \
     }
 #define SS_TRY(PL, KS_, ST_, RB_)                                                                                          \
     SS_TRY_PAIR(PL, KS_, ST_, RB_)                                                                                         \
     if (!launched && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {                                 \
-        static bool attr = false;                                                                                          \
-        if (!attr) {                                                                                                       \
-            cudaFuncSetAttribute(conv_i8_kernel<PL, KS_, ST_, RB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-            attr = true;                                                                                                   \
-        }                                                                                                                  \
+        SS_ENSURE_SMEM((conv_i8_kernel<PL, KS_, ST_, RB_>), dev, 227 * 1024);                                              \
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, ST_, RB_>, p);                                                    \
         launched = true;                                                                                                   \
     }
 #define SS_TRY_FIRST(PL)                                                                                                   \
     if (!launched && first && g->planes == PL) {                                                                           \
-        static bool attr = false;                                                                                          \
-        if (!attr) {                                                                                                       \
-            cudaFuncSetAttribute(conv_i8_kernel<PL, 1, 1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-            attr = true;                                                                                                   \
-        }                                                                                                                  \
+        SS_ENSURE_SMEM((conv_i8_kernel<PL, 1, 1, 128, true>), dev, 227 * 1024);                                            \
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 1, 1, 128, true>, p);                                                  \
         launched = true;                                                                                                   \
     }
@@ -1542,10 +1518,8 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
     p.g_mode = d->out_mode;
 
     const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
-    int dev = 0, num_sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
+    const int dev = current_device();
+    const int num_sms = device_sm_count(dev);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.nitems < num_sms ? p.nitems : num_sms));
     cfg.blockDim = dim3(THREADS);
@@ -1559,12 +1533,7 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
     bool launched = false;
 #define SS_TRY_CORR(PL, KS_, RB_)                                                                                                  \
     if (!launched && d->ntile == PL * 32 && d->ks == KS_ && p.RB == RB_) {                                                         \
-        static bool attr = false;                                                                                                  \
-        if (!attr) {                                                                                                               \
-            cudaFuncSetAttribute(conv_i8_kernel<PL, KS_, 1, RB_, false, MODE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 227 * 1024);                                                                                      \
-            attr = true;                                                                                                           \
-        }                                                                                                                          \
+        SS_ENSURE_SMEM((conv_i8_kernel<PL, KS_, 1, RB_, false, MODE_BF16>), dev, 227 * 1024);                                      \
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, 1, RB_, false, MODE_BF16>, p);                                            \
         launched = true;                                                                                                           \
     }

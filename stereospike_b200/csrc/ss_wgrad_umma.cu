@@ -508,10 +508,8 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
         set_error("ss_conv_wgrad_bf16: problem too large for 32-bit indexing");
         return SS_EINVAL;
     }
-    int dev = 0, num_sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
+    const int dev = current_device();
+    const int num_sms = device_sm_count(dev);
     const int pairs = p.nblk * p.nchunk * NGRP;
     long long ns = num_sms / pairs;                        // one wave: every CTA keeps its accumulators for its whole life,
                                                            // so a second, partial wave would double the kernel's duration
@@ -542,12 +540,7 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     bool launched = false;
 #define SS_TRY_WG(KS_, ST_, NB_, F4_, SH_)                                                                                       \
     if (!launched && g->ks == KS_ && g->stride == ST_ && NB == NB_ && first == F4_ && SH == SH_) {                               \
-        static bool attr = false;                                                                                                \
-        if (!attr) {                                                                                                             \
-            cudaFuncSetAttribute(conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_, SH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 227 * 1024);                                                                                    \
-            attr = true;                                                                                                         \
-        }                                                                                                                        \
+        SS_ENSURE_SMEM((conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_, SH_>), dev, 227 * 1024);                                      \
         conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_, SH_><<<grid, WG_THREADS, smem, st>>>(p);                                      \
         launched = true;                                                                                                         \
     }

@@ -102,19 +102,25 @@ class _NetFunction(torch.autograd.Function):
         res = eng._run_forward(x_seq, params, n_site_params, side, want_h=need_grad)
         names = side.get('spike_outputs') or ()
         spks = tuple(side['acts'][k][-1].permute(0, 3, 1, 2).float() for k in names) if need_grad else ()
+        depths = res['depths']
         if need_grad:
-            ctx.eng, ctx.side, ctx.n_site_params = eng, side, n_site_params
+            ctx.eng, ctx.n_site_params = eng, n_site_params
             ctx.params = params
-            ctx.saved = res
+            # the outputs must not be reachable from ctx (output -> grad_fn -> ctx -> output is a cycle only the cyclic GC
+            # breaks: every layer's h_seq would stay alive after a grad-enabled forward that is never back-propagated)
+            ctx.saved = {k: v for k, v in res.items() if k != 'depths'}
+            ctx.depth_shape, ctx.depth_device = tuple(depths.shape), depths.device
             ctx.spk_names = names
         side['spikes_fp32'] = spks
-        return (res['depths'],) + spks
+        return (depths,) + spks
 
     @staticmethod
     def backward(ctx, g_depths, *g_spks):
         saved = ctx.saved
+        if saved is None:
+            raise RuntimeError('stereospike_b200: backward through the same forward twice (the saved potentials were released)')
         if g_depths is None:
-            g_depths = torch.zeros_like(saved['depths'])
+            g_depths = torch.zeros(ctx.depth_shape, dtype=torch.float32, device=ctx.depth_device)
         inject = {k: gs for k, gs in zip(ctx.spk_names, g_spks) if gs is not None}
         grads = ctx.eng._run_backward(saved, ctx.params, ctx.n_site_params, g_depths.contiguous().float(), inject)
         ctx.saved = None
@@ -128,7 +134,13 @@ class Engine:
         self.weight_planes = 3
         self.keep_state = True
         self.timing = None          # bench.py: list of (site name, start event, end event) when not None
-        self.event_status = None    # optional device int32[1]: bit 0 set when an input frame was not integer counts 0..255
+        self.check_input = True     # fp32 frames must hold integer event counts 0..255 (the tensor-core path packs them to u8): a
+        #                             status word is written by ss_pack_events and checked WITHOUT a sync -- blocking on the very first
+        #                             call, then through a pinned host copy inspected at the start of a later call (ValueError)
+        self._status = None         # (device int32[1], pinned host int32[1], event) per device
+        self._status_checked_once = False
+        self.grad_hook = None       # parallel.OverlappedGradientSync: called with each weight-gradient tensor as soon as it is
+        #                             enqueued (reverse layer order), so that its all-reduce overlaps the rest of the backward
         self.fold_upsample = False  # NNConvUpsampling blocks as four folded 3x3 convs on the source + band passes (9 taps instead of
         #                             25, bit-identical integers, 3 bits less weight precision); off by default: the full-resolution blocks
         #                             are epilogue-bound, so the saved MMAs do not pay yet (profiles/r1e_fold_launches.txt)
@@ -164,12 +176,63 @@ class Engine:
             x_seq = x_seq.contiguous().float()
         params, n_site = self._flat_params()
         need_grad = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params)
+        self._poll_input_status()
+        if need_grad:
+            self._warn_truncated_bptt()
         if need_grad and x_seq.dtype == torch.uint8:
             raise NotImplementedError('packed u8 input is forward-only (the first layer\'s weight gradient reads the fp32 frames)')
         side = {'need_grad': need_grad, 'return_layers': return_layers, 'spike_outputs': tuple(spike_outputs or ())}
         outs = _NetFunction.apply(self, x_seq, side, n_site, *params)
         side['spikes_fp32'] = outs[1:]
         return outs[0], side
+
+    # ------------------------------------------------------------------ input validation without a sync
+    def _status_word(self, dev):
+        if self._status is None or self._status[0].device != dev:
+            self._status = (torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32).pin_memory(),
+                            torch.cuda.Event())
+            self._status_pending = False
+        return self._status[0]
+
+    def _poll_input_status(self, block=False):
+        """Raises ValueError if an earlier call was fed fp32 frames that are not integer event counts in 0..255 (they would have
+        been rounded / clamped by the u8 packing).  Non-blocking unless ``block``: reads a pinned copy once its event has fired."""
+        if self._status is None or not self._status_pending:
+            return
+        _, host, ev = self._status
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._status_pending = False
+        if int(host[0]) != 0:
+            self._status[0].zero_()
+            raise ValueError('stereospike_b200: an input frame passed to the tensor-core path was not integer event counts in 0..255 '
+                             '(normalised or > 255 events per pixel); its values were rounded / clamped. Use '
+                             "set_kernel_options(impl='simt') for arbitrary fp32 input.")
+
+    def _record_input_status(self):
+        dev_w, host, ev = self._status
+        host.copy_(dev_w, non_blocking=True)
+        ev.record()
+        self._status_pending = True
+        if not self._status_checked_once:
+            self._status_checked_once = True
+            self._poll_input_status(block=True)        # the first call pays one sync so that a wrong data pipeline fails at once
+
+    def _warn_truncated_bptt(self):
+        """The whole network is one autograd node per call and the carried membrane potentials are detached, so several
+        grad-enabled forward() calls before one backward() give TRUNCATED BPTT (the reference back-propagates through every call
+        until net.detach()).  Multi-step BPTT goes through forward_seq.  Warn once instead of silently differing."""
+        import warnings
+        for s in self.sites:
+            if isinstance(s.node.v, torch.Tensor) and getattr(s.node, '_v_from_grad_call', False):
+                warnings.warn('stereospike_b200: neuron state carried in from a previous grad-enabled call is detached -- gradients '
+                              'do not flow across separate forward() calls (truncated BPTT). Use forward_seq(x_seq) for multi-step '
+                              'BPTT, or call net.detach() / functional.reset_net(net) between steps to silence this.', stacklevel=4)
+                for t in self.sites:
+                    t.node._v_from_grad_call = False
+                return
 
     # ------------------------------------------------------------------ forward
     def _run_forward(self, x_seq, params, n_site, side, want_h):
@@ -206,8 +269,11 @@ class Engine:
                           tau=node._tau_value(), decay=decay, v_in=v_in, want_v_out=self.keep_state, resid=resid, want_h=want_h)
             if use_i8:
                 if first and not packed_in:
-                    xin = ops.pack_events(x_seq, self.event_status)     # fp32 NCHW counts -> u8 NHWC4
+                    status = self._status_word(dev) if self.check_input else None
+                    xin = ops.pack_events(x_seq, status)     # fp32 NCHW counts -> u8 NHWC4
                     acts['x_packed'] = xin
+                    if status is not None and not torch.cuda.is_current_stream_capturing():
+                        self._record_input_status()
                 tsum = None
                 if s.out in head_srcs and self.heads_time_sum and 1 < T <= 86:
                     tsum = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=ops.ACT_DTYPE, device=dev)
@@ -228,6 +294,7 @@ class Engine:
             acts[s.out] = out
             if self.keep_state:
                 node.v = v_out.permute(0, 3, 1, 2)     # NCHW-shaped view, as the reference exposes it
+                node._v_from_grad_call = bool(want_h)
             saved['sites'].append({'geom': g, 'w_kn': w_kn, 'decay': decay, 'h_seq': h_seq, 'v_in': v_in})
         # heads + I-neurons
         hg, hw, hb, hacts = [], [], [], []
@@ -270,6 +337,9 @@ class Engine:
         dev = g_depths.device
         grads = [None] * len(params)
         g = {}
+        hook = self.grad_hook
+        if hook is not None:
+            hook.begin()
 
         def gbuf(name, fresh_ok=False):
             if name not in g:
@@ -306,6 +376,9 @@ class Engine:
             C = saved['hg'][j].Cin
             grads[n_site + 2 * j] = gw_t[j].reshape(3, 3, C).permute(2, 0, 1).reshape(1, C, 3, 3).contiguous()
             grads[n_site + 2 * j + 1] = gb_t[j]
+            if hook is not None:
+                hook.ready(grads[n_site + 2 * j])
+                hook.ready(grads[n_site + 2 * j + 1])
 
         # ---- gradients arriving on the returned spike maps (last timestep, NCHW) join the buffers the heads just created
         for name, gs in (inject or {}).items():
@@ -357,6 +430,10 @@ class Engine:
             grads[2 * i] = ops.kn_to_weight(g_wkn, gm.Cout, gm.Cin, gm.ks)
             if g_decay is not None:
                 grads[2 * i + 1] = g_decay.reshape(params[2 * i + 1].shape)
+            if hook is not None:
+                # all-reduce this block's gradient now, on NCCL's stream, while the earlier layers' gradients are computed
+                hook.ready(grads[2 * i])
+                hook.ready(grads[2 * i + 1])
             if not first:
                 gx = gbuf(s.src)
                 if tc_d:
@@ -366,6 +443,8 @@ class Engine:
                     rc = L.ss_conv_dgrad(ctypes.byref(cg), _ptr(ym), _ptr(xm), _ptr(w_kn), _ptr(g_acc), _ptr(gx), _stream())
                     _lib.check(rc, 'ss_conv_dgrad')
             del g_acc, g_b16, g_out
+        if hook is not None:
+            hook.finish()
         return grads
 
 

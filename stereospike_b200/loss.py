@@ -50,11 +50,12 @@ class _FusedLoss(torch.autograd.Function):
         wgm = torch.tensor(w_gm, dtype=torch.float64, device=gt.device)
         ctx.save_for_backward(gt, sums, signs, *ps)
         ctx.w_si, ctx.w_gm, ctx.shapes = w_si, w_gm, [p.shape for p in preds]
-        ctx.mde = (sums[:, 4] / n).float()
-        return (wsi * si + wgm * gm).sum().float()
+        mde = (sums[:, 4] / n).float()                  # MeanDepthError of every scale, from the same pass (metrics.py:83-95)
+        ctx.mark_non_differentiable(mde)
+        return (wsi * si + wgm * gm).sum().float(), mde
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_out, _g_mde=None):
         gt, sums, signs, *ps = ctx.saved_tensors
         n = len(ps)
         B, H, W = gt.shape
@@ -74,6 +75,7 @@ def _terms(predicted, groundtruth, w_si, w_gm):
     gt_full = groundtruth
     _require_cuda(gt_full, 'groundtruth')
     total = None
+    mdes = {}
     by_size = {}
     for k, m in enumerate(predicted):
         by_size.setdefault((m.shape[-2], m.shape[-1]), []).append(k)
@@ -82,33 +84,35 @@ def _terms(predicted, groundtruth, w_si, w_gm):
         gt = _maps_bhw(gt, 'groundtruth')
         for i in range(0, len(ks), 4):
             chunk = ks[i:i + 4]
-            val = _FusedLoss.apply(gt, tuple(float(w_si[k]) for k in chunk), tuple(float(w_gm[k]) for k in chunk),
-                                   *[predicted[k] for k in chunk])
+            val, mde = _FusedLoss.apply(gt, tuple(float(w_si[k]) for k in chunk), tuple(float(w_gm[k]) for k in chunk),
+                                        *[predicted[k] for k in chunk])
+            for j, k in enumerate(chunk):
+                mdes[k] = mde[j]
             total = val if total is None else total + val
-    return total
+    return total, mdes
 
 
 def ScaleInvariant_Loss(predicted, groundtruth):
     """loss.py:7-24."""
-    return _terms([predicted], groundtruth, [1.0], [0.0])
+    return _terms([predicted], groundtruth, [1.0], [0.0])[0]
 
 
 def GradientMatching_Loss(predicted, groundtruth):
     """loss.py:44-76."""
-    return _terms([predicted], groundtruth, [0.0], [1.0])
+    return _terms([predicted], groundtruth, [0.0], [1.0])[0]
 
 
 def Multiscale_ScaleInvariant_Loss(predicted, groundtruth, factors=(1., 1., 1., 1.)):
     """loss.py:27-41."""
     ps = list(predicted)[:len(factors)]
-    return _terms(ps, groundtruth, list(factors)[:len(ps)], [0.0] * len(ps))
+    return _terms(ps, groundtruth, list(factors)[:len(ps)], [0.0] * len(ps))[0]
 
 
 def MultiScale_GradientMatching_Loss(predicted, groundtruth, factors=(1., 1., 1., 1.)):
     """loss.py:79-93."""
     ps = list(predicted)[:len(factors)]
     f = list(factors)[:len(ps)]
-    return _terms(ps, groundtruth, [0.0] * len(ps), f)
+    return _terms(ps, groundtruth, [0.0] * len(ps), f)[0]
 
 
 def SpikePenalization_Loss(intermediary_spike_tensors):
@@ -136,7 +140,8 @@ class Total_Loss(nn.Module):
     def forward(self, predicted, groundtruth, intermediary_spike_tensors=None):
         ps = list(predicted)[:len(self.scale_weights)]
         w = [float(f) for f in list(self.scale_weights)[:len(ps)]]
-        loss = _terms(ps, groundtruth, w, [self.alpha * f for f in w])
+        loss, mdes = _terms(ps, groundtruth, w, [self.alpha * f for f in w])
+        self.last_mde = mdes[0].detach()                # device scalar: no host sync unless the caller reads it
         if self.penalize_spikes:
             loss = loss + self.beta * SpikePenalization_Loss(intermediary_spike_tensors)
         return loss

@@ -44,6 +44,7 @@ class NeuromorphicNet(nn.Module):
         for m in self.modules():
             if isinstance(m, neuron.BaseNode) and isinstance(m.v, torch.Tensor):
                 m.v = m.v.detach()
+                m._v_from_grad_call = False        # an explicit truncation point, like in the reference (train.py:242)
 
     def get_network_state(self):
         return [m.v for m in self.modules() if hasattr(m, 'reset')]

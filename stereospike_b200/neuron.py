@@ -40,7 +40,7 @@ class _NeuronStep(torch.autograd.Function):
         decay = decay if decay.numel() else None
         g_s = g_s.contiguous().float()
         g_x = torch.empty_like(h)
-        g_decay = torch.zeros((), device=h.device) if decay is not None else None
+        g_decay = torch.zeros((1,), dtype=torch.float32, device=h.device) if decay is not None else None     # decay_tensor() is [1]
         sf = node.surrogate_function
         rc = _lib.lib().ss_neuron_bwd(1, h.numel(), node.kind, sf.kind, sf.alpha, 1.0, node.v_threshold,
                                       node._v_reset_value(), node._tau_value(), _ptr(decay), _ptr(h), _ptr(v0),

@@ -77,6 +77,85 @@ class GradientSynchronizer:
         return len(self.buckets)
 
 
+class OverlappedGradientSync:
+    """Gradient all-reduce issued from INSIDE the backward pass, block by block ("bucketed in
+    reverse-layer order and overlapped with the remaining backward"; the step it mirrors per rank: train.py:189-242).
+
+    The engine computes the blocks' weight gradients in reverse layer order (engine._run_backward).  As soon as the kernel that
+    produces one is enqueued, ``ready(g)`` launches ``dist.all_reduce(g, async_op=True)`` IN PLACE on that tensor: NCCL's stream
+    waits (event) for the producing kernel and then runs concurrently with the dgrad / wgrad kernels of the earlier layers on
+    the compute stream.  No flat copy-in / copy-out of the 72.6 MB gradient; only the tiny tensors (head weights / biases, PLIF
+    decays: < ``small_numel`` elements each) are coalesced into one flat message at the end.  ``finish()`` makes the compute
+    stream wait for the outstanding collectives before autograd hands the gradients to the optimizer -- by then only the last
+    (smallest: the first layer's 3 200 weights) all-reduce can still be in flight, so almost nothing is exposed.
+
+        sync = OverlappedGradientSync(net).attach()
+        sync.set_batch(local_samples=B, global_samples=B * world)
+        loss.backward()          # all-reduces happen in here
+        optimizer.step()
+
+    Gradients of a per-rank MEAN loss are scaled by local/global samples and summed -> gradient of the global-batch mean."""
+
+    def __init__(self, net, group=None, small_numel=1 << 16):
+        self.engine = net.engine if hasattr(net, 'engine') else net
+        self.group = group
+        self.small_numel = int(small_numel)
+        self.scale = None
+        self._works, self._small = [], []
+        self.collectives = 0          # issued during the last backward (tests / bench)
+
+    def attach(self):
+        self.engine.grad_hook = self
+        return self
+
+    def detach(self):
+        if self.engine.grad_hook is self:
+            self.engine.grad_hook = None
+        return self
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def set_batch(self, local_samples=1, global_samples=None):
+        world = dist.get_world_size(self.group) if self._active() else 1
+        if global_samples is None:
+            global_samples = local_samples * world
+        self.scale = float(local_samples) / float(global_samples)
+        return self
+
+    def begin(self):
+        self._works, self._small, self.collectives = [], [], 0
+
+    def ready(self, g):
+        """``g``: a finished (enqueued on the current stream) contiguous gradient tensor; reduced in place."""
+        if g is None or not self._active():
+            return
+        if g.numel() < self.small_numel:
+            self._small.append(g)
+            return
+        scale = self.scale if self.scale is not None else 1.0 / dist.get_world_size(self.group)
+        g.mul_(scale)
+        self._works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.collectives += 1
+
+    def finish(self):
+        if not self._active():
+            return
+        if self._small:
+            scale = self.scale if self.scale is not None else 1.0 / dist.get_world_size(self.group)
+            flat = torch.cat([g.reshape(-1) for g in self._small]).mul_(scale)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True).wait()
+            self.collectives += 1
+            off = 0
+            for g in self._small:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+        for w in self._works:
+            w.wait()              # the compute stream waits for NCCL's stream; the host does not block
+        self._works, self._small = [], []
+
+
 def allreduce_gradients(module_or_params, local_samples=1, global_samples=None, bucket_bytes=32 << 20, group=None):
     """One-shot helper around :class:`GradientSynchronizer` (allocates the buckets on every call)."""
     params = module_or_params.parameters() if hasattr(module_or_params, 'parameters') else module_or_params

@@ -78,3 +78,52 @@ def test_shard_bounds_cover_batch():
             spans = [parallel.shard_bounds(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from stereospike_b200 import parallel
+
+    class _Eng:            # stands in for engine.Engine: only the hook attribute is used
+        grad_hook = None
+    eng = _Eng()
+    sync = parallel.OverlappedGradientSync(eng, small_numel=32).attach()
+    sync.set_batch(local_samples=3 if rank == 0 else 1, global_samples=4)      # uneven shards
+    assert eng.grad_hook is sync
+    g = torch.Generator().manual_seed(10 + rank)
+    grads = [torch.randn(n, generator=g) for n in (5, 4096, 7, 640, 1, 100)]   # big ones reduce in place, small ones coalesce
+    sync.begin()
+    for t in grads:                 # the order the engine calls the hook in: one gradient after the other
+        sync.ready(t)
+    sync.ready(None)                # a parameter without gradient (non-PLIF decay slot)
+    sync.finish()
+    q.put((rank, sync.collectives, [t.clone() for t in grads]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_sync_reduces_in_place():
+    """OverlappedGradientSync (the hook engine._run_backward calls per block): large tensors are all-reduced in place as they
+    become ready, small ones in one coalesced message; result = sample-weighted mean over the ranks."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = []
+    gens = [torch.Generator().manual_seed(10 + r) for r in range(world)]
+    per_rank = [[torch.randn(n, generator=g) for n in (5, 4096, 7, 640, 1, 100)] for g in gens]
+    for a, b in zip(*per_rank):
+        want.append(a * 0.75 + b * 0.25)
+    for rank, ncoll, grads in got:
+        assert ncoll == 4          # 4096, 640, 100 in place + one coalesced message for 5 + 7 + 1
+        for a, b in zip(grads, want):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)

@@ -40,7 +40,7 @@ MFLOP_PER_FRAME = {'bottom': 575.7, 'conv1': 2303.0, 'conv2': 2316.3, 'conv3': 2
                    'bottleneck.1.conv2': 1764.8, 'deconv4': 9515.8, 'deconv3': 9265.2, 'deconv2': 9211.9,
                    'deconv1': 9211.9, 'heads': 777.2}
 TOTAL_GFLOP_PER_FRAME = sum(MFLOP_PER_FRAME.values()) / 1e3
-FOLD_DEFAULT = 0      # decoder blocks folded to 3x3 convs on the source by default?
+FOLD_DEFAULT = 1      # decoder blocks folded to 3x3 convs on the source (engine default)
 
 
 def measured_peaks():
@@ -442,7 +442,7 @@ def run_ours(args):
     if not train and not args.no_train:
         del xs, pipe
         torch.cuda.empty_cache()
-        tsteps, twarm = min(args.steps, 10), 3
+        tsteps, twarm = max(5, min(args.steps, 20)), 5
         ms_sync, ms_nosync, ncoll, tl = time_training(args, dev, world, rank, args.train_batch, tsteps, twarm, barrier)
         tt = torch.tensor([ms_sync, ms_nosync], dtype=torch.float64, device=dev)
         if world > 1:

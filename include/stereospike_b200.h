@@ -128,37 +128,51 @@ int ss_conv_i8_fwd(const ss_block_desc* g, const void* x, const void* w_i8, cons
                    const float* v_in, float* v_out, const void* resid, void* out, float* h_seq, void* tsum, void* stream);
 
 /* Tile iteration of ss_conv_i8_fwd_ex.  NNConvUpsampling (blocks.py:110-132) by ~2x replicates every source pixel 2 (rarely
- * 3) times, so the 5x5 conv over the upsampled image reads only 3x3 DISTINCT source pixels per output: with the integer
- * weights of the replicated taps summed (exactly), the block folds into four 3x3 convs on the SOURCE image, one per
- * (row class, column class) of the output -- 9 taps instead of 25, bit-identical integer sums.  Output rows/columns next to a
- * 3-fold replication (a few % of the image) do not fit that pattern and are computed by the general kernel on bands.
- *   SS_TILES_FOLDED   : g = the virtual conv (ks 3, stride 1, pad 0, upsample 0, Hin/Win = source, Hout/Wout = REAL output);
- *                       w_i8 holds 4 weight sets per output-channel tile (packed with Cout' = 4*Cout, set = tile*4 + class,
- *                       class = 2*row_class + col_class); ymap_out [2][Hin-2], xmap_out [2][Win-2]: real output row / column of
- *                       virtual position s for class 0 / 1, or -1
- *   SS_TILES_ROW_BANDS: g = the real upsampled conv; only output rows band_start[i] .. +band_len[i] (band_len <= band_rows)
- *   SS_TILES_COL_BANDS: same for output columns (band_len <= 8) */
+ * 3) times, so the 5 taps of an axis of the 5x5 conv over the upsampled image read only 3 (or 2) DISTINCT source pixels per
+ * output.  Per axis every output o has a first source pixel s0(o) and one of five replication patterns (the source index of
+ * its 5 taps relative to s0): L (0,1,1,2,2), M (0,0,1,1,2) -- the two regular ones -- and next to a 3-fold replication
+ * A (0,0,0,1,1), B (0,1,1,1,2), C (0,0,1,1,1).  With the integer weights of the replicated taps summed (exactly) the block
+ * becomes, bit for bit:
+ *   SS_TILES_FOLDED   : four 3x3 convs on the SOURCE image, one per (row class, column class) in {L,M}^2 -- 9 taps instead of
+ *                       25 for every output whose row AND column are regular (93 % at 260x346).  g = the virtual conv (ks 3,
+ *                       stride 1, pad 0, upsample 0, Hin/Win = source, Hout/Wout = REAL output); w_i8 holds 4 weight sets per
+ *                       output-channel tile (packed with Cout' = 4*Cout, set = tile*4 + class, class = 2*row_class +
+ *                       col_class); ymap_out [2][Hin-2], xmap_out [2][Win-2]: real output row / column of virtual position s
+ *                       for class L / M, or -1.
+ *   SS_TILES_ROW_LIST : the irregular output rows (classes A, B, C) over all columns: rows folded to 3 taps, columns still
+ *                       the 5 taps over the upsampled row -- 15 taps.  g = the real upsampled conv (ks 5, upsample 1).  A
+ *                       tile row is an entry of the class's list: rl_src / rl_out [nclass][rl_n] = pixel offset (inside one
+ *                       timestep, i.e. (b*H + row)*W) of the entry's first source row / of its output row, -1 = padding entry;
+ *                       w_i8 = nclass weight sets per output-channel tile (ss_pack_digits_i8_rect with Cout' = nclass*Cout,
+ *                       ksy 3, ksx 5).  transposed = 1: the same pass for the irregular output COLUMNS -- the list entries
+ *                       are (sample, output column) (offsets b*H*W + column), the tile columns walk the rows, the weight sets
+ *                       are those of the transposed filter, and rl_collive [Hout] masks the rows the row pass already wrote. */
 #define SS_TILES_PLAIN 0
 #define SS_TILES_FOLDED 1
-#define SS_TILES_ROW_BANDS 2
-#define SS_TILES_COL_BANDS 3
+#define SS_TILES_ROW_LIST 2
 typedef struct ss_tile_maps {
     int32_t mode;
-    int32_t nbands, band_rows;
-    int32_t reserved;
+    int32_t nclass;        /* ROW_LIST: weight sets per output-channel tile */
+    int32_t rl_n;          /* ROW_LIST: entries per class (lists padded with -1 to a common length) */
+    int32_t transposed;    /* ROW_LIST: 0 = list of output rows, 1 = list of output columns */
     const int32_t* ymap_out;
     const int32_t* xmap_out;
-    const int32_t* band_start;
-    const int32_t* band_len;
+    const int32_t* rl_src;
+    const int32_t* rl_out;
+    const uint8_t* rl_collive;
 } ss_tile_maps;
 int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
                       const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,
                       void* tsum, void* stream);
 
 /* Digit planes of ALREADY QUANTISED integer weights (fp32 holding exact integers, |q| < 2^(8*planes-1)), same layout as
- * ss_pack_weights_i8; zero_exp: device int32 [Cout] of zeros.  Used for the folded weight sets (sums of quantised taps). */
+ * ss_pack_weights_i8; zero_exp: device int32 [Cout] of zeros.  Used for the folded weight sets (sums of quantised taps).
+ * _rect: filters of ksy rows x ksx columns (OIHW [Cout][Cin][ksy][ksx]); ksy != ksx selects the 32-byte-row image of the
+ * row-list pass. */
 int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, const int32_t* zero_exp,
                       void* w_i8, void* stream);
+int ss_pack_digits_i8_rect(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ksy, int32_t ksx, int32_t planes,
+                           const int32_t* zero_exp, void* w_i8, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Same block on the CUDA cores in plain fp32 (exact fp32 weights, ascending-k accumulation): the first-layer

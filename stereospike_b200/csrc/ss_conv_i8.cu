@@ -63,11 +63,18 @@ struct I8Params {
     int Hv, Wv;            // iteration space of the tiles (== Hout, Wout except for the folded / band passes of an upsampled conv)
     int mode;              // SS_TILES_*
     int nclass;            // weight sets per output-channel tile (folded pass: 4 = {L,M} x {L,M}), else 1
-    int nbands, band_rows; // band passes
     const int* ymap_out;   // folded: [2][Hv] real output row of virtual row s for class L, M, or -1
     const int* xmap_out;   // folded: [2][Wv]
-    const int* band_start; // band passes: first output row / column of each band
-    const int* band_len;   // band passes: rows / columns in each band
+    // row-list pass (SS_TILES_ROW_LIST): tile row r of m-tile row ty of class c is entry e = ty*16 + r of the class's list
+    const int* rl_src;     // [nclass][rl_n] pixel offset (inside one timestep) of the entry's first source row at column 0, or -1
+    const int* rl_out;     // [nclass][rl_n] pixel offset of the entry's output row at column 0, or -1
+    const uint8_t* rl_collive;   // [c_nout] 1 = this output column belongs to the pass (NULL = all)
+    int rl_n;              // entries per class (padded with -1 to a common length)
+    int in_rowstep;        // pixels between the ROWSTEP source rows of an entry (Win; 1 for the transposed pass)
+    int in_colpitch;       // pixels between neighbouring source columns (1; Win for the transposed pass)
+    int out_colpitch;      // pixels between neighbouring output columns (1; Wout for the transposed pass)
+    int c_in, c_up, c_nout;   // column axis: source size, upsampled size, outputs
+    float c_scale;            // float(c_in) / c_up
     int TC, NPS, WB, PB;
     int resident;
     int nwb;               // weight buffers allocated in shared memory (1 when a single channel block is resident)
@@ -124,46 +131,56 @@ __host__ inline uint32_t div_magic(long long d, long long n_max) {
 }
 
 // ------------------------------------------------------------------------------------------------ geometry
-// Source row (b*Hin + iy) read by patch row `pr` of tile row `ty`, or -1 (zero padding / gap between stacked images).
-template <int STRIDE>
-__device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr) {
-    const int gi = ty * 16 * STRIDE + pr;
-    const int per = STRIDE * p.HsO;
-    int b = fast_div(gi, per, p.m_per);
-    int local = gi - b * per;
-    if (p.mode == SS_TILES_ROW_BANDS) {
-        // stacked mini-images: (sample, band); `local` indexes the upsampled rows band_start .. band_start + band_rows + ks - 2
-        const int band = b % p.nbands;
-        b /= p.nbands;
-        local += __ldg(p.band_start + band);
-    }
-    if (b >= p.B) return -1;
-    if (p.upsample) {
-        if (local >= p.Hup) return -1;
-        // ATen upsample_nearest: min(int(floorf(dst * scale)), in - 1), scale = float(in) / out
-        const int iy = min((int)floorf((float)local * p.yscale), p.Hin - 1);
-        return b * p.Hin + iy;
-    }
-    const int iy = local - p.pad;
-    return (iy >= 0 && iy < p.Hin) ? b * p.Hin + iy : -1;
-}
-template <int STRIDE, int PWHALF>
-__device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
-    if (p.upsample) {
-        const int u = (p.mode == SS_TILES_COL_BANDS ? __ldg(p.band_start + tx) : tx * 8) + pc;
-        if (u >= p.Wup) return -1;
-        return min((int)floorf((float)u * p.xscale), p.Win - 1);
-    }
-    int ix;
-    if (STRIDE == 1) {
-        ix = tx * 8 + pc - p.pad;
+// Pixel offset (inside one timestep) of the source row read by patch row `pr` of tile row `ty`, at column 0, or -1 (zero
+// padding / gap between stacked images / dead list entry).
+template <int STRIDE, int ROWSTEP>
+__device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr, int cls) {
+    if constexpr (ROWSTEP > 1) {
+        // row list: every tile row has its own ROWSTEP source rows (no sliding window between tile rows)
+        const int e = ty * 16 + pr / ROWSTEP;
+        if (e >= p.rl_n) return -1;
+        const int s0 = __ldg(p.rl_src + cls * p.rl_n + e);
+        return s0 < 0 ? -1 : s0 + (pr % ROWSTEP) * p.in_rowstep;
     } else {
-        // parity-split row: [even-type columns | odd-type columns]; input col = 2*(ox0 - pad/2 + idx) + plane
-        const int plane = pc / PWHALF;
-        const int idx = pc - plane * PWHALF;
-        ix = 2 * (tx * 8 - p.pad / 2 + idx) + plane;
+        const int gi = ty * 16 * STRIDE + pr;
+        const int per = STRIDE * p.HsO;
+        const int b = fast_div(gi, per, p.m_per);
+        const int local = gi - b * per;
+        if (b >= p.B) return -1;
+        if (p.upsample) {
+            if (local >= p.Hup) return -1;
+            // ATen upsample_nearest: min(int(floorf(dst * scale)), in - 1), scale = float(in) / out
+            const int iy = min((int)floorf((float)local * p.yscale), p.Hin - 1);
+            return (b * p.Hin + iy) * p.Win;
+        }
+        const int iy = local - p.pad;
+        return (iy >= 0 && iy < p.Hin) ? (b * p.Hin + iy) * p.Win : -1;
     }
-    return (ix >= 0 && ix < p.Win) ? ix : -1;
+}
+// Pixel offset along the row of patch column `pc` of tile column `tx`, or -1.
+template <int STRIDE, int PWHALF, int ROWSTEP>
+__device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
+    if constexpr (ROWSTEP > 1) {
+        const int u = tx * 8 + pc;             // column of the (virtual) upsampled image
+        if (u >= p.c_up) return -1;
+        return min((int)floorf((float)u * p.c_scale), p.c_in - 1) * p.in_colpitch;
+    } else {
+        if (p.upsample) {
+            const int u = tx * 8 + pc;
+            if (u >= p.Wup) return -1;
+            return min((int)floorf((float)u * p.xscale), p.Win - 1);
+        }
+        int ix;
+        if (STRIDE == 1) {
+            ix = tx * 8 + pc - p.pad;
+        } else {
+            // parity-split row: [even-type columns | odd-type columns]; input col = 2*(ox0 - pad/2 + idx) + plane
+            const int plane = pc / PWHALF;
+            const int idx = pc - plane * PWHALF;
+            ix = 2 * (tx * 8 - p.pad / 2 + idx) + plane;
+        }
+        return (ix >= 0 && ix < p.Win) ? ix : -1;
+    }
 }
 // patch pixel at which the A operand of tap (ky,kx) starts
 template <int STRIDE, int PWP, int PWHALF>
@@ -173,18 +190,18 @@ __device__ __forceinline__ constexpr int tap_offset(int ky, int kx) {
 
 // Issues every MMA of one (patch stage, weight buffer) pair except the very first one (tap 0, k-step 0), which the
 // caller issues itself because it carries the run-time accumulate flag.
-template <int MODE, int KS, int STRIDE, int RB, int CN, int PWP, int PWHALF, int TAP = 0, int K = 1>
+template <int MODE, int KS, int KSX, int STRIDE, int RB, int CN, int PWP, int PWHALF, int TAP = 0, int K = 1>
 __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0, uint32_t idesc) {
     constexpr int KSTEPS = RB / 32;
-    if constexpr (TAP < KS * KS) {
+    if constexpr (TAP < KS * KSX) {
         if constexpr (K < KSTEPS) {
-            constexpr int ky = TAP / KS, kx = TAP % KS;
+            constexpr int ky = TAP / KSX, kx = TAP % KSX;
             constexpr uint32_t aoff = (uint32_t)(tap_offset<STRIDE, PWP, PWHALF>(ky, kx) * RB + K * 32) >> 4;
             constexpr uint32_t boff = (uint32_t)(TAP * CN * RB + K * 32) >> 4;
             umma_i8_off<aoff, boff, MODE>(d, a0, b0, idesc);
-            issue_taps<MODE, KS, STRIDE, RB, CN, PWP, PWHALF, TAP, K + 1>(d, a0, b0, idesc);
+            issue_taps<MODE, KS, KSX, STRIDE, RB, CN, PWP, PWHALF, TAP, K + 1>(d, a0, b0, idesc);
         } else {
-            issue_taps<MODE, KS, STRIDE, RB, CN, PWP, PWHALF, TAP + 1, 0>(d, a0, b0, idesc);
+            issue_taps<MODE, KS, KSX, STRIDE, RB, CN, PWP, PWHALF, TAP + 1, 0>(d, a0, b0, idesc);
         }
     }
 }
@@ -195,14 +212,18 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // PAIR: two CTAs of a 2-cluster process two m-tiles against the same weight set with one tcgen05.mma.cta_group::2 (M = 256):
 // each CTA stages its own patch and HALF of the weight rows, so the shared-memory operand feed per MMA drops from 7 KB to
 // 5.5 KB per SM (N = 96) and the MMA leaves the feed-bound regime.  Rank 0 issues; rank 1 relays its producers' barriers.
-template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false>
+// KSX / ROWSTEP: rectangular filters (KS rows x KSX columns) and the row-list pass of a folded NNConvUpsampling block, whose
+// tile rows are arbitrary (sample, output row) entries with ROWSTEP private source rows each (patch row = ROWSTEP * tile row + ky).
+template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false, int KSX = KS, int ROWSTEP = 1>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
-    constexpr int cNTAPS = KS * KS;
-    constexpr int cPWhalf = 8 + (KS - 1) / 2;
-    constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
-    constexpr int cPH = 15 * STRIDE + KS;
+    constexpr int cNTAPS = KS * KSX;
+    constexpr int cPWhalf = 8 + (KSX - 1) / 2;
+    constexpr int cPWp = STRIDE == 1 ? 8 + KSX - 1 : 2 * cPWhalf;
+    constexpr int cPH = ROWSTEP > 1 ? 16 * ROWSTEP : 15 * STRIDE + KS;
+    static_assert(ROWSTEP == 1 || (STRIDE == 1 && ROWSTEP >= KS && !FIRST && !PAIR && MODE == MODE_I8), "row-list pass: stride-1 int8 blocks");
+    static_assert(cPH <= 48 && cPWp <= 24, "geometry tables");
     constexpr int cPPIX = cPH * cPWp;
     constexpr int cNB = PAIR ? cN / 2 : cN;                 // weight rows (of the MMA's N) held by this CTA
     constexpr int cWB = cNTAPS * cNB * RB;
@@ -218,9 +239,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     const uint32_t w_base = base;
     const uint32_t patch_base = base + (uint32_t)p.nwb * cWB;
     uint8_t* tail = sm + (size_t)p.nwb * cWB + (size_t)p.NPS * cPB;
-    int* rowsrc = reinterpret_cast<int*>(tail);              // [2][40]
-    int* colsrc = rowsrc + 80;                               // [2][24]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
+    int* rowsrc = reinterpret_cast<int*>(tail);              // [2][48]
+    int* colsrc = rowsrc + 96;                               // [2][24]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 640);
     // bars: full_p[8], empty_p[8], full_w[2], empty_w[2], full_a[8], empty_a[8], tok[2]
     // (+ raw_full[2], raw_empty[2] of the first-layer producers at bars + 38)
     // (+ CTA pairs: peer_full_p[8] at bars + 42, peer_full_w[2] at bars + 50: the peer CTA's producers, relayed to rank 0)
@@ -294,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         // shared-memory loads / 16-byte stores (bytes 100..127 = 0).  Only the expanding warps fence towards the async proxy,
         // and they never have global loads in flight, so the fence does not wait for memory.
         constexpr int PH5 = 20, PW5 = 12;            // halo patch of the real 5x5 filter (the template's KS is the single im2col "tap")
-        uint8_t* raw = tail + 1024;                  // [2][1024]
+        uint8_t* raw = tail + 1152;                  // [2][1024]
         const uint32_t bar_raw_full = smem_u32(bars + 38);
         const uint32_t bar_raw_empty = smem_u32(bars + 40);
         const size_t t_stride = (size_t)p.B * p.Hin * p.Win * 4;
@@ -316,10 +337,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             for (int it = it0; it < nit; it += its, ++itcount) {
                 const int mt = it % p.mtiles;
                 const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
-                int* rs = rowsrc + (itcount & 1) * 40;
+                int* rs = rowsrc + (itcount & 1) * 48;
                 int* cs = colsrc + (itcount & 1) * 24;
-                if (tid < PH5) rs[tid] = row_source<1>(p, ty, tid);
-                if (tid >= 32 && tid - 32 < PW5) cs[tid - 32] = col_source<1, 10>(p, tx, tid - 32);
+                if (tid < PH5) rs[tid] = row_source<1, 1>(p, ty, tid, 0);
+                if (tid >= 32 && tid - 32 < PW5) cs[tid - 32] = col_source<1, 10, 1>(p, tx, tid - 32);
                 named_sync(1, 64);
                 int goff[4];
 #pragma unroll
@@ -327,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     goff[i] = -2;
                     if (urow[i] >= 0) {
                         const int r = rs[urow[i]], c = cs[pair ? 2 * useg[i] : useg[i]];
-                        goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * 4 : -1;
+                        goff[i] = (r >= 0 && c >= 0) ? (r + c) * 4 : -1;
                     }
                 }
                 for (int t = 0; t < p.T; ++t) {
@@ -418,10 +439,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const int ntile = fast_div(it, mt_per, m_mt_per);
             const int mt = PAIR ? 2 * (it - ntile * mt_per) + (int)crank : it - ntile * mt_per;   // (an odd tail tile is all padding)
             const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
-            int* rs = rowsrc + (itcount & 1) * 40;
+            int* rs = rowsrc + (itcount & 1) * 48;
             int* cs = colsrc + (itcount & 1) * 24;
-            if (tid < cPH) rs[tid] = row_source<STRIDE>(p, ty, tid);
-            if (tid >= 64 && tid - 64 < cPWp) cs[tid - 64] = col_source<STRIDE, cPWhalf>(p, tx, tid - 64);
+            if (tid < cPH) rs[tid] = row_source<STRIDE, ROWSTEP>(p, ty, tid, ntile % p.nclass);
+            if (tid >= 64 && tid - 64 < cPWp) cs[tid - 64] = col_source<STRIDE, cPWhalf, ROWSTEP>(p, tx, tid - 64);
             named_sync(1, 128);
             int goff[cNU];
 #pragma unroll
@@ -430,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 if (urc[i] >= 0) {
                     const int r = rs[urc[i] >> 5], c = cs[urc[i] & 31];
                     const int ch = (tid + i * 128) % chunks;
-                    goff[i] = (r >= 0 && c >= 0) ? (r * p.Win + c) * p.Cin + ch * 16 : -1;
+                    goff[i] = (r >= 0 && c >= 0) ? (r + c) * p.Cin + ch * 16 : -1;
                 }
             }
             SS_ACC(0, 0);     // geometry
@@ -526,7 +547,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             constexpr uint32_t idesc = (MODE == MODE_I8 ? ((2u << 4) | (0u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
                                        ((uint32_t)(cN >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
             constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
-            constexpr uint32_t a_sbo = (uint32_t)(STRIDE * cPWp * RB);
+            constexpr uint32_t a_sbo = (uint32_t)((ROWSTEP > 1 ? ROWSTEP : STRIDE) * cPWp * RB);
             constexpr uint32_t b_sbo = (uint32_t)(8 * RB);
             int stage = 0;
             uint32_t phase = 0;
@@ -578,7 +599,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     SS_T0();
                     tc_fence_after();
                     umma_i8<MMA_MODE>(d, a0, b0, idesc, first ? 0u : 1u);
-                    issue_taps<MMA_MODE, KS, STRIDE, RB, cNB, cPWp, cPWhalf>(d, a0, b0, idesc);
+                    issue_taps<MMA_MODE, KS, KSX, STRIDE, RB, cNB, cPWp, cPWhalf>(d, a0, b0, idesc);
                     tc_fence_before();
                     mbar_arrive(tok_post);
                     commit(bar_empty_p + 8 * stage);
@@ -806,28 +827,31 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
             const int wset = ntile;                       // (output-channel tile, class)
             const int cls = wset % p.nclass;
-            const int so = ty * 16 + g;
-            int b = fast_div(so, p.HsO, p.m_hso);
-            int oy = so - b * p.HsO;
-            int ox = tx * 8 + j;
-            bool live = oy < p.Hv && ox < p.Wv;
-            if (p.mode == SS_TILES_FOLDED) {
-                // virtual (class, source position) -> real output pixel; -1 = not a regular position of this class
-                oy = live ? __ldg(p.ymap_out + (cls >> 1) * p.Hv + oy) : -1;
-                ox = live ? __ldg(p.xmap_out + (cls & 1) * p.Wv + ox) : -1;
-                live = oy >= 0 && ox >= 0;
-            } else if (p.mode == SS_TILES_ROW_BANDS) {
-                const int band = b % p.nbands;
-                b /= p.nbands;
-                live = live && oy < __ldg(p.band_len + band);
-                oy += __ldg(p.band_start + band);
-            } else if (p.mode == SS_TILES_COL_BANDS) {
-                live = live && j < __ldg(p.band_len + tx);
-                ox = __ldg(p.band_start + tx) + j;
+            size_t pix = 0;
+            bool live;
+            if constexpr (ROWSTEP > 1) {
+                // row list: the tile row is an entry of this class's list; columns are plain output columns
+                const int e = ty * 16 + g;
+                const int orow = e < p.rl_n ? __ldg(p.rl_out + cls * p.rl_n + e) : -1;
+                const int oc = tx * 8 + j;
+                live = orow >= 0 && oc < p.c_nout && (p.rl_collive == nullptr || __ldg(p.rl_collive + oc) != 0);
+                if (live) pix = (size_t)orow + (size_t)oc * p.out_colpitch;
+            } else {
+                const int so = ty * 16 + g;
+                const int b = fast_div(so, p.HsO, p.m_hso);
+                int oy = so - b * p.HsO;
+                int ox = tx * 8 + j;
+                live = oy < p.Hv && ox < p.Wv;
+                if (p.mode == SS_TILES_FOLDED) {
+                    // virtual (class, source position) -> real output pixel; -1 = not a regular position of this class
+                    oy = live ? __ldg(p.ymap_out + (cls >> 1) * p.Hv + oy) : -1;
+                    ox = live ? __ldg(p.xmap_out + (cls & 1) * p.Wv + ox) : -1;
+                    live = oy >= 0 && ox >= 0;
+                }
+                live = live && b < p.B && oy < p.Hout && ox < p.Wout;
+                if (live) pix = (size_t)(b * p.Hout + oy) * p.Wout + ox;
             }
-            live = live && b < p.B && oy < p.Hout && ox < p.Wout;
             const int nb = (wset / p.nclass) * 32 + hf * 16;
-            const size_t pix = live ? ((size_t)(b * p.Hout + oy) * p.Wout + ox) : 0;
             const size_t o0 = pix * p.Cout + nb;                  // element offset inside one timestep
             const bool use_resid = p.resid != nullptr && live;
             uint4 rs_next = make_uint4(0u, 0u, 0u, 0u);
@@ -983,9 +1007,9 @@ __global__ void __launch_bounds__(256) weight_exponent_kernel(const float* __res
 }
 
 // [ntile][cb][tap][N = planes x 32 rows][RB bytes], swizzled exactly as it must sit in shared memory
-__global__ void __launch_bounds__(256) weight_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int ks, int planes, int RB,
+__global__ void __launch_bounds__(256) weight_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int ks, int ksx, int planes, int RB,
                                                           const int* __restrict__ wexp, int8_t* __restrict__ out) {
-    const int ntaps = ks * ks;
+    const int ntaps = ks * ksx;
     const int ncb = Cin / RB;
     const long long total = (long long)Cout * Cin * ntaps;   // one thread per weight
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -999,8 +1023,8 @@ __global__ void __launch_bounds__(256) weight_pack_kernel(const float* __restric
     const int ntile = (int)r;
     const int n = ntile * 32 + r32;
     const int ch = cb * RB + c;
-    const int ky = tap / ks, kx = tap - ky * ks;
-    const float wv = w[(((size_t)n * Cin + ch) * ks + ky) * ks + kx];   // OIHW
+    const int ky = tap / ksx, kx = tap - ky * ksx;
+    const float wv = w[(((size_t)n * Cin + ch) * ks + ky) * ksx + kx];   // OIHW (ks rows x ksx columns)
     long long q = llrint(ldexp((double)wv, -wexp[n]));
     const int N = planes * 32;
     const size_t buf = (size_t)(ntile * ncb + cb) * ((size_t)ntaps * N * RB);
@@ -1122,7 +1146,7 @@ extern "C" int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin
         return check_launch("weight_pack_first");
     }
     const long long total = (long long)Cout * Cin * ks * ks;
-    weight_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_oihw, Cout, Cin, ks, planes, RB, wexp,
+    weight_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_oihw, Cout, Cin, ks, ks, planes, RB, wexp,
                                                                        reinterpret_cast<int8_t*>(w_i8));
     count_launch();
     return check_launch("weight_pack");
@@ -1190,18 +1214,19 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     }
     const bool up = g->upsample != 0;
     const int mode = tm != nullptr ? tm->mode : SS_TILES_PLAIN;
-    if (mode < SS_TILES_PLAIN || mode > SS_TILES_COL_BANDS) {
+    if (mode < SS_TILES_PLAIN || mode > SS_TILES_ROW_LIST) {
         set_error("ss_conv_i8_fwd_ex: unknown tile mode %d", mode);
         return SS_EINVAL;
     }
+    const bool rowlist = mode == SS_TILES_ROW_LIST;
     if (mode == SS_TILES_FOLDED && (tm->ymap_out == nullptr || tm->xmap_out == nullptr || g->ks != 3 || g->stride != 1 || g->pad != 0 ||
                                     up || g->Hin < 3 || g->Win < 3)) {
         set_error("ss_conv_i8_fwd_ex: the folded pass is a 3x3 stride-1 pad-0 conv on the source with output maps");
         return SS_EINVAL;
     }
-    if ((mode == SS_TILES_ROW_BANDS || mode == SS_TILES_COL_BANDS) &&
-        (!up || tm->band_start == nullptr || tm->band_len == nullptr || tm->nbands <= 0 || tm->band_rows <= 0)) {
-        set_error("ss_conv_i8_fwd_ex: band passes need an upsampled conv and the band tables");
+    if (rowlist && (!up || g->ks != 5 || first || tm->rl_src == nullptr || tm->rl_out == nullptr || tm->rl_n <= 0 || tm->nclass <= 0 ||
+                    tm->nclass > 8)) {
+        set_error("ss_conv_i8_fwd_ex: the row-list pass needs a 5x5 upsampled conv, the entry tables and 1..8 classes");
         return SS_EINVAL;
     }
     if (!(g->ks == 3 || g->ks == 5) || !(g->stride == 1 || g->stride == 2) || (up && g->stride != 1) ||
@@ -1223,6 +1248,12 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.N = g->planes * 32;
     if (first) {
         p.RB = 128; p.ncb = 1; p.ntaps = 1; p.PH = 16; p.PWhalf = 8; p.PWp = 8;
+    } else if (rowlist) {
+        // rows folded to 3 taps (class-specific sums of the 5 filter rows), columns still the 5 taps over the upsampled row
+        p.RB = 32;
+        p.ncb = g->Cin / 32;
+        p.ntaps = 15;
+        p.PH = 48; p.PWhalf = 10; p.PWp = 12;
     } else {
         p.RB = rowbytes_for(g->Cin, g->ks);
         p.ncb = g->Cin / p.RB;
@@ -1235,22 +1266,29 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.Hup = g->Hout + g->ks - 1;
     p.Wup = g->Wout + g->ks - 1;
     p.mode = mode;
-    p.nclass = mode == SS_TILES_FOLDED ? 4 : 1;
+    p.nclass = mode == SS_TILES_FOLDED ? 4 : (rowlist ? tm->nclass : 1);
     p.Hv = g->Hout; p.Wv = g->Wout;
-    p.nbands = 1; p.band_rows = 0;
-    p.ymap_out = p.xmap_out = p.band_start = p.band_len = nullptr;
+    p.ymap_out = p.xmap_out = p.rl_src = p.rl_out = nullptr;
+    p.rl_collive = nullptr;
     if (mode == SS_TILES_FOLDED) {
         p.Hv = g->Hin - 2; p.Wv = g->Win - 2;
         p.ymap_out = tm->ymap_out; p.xmap_out = tm->xmap_out;
-    } else if (mode != SS_TILES_PLAIN) {
-        p.nbands = tm->nbands; p.band_rows = tm->band_rows;
-        p.band_start = tm->band_start; p.band_len = tm->band_len;
+    } else if (rowlist) {
+        const bool tr = tm->transposed != 0;      // the list holds output COLUMNS (and the tile columns walk the rows)
+        p.rl_src = tm->rl_src; p.rl_out = tm->rl_out; p.rl_collive = tm->rl_collive; p.rl_n = tm->rl_n;
+        p.in_rowstep = tr ? 1 : g->Win;
+        p.in_colpitch = tr ? g->Win : 1;
+        p.out_colpitch = tr ? g->Wout : 1;
+        p.c_in = tr ? g->Hin : g->Win;
+        p.c_nout = tr ? g->Hout : g->Wout;
+        p.c_up = p.c_nout + g->ks - 1;
+        p.c_scale = (float)p.c_in / (float)p.c_up;
+        p.Wv = p.c_nout;
     }
     if (mode == SS_TILES_FOLDED) {
         p.HsO = g->Hin;                       // virtual 3x3 pad-0 conv: image b's rows are Hin apart, no shared padding
-    } else if (mode == SS_TILES_ROW_BANDS) {
-        p.Hv = tm->band_rows;
-        p.HsO = tm->band_rows + g->ks - 1;    // one stacked mini-image per (sample, band)
+    } else if (rowlist) {
+        p.HsO = 16;                           // unused: the tile rows come from the list
     } else if (up) {
         p.HsO = p.Hup;
     } else {
@@ -1263,13 +1301,9 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         p.HsO = (span + g->stride - 1) / g->stride;
         if (p.HsO < g->Hout) p.HsO = g->Hout;
     }
-    const long long rows = (long long)p.HsO * g->B * (mode == SS_TILES_ROW_BANDS ? p.nbands : 1);
+    const long long rows = rowlist ? (long long)tm->rl_n : (long long)p.HsO * g->B;
     const int tiles_y = (int)((rows + 15) / 16);
     p.tiles_x = (p.Wv + 7) / 8;
-    if (mode == SS_TILES_COL_BANDS) {
-        p.tiles_x = p.nbands;
-        p.Wv = 8 * p.nbands;
-    }
     p.mtiles = tiles_y * p.tiles_x;
     const int ntiles = g->Cout / 32;
     const long long nitems = (long long)p.mtiles * ntiles * p.nclass;
@@ -1308,11 +1342,11 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
     p.resident = p.ncb <= NWB ? 1 : 0;
     p.nwb = p.ncb < NWB ? p.ncb : NWB;
-    if (p.PH > 40 || p.PWp > 24) {
+    if (p.PH > 48 || p.PWp > 24) {
         set_error("ss_conv_i8_fwd: patch too large");
         return SS_EUNSUPPORTED;
     }
-    const int tail_bytes = 1024 + 2048 + 64;   // tables + barriers, first-layer raw patch double buffer
+    const int tail_bytes = 1152 + 2048 + 64;   // tables + barriers, first-layer raw patch double buffer
     const int budget = 227 * 1024 - 1024 - tail_bytes - p.nwb * p.WB;
     int nps = budget / p.PB;
     if (nps > MAX_STAGES) nps = MAX_STAGES;
@@ -1373,11 +1407,18 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 1, 1, 128, true>, p);                                                  \
         launched = true;                                                                                                   \
     }
-#define SS_TRY_PL(PL) SS_TRY_FIRST(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
+#define SS_TRY_ROWLIST(PL)                                                                                                 \
+    if (!launched && rowlist && g->planes == PL) {                                                                         \
+        SS_ENSURE_SMEM((conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>), dev, 227 * 1024);                      \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>, p);                            \
+        launched = true;                                                                                                   \
+    }
+#define SS_TRY_PL(PL) SS_TRY_ROWLIST(PL) SS_TRY_FIRST(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
     SS_TRY_PL(2)
     SS_TRY_PL(3)
     SS_TRY_PL(4)
 #undef SS_TRY_PL
+#undef SS_TRY_ROWLIST
 #undef SS_TRY_FIRST
 #undef SS_TRY
 #undef SS_TRY_PAIR
@@ -1400,19 +1441,25 @@ extern "C" int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm,
     return conv_i8_launch(g, tm, x, w_i8, wscale, decay, v_in, v_out, resid, out, h_seq, tsum, stream);
 }
 
-extern "C" int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, const int32_t* zero_exp,
-                                 void* w_i8, void* stream) {
-    if (q_oihw == nullptr || w_i8 == nullptr || zero_exp == nullptr || Cout <= 0 || Cin <= 0 || ks <= 0 || planes < 2 || planes > 4 ||
-        Cout % 32 != 0 || Cin % 32 != 0) {
+extern "C" int ss_pack_digits_i8_rect(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ksy, int32_t ksx, int32_t planes,
+                                      const int32_t* zero_exp, void* w_i8, void* stream) {
+    if (q_oihw == nullptr || w_i8 == nullptr || zero_exp == nullptr || Cout <= 0 || Cin <= 0 || ksy <= 0 || ksx <= 0 || planes < 2 ||
+        planes > 4 || Cout % 32 != 0 || Cin % 32 != 0) {
         set_error("ss_pack_digits_i8: bad argument (Cout %% 32, Cin %% 32, planes 2..4)");
         return SS_EINVAL;
     }
-    const int RB = rowbytes_for(Cin, ks);
-    const long long total = (long long)Cout * Cin * ks * ks;
-    weight_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q_oihw, Cout, Cin, ks, planes, RB, zero_exp,
-                                                                                           reinterpret_cast<int8_t*>(w_i8));
+    // square filters keep the row bytes of ss_conv_i8_fwd; the rectangular 3x5 sets of the row-list pass use 32-byte rows
+    const int RB = ksy == ksx ? rowbytes_for(Cin, ksy) : 32;
+    const long long total = (long long)Cout * Cin * ksy * ksx;
+    weight_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q_oihw, Cout, Cin, ksy, ksx, planes, RB,
+                                                                                           zero_exp, reinterpret_cast<int8_t*>(w_i8));
     count_launch();
     return check_launch("pack_digits");
+}
+
+extern "C" int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, const int32_t* zero_exp,
+                                 void* w_i8, void* stream) {
+    return ss_pack_digits_i8_rect(q_oihw, Cout, Cin, ks, ks, planes, zero_exp, w_i8, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ gradient-side correlation
@@ -1470,8 +1517,7 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
     p.mode = mapped ? SS_TILES_FOLDED : SS_TILES_PLAIN;
     p.nclass = d->nclass;
     p.Hv = d->Hv; p.Wv = d->Wv;
-    p.nbands = 1; p.band_rows = 0;
-    p.ymap_out = ymap_out; p.xmap_out = xmap_out; p.band_start = p.band_len = nullptr;
+    p.ymap_out = ymap_out; p.xmap_out = xmap_out;
     {
         // stacked virtual rows per image: past the source rows + padding, and far enough that taps reaching below the last
         // virtual row land in the next image's (zero) top padding
@@ -1501,7 +1547,7 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
     p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
     p.resident = p.ncb <= NWB ? 1 : 0;
     p.nwb = p.ncb < NWB ? p.ncb : NWB;
-    const int tail_bytes = 1024 + 2048 + 64;   // tables + barriers, first-layer raw patch double buffer
+    const int tail_bytes = 1152 + 2048 + 64;   // tables + barriers, first-layer raw patch double buffer
     const int budget = 227 * 1024 - 1024 - tail_bytes - p.nwb * p.WB;
     int nps = budget / p.PB;
     if (nps > MAX_STAGES) nps = MAX_STAGES;

@@ -54,7 +54,7 @@ class Site:
             w_kn = ops.weight_to_kn(w) if need_kn else None
             w_i8 = None
             if need_i8 and fold:
-                w_i8 = ops.pack_weights_folded(w, planes)
+                w_i8 = ops.pack_weights_folded(w, planes)          # (dense, rows, cols, wscale)
             elif need_i8:
                 cin = w.shape[1]
                 q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=4 if cin <= 4 else (cin + 31) // 32 * 32)
@@ -141,12 +141,17 @@ class Engine:
         self._status_checked_once = False
         self.grad_hook = None       # parallel.OverlappedGradientSync: called with each weight-gradient tensor as soon as it is
         #                             enqueued (reverse layer order), so that its all-reduce overlaps the rest of the backward
-        self.fold_upsample = False  # NNConvUpsampling blocks as four folded 3x3 convs on the source + band passes (9 taps instead of
-        #                             25, bit-identical integers, 3 bits less weight precision); off by default: the full-resolution blocks
-        #                             are epilogue-bound, so the saved MMAs do not pay yet (profiles/r1e_fold_launches.txt)
+        self.fold_upsample = True   # NNConvUpsampling blocks folded: four 3x3 convs on the source for the regular outputs + two small
+        #                             passes for the irregular rows / columns (9 / 15 taps instead of 25, bit-identical integers, 3-4 bits
+        #                             less weight precision).  True / False, or a collection of site names ('deconv4', ...)
+        self.flop_scale = {}        # site -> executed taps / 25 of the folded blocks of the last forward (bench.py credits these FLOPs)
         self.bwd_impl = 'umma'      # gradients of the convs: 'umma' = bf16 tensor cores (fp32 accumulation), 'simt' = fp32 CUDA cores
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
         #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
+
+    def _fold_site(self, name):
+        f = self.fold_upsample
+        return (name in f) if isinstance(f, (set, frozenset, list, tuple)) else bool(f)
 
     # ------------------------------------------------------------------ parameter flattening
     def _flat_params(self):
@@ -197,7 +202,7 @@ class Engine:
     def _poll_input_status(self, block=False):
         """Raises ValueError if an earlier call was fed fp32 frames that are not integer event counts in 0..255 (they would have
         been rounded / clamped by the u8 packing).  Non-blocking unless ``block``: reads a pinned copy once its event has fired."""
-        if self._status is None or not self._status_pending:
+        if self._status is None or not self._status_pending or torch.cuda.is_current_stream_capturing():
             return
         _, host, ev = self._status
         if block:
@@ -252,8 +257,12 @@ class Engine:
             if first and not packed_in and int(x_seq.shape[2]) != g.Cin:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
             use_i8 = impl != SS_IMPL_SIMT
-            fold = use_i8 and self.fold_upsample and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
-                min(g.Hin, g.Win) >= 8 and abs(g.Hout + 4 - 2 * g.Hin) <= g.Hin // 8 and abs(g.Wout + 4 - 2 * g.Win) <= g.Win // 8
+            fold = use_i8 and self._fold_site(s.name) and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
+                ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
+            if fold:
+                self.flop_scale[s.name] = ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).taps_per_output / 25.0
+            else:
+                self.flop_scale.pop(s.name, None)
             # the fp32 [K][Cout] copy is only read by the CUDA-core kernels (forward impl='simt', backward bwd_impl='simt')
             w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=(want_h and self.bwd_impl == 'simt') or not use_i8, fold=fold)
             decay = params[2 * i + 1]
@@ -279,7 +288,7 @@ class Engine:
                     tsum = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=ops.ACT_DTYPE, device=dev)
                     tsums[s.out] = tsum
                 if fold:
-                    out, v_out, h_seq = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], planes=self.weight_planes,
+                    out, v_out, h_seq = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], w_i8[3], planes=self.weight_planes,
                                                                tsum=tsum, **common)
                 else:
                     out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,

@@ -143,8 +143,8 @@ class _SpikingUNet(NeuromorphicNet):
             e.keep_state = bool(keep_state)
         if heads_time_sum is not None:
             e.heads_time_sum = bool(heads_time_sum)
-        if fold_upsample is not None:
-            e.fold_upsample = bool(fold_upsample)
+        if fold_upsample is not None:       # True / False, or the names of the decoder blocks to fold, e.g. ('deconv4', 'deconv3')
+            e.fold_upsample = frozenset(fold_upsample) if isinstance(fold_upsample, (set, frozenset, list, tuple)) else bool(fold_upsample)
         if bwd_impl is not None:
             assert bwd_impl in ('umma', 'simt')
             e.bwd_impl = bwd_impl

@@ -120,100 +120,147 @@ def pack_events(x_seq, status=None):
 
 
 # ----------------------------------------------------------------------------------------- folded upsampled conv
-_FOLD_GROUPS = {0: ((0,), (1, 2), (3, 4)),      # class L: the output sits on the LAST copy of its source pixel  (pattern 0,1,1,2,2)
-                1: ((0, 1), (2, 3), (4,))}      # class M: ... on the second-to-last copy                          (pattern 0,0,1,1,2)
-_FOLD_PATTERNS = {0: (0, 1, 1, 2, 2), 1: (0, 0, 1, 1, 2)}
+# Replication patterns of the 5 taps of one axis of  UpsamplingNearest2d(n_out + 4) -> valid conv(5)  (source index of tap k
+# relative to the first one): the two regular ones and the three next to a 3-fold replication (include/stereospike_b200.h).
+FOLD_PATTERNS = ((0, 1, 1, 2, 2), (0, 0, 1, 1, 2), (0, 0, 0, 1, 1), (0, 1, 1, 1, 2), (0, 0, 1, 1, 1))     # L, M, A, B, C
+
+
+def _fold_groups(pattern):
+    """filter taps that read source offset d = 0, 1, 2."""
+    return tuple(tuple(k for k in range(5) if pattern[k] == d) for d in range(3))
 
 
 def fold_axis(n_in, n_out, ks=5):
-    """Regular / irregular structure of  UpsamplingNearest2d(n_out+ks-1) -> valid conv(ks)  along one axis.
-    Returns (omap int32 [2][n_in-2]: output coordinate of source position s for class L / M or -1, bands [(start, len)] of
-    the output coordinates that do not follow either regular pattern)."""
+    """Per output coordinate o of one axis: first source pixel s0[o] and replication pattern pat[o] (index into FOLD_PATTERNS,
+    -1 = none of them: the geometry cannot be folded)."""
     assert ks == 5
     n_up = n_out + ks - 1
     scale = np.float32(n_in) / np.float32(n_up)
     src = np.minimum(np.floor(np.arange(n_up, dtype=np.float32) * scale).astype(np.int64), n_in - 1)
-    omap = np.full((2, n_in - 2), -1, dtype=np.int32)
-    irregular = []
+    s0 = src[:n_out].astype(np.int64)
+    pat = np.full(n_out, -1, dtype=np.int64)
     for o in range(n_out):
-        pat = tuple(int(src[o + k] - src[o]) for k in range(ks))
-        s0 = int(src[o])
-        hit = [c for c, pt in _FOLD_PATTERNS.items() if pt == pat]
-        if hit and s0 < n_in - 2 and omap[hit[0], s0] < 0:
-            omap[hit[0], s0] = o
-        else:
-            irregular.append(o)
-    bands = []
-    for o in irregular:
-        if bands and o == bands[-1][0] + bands[-1][1]:
-            bands[-1][1] += 1
-        else:
-            bands.append([o, 1])
-    return omap, [tuple(b) for b in bands]
+        rel = tuple(int(src[o + k] - src[o]) for k in range(ks))
+        if rel in FOLD_PATTERNS:
+            pat[o] = FOLD_PATTERNS.index(rel)
+    return s0, pat
 
 
 class FoldPlan:
-    """Device tables of one folded NNConvUpsampling geometry (cached per (Hin, Win, Hout, Wout, device))."""
+    """Device tables of one folded NNConvUpsampling geometry and batch size (cached).  Three passes write the block's output:
+    dense (4 regular class pairs, 3x3 on the source), irregular rows x all columns, irregular columns x regular rows."""
 
-    def __init__(self, Hin, Win, Hout, Wout, device):
-        ymap, ybands = fold_axis(Hin, Hout)
-        xmap, xbands = fold_axis(Win, Wout)
-        xb = []
-        for st, ln in xbands:                      # column bands are at most one 8-wide tile each
-            while ln > 0:
-                xb.append((st, min(ln, 8)))
-                st, ln = st + 8, ln - 8
+    def __init__(self, Hin, Win, Hout, Wout, B, device):
+        s0y, py = fold_axis(Hin, Hout)
+        s0x, px = fold_axis(Win, Wout)
         dev = torch.device(device)
-        t = lambda a: torch.tensor(a, dtype=torch.int32, device=dev).contiguous()
-        self.ymap, self.xmap = t(ymap), t(xmap)
-        self.yband_start, self.yband_len = t([b[0] for b in ybands]), t([b[1] for b in ybands])
-        self.xband_start, self.xband_len = t([b[0] for b in xb]), t([b[1] for b in xb])
-        self.n_ybands, self.n_xbands = len(ybands), len(xb)
-        self.yband_rows = max([b[1] for b in ybands]) if ybands else 0
-        self.covered = float((ymap >= 0).sum()) / Hout * float((xmap >= 0).sum()) / Wout      # fraction of regular outputs
+        t32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int32, device=dev).contiguous()
+        self.ok = bool((py >= 0).all() and (px >= 0).all() and (s0y + 2 < Hin).all() and (s0x + 2 < Win).all() and
+                       Hin >= 3 and Win >= 3 and (B * max(Hin * Win, Hout * Wout)) < 2 ** 31)
+        if not self.ok:
+            return
+
+        def dense_map(s0, pat, n_in):
+            m = np.full((2, n_in - 2), -1, dtype=np.int32)
+            for o in range(len(s0)):
+                if pat[o] < 2:
+                    assert m[pat[o], s0[o]] < 0
+                    m[pat[o], s0[o]] = o
+            return m
+        self.ymap, self.xmap = t32(dense_map(s0y, py, Hin)), t32(dense_map(s0x, px, Win))
+
+        def lists(s0, pat, src_off, out_off):
+            """[3][n] source / output offsets of the irregular coordinates of every sample, padded with -1."""
+            per = [[o for o in range(len(s0)) if pat[o] == 2 + c] for c in range(3)]
+            n = max(1, B * max(len(v) for v in per))
+            src = np.full((3, n), -1, dtype=np.int64)
+            out = np.full((3, n), -1, dtype=np.int64)
+            for c in range(3):
+                i = 0
+                for b in range(B):
+                    for o in per[c]:
+                        src[c, i], out[c, i] = src_off(b, s0[o]), out_off(b, o)
+                        i += 1
+            return t32(src), t32(out), n, sum(len(v) for v in per)
+        self.row_src, self.row_out, self.row_n, self.n_irr_rows = lists(
+            s0y, py, lambda b, s: (b * Hin + s) * Win, lambda b, o: (b * Hout + o) * Wout)
+        self.col_src, self.col_out, self.col_n, self.n_irr_cols = lists(
+            s0x, px, lambda b, s: b * Hin * Win + s, lambda b, o: b * Hout * Wout + o)
+        self.row_regular = torch.as_tensor((py < 2).astype(np.uint8), device=dev).contiguous()       # rows the column pass owns
+        n_reg_r, n_reg_c = int((py < 2).sum()), int((px < 2).sum())
+        self.covered = n_reg_r * n_reg_c / float(Hout * Wout)                 # fraction of outputs in the dense (9-tap) pass
+        # taps executed per output, averaged (25 = unfolded): what bench.py credits a folded block with
+        self.taps_per_output = (9.0 * n_reg_r * n_reg_c + 15.0 * self.n_irr_rows * Wout + 15.0 * self.n_irr_cols * n_reg_r) / float(Hout * Wout)
 
 
 @functools.lru_cache(maxsize=None)
-def fold_plan(Hin, Win, Hout, Wout, device):
-    return FoldPlan(Hin, Win, Hout, Wout, device)
+def fold_plan(Hin, Win, Hout, Wout, B, device):
+    return FoldPlan(Hin, Win, Hout, Wout, B, device)
 
 
-def pack_weights_folded(weight, planes):
-    """Quantises a 5x5 NNConvUpsampling weight (OIHW) with 3 bits of head-room and returns
-    (w_fold: digit planes of the four folded 3x3 weight sets, w_full: digit planes of the 5x5 taps (band passes),
-    wscale fp32 [Cout]).  The folded sets are exact integer sums of the quantised taps, so both passes produce
-    identical integers for every output they share."""
+def fold_weight_sets(weight, planes):
+    """Quantises a 5x5 NNConvUpsampling weight (OIHW) with head-room for the tap sums.  Returns (q: the quantised taps,
+    dense: the four regular 3x3 sets [class = 2*row_class + col_class], rows: the three 3x5 sets (dy, kx) of the irregular rows,
+    cols: the three 3x5 sets (dx, ky) of the irregular columns in the transposed frame, e: exponent per output channel), all
+    float64 tensors holding exact integers.  Every set is an exact sum of the same quantised taps, so every pass produces the
+    integers of the 25-tap conv with those taps."""
     w = weight.detach().double()
     co, ci, kh, kw = w.shape
     assert kh == 5 and kw == 5 and co % 32 == 0 and ci % 32 == 0
     m = w.abs().amax(dim=(1, 2, 3))
     ex = torch.where(m > 0, torch.floor(torch.log2(m)) + 1, torch.zeros_like(m))          # m < 2^ex
-    e = ex - (8 * planes - 1) + 3
-    q = torch.round(w * torch.pow(2.0, -e).view(-1, 1, 1, 1))
-    assert float(q.abs().max()) < 2 ** (8 * planes - 4) + 1
-    sets = []
-    for cy in (0, 1):
-        for cx in (0, 1):
-            f = q.new_zeros(co, ci, 3, 3)
-            for dy, kys in enumerate(_FOLD_GROUPS[cy]):
-                for dx, kxs in enumerate(_FOLD_GROUPS[cx]):
-                    for ky in kys:
-                        for kx in kxs:
-                            f[:, :, dy, dx] += q[:, :, ky, kx]
-            sets.append(f)
-    # weight-set index = output-channel tile * 4 + class  ->  stack as [tile][class][32] "output channels"
-    fold = torch.stack(sets, dim=1).view(co // 32, 32, 4, ci, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(4 * co, ci, 3, 3)
-    dev = weight.device
-    zeros = torch.zeros(4 * co, dtype=torch.int32, device=dev)
-    fold32 = fold.float().contiguous()
-    full32 = q.float().contiguous()
-    w_fold = torch.empty(4 * co * ci * 9 * planes, dtype=torch.int8, device=dev)
-    w_full = torch.empty(co * ci * 25 * planes, dtype=torch.int8, device=dev)
-    L = _lib.lib()
-    _lib.check(L.ss_pack_digits_i8(_ptr(fold32), 4 * co, ci, 3, planes, _ptr(zeros), _ptr(w_fold), _stream()), 'ss_pack_digits_i8')
-    _lib.check(L.ss_pack_digits_i8(_ptr(full32), co, ci, 5, planes, _ptr(zeros), _ptr(w_full), _stream()), 'ss_pack_digits_i8')
-    wscale = torch.pow(2.0, e).float().contiguous()
-    return w_fold, w_full, wscale
+    groups = [_fold_groups(pt) for pt in FOLD_PATTERNS]
+    limit = 127.0 * 256.0 ** (planes - 1)               # top balanced digit <= 127
+    # head-room: a folded weight sums at most 4 taps (2 x 2 in the dense sets, 3 in the row / column sets), i.e. 2 bits in the worst
+    # case and usually 1-2; start with 1 bit and give one more bit only to the output channels whose sums overflow
+    e = ex - (8 * planes - 1) + 1
+    for _ in range(4):
+        q = torch.round(w * torch.pow(2.0, -e).view(-1, 1, 1, 1))
+
+        def fold_rows(t, g):        # t [co,ci,5,n] -> [co,ci,3,n]: sum the filter rows of each group
+            return torch.stack([t[:, :, list(k), :].sum(2) if k else t.new_zeros(co, ci, t.shape[3]) for k in g], dim=2)
+        dense = []
+        for cy in (0, 1):
+            for cx in (0, 1):
+                f = fold_rows(q, groups[cy])                                              # [co,ci,3,5]
+                f = fold_rows(f.transpose(2, 3), groups[cx]).transpose(2, 3)              # [co,ci,3,3]
+                dense.append(f)
+        rows = [fold_rows(q, groups[2 + c]) for c in range(3)]                            # [co,ci,3(dy),5(kx)]
+        cols = [fold_rows(q.transpose(2, 3), groups[2 + c]) for c in range(3)]            # [co,ci,3(dx),5(ky)]
+        over = torch.stack([torch.stack(v).abs().amax(dim=(0, 2, 3, 4)) for v in (dense, rows, cols)]).amax(0) > limit
+        if not bool(over.any()):
+            break
+        e = e + over.to(e.dtype)        # one more bit of head-room for the output channels whose sums do not fit
+    else:
+        raise RuntimeError('pack_weights_folded: folded tap sums do not fit the digit planes')
+    return q, dense, rows, cols, e
+
+
+def pack_weights_folded(weight, planes):
+    """Digit-plane images (dense, rows, cols) of fold_weight_sets + wscale fp32 [Cout]."""
+    _, dense, rows, cols, e = fold_weight_sets(weight, planes)
+    co, ci = int(weight.shape[0]), int(weight.shape[1])
+
+    def stack_sets(sets):
+        """weight-set index = output-channel tile * nclass + class  ->  [tile][class][32] "output channels"."""
+        n = len(sets)
+        t = torch.stack(sets, dim=1)                                                     # [co, n, ci, kh, kw]
+        return t.view(co // 32, 32, n, *t.shape[2:]).permute(0, 2, 1, 3, 4, 5).reshape(n * co, *t.shape[2:]).float().contiguous()
+    pack = lambda t: pack_digits_i8(t.to(weight.device), planes)
+    return pack(stack_sets(dense)), pack(stack_sets(rows)), pack(stack_sets(cols)), torch.pow(2.0, e).float().contiguous().to(weight.device)
+
+
+def pack_digits_i8(q, planes):
+    """Digit-plane image of ALREADY QUANTISED integer weights (OIHW, exact integers in floating point; rectangular filters
+    allowed): ss_pack_digits_i8_rect."""
+    q = q.float().contiguous()
+    _require_cuda(q, 'q')
+    cop, ci, ky, kx = q.shape
+    zeros = torch.zeros(cop, dtype=torch.int32, device=q.device)
+    img = torch.empty(cop * ci * ky * kx * planes, dtype=torch.int8, device=q.device)
+    _lib.check(_lib.lib().ss_pack_digits_i8_rect(_ptr(q), cop, ci, ky, kx, planes, _ptr(zeros), _ptr(img), _stream()),
+               'ss_pack_digits_i8_rect')
+    return img
 
 
 def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
@@ -264,26 +311,28 @@ def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau
     return out, v_out, h_seq
 
 
-def conv_i8_fwd_folded(x, geom, w_fold, w_full, wscale, **kw):
-    """NNConvUpsampling block (5x5, ~2x) as four folded 3x3 convs on the source + the general kernel on the irregular
-    row / column bands (three launches writing the same output tensors).  Same arguments / results as conv_i8_fwd."""
+def conv_i8_fwd_folded(x, geom, w_dense, w_rows, w_cols, wscale, **kw):
+    """NNConvUpsampling block (5x5, ~2x) as: four folded 3x3 convs on the source for the regular outputs, then the irregular
+    rows and the irregular columns (3 + 2 output rows / columns per 3-fold replication) with one axis folded -- three
+    launches writing the same output tensors.  Same arguments / results as conv_i8_fwd."""
     g = geom
     assert g.kind == 'upconv' and g.ks == 5
-    plan = fold_plan(g.Hin, g.Win, g.Hout, g.Wout, str(x.device))
-    tm = _lib.TileMaps(mode=_lib.SS_TILES_FOLDED, nbands=0, band_rows=0, reserved=0, ymap_out=plan.ymap.data_ptr(),
-                       xmap_out=plan.xmap.data_ptr(), band_start=0, band_len=0)
-    res = conv_i8_fwd(x, g, w_fold, wscale, tile_maps=tm, desc_override=dict(ks=3, stride=1, pad=0, upsample=0), **kw)
+    plan = fold_plan(g.Hin, g.Win, g.Hout, g.Wout, int(kw['B']), str(x.device))
+    assert plan.ok, 'geometry cannot be folded'
+    tm = _lib.TileMaps(mode=_lib.SS_TILES_FOLDED, nclass=4, rl_n=0, transposed=0, ymap_out=plan.ymap.data_ptr(),
+                       xmap_out=plan.xmap.data_ptr(), rl_src=0, rl_out=0, rl_collive=0)
+    res = conv_i8_fwd(x, g, w_dense, wscale, tile_maps=tm, desc_override=dict(ks=3, stride=1, pad=0, upsample=0), **kw)
     kw2 = dict(kw)
-    kw2.pop('want_v_out', None)
-    kw2.pop('want_h', None)
-    if plan.n_ybands:
-        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_BANDS, nbands=plan.n_ybands, band_rows=plan.yband_rows, reserved=0, ymap_out=0,
-                           xmap_out=0, band_start=plan.yband_start.data_ptr(), band_len=plan.yband_len.data_ptr())
-        conv_i8_fwd(x, g, w_full, wscale, tile_maps=tm, outputs=res, **kw2)
-    if plan.n_xbands:
-        tm = _lib.TileMaps(mode=_lib.SS_TILES_COL_BANDS, nbands=plan.n_xbands, band_rows=8, reserved=0, ymap_out=0, xmap_out=0,
-                           band_start=plan.xband_start.data_ptr(), band_len=plan.xband_len.data_ptr())
-        conv_i8_fwd(x, g, w_full, wscale, tile_maps=tm, outputs=res, **kw2)
+    for k in ('want_v_out', 'want_h', 'outputs'):
+        kw2.pop(k, None)
+    if plan.n_irr_rows:
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=plan.row_n, transposed=0, ymap_out=0, xmap_out=0,
+                           rl_src=plan.row_src.data_ptr(), rl_out=plan.row_out.data_ptr(), rl_collive=0)
+        conv_i8_fwd(x, g, w_rows, wscale, tile_maps=tm, outputs=res, **kw2)
+    if plan.n_irr_cols:
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=plan.col_n, transposed=1, ymap_out=0, xmap_out=0,
+                           rl_src=plan.col_src.data_ptr(), rl_out=plan.col_out.data_ptr(), rl_collive=plan.row_regular.data_ptr())
+        conv_i8_fwd(x, g, w_cols, wscale, tile_maps=tm, outputs=res, **kw2)
     return res
 
 

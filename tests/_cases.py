@@ -243,7 +243,7 @@ def build_pair(variant, mono, gain, tau, seed, planes=3, impl='umma'):
     return o, n
 
 
-def teacher_forced_model(o, n, x, trace=None, planes=3, band=1e-4, fold=None):
+def teacher_forced_model(o, n, x, trace=None, planes=3, band=1e-4, fold=True):
     """Every fused block of CUDA model ``n`` fed with the ORACLE's input spikes of that block (all T timesteps, real
     geometry) and compared with the oracle's pre-reset potentials.  A neuron is compared at step t only while its spikes
     agreed at every earlier step (after a flip inside the threshold band its state legitimately differs).
@@ -277,7 +277,7 @@ def teacher_forced_model(o, n, x, trace=None, planes=3, band=1e-4, fold=None):
                   tau=node._tau_value(), decay=decay.detach().contiguous() if decay is not None else None, resid=resid,
                   want_h=True, planes=planes)
         if use_fold:
-            out, _, h_got = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], **kw)
+            out, _, h_got = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], w_i8[3], **kw)
         else:
             out, _, h_got = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], cin=4 if first else g.Cin, **kw)
         h_ref = hs[s.name].to(dev)
@@ -301,7 +301,7 @@ def teacher_forced_model(o, n, x, trace=None, planes=3, band=1e-4, fold=None):
     return res
 
 
-def parity_summary(variant='lif', gain=15.0, tau=3.0, T=5, B=1, seed=0, planes=3, x_seed=100, with_fp64=True, fold=None):
+def parity_summary(variant='lif', gain=15.0, tau=3.0, T=5, B=1, seed=0, planes=3, x_seed=100, with_fp64=True, fold=True):
     """End-to-end + teacher-forced parity of one configuration as a small dict (bench.py prints it; the GPU tests assert on
     it).  ``oracle_fp32_vs_fp64`` is the oracle's own sensitivity: |MDE(fp32) - MDE(float64)| of the same reference code."""
     import copy
@@ -309,8 +309,7 @@ def parity_summary(variant='lif', gain=15.0, tau=3.0, T=5, B=1, seed=0, planes=3
     from oracle import ref_model as rm, sj_compat as sj
     import stereospike_b200 as sb
     o, n = build_pair(variant, False, gain, tau, seed, planes)
-    if fold is not None:
-        n.set_kernel_options(fold_upsample=fold)
+    n.set_kernel_options(fold_upsample=bool(fold))
     x = rm.synthetic_inputs(B, T, 4, seed=x_seed)
     label = rm.synthetic_label(B, seed=x_seed + 1)
     sj.reset_net(o)

@@ -144,25 +144,31 @@ def test_i8_result_is_exact_and_tiling_independent():
 
 
 @pytest.mark.parametrize('Hin,Win,up,Cin,Cout,T,B', [(17, 22, (33, 44), 64, 32, 3, 2), (9, 11, (17, 21), 32, 64, 2, 3),
-                                                     (130, 173, (260, 346), 64, 32, 2, 1)])
+                                                     (17, 22, (33, 44), 512, 256, 5, 1), (130, 173, (260, 346), 64, 32, 2, 1)])
 def test_folded_upsampled_conv_is_bit_identical(Hin, Win, up, Cin, Cout, T, B):
-    """NNConvUpsampling folded into four 3x3 convs on the source (+ band passes for the irregular rows / columns) gives
-    exactly the integers of the 25-tap kernel with the same quantised weights: identical h, spikes, state and time sums."""
+    """NNConvUpsampling folded (dense 3x3 pass on the source for the regular outputs + the irregular-row and irregular-column
+    passes) gives exactly the integers of the 25-tap kernel with the same quantised weights: identical h, spikes, state and
+    time sums, every output pixel written."""
     from stereospike_b200 import ops, _lib
     g = torch.Generator().manual_seed(Hin * 7 + Cin)
     geom = ops.BlockGeom('upconv', Cin, Cout, 5, Hin, Win, up[0], up[1])
     x = ((torch.rand(T, B, Hin, Win, Cin, generator=g) < 0.25).to(torch.uint8) * torch.randint(1, 4, (T, B, Hin, Win, Cin), generator=g).to(torch.uint8)).cuda()
     w = ((torch.rand(Cout, Cin, 5, 5, generator=g) * 2 - 1) / (Cin * 25) ** 0.5).cuda()
     r = (torch.rand(T, B, up[0], up[1], Cout, generator=g) < 0.3).to(torch.uint8).cuda()
-    w_fold, w_full, wscale = ops.pack_weights_folded(w, 3)
+    q, _, _, _, _ = ops.fold_weight_sets(w, 3)
+    w_full = ops.pack_digits_i8(q, 3)                                  # the same quantised taps, unfolded
+    w_dense, w_rows, w_cols, wscale = ops.pack_weights_folded(w, 3)
     kw = dict(T=T, B=B, neuron=_lib.SS_NEURON_LIF, gain=5.0, v_th=1.0, v_reset=0.0, tau=3.0, resid=r, want_v_out=True, want_h=True, planes=3)
     ts_a = torch.zeros((B, up[0], up[1], Cout), dtype=torch.uint8, device='cuda')
-    ts_b = torch.zeros_like(ts_a)
+    ts_b = torch.full_like(ts_a, 77)
     o_a, v_a, h_a = ops.conv_i8_fwd(x, geom, w_full, wscale, tsum=ts_a, **kw)
-    o_b, v_b, h_b = ops.conv_i8_fwd_folded(x, geom, w_fold, w_full, wscale, tsum=ts_b, **kw)
+    # poison the folded run's outputs: a pixel that no pass writes would keep the poison
+    outs = (torch.full((T, B, up[0], up[1], Cout), 200, dtype=torch.uint8, device='cuda'),
+            torch.full((B, up[0], up[1], Cout), float('nan'), device='cuda'), torch.full((T, B, up[0], up[1], Cout), float('nan'), device='cuda'))
+    o_b, v_b, h_b = ops.conv_i8_fwd_folded(x, geom, w_dense, w_rows, w_cols, wscale, tsum=ts_b, outputs=outs, **kw)
     assert torch.equal(h_a, h_b) and torch.equal(o_a, o_b) and torch.equal(v_a, v_b) and torch.equal(ts_a, ts_b)
     assert 0.02 < float((o_a > 0).float().mean()) < 0.95
-    plan = ops.fold_plan(Hin, Win, up[0], up[1], 'cuda:0')
+    plan = ops.fold_plan(Hin, Win, up[0], up[1], B, 'cuda:0')
     assert plan.covered > (0.9 if Hin >= 100 else 0.3)
 
 
@@ -244,8 +250,10 @@ def test_pack_events_flags_non_integer_input():
 ])
 def test_model_end_to_end(variant, mono, gain, T, B, impl):
     from tests._cases import model_case
-    r = model_case(variant, mono, gain, T, B, impl, 3)
-    assert abs(r['mde_ref'] - r['mde_got']) <= TOL_MDE, r
+    r = model_case(variant, mono, gain, T, B, impl, 3, with_fp64=True)
+    # hard threshold => chaotic: `sens` is how far two evaluations of the REFERENCE itself (fp32 / float64) are apart in MDE
+    sens = abs(r['mde_ref'] - r['mde_ref64'])
+    assert min(abs(r['mde_ref'] - r['mde_got']), abs(r['mde_ref64'] - r['mde_got'])) <= max(TOL_MDE, 5 * sens), (r, sens)
     mm = r['mismatch(rate,firing)']
     for k, (rate, firing) in mm.items():
         assert 0.01 < firing < 0.7, (k, firing)             # live network
@@ -350,9 +358,9 @@ def test_long_sequence_and_odd_batch_end_to_end():
     assert mm['out_bottom'][0] <= 1e-6 and mm['out_conv1'][0] <= 1e-5, mm
 
 
-def test_folded_decoder_model_matches_default():
-    """fold_upsample=True changes the decoder blocks' weight quantisation (3 bits of head-room) but not the result beyond
-    fp32 tolerance: same MDE, nearly identical spikes."""
+def test_folded_decoder_model_matches_unfolded():
+    """fold_upsample (default on) changes the decoder blocks' weight quantisation (3-4 bits of head-room) but not the result
+    beyond fp32 tolerance: same MDE, nearly identical spikes as the 25-tap blocks."""
     import stereospike_b200 as sb
     from oracle import ref_model as rm
     torch.manual_seed(4)
@@ -360,11 +368,13 @@ def test_folded_decoder_model_matches_default():
     x = rm.synthetic_inputs(2, 3, 4, seed=12).cuda()
     label = rm.synthetic_label(2, seed=13)
     with torch.no_grad():
+        net.set_kernel_options(fold_upsample=False)
         sb.functional.reset_net(net)
         d0, s0 = net.forward_seq(x)
         net.set_kernel_options(fold_upsample=True)
         sb.functional.reset_net(net)
         d1, s1 = net.forward_seq(x)
+        assert set(net.engine.flop_scale) == {'deconv4', 'deconv3', 'deconv2', 'deconv1'}
     m0 = float(rm.mean_depth_error(d0[0].cpu(), label)); m1 = float(rm.mean_depth_error(d1[0].cpu(), label))
     assert abs(m0 - m1) <= TOL_MDE, (m0, m1)
     assert float((s0[-1] != s1[-1]).float().mean()) < 1e-3

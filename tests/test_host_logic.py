@@ -114,3 +114,63 @@ def test_engine_wiring():
     g = e.sites[-1].geom(130, 173)
     assert (g.Hout, g.Wout, g.K) == (260, 346, 1600)
     assert [h.src for h in e.heads] == ['out_add4', 'out_add3', 'out_add2', 'out_add1']
+
+
+@pytest.mark.parametrize('Hin,Win,Hout,Wout', [(17, 22, 33, 44), (9, 11, 17, 21), (33, 44, 65, 87), (20, 27, 40, 53)])
+def test_fold_plan_and_weight_sets_reproduce_upsampled_conv(Hin, Win, Hout, Wout):
+    """Host logic of the folded NNConvUpsampling block, emulated in float64 on CPU: the dense 3x3 pass on the source (4 class
+    pairs, output maps), the irregular-row pass (row lists, rows folded to 3 taps, 5 taps over the upsampled columns) and the
+    irregular-column pass (transposed) together write EVERY output exactly once (the column pass masks the rows of the row
+    pass) and equal UpsamplingNearest2d -> conv5x5 with the same quantised taps, integer for integer."""
+    B, Cin, Cout = 2, 32, 32
+    plan = ops.FoldPlan(Hin, Win, Hout, Wout, B, 'cpu')
+    assert plan.ok
+    g = torch.Generator().manual_seed(Hin)
+    w = (torch.rand(Cout, Cin, 5, 5, generator=g) * 2 - 1) / 20
+    x = (torch.rand(B, Cin, Hin, Win, generator=g) < 0.3).double() * torch.randint(1, 4, (B, Cin, Hin, Win), generator=g).double()
+    q, dense, rows, cols, e = ops.fold_weight_sets(w, 3)
+    assert float((q * torch.pow(2.0, e).view(-1, 1, 1, 1) - w.double()).abs().max()) < 2.0 ** -18
+    ref = F.conv2d(F.interpolate(x, size=(Hout + 4, Wout + 4), mode='nearest'), q)         # [B,Cout,Hout,Wout] exact integers
+    out = torch.full_like(ref, float('nan'))
+    writes = torch.zeros(B, Hout, Wout)
+    ymap, xmap = plan.ymap.numpy(), plan.xmap.numpy()
+    # dense pass: virtual 3x3 pad-0 conv on the source per class pair
+    for cy in (0, 1):
+        for cx in (0, 1):
+            v = F.conv2d(x, dense[2 * cy + cx])                                             # [B,Cout,Hin-2,Win-2]
+            for sy in range(Hin - 2):
+                oy = ymap[cy, sy]
+                if oy < 0:
+                    continue
+                sel = xmap[cx] >= 0
+                out[:, :, oy, xmap[cx][sel]] = v[:, :, sy, sel]
+                writes[:, oy, xmap[cx][sel]] += 1
+    xf = x.permute(0, 2, 3, 1).reshape(-1, Cin)                                             # pixel-major [B*Hin*Win, Cin]
+    of = out.permute(0, 2, 3, 1).reshape(-1, Cout).clone()
+    wf = writes.reshape(-1).clone()
+
+    def list_pass(src, dst, n, sets, rowstep, colpitch_in, colpitch_out, c_in, c_nout, collive):
+        c_up = c_nout + 4
+        scale = np.float32(c_in) / np.float32(c_up)
+        ci = np.minimum(np.floor(np.arange(c_up, dtype=np.float32) * scale).astype(np.int64), c_in - 1)
+        for c in range(3):
+            for i in range(n):
+                s0, o0 = int(src[c, i]), int(dst[c, i])
+                if s0 < 0:
+                    assert o0 < 0
+                    continue
+                for oc in range(c_nout):
+                    if collive is not None and not collive[oc]:
+                        continue
+                    acc = torch.zeros(Cout, dtype=torch.float64)
+                    for d in range(3):
+                        for k in range(5):
+                            acc += sets[c][:, :, d, k] @ xf[s0 + d * rowstep + ci[oc + k] * colpitch_in]
+                    of[o0 + oc * colpitch_out] = acc
+                    wf[o0 + oc * colpitch_out] += 1
+    list_pass(plan.row_src.numpy(), plan.row_out.numpy(), plan.row_n, rows, Win, 1, 1, Win, Wout, None)
+    list_pass(plan.col_src.numpy(), plan.col_out.numpy(), plan.col_n, cols, 1, Win, Wout, Hin, Hout, plan.row_regular.numpy())
+    assert torch.equal(wf, torch.ones_like(wf)), 'every output pixel must be written exactly once'
+    got = of.reshape(B, Hout, Wout, Cout).permute(0, 3, 1, 2)
+    assert torch.equal(got, ref)
+    assert 9.0 <= plan.taps_per_output < 25.0

@@ -58,21 +58,17 @@ inline int device_sm_count(int dev) {
 
 int launch_conv_neuron_simt(const ConvParams& p, int in_layout, cudaStream_t st);
 
-// Correctly rounded a / b for a loop-invariant divisor b:  y = refined reciprocal of b (div_const_prepare), two
-// fused residual corrections (the fast path of div.rn.f32 with the reciprocal hoisted out of the loop).  Bit-identical
-// to IEEE division whenever the quotient is a normal number (checked on 2e7 random operands per divisor); a
-// subnormal quotient (|a| < 1e-37) may differ in its last bits, which no membrane potential can observe.
-__device__ __forceinline__ float div_const_prepare(float b) {
-    float y = __frcp_rn(b);
-    const float e = fmaf(-b, y, 1.0f);
-    return fmaf(e, y, y);
-}
+// Correctly rounded a / b for a loop-invariant divisor b (Markstein): y = RN(1 / b) hoisted out of the loop, then
+//   q0 = RN(a * y);  r = RN(a - b * q0) (exact, one FMA);  q = RN(q0 + r * y).
+// Bit-identical to IEEE division for EVERY fp32 a with |a| >= 1e-30 and a normal quotient -- checked exhaustively over all 2^32
+// operands for 17 divisors, all-ones mantissas included (tools/div_probe.cu, profiles/r2h_div_probe.log); below that (and for the
+// sign of a zero quotient) it may differ in the last bits, which no membrane potential can observe.  3 instructions per division
+// instead of the 5 of the two-correction form used in round 1.
+__device__ __forceinline__ float div_const_prepare(float b) { return __frcp_rn(b); }
 __device__ __forceinline__ float div_const(float a, float b, float y) {
-    float q = __fmul_rn(a, y);
-    float r = fmaf(-b, q, a);
-    q = fmaf(r, y, q);
-    r = fmaf(-b, q, a);
-    return fmaf(r, y, q);
+    const float q0 = __fmul_rn(a, y);
+    const float r = fmaf(-b, q0, a);
+    return fmaf(r, y, q0);
 }
 
 // Loop-invariant neuron parameters (rtau = div_const_prepare(tau)).
@@ -82,24 +78,25 @@ struct NeuronConst {
 
 // One neuron step (SpikingJelly BaseNode.forward: charge -> fire -> hard reset), fp32.
 // Returns the spike (0/1); v is updated in place; h_out receives the pre-reset potential.
-template <int KIND>
+// VR0: v_reset == 0 known at compile time (every call site of the reference): x - (v - v_reset) is x - v, bit for bit
+template <int KIND, bool VR0 = false>
 __device__ __forceinline__ float neuron_step_t(float x, float& v, const NeuronConst& c, float& h_out) {
     float h;
     if (KIND == SS_NEURON_IF) {
         h = __fadd_rn(v, x);
     } else if (KIND == SS_NEURON_LIF) {
         // true division: (x - v) / tau is not (x - v) * (1 / tau) in fp32
-        const float dv = (c.v_reset == 0.0f) ? __fsub_rn(x, v) : __fsub_rn(x, __fsub_rn(v, c.v_reset));
+        const float dv = (VR0 || c.v_reset == 0.0f) ? __fsub_rn(x, v) : __fsub_rn(x, __fsub_rn(v, c.v_reset));
         h = __fadd_rn(v, div_const(dv, c.tau, c.rtau));
     } else {
-        const float dv = (c.v_reset == 0.0f) ? __fsub_rn(x, v) : __fsub_rn(x, __fsub_rn(v, c.v_reset));
+        const float dv = (VR0 || c.v_reset == 0.0f) ? __fsub_rn(x, v) : __fsub_rn(x, __fsub_rn(v, c.v_reset));
         h = __fadd_rn(v, __fmul_rn(dv, c.decay));
     }
     h_out = h;
     // heaviside(h - v_th): with gradual underflow h - v_th is zero only for h == v_th and has the sign of the exact
     // difference otherwise, so the comparison needs no subtraction
     const bool fire = h >= c.v_th;
-    v = fire ? c.v_reset : h;
+    v = fire ? (VR0 ? 0.0f : c.v_reset) : h;
     return fire ? 1.0f : 0.0f;
 }
 

@@ -214,7 +214,10 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // 5.5 KB per SM (N = 96) and the MMA leaves the feed-bound regime.  Rank 0 issues; rank 1 relays its producers' barriers.
 // KSX / ROWSTEP: rectangular filters (KS rows x KSX columns) and the row-list pass of a folded NNConvUpsampling block, whose
 // tile rows are arbitrary (sample, output row) entries with ROWSTEP private source rows each (patch row = ROWSTEP * tile row + ky).
-template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false, int KSX = KS, int ROWSTEP = 1>
+// NK: neuron kind fixed at compile time (and v_reset == 0), -1 = run-time switch.  The epilogue is instruction-issue bound on the
+// full-resolution blocks; the generic version executes the other kinds' arithmetic predicated off (~25 % of its instructions).
+template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false, int KSX = KS, int ROWSTEP = 1,
+          int NK = -1>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
@@ -875,7 +878,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = p.v_reset;
+                for (int i = 0; i < 16; ++i) v[i] = NK >= 0 ? 0.0f : p.v_reset;
             }
             for (int t0 = 0; t0 < p.T; t0 += cTC) {
                 const int tc = min(cTC, p.T - t0);
@@ -923,7 +926,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     }
                     float hbuf[16];
                     uint32_t sb[16];      // spike of each channel as 0 / 1
-                    if (p.neuron == SS_NEURON_IF) {
+                    if constexpr (NK >= 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<NK, true>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
+                    } else if (p.neuron == SS_NEURON_IF) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<SS_NEURON_IF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     } else if (p.neuron == SS_NEURON_LIF) {
@@ -1394,6 +1400,12 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, true>, p);                              \
         launched = true;                                                                                                   \
     }
+#define SS_TRY_NK(PL, KS_, ST_, RB_, NK_)                                                                                   \
+    if (!launched && spec && g->neuron == NK_ && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {     \
+        SS_ENSURE_SMEM((conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, false, KS_, 1, NK_>), dev, 227 * 1024);          \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, KS_, ST_, RB_, false, MODE_I8, false, KS_, 1, NK_>, p);                \
+        launched = true;                                                                                                   \
+    }
 #define SS_TRY(PL, KS_, ST_, RB_)                                                                                          \
     SS_TRY_PAIR(PL, KS_, ST_, RB_)                                                                                         \
     if (!launched && g->planes == PL && g->ks == KS_ && g->stride == ST_ && p.RB == RB_) {                                 \
@@ -1414,6 +1426,24 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         launched = true;                                                                                                   \
     }
 #define SS_TRY_PL(PL) SS_TRY_ROWLIST(PL) SS_TRY_FIRST(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
+    // default precision (3 planes), v_reset == 0 (every call site of the reference), no CTA pair: neuron kind compiled in
+    const bool spec = !pair && !rowlist && !first && g->planes == 3 && g->v_reset == 0.0f;
+#define SS_TRY_SPEC(NK_)                                                                                                   \
+    SS_TRY_NK(3, 5, 1, 32, NK_) SS_TRY_NK(3, 5, 2, 32, NK_) SS_TRY_NK(3, 3, 1, 64, NK_) SS_TRY_NK(3, 3, 1, 32, NK_)        \
+    if (!launched && first && g->planes == 3 && g->v_reset == 0.0f && g->neuron == NK_) {                                  \
+        SS_ENSURE_SMEM((conv_i8_kernel<3, 1, 1, 128, true, MODE_I8, false, 1, 1, NK_>), dev, 227 * 1024);                  \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<3, 1, 1, 128, true, MODE_I8, false, 1, 1, NK_>, p);                        \
+        launched = true;                                                                                                   \
+    }                                                                                                                      \
+    if (!launched && rowlist && g->planes == 3 && g->v_reset == 0.0f && g->neuron == NK_) {                                \
+        SS_ENSURE_SMEM((conv_i8_kernel<3, 3, 1, 32, false, MODE_I8, false, 5, 3, NK_>), dev, 227 * 1024);                  \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<3, 3, 1, 32, false, MODE_I8, false, 5, 3, NK_>, p);                        \
+        launched = true;                                                                                                   \
+    }
+    SS_TRY_SPEC(SS_NEURON_IF)
+    SS_TRY_SPEC(SS_NEURON_LIF)
+    SS_TRY_SPEC(SS_NEURON_PLIF)
+#undef SS_TRY_SPEC
     SS_TRY_PL(2)
     SS_TRY_PL(3)
     SS_TRY_PL(4)
@@ -1421,6 +1451,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
 #undef SS_TRY_ROWLIST
 #undef SS_TRY_FIRST
 #undef SS_TRY
+#undef SS_TRY_NK
 #undef SS_TRY_PAIR
     if (!launched) {
         set_error("ss_conv_i8_fwd: no kernel instance for planes %d ks %d stride %d rowbytes %d", g->planes, g->ks, g->stride, p.RB);

@@ -1,2 +1,11 @@
-ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -s 1300 -c 150 --csv --log-file gpurun_out/r2g_launches.csv python bench.py --steps 4 --warmup 10 --no-train --no-parity --no-cpu-baseline > gpurun_out/r2g_ncu.log 2>&1
-tail -2 gpurun_out/r2g_ncu.log | cut -c1-300
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python bench.py --steps 20 --warmup 5 --no-train > gpurun_out/r2i_bench.json 2>gpurun_out/r2i_err.log
+tail -3 gpurun_out/r2i_err.log
+python - <<'PY'
+import json
+for f in ('gpurun_out/r2i_bench.json',):
+    d=json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['kernel_ms_per_step'])
+    print(d['roofline']['per_block_ms'])
+    print(d.get('parity'))
+PY

@@ -282,6 +282,109 @@ def time_training(args, dev, world, rank, B, steps, warmup, barrier):
     return res[0][0], res[1][0], ncoll, res[0][1]
 
 
+def sj_cupy_proxy(args, dev, B, T, steps=10, warmup=3):
+    """PROXY for the reference model on SpikingJelly's multi-step cupy backend (SURVEY.md 8(d) comparison point 2; neither
+    spikingjelly nor cupy exists on the box, so this is NOT that library): what that path executes on a GPU -- cuDNN convolutions
+    over the flattened [T*B] batch (fp32 NCHW tensors), an elementwise gain, and ONE unfused per-neuron T-loop CUDA kernel per layer
+    (one thread per neuron, looping over T, reading the fp32 conv output and writing fp32 spikes: ss_neuron_fwd, the same structure
+    as MultiStepLIFNode's cupy kernel), elementwise skip adds, upsample + conv heads.  Forward only.  Returns event-frames/s for
+    cuDNN in true fp32 and with TF32 allowed (PyTorch's default, which is what an unmodified SpikingJelly script gets)."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from stereospike_b200 import _lib
+    from oracle import ref_model as rm
+    L = _lib.lib()
+    net = build_oracle(args.neuron, args.gain, args.tau).to(dev)
+    x = rm.synthetic_inputs(B, T, 4, seed=900).to(dev)
+    kind = {'if': 0, 'lif': 1, 'plif': 2}[args.neuron]
+    vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    stream = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def multistep(node, y):          # y fp32 [T*B, C, H, W] -> spikes, one T-loop kernel
+        yt = y.view(T, -1)
+        s = torch.empty_like(yt)
+        v = torch.zeros(yt.shape[1], dtype=torch.float32, device=dev)
+        k, decay, tau = kind, None, float(getattr(node, 'tau', 2.0))
+        if hasattr(node, 'w'):
+            k, decay = 2, node.w.detach().sigmoid().reshape(1).float()
+        elif not hasattr(node, 'tau'):
+            k = 0
+        _lib.check(L.ss_neuron_fwd(T, yt.shape[1], k, 1.0, 0.0, tau, vp(decay), vp(yt), vp(v), vp(s), None, stream()), 'ss_neuron_fwd')
+        return s.view_as(y)
+
+    def block(seq, xin):             # Sequential(conv | UpConv, Gain, neuron)
+        return multistep(seq[2], seq[1](seq[0](xin)))
+
+    def fwd():
+        f = x.transpose(0, 1).reshape(T * B, 4, H0, W0)          # time-major flattened batch
+        b = block(net.bottom, f)
+        c1 = block(net.conv1, b); c2 = block(net.conv2, c1); c3 = block(net.conv3, c2); c4 = block(net.conv4, c3)
+        r = c4
+        for blk in net.bottleneck:
+            m = multistep(blk.sn1, blk.conv1(r))
+            r = multistep(blk.sn2, blk.conv2(m)) + r
+        cur, depth = r, 0.0
+        for (name, _, _, _), skip, (hname, _) in zip(rm.DEC, (c3, c2, c1, b), rm.HEADS):
+            cur = block(getattr(net, name), cur) + skip
+            depth = depth + getattr(net, hname)(cur).view(T, B, 1, H0, W0).sum(0)       # I-neurons: never fire, potentials add up
+        return depth
+
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        with torch.no_grad():
+            for _ in range(warmup):
+                fwd()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize()
+        out['tf32' if tf32 else 'fp32'] = B * T * steps / (e0.elapsed_time(e1) / 1e3)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    del net, x
+    torch.cuda.empty_cache()
+    return out
+
+
+def timestep_sweep(args, dev, B=16, Ts=(1, 5, 10, 20), steps=10, warmup=3):
+    """BASELINE.json configs[4]: T in {1, 5, 10, 20} at batch 16 on one GPU, stateless inference, device-resident frames."""
+    import torch
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm
+    net = make_net(args, dev)
+    net.set_kernel_options(keep_state=False)
+    res = {}
+    for T in Ts:
+        xs = [rm.synthetic_inputs(B, T, 4, seed=700 + i).to(dev) for i in range(2)]
+        with torch.no_grad():
+            for i in range(warmup):
+                sb.functional.reset_net(net)
+                net.forward_seq(xs[i % 2])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                sb.functional.reset_net(net)
+                net.forward_seq(xs[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[f'T={T}'] = {'ms_per_step': ms, 'event_frames_per_s': B * T / (ms / 1e3), 'depth_maps_per_s': B / (ms / 1e3)}
+        del xs
+        torch.cuda.empty_cache()
+    del net
+    torch.cuda.empty_cache()
+    return {'batch': B, 'steps': steps, 'warmup': warmup, 'results': res}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -511,6 +614,14 @@ def run_ours(args):
                                           'value': B * T * world / (alt_ms / 1e3)}
         if train_rec is not None:
             line['train'] = train_rec
+        if world == 1 and not train and not args.no_extras:
+            line['timestep_sweep'] = timestep_sweep(args, dev)
+            px = sj_cupy_proxy(args, dev, B, T)
+            line['sj_cupy_proxy'] = {'value_fp32': px['fp32'], 'value_tf32_allowed': px['tf32'], 'unit': 'event-frames/s',
+                                     'speedup_vs_fp32': value / px['fp32'], 'speedup_vs_tf32_allowed': value / px['tf32'],
+                                     'what': 'PROXY (spikingjelly / cupy are not installable here): cuDNN convs over the flattened [T*B] batch '
+                                             '+ one unfused per-neuron T-loop CUDA kernel per layer + elementwise gain / skip adds, fp32 NCHW, '
+                                             f'forward, B={B}, T={T}, same GPU, same run'}
         if world == 1 and not args.no_parity and not train:
             from tests._cases import parity_summary          # the oracle as the checker, outside every timed region
             line['parity'] = parity_summary(args.neuron, args.gain, args.tau, T=T, B=1, seed=0, planes=args.planes,
@@ -552,6 +663,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the timestep sweep and the SpikingJelly-cupy proxy (N=1 only)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

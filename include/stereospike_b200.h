@@ -99,6 +99,11 @@ int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t k
  * may be NULL) is set. */
 int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw4,
                    int32_t* status, void* stream);
+/* Same into u8 [T][B][H][W][Cpad], C <= Cpad, Cpad = 4 or a multiple of 32 (<= 256): the channel-concatenated temporal mode of
+ * the reference (train.py:206-218: the first conv gets 2 * nfpdm * cameras channels), whose first block then runs as an ordinary
+ * Cin = Cpad block of ss_conv_i8_fwd with zero weights for the padding channels. */
+int ss_pack_events_c(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t Cpad, int32_t H, int32_t W, void* out,
+                     int32_t* status, void* stream);
 
 /* Event stream -> event-count frames (the step in front of the path; replaces mvsecRectifyEvents and
  * mvsecCumulateSpikesIntoFrames, datasets/MVSEC/utils.py:31-56,215-281).
@@ -160,6 +165,9 @@ typedef struct ss_tile_maps {
     const int32_t* rl_src;
     const int32_t* rl_out;
     const uint8_t* rl_collive;
+    uint64_t* stats;       /* any mode, optional: [6] counters this launch ADDS to -- {spikes fired, nonzero outputs (spikes + skip),
+                              sum of outputs^2} over all T steps, then the same three over the last step only.  The firing rates of
+                              SNN_models.py:194-245 and the spike penalty of loss.py:96-107 without a pass over the spike maps. */
 } ss_tile_maps;
 int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
                       const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,

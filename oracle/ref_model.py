@@ -76,7 +76,7 @@ class SpikingUNet(nn.Module):
     """variant: 'if' (StereoSpike), 'lif', 'plif' (the two fromZero classes; ``monocular`` picks Cin=2)."""
 
     def __init__(self, variant='if', monocular=False, surrogate_function=None, tau=10.0,
-                 v_threshold=1.0, v_reset=0.0, multiply_factor=1.0):
+                 v_threshold=1.0, v_reset=0.0, multiply_factor=1.0, in_channels=None):
         super().__init__()
         assert variant in ('if', 'lif', 'plif')
         self.variant, self.monocular = variant, monocular
@@ -100,7 +100,9 @@ class SpikingUNet(nn.Module):
             inner = lambda: sj.ParametricLIFNode(tau, v_threshold, v_reset, sj.Sigmoid(), detach_reset=True)
             i_sf = sj.ATan()
 
-        cin0 = 2 if monocular else 4
+        # in_channels: the hand edit train.py:206-213 asks for in the channel-concatenated temporal mode ("number of filters in the
+        # first convolution should be changed accordingly"): 2 * nfpdm * cameras input channels
+        cin0 = in_channels if in_channels is not None else (2 if monocular else 4)
         self.bottom = nn.Sequential(nn.Conv2d(cin0, 32, 5, 1, 2, bias=False), Gain(g), outer())
         for name, ci, co in ENC:
             setattr(self, name, nn.Sequential(nn.Conv2d(ci, co, 5, 2, 2, bias=False), Gain(g), outer()))

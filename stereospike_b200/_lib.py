@@ -15,7 +15,7 @@ SS_IN_U8_TBHWC, SS_IN_F32_BTCHW = 0, 1
 SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
-SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_pack_digits_i8_rect', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_conv_neuron_fwd',
+SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_pack_digits_i8_rect', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_pack_events_c', 'ss_conv_neuron_fwd',
            'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_neuron_bwd_ex', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
            'ss_pack_weights_bf16', 'ss_corr_bf16', 'ss_conv_wgrad_bf16', 'ss_loss_fwd', 'ss_loss_bwd',
            'ss_abi_version', 'ss_last_error', 'ss_launch_count')
@@ -34,7 +34,7 @@ class BlockDesc(ctypes.Structure):
 class TileMaps(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('nclass', ctypes.c_int32), ('rl_n', ctypes.c_int32), ('transposed', ctypes.c_int32),
                 ('ymap_out', ctypes.c_void_p), ('xmap_out', ctypes.c_void_p), ('rl_src', ctypes.c_void_p),
-                ('rl_out', ctypes.c_void_p), ('rl_collive', ctypes.c_void_p)]
+                ('rl_out', ctypes.c_void_p), ('rl_collive', ctypes.c_void_p), ('stats', ctypes.c_void_p)]
 
 
 SS_TILES_PLAIN, SS_TILES_FOLDED, SS_TILES_ROW_LIST = 0, 1, 2
@@ -104,6 +104,8 @@ def lib():
     L.ss_pack_weights_i8.restype = ctypes.c_int
     L.ss_pack_events.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
     L.ss_pack_events.restype = ctypes.c_int
+    L.ss_pack_events_c.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.ss_pack_events_c.restype = ctypes.c_int
     L.ss_conv_neuron_fwd.argtypes = [ctypes.POINTER(ConvGeom)] + [vp] * 11
     L.ss_conv_neuron_fwd.restype = ctypes.c_int
     L.ss_heads_fwd.argtypes = [ctypes.POINTER(HeadsArgs), vp, vp, vp]

@@ -91,6 +91,7 @@ struct I8Params {
     uint8_t* out;
     float* h_seq;
     uint8_t* tsum;
+    unsigned long long* stats;   // optional [6]: {spikes, nonzero outputs, sum of out^2} over all steps, then over the last step
     float* g_dst;          // MODE_BF16 (gradient-side correlation): fp32 NHWC destination [T][B][Hout][Wout][Cout]
     int g_mode;            // SS_CORR_STORE / SS_CORR_ACCUMULATE / SS_CORR_ATOMIC
 };
@@ -824,6 +825,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
         SS_DECL();
         int sc_ntile = -1;
         float sc[16];                 // wscale * gain (wscale is a power of two, so this product is exact)
+        // firing statistics (SNN_models.py:194-245, loss.py:96-107) straight from the registers that hold the spikes: per thread
+        // {spikes, nonzero outputs, sum out^2} over all steps [0..2] and over the last step [3..5]; one atomic per warp at the end
+        uint32_t st[6] = {0u, 0u, 0u, 0u, 0u, 0u};
         for (int it = it0; it < nit; it += its) {
             const int ntile = fast_div(it, mt_per, m_mt_per);
             const int mt = PAIR ? 2 * (it - ntile * mt_per) + (int)crank : it - ntile * mt_per;
@@ -945,7 +949,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     for (int q = 0; q < 4; ++q)
                         pk[q] = sb[4 * q] | (sb[4 * q + 1] << 8) | (sb[4 * q + 2] << 16) | (sb[4 * q + 3] << 24);
                     const size_t o = (size_t)t * t_out + o0;
+                    uint32_t n_spk = 0u;
+                    if (p.stats != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) n_spk = __dp4a(pk[q], 0x01010101u, n_spk);
+                    }
                     pk[0] += rs_cur.x; pk[1] += rs_cur.y; pk[2] += rs_cur.z; pk[3] += rs_cur.w;
+                    if (p.stats != nullptr) {
+                        uint32_t n_nz = 0u, n_sq = 0u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            n_nz = __dp4a((pk[q] | (pk[q] >> 1)) & 0x01010101u, 0x01010101u, n_nz);   // bytes are 0..3
+                            n_sq = __dp4a(pk[q], pk[q], n_sq);
+                        }
+                        st[0] += n_spk; st[1] += n_nz; st[2] += n_sq;
+                        if (t + 1 == p.T) { st[3] += n_spk; st[4] += n_nz; st[5] += n_sq; }
+                    }
                     *reinterpret_cast<uint4*>(p.out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     if (t + 1 < p.T) {
                         ts[0] += pk[0]; ts[1] += pk[1]; ts[2] += pk[2]; ts[3] += pk[3];
@@ -963,6 +982,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 float4* vo = reinterpret_cast<float4*>(p.v_out + o0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+        }
+        if (p.stats != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                uint32_t a = st[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0 && a != 0u) atomicAdd(p.stats + k, (unsigned long long)a);
             }
         }
         if (threadIdx.x == 256) SS_DUMP(3);
@@ -1074,24 +1102,48 @@ __global__ void __launch_bounds__(256) weight_pack_first_kernel(const float* __r
     }
 }
 
-// fp32 NCHW event-count frames [B][T][C][H][W] (reference layout, train.py:201-218) -> u8 NHWC [T][B][H][W][4]
-__global__ void __launch_bounds__(256) pack_events_kernel(const float* __restrict__ x, int B, int T, int C, int H, int W,
+// fp32 NCHW event-count frames [B][T][C][H][W] (reference layout, train.py:201-218) -> u8 NHWC [T][B][H][W][Cpad], channels >= C zero.
+// One thread = PX consecutive pixels x one group of 4 channels: PX = 4 reads each channel plane with 16-byte loads (the scalar
+// version moved 72 MB at 1.9 TB/s).  Cpad = 4: the first-layer im2col mode; Cpad = 32, 64: the channel-concatenated temporal mode
+// (train.py:206-218: first conv with 2 * nfpdm * cameras input channels), which runs as an ordinary 32-byte-row block.
+template <int PX>
+__global__ void __launch_bounds__(256) pack_events_kernel(const float* __restrict__ x, int B, int T, int C, int Cpad, int H, int W,
                                                           uint32_t* __restrict__ out, int* __restrict__ status) {
     const long long HW = (long long)H * W;
+    const int groups = Cpad >> 2;
+    const long long npg = HW / PX;                        // pixel groups per frame
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)T * B * HW) return;
-    const long long hw = idx % HW;
-    const int b = (int)((idx / HW) % B);
-    const int t = (int)(idx / (HW * B));
-    uint32_t lo = 0;
+    if (idx >= (long long)T * B * npg * groups) return;
+    const int grp = (int)(idx % groups);
+    const long long pg = (idx / groups) % npg;
+    const int b = (int)((idx / (groups * npg)) % B);
+    const int t = (int)(idx / (groups * npg * B));
+    uint32_t word[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) word[i] = 0u;
     bool bad = false;
-    for (int c = 0; c < C; ++c) {
-        const float f = __ldg(x + (((size_t)b * T + t) * C + c) * HW + hw);
-        const float r = fminf(fmaxf(rintf(f), 0.0f), 255.0f);
-        bad |= (r != f);
-        lo |= (uint32_t)r << (8 * c);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c = grp * 4 + cc;
+        if (c >= C) break;
+        const float* src = x + (((size_t)b * T + t) * C + c) * HW + pg * PX;
+        float f[PX];
+        if constexpr (PX == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+            f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+        } else {
+            f[0] = __ldg(src);
+        }
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            const float r = fminf(fmaxf(rintf(f[i]), 0.0f), 255.0f);
+            bad |= (r != f[i]);
+            word[i] |= (uint32_t)r << (8 * cc);
+        }
     }
-    out[idx] = lo;
+    const size_t o = ((((size_t)t * B + b) * HW + pg * PX) * groups) + grp;     // in 4-byte words
+#pragma unroll
+    for (int i = 0; i < PX; ++i) out[o + (size_t)i * groups] = word[i];
     if (bad && status != nullptr) atomicOr(status, 1);
 }
 
@@ -1158,18 +1210,31 @@ extern "C" int ss_pack_weights_i8(const float* w_oihw, int32_t Cout, int32_t Cin
     return check_launch("weight_pack");
 }
 
-extern "C" int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw4,
-                              int32_t* status, void* stream) {
-    if (x_btchw == nullptr || out_tbhw4 == nullptr || C <= 0 || C > 4 || B < 0 || T < 0 || H <= 0 || W <= 0) {
-        set_error("ss_pack_events: bad argument (1 <= C <= 4)");
+extern "C" int ss_pack_events_c(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t Cpad, int32_t H, int32_t W, void* out,
+                                int32_t* status, void* stream) {
+    if (x_btchw == nullptr || out == nullptr || C <= 0 || C > Cpad || !(Cpad == 4 || (Cpad % 32 == 0 && Cpad <= 256)) || B < 0 || T < 0 ||
+        H <= 0 || W <= 0) {
+        set_error("ss_pack_events: bad argument (1 <= C <= Cpad, Cpad = 4 or a multiple of 32)");
         return SS_EINVAL;
     }
-    const long long n = (long long)T * B * H * W;
-    if (n == 0) return SS_OK;
-    pack_events_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_btchw, B, T, C, H, W,
-                                                                                      reinterpret_cast<uint32_t*>(out_tbhw4), status);
+    const long long HW = (long long)H * W;
+    if ((long long)T * B * HW == 0) return SS_OK;
+    const bool vec = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(x_btchw) & 15u) == 0;
+    const long long n = (long long)T * B * (HW / (vec ? 4 : 1)) * (Cpad / 4);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (vec) pack_events_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x_btchw, B, T, C, Cpad, H, W, reinterpret_cast<uint32_t*>(out), status);
+    else pack_events_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x_btchw, B, T, C, Cpad, H, W, reinterpret_cast<uint32_t*>(out), status);
     count_launch();
     return check_launch("pack_events");
+}
+
+extern "C" int ss_pack_events(const float* x_btchw, int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, void* out_tbhw4,
+                              int32_t* status, void* stream) {
+    if (C > 4) {
+        set_error("ss_pack_events: bad argument (1 <= C <= 4); use ss_pack_events_c for more channels");
+        return SS_EINVAL;
+    }
+    return ss_pack_events_c(x_btchw, B, T, C, 4, H, W, out_tbhw4, status, stream);
 }
 
 static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
@@ -1371,6 +1436,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.out = reinterpret_cast<uint8_t*>(out);
     p.h_seq = h_seq;
     p.tsum = reinterpret_cast<uint8_t*>(tsum);
+    p.stats = tm != nullptr ? reinterpret_cast<unsigned long long*>(tm->stats) : nullptr;
 
     const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
     const int num_sms = sms;

@@ -57,7 +57,7 @@ class Site:
                 w_i8 = ops.pack_weights_folded(w, planes)          # (dense, rows, cols, wscale)
             elif need_i8:
                 cin = w.shape[1]
-                q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=4 if cin <= 4 else (cin + 31) // 32 * 32)
+                q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=ops.first_layer_channels(cin) if cin % 32 else cin)
                 w_i8 = (q, sc)
             self._pack = (key, w_kn, w_i8)
         return self._pack[1], self._pack[2]
@@ -102,6 +102,13 @@ class _NetFunction(torch.autograd.Function):
         res = eng._run_forward(x_seq, params, n_site_params, side, want_h=need_grad)
         names = side.get('spike_outputs') or ()
         spks = tuple(side['acts'][k][-1].permute(0, 3, 1, 2).float() for k in names) if need_grad else ()
+        if names and need_grad and side.get('stats') is not None:
+            # SpikePenalization_Loss (loss.py:96-107) of the returned maps from the counters the block epilogues accumulated:
+            # sum_k  sum(s_k^2) / (2 numel_k)  over the last timestep -- no pass over the spike maps
+            pen = side['stats'].new_zeros((), dtype=torch.float64)
+            for k in names:
+                pen = pen + side['stats'][eng.site_index_of_output(k), 5].double() / (2.0 * side['acts'][k][-1].numel())
+            spks = spks + (pen.float(),)
         depths = res['depths']
         if need_grad:
             ctx.eng, ctx.n_site_params = eng, n_site_params
@@ -122,6 +129,14 @@ class _NetFunction(torch.autograd.Function):
         if g_depths is None:
             g_depths = torch.zeros(ctx.depth_shape, dtype=torch.float32, device=ctx.depth_device)
         inject = {k: gs for k, gs in zip(ctx.spk_names, g_spks) if gs is not None}
+        g_pen = g_spks[len(ctx.spk_names)] if len(g_spks) > len(ctx.spk_names) else None
+        if g_pen is not None:
+            # d/ds of sum(s^2) / (2 n) = s / n on the last timestep of every penalised layer (device-side, no sync)
+            acts = saved['acts']
+            for k in ctx.spk_names:
+                s_last = acts[k][-1].permute(0, 3, 1, 2).float()
+                term = s_last * (g_pen.float() / s_last.numel())
+                inject[k] = term if k not in inject else inject[k] + term
         grads = ctx.eng._run_backward(saved, ctx.params, ctx.n_site_params, g_depths.contiguous().float(), inject)
         ctx.saved = None
         return (None, None, None, None) + tuple(grads)
@@ -139,6 +154,9 @@ class Engine:
         #                             call, then through a pinned host copy inspected at the start of a later call (ValueError)
         self._status = None         # (device int32[1], pinned host int32[1], event) per device
         self._status_checked_once = False
+        self.collect_stats = False  # every block adds {spikes, nonzero outputs, sum out^2} (all steps / last step) to side['stats'] [n_sites, 6]
+        #                             from its epilogue registers (dp4a + one atomic per warp); always on for a grad-enabled
+        #                             forward_seq(spikes_fp32=True) (fused spike penalty) and for calculate_firing_rates
         self.grad_hook = None       # parallel.OverlappedGradientSync: called with each weight-gradient tensor as soon as it is
         #                             enqueued (reverse layer order), so that its all-reduce overlaps the rest of the backward
         self.fold_upsample = True   # NNConvUpsampling blocks folded: four 3x3 convs on the source for the regular outputs + two small
@@ -148,6 +166,12 @@ class Engine:
         self.bwd_impl = 'umma'      # gradients of the convs: 'umma' = bf16 tensor cores (fp32 accumulation), 'simt' = fp32 CUDA cores
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
         #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
+
+    def site_index_of_output(self, out_name):
+        for i, s in enumerate(self.sites):
+            if s.out == out_name:
+                return i
+        raise KeyError(out_name)
 
     def _fold_site(self, name):
         f = self.fold_upsample
@@ -174,8 +198,9 @@ class Engine:
             raise ValueError('expected x of shape [B, T, C, H, W]')
         if x_seq.dtype == torch.uint8:
             # packed event frames u8 [T, B, H, W, 4] (stereospike_b200.events / ss_pack_events): inference only
-            if x_seq.shape[-1] != 4 or IMPLS[self.impl] == SS_IMPL_SIMT:
-                raise ValueError('packed input must be u8 [T, B, H, W, 4] and needs the tensor-core path')
+            if x_seq.shape[-1] != ops.first_layer_channels(self.sites[0].conv.in_channels) or IMPLS[self.impl] == SS_IMPL_SIMT:
+                raise ValueError('packed input must be u8 [T, B, H, W, 4] (32 per 32 channels in the channel-concatenated mode) '
+                                 'and needs the tensor-core path')
             x_seq = x_seq.contiguous()
         else:
             x_seq = x_seq.contiguous().float()
@@ -249,6 +274,10 @@ class Engine:
         saved = {'B': B, 'T': T, 'sites': [], 'acts': acts}
         head_srcs = {h.src for h in self.heads}
         tsums = {}
+        stats = None
+        if (self.collect_stats or (want_h and side.get('spike_outputs'))) and impl != SS_IMPL_SIMT:
+            stats = torch.zeros((len(self.sites), 6), dtype=torch.int64, device=dev)
+        side['stats'] = stats
         for i, s in enumerate(self.sites):
             xin = acts[s.src]
             first = s.src == 'x'
@@ -257,7 +286,9 @@ class Engine:
             if first and not packed_in and int(x_seq.shape[2]) != g.Cin:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
             use_i8 = impl != SS_IMPL_SIMT
-            fold = use_i8 and self._fold_site(s.name) and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
+            # (not while training: the weights change every step and the folded sets are derived on the host side of the C ABI --
+            #  re-deriving them costs more than the taps they save; the 25-tap kernel packs its image in one small launch)
+            fold = use_i8 and self._fold_site(s.name) and not want_h and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
                 ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
             if fold:
                 self.flop_scale[s.name] = ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).taps_per_output / 25.0
@@ -289,10 +320,11 @@ class Engine:
                     tsums[s.out] = tsum
                 if fold:
                     out, v_out, h_seq = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], w_i8[3], planes=self.weight_planes,
-                                                               tsum=tsum, **common)
+                                                               tsum=tsum, stats=stats[i] if stats is not None else None, **common)
                 else:
                     out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
-                                                        cin=4 if first else g.Cin, tsum=tsum, **common)
+                                                        cin=ops.first_layer_channels(g.Cin) if first else g.Cin, tsum=tsum,
+                                                        stats=stats[i] if stats is not None else None, **common)
             else:
                 out, v_out, h_seq = ops.conv_neuron_fwd(xin, g, w_kn, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC,
                                                         **common)

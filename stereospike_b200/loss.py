@@ -143,7 +143,8 @@ class Total_Loss(nn.Module):
         loss, mdes = _terms(ps, groundtruth, w, [self.alpha * f for f in w])
         self.last_mde = mdes[0].detach()                # device scalar: no host sync unless the caller reads it
         if self.penalize_spikes:
-            loss = loss + self.beta * SpikePenalization_Loss(intermediary_spike_tensors)
+            fused = getattr(intermediary_spike_tensors, 'penalty', None)      # models.SpikeList: computed in the block epilogues
+            loss = loss + self.beta * (fused if fused is not None else SpikePenalization_Loss(intermediary_spike_tensors))
         return loss
 
 

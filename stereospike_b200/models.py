@@ -28,6 +28,13 @@ LAYER_NAMES = ('out_bottom', 'out_conv1', 'out_conv2', 'out_conv3', 'out_conv4',
                'out_add4', 'out_deconv3', 'out_add3', 'out_deconv2', 'out_add2', 'out_deconv1', 'out_add1')
 
 
+class SpikeList(list):
+    """The list of spike maps a model returns; ``penalty`` (when gradients are enabled and fp32 maps were asked for) is the
+    reference's SpikePenalization_Loss of these maps as a differentiable scalar, computed from counters the block epilogues
+    accumulate -- stereospike_b200.loss.Total_Loss(penalize_spikes=True) uses it instead of a pass over the maps."""
+    penalty = None
+
+
 class NeuromorphicNet(nn.Module):
     def __init__(self, surrogate_function=None, detach_reset=True, v_threshold=1.0, v_reset=0.0):
         super().__init__()
@@ -157,8 +164,12 @@ class _SpikingUNet(NeuromorphicNet):
         d = [depths[3].unsqueeze(1), depths[2].unsqueeze(1), depths[1].unsqueeze(1), depths[0].unsqueeze(1)]
         if not self._returns_spikes:
             return d
-        if spikes_fp32 and len(side.get('spikes_fp32', ())) == len(self._SPIKE_OUTPUTS):
-            return d, list(side['spikes_fp32'])    # differentiable: a loss on them reaches the weights through the surrogates
+        if spikes_fp32 and len(side.get('spikes_fp32', ())) >= len(self._SPIKE_OUTPUTS):
+            # differentiable: a loss on them reaches the weights through the surrogates
+            out = SpikeList(side['spikes_fp32'][:len(self._SPIKE_OUTPUTS)])
+            if len(side['spikes_fp32']) > len(self._SPIKE_OUTPUTS):
+                out.penalty = side['spikes_fp32'][len(self._SPIKE_OUTPUTS)]
+            return d, out
         acts = side['acts']
         spks = []
         for k in self._SPIKE_OUTPUTS:
@@ -186,33 +197,56 @@ class _SpikingUNet(NeuromorphicNet):
         self.Ineurons.v = depth_prior
 
     def calculate_firing_rates(self, x):
-        """Per-layer spike densities count_nonzero/numel of frame 0 (SNN_models.py:194-245).  Like the reference,
-        this advances the neuron state by one step."""
-        with torch.no_grad():
-            _, side = self.engine.run(x[:, 0:1])
+        """Per-layer spike densities count_nonzero/numel of frame 0 (SNN_models.py:194-245).  Like the reference, this
+        advances the neuron state by one step.  The counts come from the block epilogues (side['stats']: spikes fired and
+        nonzero outputs per block, accumulated with dp4a from the registers that hold the spikes) -- one small device-to-host
+        copy instead of 14 count_nonzero passes over the activations."""
+        eng = self.engine
+        keep = eng.collect_stats
+        eng.collect_stats = True
+        try:
+            with torch.no_grad():
+                _, side = eng.run(x[:, 0:1])
+        finally:
+            eng.collect_stats = keep
         acts = side['acts']
+        if side.get('stats') is None:           # CUDA-core path (impl='simt'): count on the stored activations
+            rates = {}
+            for k in LAYER_NAMES:
+                if k.startswith('out_deconv'):
+                    n = k[-1]
+                    skip = {'4': 'out_conv3', '3': 'out_conv2', '2': 'out_conv1', '1': 'out_bottom'}[n]
+                    t = acts['out_add' + n][-1].float() - acts[skip][-1].float()
+                else:
+                    t = acts[k][-1]
+                rates[k] = float(t.count_nonzero()) / t.numel()
+            return rates
+        st = side['stats'].cpu()
         rates = {}
         for k in LAYER_NAMES:
-            if k.startswith('out_deconv'):
-                n = k[-1]
-                skip = {'4': 'out_conv3', '3': 'out_conv2', '2': 'out_conv1', '1': 'out_bottom'}[n]
-                t = acts['out_add' + n][-1].float() - acts[skip][-1].float()
-            else:
-                t = acts[k][-1]
-            rates[k] = float(t.count_nonzero()) / t.numel()
+            fired = k.startswith('out_deconv')                  # the block's own spikes, before the skip connection is added
+            name = 'out_add' + k[-1] if fired else k
+            i = eng.site_index_of_output(name)
+            rates[k] = float(st[i, 0 if fired else 1]) / acts[name][-1].numel()
         return rates
 
 
 class StereoSpike(_SpikingUNet):
     """Baseline binocular model: IF neurons, ATan surrogate outside the bottleneck, default Sigmoid inside
     (SNN_models.py:63-150; the reference does not forward v_threshold / v_reset to its base, so they are
-    always 1.0 / 0.0 -- reproduced here)."""
+    always 1.0 / 0.0 -- reproduced here).
 
-    def __init__(self, surrogate_function=None, detach_reset=True, v_threshold=1.0, v_reset=0.0, multiply_factor=1.):
+    ``in_channels`` (extension, all three classes): the channel-concatenated temporal mode of the reference's scripts
+    (train.py:206-218: ``nfpdm`` frames per depth map folded into the channel axis, "number of filters in the first convolution
+    should be changed accordingly") -- e.g. ``in_channels = 2 * nfpdm * 2`` for the binocular model.  More than 4 channels run the
+    first block as an ordinary 32-channel tensor-core block on frames packed to u8 [T,B,H,W,32]."""
+
+    def __init__(self, surrogate_function=None, detach_reset=True, v_threshold=1.0, v_reset=0.0, multiply_factor=1.,
+                 in_channels=4):
         super().__init__(surrogate_function=surrogate_function, detach_reset=detach_reset)
         sf = self.surrogate_fct
         outer = lambda: neuron.IFNode(v_threshold=self.v_th, v_reset=self.v_rst, surrogate_function=sf, detach_reset=True)
-        self._build(4, outer, dict(v_threshold=self.v_th, v_reset=self.v_rst), multiply_factor,
+        self._build(in_channels, outer, dict(v_threshold=self.v_th, v_reset=self.v_rst), multiply_factor,
                     neuron.IFNode(v_threshold=float('inf'), v_reset=0.0, surrogate_function=sf))
 
 
@@ -222,9 +256,12 @@ class fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(_SpikingUNet):
 
     _cin0 = 4
 
-    def __init__(self, use_plif=False, detach_reset=True, tau=10., v_threshold=1.0, v_reset=0.0, multiply_factor=1.):
+    def __init__(self, use_plif=False, detach_reset=True, tau=10., v_threshold=1.0, v_reset=0.0, multiply_factor=1.,
+                 in_channels=None):
         super().__init__(detach_reset=detach_reset)
         self.is_cext_model = False
+        if in_channels is not None:
+            self._cin0 = int(in_channels)
         if use_plif:
             outer = lambda: neuron.ParametricLIFNode(init_tau=tau, v_threshold=v_threshold, v_reset=v_reset,
                                                      detach_reset=True)
@@ -244,7 +281,7 @@ class fromZero_feedforward_multiscale_tempo_monocular_SpikeFlowNetLike(
     _returns_spikes = False
 
     def __init__(self, use_plif=False, detach_reset=True, tau=10., v_threshold=1.0, v_reset=0.0,
-                 final_activation=nn.Identity, multiply_factor=1.):
+                 final_activation=nn.Identity, multiply_factor=1., in_channels=None):
         super().__init__(use_plif=use_plif, detach_reset=detach_reset, tau=tau, v_threshold=v_threshold,
-                         v_reset=v_reset, multiply_factor=multiply_factor)
+                         v_reset=v_reset, multiply_factor=multiply_factor, in_channels=in_channels)
         self.final_activation = final_activation

@@ -110,12 +110,19 @@ def pack_weights_i8(weight, planes, cin_pad=None):
     return out, wscale, wexp
 
 
+def first_layer_channels(C):
+    """Channels of the packed first-layer input for C frame channels: 4 (im2col mode) up to 4, else the next multiple of 32."""
+    return 4 if C <= 4 else (C + 31) // 32 * 32
+
+
 def pack_events(x_seq, status=None):
-    """fp32 [B,T,C,H,W] event-count frames -> u8 [T,B,H,W,4] (the first block's tensor-core input)."""
+    """fp32 [B,T,C,H,W] event-count frames -> u8 [T,B,H,W,Cpad] (the first block's tensor-core input; Cpad = 4, or a multiple of
+    32 for the channel-concatenated temporal mode with C > 4 channels)."""
     _require_cuda(x_seq, 'x')
     B, T, C, H, W = x_seq.shape
-    out = torch.empty((T, B, H, W, 4), dtype=torch.uint8, device=x_seq.device)
-    _lib.check(_lib.lib().ss_pack_events(_ptr(x_seq), B, T, C, H, W, _ptr(out), _ptr(status), _stream()), 'ss_pack_events')
+    cpad = first_layer_channels(C)
+    out = torch.empty((T, B, H, W, cpad), dtype=torch.uint8, device=x_seq.device)
+    _lib.check(_lib.lib().ss_pack_events_c(_ptr(x_seq), B, T, C, cpad, H, W, _ptr(out), _ptr(status), _stream()), 'ss_pack_events')
     return out
 
 
@@ -275,14 +282,22 @@ def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
 # ----------------------------------------------------------------------------------------- fused block
 def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau=2.0, decay=None, v_in=None,
                 want_v_out=False, resid=None, want_h=False, planes=3, cin=None, tsum=None, outputs=None, tile_maps=None,
-                desc_override=None):
+                desc_override=None, stats=None):
     """Tensor-core fused block over all T timesteps (ss_conv_i8_fwd).  x: u8 [T,B,Hin,Win,Cin].
     ``tsum``: optional u8 [B,Hout,Wout,Cout] receiving the sum of the first T-1 output steps (input of the linear heads).
+    ``stats``: optional int64 [6] device tensor the launch ADDS its firing statistics to ({spikes, nonzero outputs, sum out^2} over
+    all steps, then over the last step).
     Returns (out u8 [T,B,Hout,Wout,Cout], v_out, h_seq)."""
     _require_cuda(x, 'x')
     dev = x.device
     g = geom
     cin = g.Cin if cin is None else cin
+    if stats is not None:
+        assert stats.dtype == torch.int64 and stats.numel() == 6 and stats.is_contiguous() and stats.is_cuda
+        if tile_maps is None:
+            tile_maps = _lib.TileMaps(mode=_lib.SS_TILES_PLAIN, nclass=1, rl_n=0, transposed=0, ymap_out=0, xmap_out=0, rl_src=0,
+                                      rl_out=0, rl_collive=0, stats=0)
+        tile_maps.stats = stats.data_ptr()
     assert x.dtype == ACT_DTYPE and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, cin), \
         (x.dtype, tuple(x.shape), (T, B, g.Hin, g.Win, cin))
     out_shape = (T, B, g.Hout, g.Wout, g.Cout)
@@ -320,18 +335,19 @@ def conv_i8_fwd_folded(x, geom, w_dense, w_rows, w_cols, wscale, **kw):
     plan = fold_plan(g.Hin, g.Win, g.Hout, g.Wout, int(kw['B']), str(x.device))
     assert plan.ok, 'geometry cannot be folded'
     tm = _lib.TileMaps(mode=_lib.SS_TILES_FOLDED, nclass=4, rl_n=0, transposed=0, ymap_out=plan.ymap.data_ptr(),
-                       xmap_out=plan.xmap.data_ptr(), rl_src=0, rl_out=0, rl_collive=0)
+                       xmap_out=plan.xmap.data_ptr(), rl_src=0, rl_out=0, rl_collive=0, stats=0)
     res = conv_i8_fwd(x, g, w_dense, wscale, tile_maps=tm, desc_override=dict(ks=3, stride=1, pad=0, upsample=0), **kw)
     kw2 = dict(kw)
     for k in ('want_v_out', 'want_h', 'outputs'):
         kw2.pop(k, None)
     if plan.n_irr_rows:
         tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=plan.row_n, transposed=0, ymap_out=0, xmap_out=0,
-                           rl_src=plan.row_src.data_ptr(), rl_out=plan.row_out.data_ptr(), rl_collive=0)
+                           rl_src=plan.row_src.data_ptr(), rl_out=plan.row_out.data_ptr(), rl_collive=0, stats=0)
         conv_i8_fwd(x, g, w_rows, wscale, tile_maps=tm, outputs=res, **kw2)
     if plan.n_irr_cols:
         tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=plan.col_n, transposed=1, ymap_out=0, xmap_out=0,
-                           rl_src=plan.col_src.data_ptr(), rl_out=plan.col_out.data_ptr(), rl_collive=plan.row_regular.data_ptr())
+                           rl_src=plan.col_src.data_ptr(), rl_out=plan.col_out.data_ptr(), rl_collive=plan.row_regular.data_ptr(),
+                           stats=0)
         conv_i8_fwd(x, g, w_cols, wscale, tile_maps=tm, outputs=res, **kw2)
     return res
 

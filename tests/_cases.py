@@ -224,19 +224,21 @@ def oracle_trace(o, x):
     return depths, {k: to_u8(v) for k, v in acts.items()}, {k: torch.stack(v) for k, v in h.items()}
 
 
-def build_pair(variant, mono, gain, tau, seed, planes=3, impl='umma'):
+def build_pair(variant, mono, gain, tau, seed, planes=3, impl='umma', in_channels=None):
     """(oracle, CUDA model) with identical weights."""
     import torch
     from oracle import ref_model as rm, sj_compat as sj
     import stereospike_b200 as sb
     torch.manual_seed(seed)
-    o = rm.SpikingUNet(variant, mono, surrogate_function=sj.ATan() if variant == 'if' else None, tau=tau, multiply_factor=gain)
+    o = rm.SpikingUNet(variant, mono, surrogate_function=sj.ATan() if variant == 'if' else None, tau=tau, multiply_factor=gain,
+                       in_channels=in_channels)
+    kw = {} if in_channels is None else {'in_channels': in_channels}
     if variant == 'if':
-        n = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), multiply_factor=gain)
+        n = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), multiply_factor=gain, **kw)
     elif mono:
-        n = sb.fromZero_feedforward_multiscale_tempo_monocular_SpikeFlowNetLike(use_plif=variant == 'plif', tau=tau, multiply_factor=gain)
+        n = sb.fromZero_feedforward_multiscale_tempo_monocular_SpikeFlowNetLike(use_plif=variant == 'plif', tau=tau, multiply_factor=gain, **kw)
     else:
-        n = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=variant == 'plif', tau=tau, multiply_factor=gain)
+        n = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=variant == 'plif', tau=tau, multiply_factor=gain, **kw)
     n.load_state_dict(o.state_dict())
     n = n.cuda()
     n.set_kernel_options(impl=impl, weight_planes=planes)
@@ -279,7 +281,7 @@ def teacher_forced_model(o, n, x, trace=None, planes=3, band=1e-4, fold=True):
         if use_fold:
             out, _, h_got = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], w_i8[3], **kw)
         else:
-            out, _, h_got = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], cin=4 if first else g.Cin, **kw)
+            out, _, h_got = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], cin=ops.first_layer_channels(g.Cin) if first else g.Cin, **kw)
         h_ref = hs[s.name].to(dev)
         vth = float(node.v_threshold)
         s_ref, s_got = h_ref >= vth, h_got >= vth

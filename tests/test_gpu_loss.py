@@ -105,6 +105,9 @@ def test_spike_penalisation_back_propagates_like_the_oracle():
         net.zero_grad()
         sb.functional.reset_net(net)
         d, s = net.forward_seq(x.cuda(), spikes_fp32=True)
+        # the fused penalty (counters accumulated in the block epilogues) is the reference formula on the returned maps
+        assert s.penalty is not None and s.penalty.requires_grad
+        torch.testing.assert_close(s.penalty.detach(), sl.SpikePenalization_Loss(list(s)).detach(), rtol=1e-6, atol=0)
         sl.Total_Loss(penalize_spikes=penal, beta=beta)(d, label.cuda(), s).backward()
         got[penal] = {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}
     ref = dict(oracle.named_parameters())

@@ -23,20 +23,25 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: an instrumentation build next to the product library (e.g. build/timing/… with SS_ROLE_TIMING)."""
+    if out is None and not force and not _stale():
         return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    out = out or OUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + \
+    cmd = [nvcc] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-o', out] + \
         [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed building libstereospike_b200.so')
-    return OUT
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--timing' in sys.argv:
+        print(build(out=os.path.join(ROOT, 'build', 'timing', 'libstereospike_b200.so'), defines=('SS_ROLE_TIMING',)))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -35,6 +35,8 @@
 #include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 #include "ss_common.cuh"
 #include "ss_umma.cuh"
@@ -49,7 +51,13 @@ constexpr int MAX_STAGES = 8;
 constexpr int MAX_SLOTS = 8;
 constexpr int THREADS = 512;
 
+// box heights of the TMA tensor maps: a run of patch rows inside one image is loaded as a binary decomposition of its length
+constexpr int TMA_NMAPS = 6;    // 1, 2, 4, 8, 16, 32 rows
+
 struct I8Params {
+    // tensor maps of the activation tensor u8 [T*B][Hin][Win][Cin] (box = RB bytes x one patch row x 2^k rows), see the TMA producer
+    alignas(64) CUtensorMap tmap[TMA_NMAPS];
+    int tma;               // 1 = the halo patches are staged by cp.async.bulk.tensor (non-upsampled blocks), 0 = cp.async gathers
     int T, B, Hin, Win, Cin, Hout, Wout, Cout;
     int ks, stride, pad, upsample;
     int N;                 // planes * 32
@@ -183,26 +191,30 @@ __device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
         return (ix >= 0 && ix < p.Win) ? ix : -1;
     }
 }
+// Stride-2 patches are stored PLANE-major: [even-type columns: PH rows x PWHALF pixels][odd-type columns: same], each plane padded
+// to a multiple of 4 pixels (128 bytes at 32-byte rows) so that both planes are legal TMA destinations; a plane row is then a
+// dense run of PWHALF pixels, which is exactly what one row of a tensor-map box with element stride 2 along W delivers.
+__host__ __device__ constexpr int plane_pixels(int PH, int PWHALF) { return (PH * PWHALF + 3) / 4 * 4; }
 // patch pixel at which the A operand of tap (ky,kx) starts
-template <int STRIDE, int PWP, int PWHALF>
+template <int STRIDE, int PWP, int PWHALF, int PH>
 __device__ __forceinline__ constexpr int tap_offset(int ky, int kx) {
-    return STRIDE == 1 ? ky * PWP + kx : ky * PWP + (kx & 1) * PWHALF + (kx >> 1);
+    return STRIDE == 1 ? ky * PWP + kx : (kx & 1) * plane_pixels(PH, PWHALF) + ky * PWHALF + (kx >> 1);
 }
 
 // Issues every MMA of one (patch stage, weight buffer) pair except the very first one (tap 0, k-step 0), which the
 // caller issues itself because it carries the run-time accumulate flag.
-template <int MODE, int KS, int KSX, int STRIDE, int RB, int CN, int PWP, int PWHALF, int TAP = 0, int K = 1>
+template <int MODE, int KS, int KSX, int STRIDE, int RB, int CN, int PWP, int PWHALF, int PH, int TAP = 0, int K = 1>
 __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0, uint32_t idesc) {
     constexpr int KSTEPS = RB / 32;
     if constexpr (TAP < KS * KSX) {
         if constexpr (K < KSTEPS) {
             constexpr int ky = TAP / KSX, kx = TAP % KSX;
-            constexpr uint32_t aoff = (uint32_t)(tap_offset<STRIDE, PWP, PWHALF>(ky, kx) * RB + K * 32) >> 4;
+            constexpr uint32_t aoff = (uint32_t)(tap_offset<STRIDE, PWP, PWHALF, PH>(ky, kx) * RB + K * 32) >> 4;
             constexpr uint32_t boff = (uint32_t)(TAP * CN * RB + K * 32) >> 4;
             umma_i8_off<aoff, boff, MODE>(d, a0, b0, idesc);
-            issue_taps<MODE, KS, KSX, STRIDE, RB, CN, PWP, PWHALF, TAP, K + 1>(d, a0, b0, idesc);
+            issue_taps<MODE, KS, KSX, STRIDE, RB, CN, PWP, PWHALF, PH, TAP, K + 1>(d, a0, b0, idesc);
         } else {
-            issue_taps<MODE, KS, KSX, STRIDE, RB, CN, PWP, PWHALF, TAP + 1, 0>(d, a0, b0, idesc);
+            issue_taps<MODE, KS, KSX, STRIDE, RB, CN, PWP, PWHALF, PH, TAP + 1, 0>(d, a0, b0, idesc);
         }
     }
 }
@@ -219,7 +231,7 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // full-resolution blocks; the generic version executes the other kinds' arithmetic predicated off (~25 % of its instructions).
 template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false, int KSX = KS, int ROWSTEP = 1,
           int NK = -1>
-__global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
+__global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_constant__ I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
     constexpr int cNTAPS = KS * KSX;
@@ -228,12 +240,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
     constexpr int cPH = ROWSTEP > 1 ? 16 * ROWSTEP : 15 * STRIDE + KS;
     static_assert(ROWSTEP == 1 || (STRIDE == 1 && ROWSTEP >= KS && !FIRST && !PAIR && MODE == MODE_I8), "row-list pass: stride-1 int8 blocks");
     static_assert(cPH <= 48 && cPWp <= 24, "geometry tables");
-    constexpr int cPPIX = cPH * cPWp;
+    constexpr int cPPIX = cPH * cPWp;                        // pixels of the patch that carry data
+    constexpr int cPLANE = plane_pixels(cPH, cPWhalf);       // stride 2: pixels per parity plane (padded)
+    constexpr int cPALLOC = STRIDE == 1 ? cPPIX : 2 * cPLANE;
     constexpr int cNB = PAIR ? cN / 2 : cN;                 // weight rows (of the MMA's N) held by this CTA
     constexpr int cWB = cNTAPS * cNB * RB;
     constexpr int MMA_MODE = PAIR ? 2 : MODE;
     static_assert(!PAIR || (MODE == MODE_I8 && !FIRST && cN % 16 == 0), "CTA pairs: int8 forward blocks only");
-    constexpr int cPB = (cPPIX * RB + 1023) / 1024 * 1024;
+    constexpr int cPB = (cPALLOC * RB + 1023) / 1024 * 1024;
     constexpr int cTC = (512 / cN) < MAX_SLOTS ? (512 / cN) : MAX_SLOTS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
-            mbar_init(bar_full_p + 8 * s, FIRST ? 64 : 128);
+            mbar_init(bar_full_p + 8 * s, FIRST ? 64 : (p.tma ? 1 : 128));   // TMA: one arrive.expect_tx, the bytes do the rest
             mbar_init(bar_empty_p + 8 * s, 1);
         }
         for (int s = 0; s < NWB; ++s) {
@@ -411,6 +425,90 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                 }
             }
         }
+    } else if (warp < 4 && p.tma) {
+        // ================================================================== patch producer, TMA edition (non-upsampled blocks)
+        // The activation tensor is a 4-d tensor map u8 [T*B][Hin][Win][Cin]; a halo patch is a box of it: RB channel bytes x one
+        // patch row of pixels (element stride 2 along W for the parity planes of a stride-2 conv) x a run of rows, written by the
+        // TMA unit straight into the swizzled layout the MMA descriptors read (the hardware swizzle of cp.async.bulk.tensor is a
+        // function of the absolute shared-memory address, like the UMMA one: tools/tma_probe.cu).  Zero padding, the right / bottom
+        // image borders and the batch tail are the tensor map's out-of-bounds zero fill.  The vertically stacked batch makes a
+        // patch straddle images, and the box height is a property of the map, so the rows of one image are loaded as the binary
+        // decomposition of their count (maps with 1, 2, 4 .. 32 rows).  One elected thread issues everything: ~2-8 instructions
+        // per stage instead of 128 threads x 6-18 cp.async.
+        if (warp == 0 && elect_one()) {
+            constexpr int ROWPIX = STRIDE == 1 ? cPWp : cPWhalf;              // pixels per patch row (of one plane)
+            constexpr uint32_t ROWBYTES = (uint32_t)(ROWPIX * RB);
+            constexpr bool EVEN = ROWBYTES % 128u != 0u;                        // a box must start on 128 bytes: even rows only
+            constexpr uint32_t STAGE_TX = (uint32_t)((STRIDE == 1 ? 1 : 2) * cPH) * ROWBYTES;
+            const int per = STRIDE * p.HsO;
+            const int n_oob = p.T * p.B;
+            int stage = 0;
+            uint32_t phase = 0;
+            SS_DECL();
+            for (int it = it0; it < nit; it += its) {
+                const int ntile = fast_div(it, mt_per, m_mt_per);
+                const int mt = PAIR ? 2 * (it - ntile * mt_per) + (int)crank : it - ntile * mt_per;
+                const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
+                const int x0 = STRIDE == 1 ? tx * 8 - p.pad : 2 * (tx * 8 - p.pad / 2);
+                const int gi0 = ty * 16 * STRIDE;
+                const int b0 = fast_div(gi0, per, p.m_per);
+                const int local0 = gi0 - b0 * per;
+                for (int t0 = 0; t0 < p.T; t0 += cTC) {
+                    const int tc = min(cTC, p.T - t0);
+                    const int n_outer = p.resident ? tc : p.ncb;
+                    const int n_inner = p.resident ? p.ncb : tc;
+                    for (int o = 0; o < n_outer; ++o) {
+                        for (int in = 0; in < n_inner; ++in) {
+                            const int cb = p.resident ? in : o;
+                            const int t = t0 + (p.resident ? o : in);
+                            {
+                                SS_T0();
+                                mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
+                                SS_ACC(0, 1);     // wait for a free patch stage
+                            }
+                            SS_T0();
+                            const uint32_t full = bar_full_p + 8 * stage;
+                            mbar_arrive_expect_tx(full, STAGE_TX);
+                            const uint32_t dst0 = patch_base + (uint32_t)stage * cPB;
+                            const int c0 = cb * RB;
+                            int r = 0, b = b0, local = local0;
+                            while (r < cPH) {
+                                // rows [r, r + L) of the patch = rows local .. of image b (its zero padding included)
+                                int L = min(per - local, cPH - r);
+                                // the next image's first row is zero padding from either side: split one row later when that makes
+                                // the next run start on an even row
+                                if (EVEN && ((r + L) & 1) && r + L < cPH) ++L;
+                                const int n = b < p.B ? t * p.B + b : n_oob;
+                                int rr = r, yy = local - p.pad;
+#pragma unroll
+                                for (int lg = TMA_NMAPS - 1; lg >= 0; --lg) {
+                                    if (L & (1 << lg)) {
+                                        const uint32_t dst = dst0 + (uint32_t)rr * ROWBYTES;
+                                        tma_load_4d(dst, &p.tmap[lg], c0, x0, yy, n, full);
+                                        if constexpr (STRIDE == 2) tma_load_4d(dst + (uint32_t)(cPLANE * RB), &p.tmap[lg], c0, x0 + 1, yy, n, full);
+                                        rr += 1 << lg;
+                                        yy += 1 << lg;
+                                    }
+                                }
+                                r += L;
+                                local += L;
+                                if (local >= per) {
+                                    local -= per;
+                                    ++b;
+                                }
+                            }
+                            SS_ACC(0, 2);         // copy issue
+                            if (++stage == p.NPS) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+                }
+            }
+            SS_DUMP(0);
+        }
+        __syncwarp();
     } else if (warp < 4) {
         // ================================================================== patch producers
         // Work unit = one 16-byte chunk of one patch pixel.  Consecutive lanes take consecutive chunks of consecutive INPUT
@@ -433,8 +531,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             const int pixl = u / chunks, ch = u - pixl * chunks;
             int pr = pixl / cPWp;
             int pc = pixl - pr * cPWp;
-            if (STRIDE == 2) pc = (pc & 1) * cPWhalf + (pc >> 1);      // neighbours in memory = alternating parity planes
-            soff[i] = swizzle_off((uint32_t)((pr * cPWp + pc) * RB + ch * 16), swz_mask);
+            int spix = pr * cPWp + pc;                                 // pixel of the patch in shared memory
+            if (STRIDE == 2) {
+                // neighbours in memory = alternating parity planes; the planes are stored one after the other
+                spix = (pc & 1) * cPLANE + pr * cPWhalf + (pc >> 1);
+                pc = (pc & 1) * cPWhalf + (pc >> 1);
+            }
+            soff[i] = swizzle_off((uint32_t)(spix * RB + ch * 16), swz_mask);
             urc[i] = u < cUNITS ? pr * 32 + pc : -1;
         }
         SS_DECL();
@@ -551,7 +654,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
             constexpr uint32_t idesc = (MODE == MODE_I8 ? ((2u << 4) | (0u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
                                        ((uint32_t)(cN >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
             constexpr uint32_t layout = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
-            constexpr uint32_t a_sbo = (uint32_t)((ROWSTEP > 1 ? ROWSTEP : STRIDE) * cPWp * RB);
+            // 8-row groups = 8 pixels of one output row; the next output row is ROWSTEP / STRIDE patch rows further (of one plane)
+            constexpr uint32_t a_sbo = (uint32_t)((ROWSTEP > 1 ? ROWSTEP * cPWp : (STRIDE == 1 ? cPWp : 2 * cPWhalf)) * RB);
             constexpr uint32_t b_sbo = (uint32_t)(8 * RB);
             int stage = 0;
             uint32_t phase = 0;
@@ -603,7 +707,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const I8Params p) {
                     SS_T0();
                     tc_fence_after();
                     umma_i8<MMA_MODE>(d, a0, b0, idesc, first ? 0u : 1u);
-                    issue_taps<MMA_MODE, KS, KSX, STRIDE, RB, cNB, cPWp, cPWhalf>(d, a0, b0, idesc);
+                    issue_taps<MMA_MODE, KS, KSX, STRIDE, RB, cNB, cPWp, cPWhalf, cPH>(d, a0, b0, idesc);
                     tc_fence_before();
                     mbar_arrive(tok_post);
                     commit(bar_empty_p + 8 * stage);
@@ -1173,6 +1277,92 @@ __global__ void __launch_bounds__(256) weight_pack_bf16_kernel(const float* __re
     out[(buf + (off ^ (((off >> 7) & mask) << 4))) >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(wv));
 }
 
+// ------------------------------------------------------------------------------------------------ TMA tensor maps (host)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// the driver API entry point is fetched through the runtime (the library does not link libcuda)
+TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeFn>(f);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+struct TmapKey {
+    const void* x;
+    long long nimg;
+    int Hin, Win, Cin, RB, stride, ks;
+    bool operator==(const TmapKey& o) const {
+        return x == o.x && nimg == o.nimg && Hin == o.Hin && Win == o.Win && Cin == o.Cin && RB == o.RB && stride == o.stride && ks == o.ks;
+    }
+};
+struct TmapEntry {
+    TmapKey key;
+    CUtensorMap maps[TMA_NMAPS];
+    bool valid;
+};
+
+// Fills p.tmap / p.tma for a non-upsampled block whose patches can be staged by TMA (see the producer): x = u8 [nimg][Hin][Win][Cin]
+// (Cin in BYTES), RB-byte channel blocks, patch rows of PWp pixels (stride 1) or PWhalf pixels per parity plane (stride 2).
+// Encoding a map costs a few microseconds on the host, so the maps of the last calls are kept (the activation buffers of a model
+// come back at the same addresses from the caching allocator; a graph capture bakes them into the launch anyway).
+void setup_tma(I8Params& p, const void* x, long long nimg, int Hin, int Win, int Cin, int RB, int stride, int ks, int pad) {
+    p.tma = 0;
+    static int tma_env = -1;
+    if (tma_env < 0) {
+        const char* e = getenv("SS_TMA");
+        tma_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (tma_env == 0) return;
+    const int rowpix = stride == 1 ? 8 + ks - 1 : 8 + (ks - 1) / 2;
+    const int rowbytes = rowpix * RB;
+    // every box lands on a 128-byte boundary: any row when the row pitch allows it, else even rows only, which needs a zero row
+    // between stacked images to move the split (pad >= 1) -- and stride 2 needs an even pad for the plane origin
+    const bool even_only = rowbytes % 128 != 0;
+    if (even_only && ((2 * rowbytes) % 128 != 0 || pad < 1)) return;
+    if (stride == 2 && (pad & 1)) return;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0 || Cin % 16 != 0 || !(RB == 32 || RB == 64 || RB == 128)) return;
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (enc == nullptr) return;
+    static TmapEntry cache[64];
+    static int next = 0;
+    static std::mutex mu;
+    const TmapKey key{x, nimg, Hin, Win, Cin, RB, stride, ks};
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < 64; ++i)
+        if (cache[i].valid && cache[i].key == key) {
+            memcpy(p.tmap, cache[i].maps, sizeof(p.tmap));
+            p.tma = 1;
+            return;
+        }
+    TmapEntry& e = cache[next];
+    e.valid = false;
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)nimg};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin, (cuuint64_t)Win * Cin, (cuuint64_t)Hin * Win * Cin};
+    const cuuint32_t es[4] = {1u, (cuuint32_t)stride, 1u, 1u};
+    const CUtensorMapSwizzle sw = RB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (RB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    for (int lg = 0; lg < TMA_NMAPS; ++lg) {
+        // box: RB channel bytes x one patch row (stride 2: every other pixel of 2 * rowpix) x 2^lg rows x one image
+        const cuuint32_t box[4] = {(cuuint32_t)RB, (cuuint32_t)(stride * rowpix), 1u << lg, 1u};
+        if (enc(&e.maps[lg], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return;
+    }
+    e.key = key;
+    e.valid = true;
+    next = (next + 1) % 64;
+    memcpy(p.tmap, e.maps, sizeof(p.tmap));
+    p.tma = 1;
+}
+
 int rowbytes_for(int Cin, int ks) { return (ks <= 3 && Cin % 64 == 0) ? 64 : 32; }
 // gradient-side correlation: row bytes of the bf16 source patch (Cg channels = 2*Cg bytes per pixel)
 int corr_rowbytes_for(int Cg, int ks) { return (ks <= 3 && (2 * Cg) % 64 == 0) ? 64 : 32; }
@@ -1410,7 +1600,8 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.TC = 512 / p.N;
     if (p.TC > MAX_SLOTS) p.TC = MAX_SLOTS;
     p.WB = p.ntaps * (pair ? p.N / 2 : p.N) * p.RB;       // per CTA
-    p.PB = (p.ppix * p.RB + 1023) / 1024 * 1024;
+    // stride 2: two parity planes, each padded to a multiple of 4 pixels (see plane_pixels)
+    p.PB = ((g->stride == 2 && !first && !rowlist ? 2 * plane_pixels(p.PH, p.PWhalf) : p.ppix) * p.RB + 1023) / 1024 * 1024;
     p.resident = p.ncb <= NWB ? 1 : 0;
     p.nwb = p.ncb < NWB ? p.ncb : NWB;
     if (p.PH > 48 || p.PWp > 24) {
@@ -1437,6 +1628,8 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.h_seq = h_seq;
     p.tsum = reinterpret_cast<uint8_t*>(tsum);
     p.stats = tm != nullptr ? reinterpret_cast<unsigned long long*>(tm->stats) : nullptr;
+    p.tma = 0;
+    if (!first && !up && !rowlist) setup_tma(p, x, (long long)g->T * g->B, g->Hin, g->Win, g->Cin, p.RB, g->stride, g->ks, p.pad);
 
     const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
     const int num_sms = sms;
@@ -1659,6 +1852,7 @@ extern "C" int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const v
     p.w = reinterpret_cast<const int8_t*>(w_img);
     p.g_dst = dst;
     p.g_mode = d->out_mode;
+    setup_tma(p, src_bf16, (long long)d->T * d->B, d->Hg, d->Wg, p.Cin, p.RB, 1, d->ks, d->pad);
 
     const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
     const int dev = current_device();

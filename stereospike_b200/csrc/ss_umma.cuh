@@ -58,6 +58,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// TMA tiled load of a 4-d box (coordinates innermost first) into shared memory; completion = transaction bytes on `bar`
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+                 : "memory");
+}
 template <int MODE = 0>
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     if constexpr (MODE == 0) {

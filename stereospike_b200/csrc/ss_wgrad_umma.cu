@@ -26,8 +26,15 @@
 // (SH-1-i)*stride further right, and one MMA produces SH taps -- 15 or 10 MMAs per K step instead of 25.  The g patch gets
 // SH-1 halo columns on the left so that every copy still sees every pixel exactly once across the tiles of a row.
 //
+// N = 64 input channels per accumulator (stride-1 blocks with Cin % 64 == 0).  At N <= 32 every MMA costs the ~45-cycle
+// per-instruction floor (16 cycles of math); at N = 64 it costs 48 (32 of math + the operand feed), so the same taps take half
+// as many MMA cycles.  512 TMEM columns then hold 8 accumulators: the taps of a filter are cut into balanced groups of <= 8
+// (5x5: 6+6+6+7, 3x3: 4+5; with shifted copies: groups of filter rows), one CTA family per group -- more passes over the
+// patches (L2 traffic ~40 % of its peak instead of 12 %) for half the tensor-pipe time.
+//
 // Warp roles: 0-3 x-patch producers (LDG u8 -> bf16 -> swizzled STS), 4-7 g-tile producers (cp.async), 8 MMA issuer.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "ss_common.cuh"
 #include "ss_umma.cuh"
@@ -51,7 +58,13 @@ struct WgParams {
     const uint8_t* x;
     const __nv_bfloat16* g;
     float* g_w;
+    int dbg;                     // instrumentation build only (-DSS_ROLE_TIMING, SS_WG_DBG): 1 = no MMA issue, 2 = no x staging, 4 = no g staging
 };
+#ifdef SS_ROLE_TIMING
+#define WG_DBG(bit) ((p.dbg & (bit)) != 0)
+#else
+#define WG_DBG(bit) false
+#endif
 
 // MN-major descriptor: lbo = bytes between channel blocks, sbo = bytes between 8-pixel groups
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -132,6 +145,19 @@ __host__ __device__ constexpr int wg_shift(int si) {
     return SH == 1 ? si : (STRIDE == 1 ? si * SH : si);     // stride 1: {0, SH, 2*SH..};  stride 2, SH 2: {0, 1, 2}
 }
 
+// filter rows per CTA: as many as fit 512 TMEM columns, then balanced over the resulting number of groups (5 rows, 4 fit -> 3 + 2)
+template <int KS, int NB, int NS>
+__host__ __device__ constexpr int wg_rows_per_group() {
+    constexpr int fit = (512 / NB) / NS < KS ? (512 / NB) / NS : KS;
+    constexpr int ngrp = (KS + fit - 1) / fit;
+    return (KS + ngrp - 1) / ngrp;
+}
+// tap groups of the N = 64 kernels: <= 8 accumulators each; group g owns taps [KS*KS*g/G, KS*KS*(g+1)/G)
+template <int KS>
+__host__ __device__ constexpr int wg_tap_groups() {
+    return (KS * KS + 7) / 8;
+}
+
 template <int KS, int STRIDE, int NB, bool FIRST4, int SH>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const WgParams p) {
     constexpr int RBX = 2 * NB;
@@ -141,9 +167,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
     constexpr int NPIXG = 16 * GPW;
     constexpr int G_BYTES = SH == 1 ? G_TILE_BYTES : (NPIXG * RBG + 1023) / 1024 * 1024;
     constexpr int NS = wg_nshift<KS, STRIDE, SH>();
-    constexpr int GK = (512 / NB) / NS < KS ? (512 / NB) / NS : KS;   // filter rows per CTA (TMEM: 512 columns)
-    constexpr int NGRP = (KS + GK - 1) / GK;            // groups of filter rows
-    constexpr int NACC = GK * NS;                       // accumulators ([128][NB] each)
+    // TAPMODE (no shifted copies, N = 64): a CTA owns a contiguous range of the KS*KS taps (row-major) instead of whole filter rows
+    constexpr bool TAPMODE = SH == 1 && NB == 64;
+    constexpr int GK = wg_rows_per_group<KS, NB, NS>();  // filter rows per CTA (TMEM: 512 columns)
+    constexpr int NGRP = TAPMODE ? wg_tap_groups<KS>() : (KS + GK - 1) / GK;            // groups of filter rows / of taps
+    constexpr int NACC = TAPMODE ? 512 / NB : GK * NS;   // accumulators ([128][NB] each)
+    static_assert(!TAPMODE || STRIDE == 1, "tap groups: stride-1 blocks");
     static_assert(SH == 1 || (KS == 5 && (STRIDE == 1 || SH == 2)), "shifted copies: 5x5 only; stride 2 with SH = 2");
     constexpr int cPWhalf = 8 + (KS - 1) / 2;
     constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
@@ -192,8 +221,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
     // this CTA's (output-channel block, input-channel chunk, unit range)
     int item = blockIdx.x;
     const int grp = item % NGRP; item /= NGRP;
-    const int ky0 = grp * GK;
+    const int ky0 = TAPMODE ? 0 : grp * GK;
     const int nky = min(GK, KS - ky0);
+    const int tap0 = KS * KS * grp / NGRP;                    // TAPMODE: this CTA's taps [tap0, tap0 + ntap)
+    const int ntap = KS * KS * (grp + 1) / NGRP - tap0;
     const int split = item % p.nsplit; item /= p.nsplit;
     const int chunk = item % p.nchunk;
     const int nblk = item / p.nchunk;
@@ -241,7 +272,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             for (int i = 0; i < cNPIX; ++i) {
 #pragma unroll
                 for (int h = 0; h < NB / 16; ++h) raw[i][h] = make_uint4(0u, 0u, 0u, 0u);
-                if (goff[i] >= 0) {
+                if (goff[i] >= 0 && !WG_DBG(2)) {
                     if (FIRST4) {
                         raw[i][0].x = __ldg(reinterpret_cast<const uint32_t*>(xt + goff[i]));
                     } else {
@@ -254,7 +285,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             uint8_t* dst0 = sm + (size_t)stage * cSTAGE + G_BYTES;
 #pragma unroll
             for (int i = 0; i < cNPIX; ++i) {
-                if (goff[i] != -2) {
+                if (goff[i] != -2 && !WG_DBG(2)) {
                     const uint32_t off = (uint32_t)(tid + i * 128) * RBX;
 #pragma unroll
                     for (int h = 0; h < NB / 16; ++h) {
@@ -281,9 +312,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             const int n = n0 + (L - copy * CH);
             const bool n_ok = n < p.Cout;
             const int Kc = p.cin_real;                    // g_w row = tap * Kc + channel
-            for (int a = 0; a < nky * NS; ++a) {
-                const int ky = ky0 + a / NS;
-                const int shift = wg_shift<KS, STRIDE, SH>(a % NS);
+            for (int a = 0; a < (TAPMODE ? ntap : nky * NS); ++a) {
+                const int ky = TAPMODE ? (tap0 + a) / KS : ky0 + a / NS;
+                const int shift = TAPMODE ? (tap0 + a) - ky * KS : wg_shift<KS, STRIDE, SH>(a % NS);
                 const int kx = shift + STRIDE * (SH - 1 - copy);
                 const int tap = ky * KS + kx;
                 // stride 2: shift 2 of the un-shifted copy is the same tap as shift 0 of the shifted one -- count it once
@@ -331,7 +362,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                 const uint32_t dst0 = base + (uint32_t)stage * cSTAGE + (uint32_t)m * 128u;
                 const __nv_bfloat16* src = p.g + (size_t)t * t_stride + (pix_off >= 0 ? pix_off : 0) + n0;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < (WG_DBG(4) ? 0 : 16); ++c) {
                     const bool ok = pix_off >= 0 && n0 + c * 8 < p.Cout;
                     const uint32_t dst = dst0 + (uint32_t)(c >> 3) * 16384u + ((uint32_t)((c & 7) ^ (m & 7)) << 4);
                     cp_async_16(dst, ok ? (const void*)(src + c * 8) : (const void*)p.g, ok ? 16u : 0u);
@@ -370,7 +401,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
 #pragma unroll
                 for (int i = 0; i < NPT; ++i) {
                     const int pix = m + i * 128;
-                    if (pix < NPIXG) {
+                    if (pix < NPIXG && !WG_DBG(4)) {
                         const __nv_bfloat16* src = p.g + (size_t)t * t_stride + (pix_off[i] >= 0 ? pix_off[i] : 0);
 #pragma unroll
                         for (int c = 0; c < RBG / 16; ++c) {
@@ -419,11 +450,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                     const uint32_t acc = (ks == 0) ? first : 1u;
 #pragma unroll
                     for (int ai = 0; ai < NACC; ++ai) {
-                        const int ky = ai / NS;       // relative to this CTA's first filter row
-                        const int kx = wg_shift<KS, STRIDE, SH>(ai - ky * NS);
-                        const int toff = STRIDE == 1 ? ky * cPWp + kx : ky * cPWp + (kx & 1) * cPWhalf + (kx >> 1);
-                        if (ky < nky)
-                            umma_f16(tmem_base + (uint32_t)(ai * NB), a, bk + (uint64_t)((uint32_t)(toff * RBX) >> 4), idesc, acc);
+                        if (WG_DBG(1)) continue;
+                        if constexpr (TAPMODE) {
+                            const int tap = tap0 + ai;
+                            const int ky = tap / KS, kx = tap - ky * KS;
+                            if (ai < ntap)
+                                umma_f16(tmem_base + (uint32_t)(ai * NB), a, bk + (uint64_t)((uint32_t)((ky * cPWp + kx) * RBX) >> 4), idesc, acc);
+                        } else {
+                            const int ky = ai / NS;       // relative to this CTA's first filter row
+                            const int kx = wg_shift<KS, STRIDE, SH>(ai - ky * NS);
+                            const int toff = STRIDE == 1 ? ky * cPWp + kx : ky * cPWp + (kx & 1) * cPWhalf + (kx >> 1);
+                            if (ky < nky)
+                                umma_f16(tmem_base + (uint32_t)(ai * NB), a, bk + (uint64_t)((uint32_t)(toff * RBX) >> 4), idesc, acc);
+                        }
                     }
                 }
                 umma_commit(bar_empty + 8 * stage);
@@ -494,11 +533,21 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     p.tiles_x = (g->Wout + (SH - 1) + 7) / 8;
     p.mtiles = (int)((rows + 15) / 16) * p.tiles_x;
     // input channels per CTA
-    const int NB = (!first && g->Cin % 32 == 0) ? 32 : 16;
+    static int nb64_env = -1;
+    if (nb64_env < 0) {
+        const char* e = getenv("SS_WGRAD_N64");
+        nb64_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const int NB = (!first && nb64_env && g->stride == 1 && g->Cin % 64 == 0) ? 64 : ((!first && g->Cin % 32 == 0) ? 32 : 16);
     const int NS = SH == 1 ? g->ks : (g->stride == 1 ? (g->ks + SH - 1) / SH : 3);
-    int GK = (512 / NB) / NS;
-    if (GK > g->ks) GK = g->ks;
-    const int NGRP = (g->ks + GK - 1) / GK;
+    int NGRP;
+    if (SH == 1 && NB == 64) {
+        NGRP = (g->ks * g->ks + 7) / 8;                    // tap groups (wg_tap_groups)
+    } else {
+        int GK = (512 / NB) / NS;                          // wg_rows_per_group
+        if (GK > g->ks) GK = g->ks;
+        NGRP = (g->ks + GK - 1) / GK;
+    }
     p.nblk = SH > 1 ? 1 : (g->Cout + 127) / 128;
     p.nchunk = first ? 1 : g->Cin / NB;
     p.cin_real = g->Cin;
@@ -521,6 +570,12 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     p.x = reinterpret_cast<const uint8_t*>(x);
     p.g = reinterpret_cast<const __nv_bfloat16*>(g_bf16);
     p.g_w = g_w;
+#ifdef SS_ROLE_TIMING
+    {
+        const char* e = getenv("SS_WG_DBG");
+        p.dbg = e != nullptr ? atoi(e) : 0;
+    }
+#endif
     const int PH = 15 * g->stride + g->ks;
     const int PWp = g->stride == 1 ? 8 + g->ks - 1 : 2 * (8 + (g->ks - 1) / 2);
     const int PBX = (PH * PWp * 2 * NB + 1023) / 1024 * 1024;
@@ -544,6 +599,10 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
         conv_wgrad_umma_kernel<KS_, ST_, NB_, F4_, SH_><<<grid, WG_THREADS, smem, st>>>(p);                                      \
         launched = true;                                                                                                         \
     }
+    SS_TRY_WG(5, 1, 64, false, 1)
+    SS_TRY_WG(5, 1, 64, false, 2)
+    SS_TRY_WG(5, 1, 64, false, 4)
+    SS_TRY_WG(3, 1, 64, false, 1)
     SS_TRY_WG(5, 1, 32, false, 1)
     SS_TRY_WG(5, 1, 32, false, 2)
     SS_TRY_WG(5, 1, 32, false, 4)

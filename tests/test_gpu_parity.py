@@ -448,21 +448,32 @@ def test_graphed_inference_equals_eager(B, T):
 
 
 @pytest.mark.gpu
-def test_cta_pair_kernels_are_bit_identical():
-    """The cta_group::2 variant of the block kernel (two m-tiles per MMA, weights split between the CTAs of a 2-cluster) must
-    produce exactly the single-CTA results.  The choice is made once per process from SS_PAIR, so each setting runs in its
-    own interpreter: SS_PAIR=2 forces pairs wherever they are possible, SS_PAIR=0 forbids them."""
+def test_cta_pair_and_tma_kernels_are_bit_identical():
+    """The cta_group::2 variant of the block kernel (two m-tiles per MMA, weights split between the CTAs of a 2-cluster) and the
+    TMA-staged halo patches (cp.async.bulk.tensor instead of cp.async gathers) must produce exactly the same results as the
+    single-CTA gather kernel.  The choices are made once per process from SS_PAIR / SS_TMA, so each setting runs in its own
+    interpreter: SS_PAIR=2 forces pairs wherever they are possible, SS_PAIR=0 forbids them; SS_TMA=0 forbids tensor maps.
+    (Integer accumulation is order-independent, so the forward blocks are bit-reproducible; the bf16 gradient kernels share the
+    producer code but accumulate in fp32 and are only reproducible to the last bit or two -- tools/dgrad_determinism.py -- so they
+    are checked against float64 autograd in test_gpu_grad_umma.py instead.)"""
     import subprocess
     import sys
     code = r'''
 import hashlib, torch
 from stereospike_b200 import ops
 dev = torch.device('cuda')
-h = hashlib.sha256()
+def dig(name, *ts):
+    h = hashlib.sha256()
+    for t in ts:
+        h.update(t.cpu().numpy().tobytes())
+    print('DIGEST', name, h.hexdigest()[:16])
 for (kind, Cin, Cout, ks, Hin, Win, stride, pad, up, T, B) in [
         ('conv', 64, 64, 3, 17, 22, 1, 1, None, 5, 3), ('conv', 32, 64, 5, 37, 45, 2, 2, None, 2, 2),
         ('upconv', 64, 32, 5, 17, 22, 1, 0, (33, 44), 5, 2), ('upconv', 512, 256, 5, 17, 22, 1, 0, (33, 44), 5, 2),
-        ('conv', 256, 512, 5, 33, 44, 2, 2, None, 7, 1), ('conv', 512, 512, 3, 17, 22, 1, 1, None, 1, 3)]:
+        ('conv', 256, 512, 5, 33, 44, 2, 2, None, 7, 1), ('conv', 512, 512, 3, 17, 22, 1, 1, None, 1, 3),
+        ('conv', 32, 32, 3, 20, 30, 1, 1, None, 3, 2), ('conv', 64, 64, 5, 18, 21, 1, 2, None, 2, 9),
+        ('conv', 64, 32, 5, 9, 12, 2, 2, None, 6, 11)]:
+    name = f'{kind}-{Cin}to{Cout}-k{ks}s{stride}-{Hin}x{Win}-T{T}B{B}'
     g = torch.Generator().manual_seed(3)
     if kind == 'conv':
         Hout, Wout = ops.conv_out_size(Hin, ks, stride, pad), ops.conv_out_size(Win, ks, stride, pad)
@@ -475,18 +486,30 @@ for (kind, Cin, Cout, ks, Hin, Win, stride, pad, up, T, B) in [
     out, v, hs = ops.conv_i8_fwd(x, geom, q, sc, T=T, B=B, neuron=1, gain=12.0, v_th=1.0, v_reset=0.0, tau=3.0,
                                  want_v_out=True, want_h=True)
     torch.cuda.synchronize()
-    for t in (out, v, hs):
-        h.update(t.cpu().numpy().tobytes())
+    dig(name + ':fwd', out, v, hs)
     assert 0.01 < float(out.float().mean()) < 0.9
-print(h.hexdigest())
+# folded NNConvUpsampling block: dense 3x3 pass on the source (TMA-staged) + row-list passes (gathers)
+g = torch.Generator().manual_seed(5)
+geom = ops.BlockGeom('upconv', 64, 32, 5, 17, 22, 33, 44)
+x = (torch.rand(3, 2, 17, 22, 64, generator=g) < 0.15).to(torch.uint8).to(dev)
+w = ((torch.rand(32, 64, 5, 5, generator=g) * 2 - 1) / 40.0).to(dev)
+wd, wr, wc, sc = ops.pack_weights_folded(w, 3)
+out, v, hs = ops.conv_i8_fwd_folded(x, geom, wd, wr, wc, sc, T=3, B=2, neuron=1, gain=12.0, v_th=1.0, v_reset=0.0, tau=3.0,
+                                    want_v_out=True, want_h=True)
+torch.cuda.synchronize()
+dig('folded', out, v, hs)
 '''
-    digests = []
-    for mode in ('0', '2'):
-        env = dict(os.environ, SS_PAIR=mode, PYTHONPATH=ROOT)
+    results = []
+    modes = (('0', '0'), ('2', '0'), ('0', '1'), ('2', '1'))       # (SS_PAIR, SS_TMA): gathers / TMA patches x single CTA / pairs
+    for pair, tma in modes:
+        env = dict(os.environ, SS_PAIR=pair, SS_TMA=tma, PYTHONPATH=ROOT)
         r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        digests.append(r.stdout.strip().splitlines()[-1])
-    assert digests[0] == digests[1], digests
+        results.append([ln for ln in r.stdout.splitlines() if ln.startswith('DIGEST')])
+    assert len(results[0]) == 10
+    for (pair, tma), res in zip(modes[1:], results[1:]):
+        diff = [(a, b) for a, b in zip(results[0], res) if a != b]
+        assert not diff and len(res) == len(results[0]), (f'SS_PAIR={pair} SS_TMA={tma}', diff)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -301,9 +301,11 @@ int ss_corr_bf16(const ss_corr_desc* d, const void* src_bf16, const void* w_img,
                  const int32_t* xmap_out, float* dst, void* stream);
 
 /* ss_conv_wgrad_bf16: weight gradient of one fused block (geometry as ss_conv_i8_fwd's descriptor; gain / neuron fields
- * ignored).  The contraction runs over pixels, the slow dimension of NHWC, so both MMA operands are MN-major: A = a tile of
- * g (pixels x 128 output channels), B = the halo patch of x converted to bf16 (pixels x 16 or 32 input channels), one
- * accumulator per filter tap in TMEM; a tap is again a start-address shift of the patch.
+ * ignored; planes == 0 declares that x may hold any u8 value -- event-count frames -- otherwise every x value must be < 128,
+ * which holds for spikes and spike sums and selects the two-lane u8 -> bf16 conversion of the patch producers).  The contraction runs over pixels, the slow dimension of NHWC, so both MMA operands are MN-major: A = a tile of
+ * g (pixels x 128 output channels), B = the halo patch of x converted to bf16 (pixels x 16, 32 or 64 input channels), one
+ * accumulator per filter tap in TMEM (the taps are cut into groups of <= 512 / N handled by different CTAs); a tap is again a
+ * start-address shift of the patch.
  *   x u8 [T][B][Hin][Win][Cin] (Cin % 16 == 0; Cin == 4: packed event frames);  g_bf16 bf16 [T][B][Hout][Wout][Cout];
  *   g_w fp32 [ks*ks*Cin][Cout] accumulated with atomics. */
 int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const void* g_bf16, float* g_w, void* stream);

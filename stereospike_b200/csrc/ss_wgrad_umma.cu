@@ -26,11 +26,12 @@
 // (SH-1-i)*stride further right, and one MMA produces SH taps -- 15 or 10 MMAs per K step instead of 25.  The g patch gets
 // SH-1 halo columns on the left so that every copy still sees every pixel exactly once across the tiles of a row.
 //
-// N = 64 input channels per accumulator (stride-1 blocks with Cin % 64 == 0).  At N <= 32 every MMA costs the ~45-cycle
-// per-instruction floor (16 cycles of math); at N = 64 it costs 48 (32 of math + the operand feed), so the same taps take half
-// as many MMA cycles.  512 TMEM columns then hold 8 accumulators: the taps of a filter are cut into balanced groups of <= 8
-// (5x5: 6+6+6+7, 3x3: 4+5; with shifted copies: groups of filter rows), one CTA family per group -- more passes over the
-// patches (L2 traffic ~40 % of its peak instead of 12 %) for half the tensor-pipe time.
+// N = 64 input channels per accumulator (stride-1 blocks with Cin % 64 == 0).  Both operands are MN-major, and the tensor core
+// reads MN-major shared memory at ~85 B/clk: an MMA costs ~57 cycles at N = 32 and ~70 at N = 64 (tools/wgrad_probe.py: the
+// issuing thread sits in the issue queue 87 % of the time), so twice the channels per MMA is 1.6x the throughput.  512 TMEM
+// columns then hold 8 accumulators: the KS x (column shifts) accumulators of a filter are cut into balanced groups of <= 8
+// (5x5: 6+6+6+7, 3x3: 4+5, 2 copies: 5+5+5, 4 copies: 5+5), one CTA family per group.  The groups of one unit range sit on
+// neighbouring CTAs and advance in lock step, so the g tiles / x patches they all read come from HBM once.
 //
 // Warp roles: 0-3 x-patch producers (LDG u8 -> bf16 -> swizzled STS), 4-7 g-tile producers (cp.async), 8 MMA issuer.
 #include <cuda_bf16.h>
@@ -51,9 +52,10 @@ struct WgParams {
     int pad, upsample;
     int HsO, Hup, Wup;
     int tiles_x, mtiles;
-    int nblk, nchunk, nsplit;    // grid = nblk * nchunk * nsplit
+    int nblk, nchunk, nsplit;    // grid = nblk * nchunk * nsplit * groups
     int NPS;
     int cin_real;                // channels of x that exist in g_w's K index (Cin, or <= 4 for the packed first layer)
+    int x_small;                 // 1 = every x value is < 128 (spikes / spike sums): fast u8 -> bf16 conversion
     float yscale, xscale;
     const uint8_t* x;
     const __nv_bfloat16* g;
@@ -62,8 +64,23 @@ struct WgParams {
 };
 #ifdef SS_ROLE_TIMING
 #define WG_DBG(bit) ((p.dbg & (bit)) != 0)
+// per-role cycle counters of CTA 0 (tools/wgrad_probe.py): [role][slot], role 0 = x producer, 1 = g producer, 2 = MMA thread
+__device__ unsigned long long ss_wg_dbg[3 * 8];
+#define WG_DECL() unsigned long long wg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long wg_start = clock64()
+#define WG_T0() const long long wg_t0 = clock64()
+#define WG_ACC(slot) wg_acc[slot] += (unsigned long long)(clock64() - wg_t0)
+#define WG_DUMP(role)                                                                              \
+    do {                                                                                           \
+        wg_acc[7] = (unsigned long long)(clock64() - wg_start);                                    \
+        if (blockIdx.x == 0)                                                                       \
+            for (int _i = 0; _i < 8; ++_i) ss_wg_dbg[(role) * 8 + _i] = wg_acc[_i];                 \
+    } while (0)
 #else
 #define WG_DBG(bit) false
+#define WG_DECL()
+#define WG_T0()
+#define WG_ACC(slot)
+#define WG_DUMP(role)
 #endif
 
 // MN-major descriptor: lbo = bytes between channel blocks, sbo = bytes between 8-pixel groups
@@ -82,6 +99,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// same MMA with the descriptors given as (low, high) words and the accumulate flag as an immediate
+template <int ACC>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, %6;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
         : "memory");
 }
 
@@ -133,6 +162,28 @@ __device__ __forceinline__ void cvt16(const uint4 v, uint4& lo, uint4& hi) {
     hi = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// 16 u8 -> 16 bf16 for values < 128 (spikes {0,1} and spike sums {0..3}: every activation behind the first layer): the byte is
+// dropped into the mantissa of bf16 128.0 (0x4300 | b == 128 + b exactly, 7 mantissa bits) and 128 is subtracted two lanes at a
+// time -- 2 PRMT + 2 HSUB2 per four values instead of 4 I2F (quarter-rate pipe) + 2 F2FP, which made the x producers the
+// bottleneck of the N = 64 kernels (tools/wgrad_probe.py).
+__device__ __forceinline__ void cvt16_small(const uint4 v, uint4& lo, uint4& hi) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+    const uint32_t k128 = 0x43004300u;
+    const __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(&k128);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t p01 = __byte_perm(w[i], 0x43434343u, 0x4140);   // bytes {b0, 0x43, b1, 0x43}
+        const uint32_t p23 = __byte_perm(w[i], 0x43434343u, 0x4342);   // bytes {b2, 0x43, b3, 0x43}
+        const __nv_bfloat162 a = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&p01), m);
+        const __nv_bfloat162 b = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&p23), m);
+        o[2 * i] = *reinterpret_cast<const uint32_t*>(&a);
+        o[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    lo = make_uint4(o[0], o[1], o[2], o[3]);
+    hi = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 // NB: input channels per CTA (16 -> 32-byte patch rows, 32 -> 64-byte rows).  FIRST4: x is the packed first-layer input
 // u8 [..][4]; its 4 channels are widened to one 16-channel chunk (channels 4..15 zero).
 // column shifts of the B operand issued per filter row, and how many of them
@@ -152,10 +203,10 @@ __host__ __device__ constexpr int wg_rows_per_group() {
     constexpr int ngrp = (KS + fit - 1) / fit;
     return (KS + ngrp - 1) / ngrp;
 }
-// tap groups of the N = 64 kernels: <= 8 accumulators each; group g owns taps [KS*KS*g/G, KS*KS*(g+1)/G)
-template <int KS>
+// accumulator groups of the N = 64 kernels: <= 8 accumulators each; group g owns accumulators [NALL*g/G, NALL*(g+1)/G)
+template <int NALL>
 __host__ __device__ constexpr int wg_tap_groups() {
-    return (KS * KS + 7) / 8;
+    return (NALL + 7) / 8;
 }
 
 template <int KS, int STRIDE, int NB, bool FIRST4, int SH>
@@ -167,12 +218,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
     constexpr int NPIXG = 16 * GPW;
     constexpr int G_BYTES = SH == 1 ? G_TILE_BYTES : (NPIXG * RBG + 1023) / 1024 * 1024;
     constexpr int NS = wg_nshift<KS, STRIDE, SH>();
-    // TAPMODE (no shifted copies, N = 64): a CTA owns a contiguous range of the KS*KS taps (row-major) instead of whole filter rows
-    constexpr bool TAPMODE = SH == 1 && NB == 64;
+    // TAPMODE (N = 64): a CTA owns a contiguous, balanced range of the KS * NS accumulators (filter row x column shift, row-major)
+    // instead of whole filter rows, so that every group issues the same number of MMAs (+-1)
+    constexpr bool TAPMODE = NB == 64;
+    constexpr int NALL = KS * NS;                        // accumulators of the whole filter
     constexpr int GK = wg_rows_per_group<KS, NB, NS>();  // filter rows per CTA (TMEM: 512 columns)
-    constexpr int NGRP = TAPMODE ? wg_tap_groups<KS>() : (KS + GK - 1) / GK;            // groups of filter rows / of taps
-    constexpr int NACC = TAPMODE ? 512 / NB : GK * NS;   // accumulators ([128][NB] each)
-    static_assert(!TAPMODE || STRIDE == 1, "tap groups: stride-1 blocks");
+    constexpr int NGRP = TAPMODE ? wg_tap_groups<NALL>() : (KS + GK - 1) / GK;          // groups of accumulators / of filter rows
+    constexpr int NACC = TAPMODE ? (NALL + NGRP - 1) / NGRP : GK * NS;   // accumulators ([128][NB] each) of one CTA
+    static_assert(!TAPMODE || STRIDE == 1, "accumulator groups: stride-1 blocks");
     static_assert(SH == 1 || (KS == 5 && (STRIDE == 1 || SH == 2)), "shifted copies: 5x5 only; stride 2 with SH = 2");
     constexpr int cPWhalf = 8 + (KS - 1) / 2;
     constexpr int cPWp = STRIDE == 1 ? 8 + KS - 1 : 2 * cPWhalf;
@@ -219,18 +272,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
     const uint32_t tmem_base = *tmem_slot;
 
     // this CTA's (output-channel block, input-channel chunk, unit range)
+    // The groups of one (block, chunk, unit range) sit on neighbouring CTAs and walk the same units at the same pace (equal MMA
+    // counts), so the g tiles and x patches they all read come from HBM once and from L2 afterwards: handing the groups different
+    // numbers of CTAs de-synchronised them and cost 15-30 % on the full-resolution blocks (0.2-0.5 GB of g per pass).
     int item = blockIdx.x;
     const int grp = item % NGRP; item /= NGRP;
+    const int nsplit = p.nsplit;
     const int ky0 = TAPMODE ? 0 : grp * GK;
     const int nky = min(GK, KS - ky0);
-    const int tap0 = KS * KS * grp / NGRP;                    // TAPMODE: this CTA's taps [tap0, tap0 + ntap)
-    const int ntap = KS * KS * (grp + 1) / NGRP - tap0;
-    const int split = item % p.nsplit; item /= p.nsplit;
+    const int tap0 = NALL * grp / NGRP;                       // TAPMODE: this CTA's accumulators [tap0, tap0 + ntap) of the filter
+    const int ntap = NALL * (grp + 1) / NGRP - tap0;
+    const int split = item % nsplit; item /= nsplit;
     const int chunk = item % p.nchunk;
     const int nblk = item / p.nchunk;
     const long long U = (long long)p.mtiles * p.T;
-    const int u0 = (int)(U * split / p.nsplit);
-    const int u1 = (int)(U * (split + 1) / p.nsplit);
+    const int u0 = (int)(U * split / nsplit);
+    const int u1 = (int)(U * (split + 1) / nsplit);
     const int n0 = nblk * 128;
     const int c0 = chunk * NB;
 
@@ -243,7 +300,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
         uint32_t phase = 0;
         int cur_mt = -1;
         int goff[cNPIX];
-        for (int u = u0; u < u1; ++u) {
+        // Software pipeline: the global loads of unit u + 1 are issued BEFORE unit u is converted and stored, so their L2 round
+        // trip overlaps the conversion instead of adding to every stage (the loads / wait / convert / store chain was serial).
+        using Raw = uint4[cNPIX][NB / 16];
+        auto issue_loads = [&](int u, Raw& raw) {
             const int mt = u / p.T;
             const int t = u - mt * p.T;
             if (mt != cur_mt) {
@@ -266,8 +326,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                 }
             }
             const uint8_t* xt = p.x + (size_t)t * t_stride + (FIRST4 ? 0 : c0);
-            // loads first (all in flight), then wait for the stage, then convert + store
-            uint4 raw[cNPIX][NB / 16];
 #pragma unroll
             for (int i = 0; i < cNPIX; ++i) {
 #pragma unroll
@@ -281,16 +339,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                     }
                 }
             }
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        };
+        WG_DECL();
+        auto convert_store = [&](const Raw& raw) {
+            {
+                WG_T0();
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                WG_ACC(0);      // wait for a free stage
+            }
+            WG_T0();
             uint8_t* dst0 = sm + (size_t)stage * cSTAGE + G_BYTES;
 #pragma unroll
             for (int i = 0; i < cNPIX; ++i) {
-                if (goff[i] != -2 && !WG_DBG(2)) {
+                if ((int)(tid + i * 128) < cPPIX && !WG_DBG(2)) {
                     const uint32_t off = (uint32_t)(tid + i * 128) * RBX;
 #pragma unroll
                     for (int h = 0; h < NB / 16; ++h) {
                         uint4 lo, hi;
-                        cvt16(raw[i][h], lo, hi);
+                        if (FIRST4 || !p.x_small) cvt16(raw[i][h], lo, hi);   // event counts: the full 0..255 range
+                        else cvt16_small(raw[i][h], lo, hi);                  // spikes and spike sums (< 128): two values per instruction
                         *reinterpret_cast<uint4*>(dst0 + swizzle_off(off + h * 32, swz_mask)) = lo;
                         *reinterpret_cast<uint4*>(dst0 + swizzle_off(off + h * 32 + 16, swz_mask)) = hi;
                     }
@@ -298,14 +365,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             }
             fence_proxy_async();        // generic-proxy stores -> visible to the tensor core's async-proxy reads
             mbar_arrive(bar_full_x + 8 * stage);
+            WG_ACC(1);          // convert + store + fence
             if (++stage == p.NPS) {
                 stage = 0;
                 phase ^= 1u;
             }
+        };
+        Raw raw_a, raw_b;
+        if (u0 < u1) issue_loads(u0, raw_a);
+        for (int u = u0; u < u1; u += 2) {
+            if (u + 1 < u1) issue_loads(u + 1, raw_b);
+            convert_store(raw_a);
+            if (u + 1 < u1) {
+                if (u + 2 < u1) issue_loads(u + 2, raw_a);
+                convert_store(raw_b);
+            }
         }
         // ================================================================== epilogue: accumulators -> g_w (atomics)
         if (u1 > u0) {
+            WG_T0();
             mbar_wait(bar_done, 0);
+            WG_ACC(2);          // wait for the last MMA
             tc_fence_after();
             const int L = warp * 32 + lane;               // TMEM lane = (copy, output channel)
             const int copy = L / CH;
@@ -313,8 +393,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             const bool n_ok = n < p.Cout;
             const int Kc = p.cin_real;                    // g_w row = tap * Kc + channel
             for (int a = 0; a < (TAPMODE ? ntap : nky * NS); ++a) {
-                const int ky = TAPMODE ? (tap0 + a) / KS : ky0 + a / NS;
-                const int shift = TAPMODE ? (tap0 + a) - ky * KS : wg_shift<KS, STRIDE, SH>(a % NS);
+                const int ky = TAPMODE ? (tap0 + a) / NS : ky0 + a / NS;
+                const int shift = wg_shift<KS, STRIDE, SH>(TAPMODE ? (tap0 + a) - ky * NS : a % NS);
                 const int kx = shift + STRIDE * (SH - 1 - copy);
                 const int tap = ky * KS + kx;
                 // stride 2: shift 2 of the un-shifted copy is the same tap as shift 0 of the shifted one -- count it once
@@ -336,6 +416,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             }
             tc_fence_before();
         }
+        if (threadIdx.x == 0) WG_DUMP(0);
     } else if (warp < 8) {
         // ================================================================== g-tile producers (cp.async, zero fill)
         const int m = threadIdx.x - 128;
@@ -428,9 +509,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
             constexpr uint32_t b_sbo = (uint32_t)(STRIDE * cPWp * RBX);
             int stage = 0;
             uint32_t phase = 0;
+            // per-accumulator constants of this CTA: descriptor offset (16-byte units) of the tap's patch shift, and whether it exists
+            uint32_t boff[NACC];
+            uint32_t live = 0u;
+#pragma unroll
+            for (int ai = 0; ai < NACC; ++ai) {
+                int ky, kx;
+                bool ok;
+                if constexpr (TAPMODE) {
+                    const int acc = tap0 + ai;
+                    ky = acc / NS;
+                    kx = wg_shift<KS, STRIDE, SH>(acc - ky * NS);
+                    ok = ai < ntap;
+                } else {
+                    ky = ai / NS;             // relative to this CTA's first filter row
+                    kx = wg_shift<KS, STRIDE, SH>(ai - ky * NS);
+                    ok = ky < nky;
+                }
+                const int toff = STRIDE == 1 ? ky * cPWp + kx : ky * cPWp + (kx & 1) * cPWhalf + (kx >> 1);
+                boff[ai] = (uint32_t)(toff * RBX) >> 4;
+                if (ok) live |= 1u << ai;
+            }
+            WG_DECL();
             for (int u = u0; u < u1; ++u) {
-                mbar_wait(bar_full_x + 8 * stage, phase);
-                mbar_wait(bar_full_g + 8 * stage, phase);
+                {
+                    WG_T0();
+                    mbar_wait(bar_full_x + 8 * stage, phase);
+                    WG_ACC(0);      // wait for the x patch
+                }
+                {
+                    WG_T0();
+                    mbar_wait(bar_full_g + 8 * stage, phase);
+                    WG_ACC(1);      // wait for the g tile
+                }
+                WG_T0();
                 fence_proxy_async();      // the g tile arrived through cp.async (generic proxy)
                 tc_fence_after();
                 const uint32_t sbase = base + (uint32_t)stage * cSTAGE;
@@ -441,22 +553,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                 const uint64_t a0 = SH == 1 ? make_desc_mn(sbase, 16384u, 1024u, 2u)
                                             : make_desc_mn(sbase, (uint32_t)RBG, (uint32_t)(GPW * RBG), a_layout);
                 const uint64_t b0 = make_desc_mn(sbase + G_BYTES + (uint32_t)(ky0 * cPWp * RBX), 16u, b_sbo, b_layout);
-                const uint32_t first = (u == u0) ? 0u : 1u;
-#pragma unroll 1
-                for (int ks = 0; ks < 8; ++ks) {
-                    // K = 16 pixels = tile rows 2*ks, 2*ks + 1
-                    const uint64_t a = a0 + (uint64_t)(((uint32_t)ks * a_kstep) >> 4);
-                    const uint64_t bk = b0 + (uint64_t)((uint32_t)(ks * 2 * STRIDE * cPWp * RBX) >> 4);
-                    const uint32_t acc = (ks == 0) ? first : 1u;
+                // The issuing thread is a single instruction stream: at ~25 scalar instructions per MMA (tap -> (ky, kx) division,
+                // 64-bit descriptor adds, predicate set-up) it spent ~70 cycles per MMA and WAS the bound of the N = 64 kernels
+                // (tools/wgrad_probe.py).  Everything tap-dependent is hoisted into boff[] / live, the K loop is unrolled, and
+                // the descriptors advance by 32-bit adds on their low words (the 14-bit address field cannot carry out of it).
+                const uint32_t a_hi = (uint32_t)(a0 >> 32), b_hi = (uint32_t)(b0 >> 32);
+                const uint32_t a_lo0 = (uint32_t)a0, b_lo0 = (uint32_t)b0;
+                const bool first_unit = u == u0;
+                if constexpr (TAPMODE) {
 #pragma unroll
-                    for (int ai = 0; ai < NACC; ++ai) {
-                        if (WG_DBG(1)) continue;
-                        if constexpr (TAPMODE) {
-                            const int tap = tap0 + ai;
-                            const int ky = tap / KS, kx = tap - ky * KS;
-                            if (ai < ntap)
-                                umma_f16(tmem_base + (uint32_t)(ai * NB), a, bk + (uint64_t)((uint32_t)((ky * cPWp + kx) * RBX) >> 4), idesc, acc);
-                        } else {
+                    for (int ks = 0; ks < 8; ++ks) {
+                        // K = 16 pixels = tile rows 2*ks, 2*ks + 1
+                        const uint32_t a_lo = a_lo0 + (((uint32_t)ks * a_kstep) >> 4);
+                        const uint32_t bk_lo = b_lo0 + ((uint32_t)(ks * 2 * STRIDE * cPWp * RBX) >> 4);
+#pragma unroll
+                        for (int ai = 0; ai < NACC; ++ai) {
+                            if (WG_DBG(1)) continue;
+                            if (live & (1u << ai)) {
+                                if (ks == 0 && first_unit) umma_f16_lohi<0>(tmem_base + (uint32_t)(ai * NB), a_lo, a_hi, bk_lo + boff[ai], b_hi, idesc);
+                                else umma_f16_lohi<1>(tmem_base + (uint32_t)(ai * NB), a_lo, a_hi, bk_lo + boff[ai], b_hi, idesc);
+                            }
+                        }
+                    }
+                } else {
+                    // 10 - 15 accumulators of N <= 32: the tap offsets are compile-time constants; unrolling the K loop as well
+                    // thrashes the instruction cache (+5-10 %), and the register-array form above is slower than this one
+                    const uint32_t first = first_unit ? 0u : 1u;
+#pragma unroll 1
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t a = a0 + (uint64_t)(((uint32_t)ks * a_kstep) >> 4);
+                        const uint64_t bk = b0 + (uint64_t)((uint32_t)(ks * 2 * STRIDE * cPWp * RBX) >> 4);
+                        const uint32_t acc = (ks == 0) ? first : 1u;
+#pragma unroll
+                        for (int ai = 0; ai < NACC; ++ai) {
+                            if (WG_DBG(1)) continue;
                             const int ky = ai / NS;       // relative to this CTA's first filter row
                             const int kx = wg_shift<KS, STRIDE, SH>(ai - ky * NS);
                             const int toff = STRIDE == 1 ? ky * cPWp + kx : ky * cPWp + (kx & 1) * cPWhalf + (kx >> 1);
@@ -466,12 +596,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_umma_kernel(const Wg
                     }
                 }
                 umma_commit(bar_empty + 8 * stage);
+                WG_ACC(2);          // issue
                 if (++stage == p.NPS) {
                     stage = 0;
                     phase ^= 1u;
                 }
             }
             if (u1 > u0) umma_commit(bar_done);
+            WG_DUMP(2);
         }
         __syncwarp();
     }
@@ -541,8 +673,8 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     const int NB = (!first && nb64_env && g->stride == 1 && g->Cin % 64 == 0) ? 64 : ((!first && g->Cin % 32 == 0) ? 32 : 16);
     const int NS = SH == 1 ? g->ks : (g->stride == 1 ? (g->ks + SH - 1) / SH : 3);
     int NGRP;
-    if (SH == 1 && NB == 64) {
-        NGRP = (g->ks * g->ks + 7) / 8;                    // tap groups (wg_tap_groups)
+    if (NB == 64) {
+        NGRP = (g->ks * NS + 7) / 8;                       // accumulator groups (wg_tap_groups)
     } else {
         int GK = (512 / NB) / NS;                          // wg_rows_per_group
         if (GK > g->ks) GK = g->ks;
@@ -551,6 +683,7 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     p.nblk = SH > 1 ? 1 : (g->Cout + 127) / 128;
     p.nchunk = first ? 1 : g->Cin / NB;
     p.cin_real = g->Cin;
+    p.x_small = g->planes != 0 ? 1 : 0;
     const long long U = (long long)p.mtiles * g->T;
     if (U > 0x7fffffffLL || (long long)g->B * g->Hin * g->Win * g->Cin > 0x7fffffffLL ||
         (long long)g->B * g->Hout * g->Wout * g->Cout > 0x7fffffffLL) {
@@ -626,3 +759,9 @@ extern "C" int ss_conv_wgrad_bf16(const ss_block_desc* g, const void* x, const v
     count_launch();
     return check_launch("conv_wgrad_umma");
 }
+
+#ifdef SS_ROLE_TIMING
+extern "C" int ss_wg_debug_read(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, ss::ss_wg_dbg, sizeof(unsigned long long) * 3 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -461,7 +461,7 @@ class Engine:
             ym, xm = gm.maps(dev)
             if tc_w:
                 cin_dev = int(x_in.shape[-1])
-                g_wkn = ops.conv_wgrad_bf16(x_in, g_b16, gm, T, B, cin=cin_dev)
+                g_wkn = ops.conv_wgrad_bf16(x_in, g_b16, gm, T, B, cin=cin_dev, x_full_range=first)   # event counts may exceed 127
                 if cin_dev != gm.Cin:       # packed first layer: drop the padding channels
                     g_wkn = g_wkn.view(gm.ks * gm.ks, cin_dev, gm.Cout)[:, :gm.Cin].reshape(gm.K, gm.Cout)
             else:

@@ -494,15 +494,16 @@ class DgradPlan:
                                            _ptr(dst), _stream()), 'ss_corr_bf16')
 
 
-def conv_wgrad_bf16(x, g_bf16, geom, T, B, cin=None):
-    """Weight gradient of one fused block on the tensor cores -> fp32 [K][Cout] (k = (ky*ks + kx)*Cin + c)."""
+def conv_wgrad_bf16(x, g_bf16, geom, T, B, cin=None, x_full_range=False):
+    """Weight gradient of one fused block on the tensor cores -> fp32 [K][Cout] (k = (ky*ks + kx)*Cin + c).
+    x_full_range: x may hold any u8 value (event-count frames); otherwise every value must be < 128 (spikes, spike sums)."""
     g = geom
     cin = g.Cin if cin is None else cin
     assert x.dtype == ACT_DTYPE and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, cin)
     assert g_bf16.dtype == torch.bfloat16 and g_bf16.is_contiguous() and tuple(g_bf16.shape) == (T, B, g.Hout, g.Wout, g.Cout)
     g_w = torch.zeros((g.ks * g.ks * cin, g.Cout), dtype=torch.float32, device=x.device)
     d = _lib.BlockDesc(T=T, B=B, Hin=g.Hin, Win=g.Win, Cin=cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
-                       stride=g.stride, pad=g.pad, upsample=1 if g.kind == 'upconv' else 0, neuron=0, planes=3,
+                       stride=g.stride, pad=g.pad, upsample=1 if g.kind == 'upconv' else 0, neuron=0, planes=0 if x_full_range else 3,
                        gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0)
     _lib.check(_lib.lib().ss_conv_wgrad_bf16(ctypes.byref(d), _ptr(x), _ptr(g_bf16), _ptr(g_w), _stream()), 'ss_conv_wgrad_bf16')
     return g_w

@@ -96,3 +96,26 @@ def test_wgrad_tensor_core(case):
     scale = float(gw_ref.abs().max())
     assert float((got - gw_ref).abs().max()) <= 2e-4 * scale + 1e-6, (float((got - gw_ref).abs().max()), scale)
     assert _cos(got, gw_full) >= 0.9999
+
+
+@pytest.mark.parametrize('cin', [32, 64])
+def test_wgrad_full_range_inputs(cin):
+    """Event-count frames as a multi-channel first layer (channel-concatenated temporal mode, reference train.py:206-218): x holds
+    any u8 value, which needs the full-range u8 -> bf16 conversion of the patch producers (x_full_range=True); the default
+    conversion is only defined below 128."""
+    from stereospike_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    geom, x, w, gy = _case('conv', cin, 64, 5, 20, 30, 1, 2, None, 2, 2)
+    T, B = x.shape[:2]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(0, 256, x.shape, generator=g).float() * (torch.rand(x.shape, generator=g) < 0.3)
+    assert float(x.max()) > 200
+    dev = torch.device('cuda')
+    gy16 = gy.bfloat16()
+    _, gw_ref = _autograd(geom, x.cuda(), w.cuda(), gy16.float().cuda())
+    xb = x.permute(0, 1, 3, 4, 2).contiguous().to(dev, torch.uint8)
+    g_dev = gy16.permute(0, 1, 3, 4, 2).contiguous().to(dev)
+    got = ops.kn_to_weight(ops.conv_wgrad_bf16(xb, g_dev, geom, T, B, x_full_range=True), geom.Cout, geom.Cin, geom.ks)
+    torch.cuda.synchronize()
+    scale = float(gw_ref.abs().max())
+    assert float((got - gw_ref).abs().max()) <= 2e-4 * scale + 1e-6, (float((got - gw_ref).abs().max()), scale)

@@ -1,5 +1,9 @@
 export PYTHONPATH=.
-python tools/dgrad_determinism.py 2>&1 | tail -12
-export STEREOSPIKE_B200_LIB=build/timing/libstereospike_b200.so
-for d in 0 1 2 4 6 7; do SS_WG_DBG=$d python tools/wgrad_probe.py 2>&1 | grep dbg; done
-for d in 0 1 2 4 6; do SS_WGRAD_N64=0 SS_WG_DBG=$d python tools/wgrad_probe.py 2>&1 | grep dbg; done
+timeout 900 python -m pytest tests/test_gpu_grad_umma.py -m gpu -q -x 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -x -q -k "gradients" 2>&1 | tail -4
+python tools/wgrad_probe.py 2>&1 | grep "dbg"
+SS_WGRAD_N64=0 python tools/wgrad_probe.py 2>&1 | grep "dbg"
+timeout 600 python bench.py --mode train --batch 16 --steps 10 --warmup 3 --no-cpu-baseline --no-extras --no-parity > gpurun_out/r2u_train.json 2> gpurun_out/r2u_err.log
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2u_train.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"

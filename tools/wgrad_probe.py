@@ -29,4 +29,16 @@ for name, kind, Cin, Cout, ks, Hin, Win, stride, pad, up in CASES:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     flop = 2.0 * T * B * geom.Hout * geom.Wout * Cout * Cin * ks * ks
+    import ctypes
+    import numpy as np
+    from stereospike_b200 import _lib
+    L = _lib.lib()
+    if hasattr(L, 'ss_wg_debug_read'):
+        buf = np.zeros(24, dtype=np.uint64)
+        L.ss_wg_debug_read.argtypes = [ctypes.c_void_p]
+        if L.ss_wg_debug_read(buf.ctypes.data) == 0:
+            d = buf.reshape(3, 8).astype(float)
+            print(f'    CTA 0: x producer {d[0, 7]:.0f} cycles: wait stage {100 * d[0, 0] / d[0, 7]:.0f}%, convert+store {100 * d[0, 1] / d[0, 7]:.0f}%, '
+                  f'wait last MMA {100 * d[0, 2] / d[0, 7]:.0f}% | MMA thread {d[2, 7]:.0f} cycles: wait x {100 * d[2, 0] / d[2, 7]:.0f}%, '
+                  f'wait g {100 * d[2, 1] / d[2, 7]:.0f}%, issue {100 * d[2, 2] / d[2, 7]:.0f}%')
     print(f'dbg={os.environ.get("SS_WG_DBG", "0")} n64={os.environ.get("SS_WGRAD_N64", "1")} {name:10s} {ms:7.3f} ms  {flop / ms / 1e9:7.1f} TFLOP/s')

@@ -271,6 +271,7 @@ class Engine:
         dev = x_seq.device
         impl = IMPLS[self.impl]
         acts = {'x': x_seq}
+        acts.update(side.get('seed_acts') or {})       # stand-alone blocks: the block input under its own name (u8 [T,B,H,W,C])
         saved = {'B': B, 'T': T, 'sites': [], 'acts': acts}
         head_srcs = {h.src for h in self.heads}
         tsums = {}
@@ -337,6 +338,13 @@ class Engine:
                 node.v = v_out.permute(0, 3, 1, 2)     # NCHW-shaped view, as the reference exposes it
                 node._v_from_grad_call = bool(want_h)
             saved['sites'].append({'geom': g, 'w_kn': w_kn, 'decay': decay, 'h_seq': h_seq, 'v_in': v_in})
+        if not self.heads:
+            # stand-alone block (run_sew_block): no readout
+            saved['depths'] = None
+            side['acts'] = acts
+            if not want_h:
+                saved['acts'] = None
+            return saved
         # heads + I-neurons
         hg, hw, hb, hacts = [], [], [], []
         for j, h in enumerate(self.heads):
@@ -344,7 +352,11 @@ class Engine:
             g = h.geom(int(a.shape[2]), int(a.shape[3]))
             hg.append(g)
             w = params[n_site + 2 * j].detach()
-            hw.append(w[0].permute(1, 2, 0).reshape(9, g.Cin).contiguous().float())
+            # [9][C] tap-major copy of the head weight, cached on the parameter's version (one small copy kernel per head and call)
+            key = (w.data_ptr(), params[n_site + 2 * j]._version, str(w.device), g.Cin)
+            if getattr(h, '_w9c', None) is None or h._w9c[0] != key:
+                h._w9c = (key, w[0].permute(1, 2, 0).reshape(9, g.Cin).contiguous().float())
+            hw.append(h._w9c[1])
             hb.append(params[n_site + 2 * j + 1].detach().reshape(1).contiguous().float())
             hacts.append(a)
         H, W = hg[0].Hout, hg[0].Wout
@@ -371,11 +383,13 @@ class Engine:
         return saved
 
     # ------------------------------------------------------------------ backward
-    def _run_backward(self, saved, params, n_site, g_depths, inject=None):
+    def _run_backward(self, saved, params, n_site, g_depths, inject=None, input_grad_of=None):
+        """Returns the parameter gradients (and, for stand-alone blocks, the gradient buffer of activation ``input_grad_of``)."""
         L = _lib.lib()
-        B, T, H, W = saved['B'], saved['T'], saved['H'], saved['W']
+        B, T = saved['B'], saved['T']
+        H, W = saved.get('H'), saved.get('W')
         acts = saved['acts']
-        dev = g_depths.device
+        dev = g_depths.device if g_depths is not None else next(iter(inject.values())).device
         grads = [None] * len(params)
         g = {}
         hook = self.grad_hook
@@ -389,37 +403,38 @@ class Engine:
             return g[name]
 
         # ---- heads
-        a = _lib.HeadsArgs()
-        a.T, a.B, a.H, a.W, a.gain = T, B, H, W, saved['gain']
-        keep = []
-        vp4 = ctypes.c_void_p * 4
-        g_acts, g_w, g_b, bins = vp4(), vp4(), vp4(), vp4()
-        gw_t, gb_t = [], []
-        store_heads = len({h.src for h in self.heads}) == len(self.heads)     # distinct sources: each buffer has one writer here
-        for j, h in enumerate(self.heads):
-            gm = saved['hg'][j]
-            ym, xm = gm.maps(dev)
-            a.C[j], a.Hs[j], a.Ws[j] = gm.Cin, gm.Hin, gm.Win
-            a.acts[j] = saved['hacts'][j].data_ptr()
-            a.w[j] = saved['hw'][j].data_ptr()
-            a.ymap[j], a.xmap[j] = ym.data_ptr(), xm.data_ptr()
-            ga = gbuf(h.src, fresh_ok=store_heads)
-            gw = torch.zeros((9, gm.Cin), dtype=torch.float32, device=dev)
-            gb = torch.zeros((1,), dtype=torch.float32, device=dev)
-            bn = torch.zeros((2, B, gm.Hin, gm.Win, 9), dtype=torch.float32, device=dev)
-            keep += [ym, xm, bn]
-            gw_t.append(gw)
-            gb_t.append(gb)
-            g_acts[j], g_w[j], g_b[j], bins[j] = ga.data_ptr(), gw.data_ptr(), gb.data_ptr(), bn.data_ptr()
-        _lib.check(L.ss_heads_bwd(ctypes.byref(a), _ptr(g_depths), g_acts, g_w, g_b, bins, 1 if store_heads else 0, _stream()),
-                   'ss_heads_bwd')
-        for j, h in enumerate(self.heads):
-            C = saved['hg'][j].Cin
-            grads[n_site + 2 * j] = gw_t[j].reshape(3, 3, C).permute(2, 0, 1).reshape(1, C, 3, 3).contiguous()
-            grads[n_site + 2 * j + 1] = gb_t[j]
-            if hook is not None:
-                hook.ready(grads[n_site + 2 * j])
-                hook.ready(grads[n_site + 2 * j + 1])
+        if self.heads:
+            a = _lib.HeadsArgs()
+            a.T, a.B, a.H, a.W, a.gain = T, B, H, W, saved['gain']
+            keep = []
+            vp4 = ctypes.c_void_p * 4
+            g_acts, g_w, g_b, bins = vp4(), vp4(), vp4(), vp4()
+            gw_t, gb_t = [], []
+            store_heads = len({h.src for h in self.heads}) == len(self.heads)     # distinct sources: each buffer has one writer here
+            for j, h in enumerate(self.heads):
+                gm = saved['hg'][j]
+                ym, xm = gm.maps(dev)
+                a.C[j], a.Hs[j], a.Ws[j] = gm.Cin, gm.Hin, gm.Win
+                a.acts[j] = saved['hacts'][j].data_ptr()
+                a.w[j] = saved['hw'][j].data_ptr()
+                a.ymap[j], a.xmap[j] = ym.data_ptr(), xm.data_ptr()
+                ga = gbuf(h.src, fresh_ok=store_heads)
+                gw = torch.zeros((9, gm.Cin), dtype=torch.float32, device=dev)
+                gb = torch.zeros((1,), dtype=torch.float32, device=dev)
+                bn = torch.zeros((2, B, gm.Hin, gm.Win, 9), dtype=torch.float32, device=dev)
+                keep += [ym, xm, bn]
+                gw_t.append(gw)
+                gb_t.append(gb)
+                g_acts[j], g_w[j], g_b[j], bins[j] = ga.data_ptr(), gw.data_ptr(), gb.data_ptr(), bn.data_ptr()
+            _lib.check(L.ss_heads_bwd(ctypes.byref(a), _ptr(g_depths), g_acts, g_w, g_b, bins, 1 if store_heads else 0, _stream()),
+                       'ss_heads_bwd')
+            for j, h in enumerate(self.heads):
+                C = saved['hg'][j].Cin
+                grads[n_site + 2 * j] = gw_t[j].reshape(3, 3, C).permute(2, 0, 1).reshape(1, C, 3, 3).contiguous()
+                grads[n_site + 2 * j + 1] = gb_t[j]
+                if hook is not None:
+                    hook.ready(grads[n_site + 2 * j])
+                    hook.ready(grads[n_site + 2 * j + 1])
 
         # ---- gradients arriving on the returned spike maps (last timestep, NCHW) join the buffers the heads just created
         for name, gs in (inject or {}).items():
@@ -486,6 +501,8 @@ class Engine:
             del g_acc, g_b16, g_out
         if hook is not None:
             hook.finish()
+        if input_grad_of is not None:
+            return grads, g.get(input_grad_of)
         return grads
 
 
@@ -500,47 +517,116 @@ def _tbhwc_to_nchw(a):
     return a[0].permute(0, 3, 1, 2).float()
 
 
-def _run_site_single(site, x_bf, resid=None, planes=3):
-    _, B, Hin, Win, _ = x_bf.shape
-    g = site.geom(Hin, Win)
-    node = site.node
-    v_in = _node_v_in(node, (B, g.Hout, g.Wout, g.Cout), x_bf.device)
-    decay = node.decay_tensor()
-    common = dict(T=1, B=B, neuron=node.kind, gain=site.gain_mod.gain(), v_th=node.v_threshold, v_reset=node.v_reset,
-                  tau=node._tau_value(), decay=decay.detach() if decay is not None else None, v_in=v_in, want_v_out=True,
-                  resid=resid)
-    if g.Cin % 32 == 0 and g.Cout % 32 == 0:
-        _, w_i8 = site.packed(planes, True, need_kn=False)
-        out, v_out, _ = ops.conv_i8_fwd(x_bf, g, w_i8[0], w_i8[1], planes=planes, **common)
-    else:
-        w_kn, _ = site.packed(planes, False)
-        out, v_out, _ = ops.conv_neuron_fwd(x_bf, g, w_kn, in_layout=SS_IN_U8_TBHWC, **common)
-    node.v = v_out.permute(0, 3, 1, 2)
-    return out
+class _BlockFunction(torch.autograd.Function):
+    """Stand-alone spiking blocks (SEWResBlock.forward on its own): a head-less engine over the block's sites.  Input / output are
+    the reference's NCHW fp32 spike tensors, one timestep per call; the gradient flows to the block input and to the weights
+    through the same kernels as inside the models (surrogate scan, tensor-core dgrad / wgrad)."""
+
+    @staticmethod
+    def forward(ctx, eng, x, in_name, out_name, need_grad, *params):
+        xb = _nchw_to_tbhwc(x)
+        side = {'need_grad': need_grad, 'return_layers': False, 'spike_outputs': (), 'seed_acts': {in_name: xb}}
+        n_site = len(params)
+        res = eng._run_forward(xb, params, n_site, side, want_h=need_grad)
+        out = _tbhwc_to_nchw(side['acts'][out_name])
+        ctx.saved = None
+        if need_grad:
+            ctx.eng, ctx.params, ctx.n_site, ctx.saved = eng, params, n_site, res
+            ctx.in_name, ctx.out_name = in_name, out_name
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        if ctx.saved is None:
+            raise RuntimeError('stereospike_b200: backward through the same forward twice (the saved potentials were released)')
+        grads, g_in = ctx.eng._run_backward(ctx.saved, ctx.params, ctx.n_site, None, {ctx.out_name: g_out.contiguous().float()},
+                                            input_grad_of=ctx.in_name)
+        ctx.saved = None
+        gx = g_in[0].permute(0, 3, 1, 2).contiguous() if g_in is not None else None
+        return (None, gx, None, None, None) + tuple(grads)
 
 
 def run_sew_block(blk, x):
-    """SEWResBlock.forward for a stand-alone call: x [B,C,H,W] fp32 spikes -> [B,C,H,W] fp32 (inference only)."""
-    if torch.is_grad_enabled() and any(p.requires_grad for p in blk.parameters()) and x.requires_grad:
-        raise NotImplementedError('stand-alone SEWResBlock is forward-only; train through the model classes')
-    if not hasattr(blk, '_sites'):
-        object.__setattr__(blk, '_sites', (Site('conv1', 'mid', 'in', blk.conv1[0], blk.conv1[1], blk.sn1),
-                                          Site('conv2', 'out', 'mid', blk.conv2[0], blk.conv2[1], blk.sn2, resid='in')))
-    s1, s2 = blk._sites
-    xb = _nchw_to_tbhwc(x)
-    mid = _run_site_single(s1, xb)
-    out = _run_site_single(s2, mid, resid=xb)
-    return _tbhwc_to_nchw(out)
+    """SEWResBlock.forward for a stand-alone call: x [B,C,H,W] fp32 spikes -> [B,C,H,W] fp32, stateful (one timestep per call),
+    differentiable w.r.t. x and the block's parameters (reference network/blocks.py:161-171 under autograd)."""
+    ops._require_cuda(x, 'x')
+    if not hasattr(blk, '_engine'):
+        sites = [Site('conv1', 'mid', 'in', blk.conv1[0], blk.conv1[1], blk.sn1),
+                 Site('conv2', 'out', 'mid', blk.conv2[0], blk.conv2[1], blk.sn2, resid='in')]
+        eng = Engine(sites, [], None)
+        eng.check_input = False
+        object.__setattr__(blk, '_engine', eng)
+    eng = blk._engine
+    if blk.conv1[0].in_channels % 32 != 0:
+        raise NotImplementedError('stand-alone SEWResBlock: the fused kernels tile 32 channels (every SEWResBlock of the reference '
+                                  f'models has 512); got {blk.conv1[0].in_channels}')
+    params, _ = eng._flat_params()
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p is not None and p.requires_grad for p in params))
+    if need_grad:
+        eng._warn_truncated_bptt()
+    return _BlockFunction.apply(eng, x, 'in', 'out', need_grad, *params)
+
+
+class _LinearBlockFunction(torch.autograd.Function):
+    """NNConvUpsampling on its own, any channel counts / kernel size, arbitrary fp32 input: upsample-gather + valid conv on the fp32
+    CUDA-core kernel (a non-firing IF step from rest returns the conv result as its potential), gradients through ss_conv_dgrad /
+    ss_conv_wgrad.  The 1-channel 3x3 heads inside the models go through the dedicated heads kernels instead."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, up_size):
+        B, C, Hs, Ws = x.shape
+        co, ci, ks, _ = weight.shape
+        cp = (co + 31) // 32 * 32                               # the kernel tiles 32 output channels
+        g = BlockGeom('upconv', C, cp, ks, Hs, Ws, up_size[0], up_size[1])
+        w_kn = torch.zeros((ks * ks * C, cp), dtype=torch.float32, device=x.device)
+        w_kn[:, :co] = ops.weight_to_kn(weight.detach().float())
+        x5 = x.detach().float().contiguous().view(B, 1, C, Hs, Ws)
+        _, _, h = ops.conv_neuron_fwd(x5, g, w_kn, T=1, B=B, in_layout=SS_IN_F32_BTCHW, neuron=_lib.SS_NEURON_IF, gain=1.0,
+                                      v_th=3.0e38, v_reset=0.0, want_h=True)
+        y = h[0, :, :, :, :co].permute(0, 3, 1, 2)
+        if bias is not None:
+            y = y + bias.detach().float().view(1, co, 1, 1)
+        ctx.save_for_backward(x5, w_kn)
+        ctx.geom, ctx.co = g, co
+        return y.contiguous()
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x5, w_kn = ctx.saved_tensors
+        g, co = ctx.geom, ctx.co
+        B = int(x5.shape[0])
+        dev = g_y.device
+        L = _lib.lib()
+        g_acc = torch.zeros((1, B, g.Hout, g.Wout, g.Cout), dtype=torch.float32, device=dev)
+        g_acc[0, :, :, :, :co] = g_y.float().permute(0, 2, 3, 1)
+        cg = _lib.ConvGeom(T=1, B=B, Hin=g.Hin, Win=g.Win, Cin=g.Cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
+                           in_layout=SS_IN_F32_BTCHW, neuron=_lib.SS_NEURON_IF, reserved0=0, gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0,
+                           reserved1=0, reserved2=0)
+        ym, xm = g.maps(dev)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            g_x = torch.zeros((1, B, g.Hin, g.Win, g.Cin), dtype=torch.float32, device=dev)
+            _lib.check(L.ss_conv_dgrad(ctypes.byref(cg), _ptr(ym), _ptr(xm), _ptr(w_kn), _ptr(g_acc), _ptr(g_x), _stream()), 'ss_conv_dgrad')
+            gx = g_x[0].permute(0, 3, 1, 2).contiguous()
+        if ctx.needs_input_grad[1]:
+            g_wkn = torch.zeros((g.K, g.Cout), dtype=torch.float32, device=dev)
+            _lib.check(L.ss_conv_wgrad(ctypes.byref(cg), _ptr(x5), _ptr(ym), _ptr(xm), _ptr(g_acc), _ptr(g_wkn), _stream()), 'ss_conv_wgrad')
+            gw = ops.kn_to_weight(g_wkn, g.Cout, g.Cin, g.ks)[:co].contiguous()
+        if ctx.needs_input_grad[2]:
+            gb = g_y.float().sum(dim=(0, 2, 3))
+        return gx, gw, gb, None
 
 
 def run_linear_block(up, x):
-    """NNConvUpsampling.forward for a stand-alone call (no neuron): routed through the heads kernel when Cout == 1,
-    which is the only stand-alone use in the reference (predict_depthK)."""
+    """NNConvUpsampling.forward for a stand-alone call (no neuron; reference network/blocks.py:130-132).  The 1-channel 3x3 heads
+    (the only stand-alone use in the reference, predict_depthK) run on the heads kernel when no gradient is needed; every other
+    shape, and any grad-enabled call, runs the general fp32 kernel with gradients w.r.t. input, weight and bias."""
     conv = up.up[1]
-    if conv.out_channels != 1 or conv.kernel_size[0] != 3:
-        raise NotImplementedError('stand-alone NNConvUpsampling is implemented for the 1-channel 3x3 heads only; '
-                                  'spiking NNConvUpsampling blocks run fused inside the model classes')
     ops._require_cuda(x, 'x')
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in conv.parameters()))
+    spikes_like = x.dtype == torch.float32 and conv.in_channels % 8 == 0
+    if need_grad or conv.out_channels != 1 or conv.kernel_size[0] != 3 or not spikes_like:
+        return _LinearBlockFunction.apply(x, conv.weight, conv.bias, up.up_size)
     B, C, Hs, Ws = x.shape
     xb = _nchw_to_tbhwc(x)
     g = BlockGeom('upconv', C, 1, 3, Hs, Ws, up.up_size[0], up.up_size[1])

@@ -120,7 +120,17 @@ class ParametricLIFNode(BaseNode):
 
     def decay_tensor(self):
         # 1/tau = sigmoid(w): a one-element device tensor; torch autograd carries d sigmoid / d w
-        return self.w.sigmoid().reshape(1).float()
+        if torch.is_grad_enabled() and self.w.requires_grad:
+            return self.w.sigmoid().reshape(1).float()
+        # inference: one tiny launch per PLIF layer and call otherwise (4 of the ~30 launches of a forward); cached on the
+        # parameter's version counter (optimizer steps and load_state_dict bump it)
+        key = (self.w.data_ptr(), self.w._version, self.w.device)
+        c = getattr(self, '_decay_cache', None)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                c = (key, self.w.sigmoid().reshape(1).float())
+            object.__setattr__(self, '_decay_cache', c)
+        return c[1]
 
     def extra_repr(self):
         with torch.no_grad():

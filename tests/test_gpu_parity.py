@@ -426,6 +426,63 @@ def test_standalone_blocks():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('cin,cout,ks,bias', [(12, 5, 3, True), (32, 64, 5, False), (7, 1, 3, True)])
+def test_standalone_upconv_general_with_gradients(cin, cout, ks, bias):
+    """NNConvUpsampling on its own is a general module upstream (network/blocks.py:110-132): any channel counts / kernel size,
+    arbitrary fp32 input, differentiable w.r.t. input, weight and bias."""
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm
+    torch.manual_seed(3)
+    up_o = rm.UpConv(cin, cout, ks, (11, 14), bias=bias)
+    up = sb.NNConvUpsampling(cin, cout, ks, (11, 14), bias=bias)
+    up.load_state_dict(up_o.state_dict())
+    up = up.cuda()
+    x_o = torch.randn(2, cin, 6, 5, requires_grad=True)
+    x = x_o.detach().clone().cuda().requires_grad_(True)
+    y_o, y = up_o(x_o), up(x)
+    torch.testing.assert_close(y.detach().cpu(), y_o.detach(), rtol=1e-4, atol=1e-5)
+    gy = torch.randn_like(y_o)
+    y_o.backward(gy)
+    y.backward(gy.cuda())
+    torch.testing.assert_close(x.grad.cpu(), x_o.grad, rtol=1e-4, atol=1e-5)
+    for (n, p_o), (_, p) in zip(up_o.named_parameters(), up.named_parameters()):
+        torch.testing.assert_close(p.grad.cpu(), p_o.grad, rtol=1e-4, atol=1e-4, msg=n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('C,plif', [(64, False), (64, True), (32, False)])
+def test_standalone_sew_block_gradients(C, plif):
+    """SEWResBlock on its own under autograd (network/blocks.py:161-171): gradients w.r.t. the input spikes and the weights
+    against the oracle block (same surrogate BPTT; the tensor-core gradient kernels round their operands to bf16)."""
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm, sj_compat as sj
+    torch.manual_seed(5)
+    if plif:
+        mk = lambda: sj.ParametricLIFNode(2.0, 1.0, 0.0, sj.ATan(), True)
+        blk = sb.SEWResBlock(C, multiply_factor=6.0, use_plif=True, tau=2.0, surrogate_function=sb.surrogate.ATan())
+    else:
+        mk = lambda: sj.IFNode(1.0, 0.0, sj.Sigmoid(), True)
+        blk = sb.SEWResBlock(C, multiply_factor=4.0)
+    o = rm.SEWBlock(C, mk, 6.0 if plif else 4.0)
+    blk.load_state_dict(o.state_dict())
+    blk = blk.cuda()
+    xs = (torch.rand(2, C, 9, 7) < 0.25).float()
+    x_o = xs.clone().requires_grad_(True)
+    x = xs.clone().cuda().requires_grad_(True)
+    y_o, y = o(x_o), blk(x)
+    assert float((y_o != y.detach().cpu()).float().mean()) < 1e-3 and 0.02 < float((y_o > 0).float().mean())
+    gy = torch.randn_like(y_o)
+    y_o.backward(gy)
+    y.backward(gy.cuda())
+
+    def cos(a, b):
+        return float((a.double() * b.double()).sum() / (a.double().norm() * b.double().norm() + 1e-300))
+    assert cos(x.grad.cpu(), x_o.grad) > 0.995, cos(x.grad.cpu(), x_o.grad)
+    for (n, p_o), (_, p) in zip(o.named_parameters(), blk.named_parameters()):
+        assert p.grad is not None and cos(p.grad.cpu(), p_o.grad) > 0.995, (n, cos(p.grad.cpu(), p_o.grad))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('B,T', [(1, 1), (2, 3)])
 def test_graphed_inference_equals_eager(B, T):
     """CUDA-graph replay of reset + forward_seq (stereospike_b200.pipeline.GraphedInference) is bit-identical to the eager

@@ -4,6 +4,13 @@ import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
+
+
+def is_step_start(name):
+    """A step starts at the first-layer block (conv_i8_kernel<.., 1, 1, 128, 1, ..>: fp32 frames are packed just before it, packed
+    u8 frames arrive from the host already in that form)."""
+    return 'conv_i8_kernel<' in name and ', 1, 1, 128, 1,' in name
+
 hdr = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 h = rows[hdr]
 ki, vi, gi = h.index('Kernel Name'), h.index('Metric Value'), h.index('Grid Size')
@@ -14,7 +21,7 @@ for r in rows[hdr + 2:]:
             seq.append((r[ki], float(r[vi].replace(',', '')), r[gi]))
         except ValueError:
             pass
-idx = [i for i, s in enumerate(seq) if 'pack_events' in s[0]]
+idx = [i for i, s in enumerate(seq) if is_step_start(s[0])]
 step = seq[idx[-2]:idx[-1]] if len(idx) > 1 else seq
 agg = collections.OrderedDict()
 for n, v, g in step:

@@ -4,6 +4,13 @@ import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
+
+
+def is_step_start(name):
+    """A step starts at the first-layer block (conv_i8_kernel<.., 1, 1, 128, 1, ..>: fp32 frames are packed just before it, packed
+    u8 frames arrive from the host already in that form)."""
+    return 'conv_i8_kernel<' in name and ', 1, 1, 128, 1,' in name
+
 h = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
 hdr = rows[h]
 ki, mi, vi, ii, gi = (hdr.index(n) for n in ('Kernel Name', 'Metric Name', 'Metric Value', 'ID', 'Grid Size'))
@@ -12,7 +19,7 @@ for r in rows[h + 1:]:
     if len(r) > vi:
         d.setdefault(r[ii], {'k': r[ki], 'g': r[gi]})[r[mi]] = r[vi]
 ids = sorted(d, key=int)
-pe = [i for i in ids if 'pack_events' in d[i]['k']]
+pe = [i for i in ids if is_step_start(d[i]['k'])]
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 seg = [i for i in ids if int(pe[k]) <= int(i) < int(pe[k + 1])]
 tot = 0.0

@@ -1,4 +1,12 @@
 export PYTHONPATH=.
-timeout 900 python -m pytest tests -m gpu -x -q -k "standalone" 2>&1 | tail -30
-timeout 800 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -c 6000 --csv --log-file gpurun_out/r2w_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --no-parity --no-train > gpurun_out/r2w_ncu_list.log 2>&1
-python tools/launch_table.py gpurun_out/r2w_launches.csv 1
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2y_bench.json 2> gpurun_out/r2y_err.log
+tail -3 gpurun_out/r2y_err.log
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2y_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['traffic'])
+print(d['roofline']['per_block_ms'])
+print(d.get('train',{}).get('ms_per_step'), d.get('parity'))
+print(d.get('cpu_baseline'))
+P

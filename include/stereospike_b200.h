@@ -182,6 +182,16 @@ int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks
 int ss_pack_digits_i8_rect(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ksy, int32_t ksx, int32_t planes,
                            const int32_t* zero_exp, void* w_i8, void* stream);
 
+/* The three weight images of a folded NNConvUpsampling block (ss_conv_i8_fwd_ex: SS_TILES_FOLDED dense pass, the two
+ * SS_TILES_ROW_LIST passes) straight from its fp32 5x5 OIHW weight, one launch: per output channel a power-of-two fixed point
+ * with head-room for the tap sums (1 bit, one more while any folded sum overflows the top balanced digit), the quantised taps
+ * summed per replication pattern (exact integers), digit planes written in the kernels' shared-memory layout.
+ *   w_dense: 4 sets of 3x3 per output-channel tile (class = 2*row_class + col_class)  4*Cout*Cin*9*planes bytes
+ *   w_rows / w_cols: 3 sets of 3x5 each (irregular rows; irregular columns, transposed frame)  3*Cout*Cin*15*planes bytes each
+ *   wscale fp32 [Cout] = 2^e, wexp int32 [Cout] = e (workspace / by-product).   planes 2 or 3. */
+int ss_pack_weights_folded(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t planes, void* w_dense, void* w_rows,
+                           void* w_cols, float* wscale, int32_t* wexp, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Same block on the CUDA cores in plain fp32 (exact fp32 weights, ascending-k accumulation): the first-layer
  * path for non-integer inputs and the on-device cross-check of the tensor-core path. */

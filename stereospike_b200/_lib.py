@@ -15,7 +15,7 @@ SS_IN_U8_TBHWC, SS_IN_F32_BTCHW = 0, 1
 SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
-SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_pack_digits_i8_rect', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_pack_events_c', 'ss_conv_neuron_fwd',
+SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_pack_digits_i8_rect', 'ss_pack_weights_folded', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_pack_events_c', 'ss_conv_neuron_fwd',
            'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_neuron_bwd_ex', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
            'ss_pack_weights_bf16', 'ss_corr_bf16', 'ss_conv_wgrad_bf16', 'ss_loss_fwd', 'ss_loss_bwd',
            'ss_abi_version', 'ss_last_error', 'ss_launch_count')
@@ -94,6 +94,8 @@ def lib():
     L.ss_pack_digits_i8.restype = ctypes.c_int
     L.ss_pack_digits_i8_rect.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
     L.ss_pack_digits_i8_rect.restype = ctypes.c_int
+    L.ss_pack_weights_folded.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.ss_pack_weights_folded.restype = ctypes.c_int
     L.ss_events_accumulate.argtypes = [vp, i64, vp, vp, ctypes.c_double, vp, vp, i32, i32, i32, i32, vp, vp]
     L.ss_events_accumulate.restype = ctypes.c_int
     L.ss_events_pack.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]

@@ -1364,6 +1364,177 @@ void setup_tma(I8Params& p, const void* x, long long nimg, int Hin, int Win, int
 }
 
 int rowbytes_for(int Cin, int ks) { return (ks <= 3 && Cin % 64 == 0) ? 64 : 32; }
+// ------------------------------------------------------------------------------------------------ folded weight sets
+// Digit-plane images of a folded NNConvUpsampling block straight from its fp32 5x5 weight (one launch; the same derivation as
+// stereospike_b200.ops.fold_weight_sets, which needed ~250 small torch launches per block and therefore kept the fold out of the
+// training step, where the weights change every iteration).
+//   patterns of the 5 taps of one axis (source offset of tap k): L 0,1,1,2,2   M 0,0,1,1,2   A 0,0,0,1,1   B 0,1,1,1,2   C 0,0,1,1,1
+//   dense[cy][cx] (cy, cx in {L, M}): 3x3, f[dy][dx] = sum of the taps (ky, kx) with pat_cy[ky] == dy and pat_cx[kx] == dx
+//   rows[c] (c in {A, B, C}): 3x5, f[dy][kx] = sum over ky with pat_c[ky] == dy;   cols[c]: 3x5 in the transposed frame, f[dx][ky]
+// Quantise with 1 bit of head-room for the tap sums, add a bit while any folded sum overflows the top balanced digit (<= 3 more bits
+// can ever be needed: a sum has at most 4 taps), then write the three images.
+// (a constexpr function, not a __constant__ table: with the loops unrolled every accumulator index below is a compile-time constant
+//  and the accumulators stay in registers; indexed through constant memory they lived in local memory and the kernel took 0.2 ms)
+__host__ __device__ constexpr int fold_pat(int p, int k) {
+    constexpr int T[5][5] = {{0, 1, 1, 2, 2}, {0, 0, 1, 1, 2}, {0, 0, 0, 1, 1}, {0, 1, 1, 1, 2}, {0, 0, 1, 1, 1}};
+    return T[p][k];
+}
+
+// folded sums of one (output channel, input channel) filter q[5][5]; calls f(set kind, set index, tap, value)
+template <typename F>
+__device__ __forceinline__ void fold_sums(const int (&q)[25], F&& f) {
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+            int acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) acc[fold_pat(cy, ky) * 3 + fold_pat(cx, kx)] += q[ky * 5 + kx];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) f(0, cy * 2 + cx, t, acc[t]);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int ar[15], ac[15];
+#pragma unroll
+        for (int t = 0; t < 15; ++t) ar[t] = ac[t] = 0;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                ar[fold_pat(2 + c, ky) * 5 + kx] += q[ky * 5 + kx];      // rows: [dy][kx]
+                ac[fold_pat(2 + c, kx) * 5 + ky] += q[ky * 5 + kx];      // cols: [dx][ky]
+            }
+#pragma unroll
+        for (int t = 0; t < 15; ++t) {
+            f(1, c, t, ar[t]);
+            f(2, c, t, ac[t]);
+        }
+    }
+}
+
+// Kernel A, one block per output channel: the exponent (1 bit of head-room, one more while any folded sum overflows).
+__global__ void __launch_bounds__(256) weight_fold_exponent_kernel(const float* __restrict__ w, int Cin, int planes, float* __restrict__ wscale,
+                                                                   int* __restrict__ wexp) {
+    const int n = blockIdx.x;
+    const float* wn = w + (size_t)n * Cin * 25;
+    __shared__ float redf[8];
+    __shared__ int redi[8];
+    __shared__ int s_e;
+    float m = 0.0f;
+    for (int i = threadIdx.x; i < Cin * 25; i += blockDim.x) m = fmaxf(m, fabsf(wn[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) m = fmaxf(m, redf[i]);
+        int ex = 0;
+        if (m > 0.0f) frexpf(m, &ex);                 // m = f * 2^ex, f in [0.5, 1)  ==  floor(log2 m) + 1
+        s_e = ex - (8 * planes - 1) + 1;
+    }
+    __syncthreads();
+    int ilimit = 127;
+    for (int pl = 1; pl < planes; ++pl) ilimit *= 256;      // planes <= 3 (the host refuses 4: 127 * 2^24 does not fit)
+    // w * 2^-e is exact in fp32 (a power-of-two scaling of an fp32 number, |result| < 2^24), so rounding it to the nearest-even
+    // integer in fp32 gives the same q as the float64 host derivation
+    for (int it = 0; it < 4; ++it) {
+        const int e = s_e;
+        const float sc = ldexpf(1.0f, -e);
+        int worst = 0;
+        for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+            int q[25];
+#pragma unroll
+            for (int k = 0; k < 25; ++k) q[k] = __float2int_rn(wn[ci * 25 + k] * sc);
+            fold_sums(q, [&](int, int, int, int v) { worst = max(worst, abs(v)); });
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        __syncthreads();                              // everybody has read s_e
+        if ((threadIdx.x & 31) == 0) redi[threadIdx.x >> 5] = worst;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 8; ++i) worst = max(worst, redi[i]);
+            if (worst > ilimit) s_e = e + 1;
+        }
+        __syncthreads();
+        if (s_e == e) break;
+    }
+    if (threadIdx.x == 0) {
+        wexp[n] = s_e;
+        wscale[n] = ldexpf(1.0f, s_e);
+    }
+}
+
+// Kernel B, one block per (output channel, 64 input channels): the quantised taps go through shared memory, then every thread
+// owns (folded tap, 16 consecutive input channels) items: 16 sums, their digits, one 16-byte store per plane -- 16 consecutive
+// channels of one (tap, plane, output channel) row are one 16-byte chunk of the image.  (One thread per input channel writing its
+// 378 bytes one by one took 0.09-0.16 ms per block: ~100 dependent instructions per byte-sized store.)
+constexpr int FOLD_ITEMS = 36 + 45 + 45;      // dense 4 x 9, rows 3 x 15, cols 3 x 15
+__constant__ uint32_t c_fold_mask[FOLD_ITEMS];  // bit (ky * 5 + kx) set: the tap belongs to the item's sum
+
+__global__ void __launch_bounds__(256) weight_fold_write_kernel(const float* __restrict__ w, int Cin, int planes, int RBd,
+                                                                const int* __restrict__ wexp, int8_t* __restrict__ w_dense,
+                                                                int8_t* __restrict__ w_rows, int8_t* __restrict__ w_cols) {
+    const int n = blockIdx.x;
+    const int ci0 = blockIdx.y * 64;
+    __shared__ int q[25][64 + 1];
+    const float sc = ldexpf(1.0f, -wexp[n]);
+    const float* wn = w + ((size_t)n * Cin + ci0) * 25;
+    for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) {
+        const int ci = i / 25, k = i - ci * 25;
+        q[k][ci] = (ci0 + ci < Cin) ? __float2int_rn(wn[i] * sc) : 0;
+    }
+    __syncthreads();
+    const int tile = n >> 5, r32 = n & 31;
+    const int N = planes * 32;
+    for (int idx = threadIdx.x; idx < FOLD_ITEMS * 4; idx += blockDim.x) {
+        const int item = idx >> 2, cg = idx & 3;          // 16-channel group of the 64
+        const int ch0 = ci0 + cg * 16;
+        if (ch0 >= Cin) continue;
+        int v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0;
+        uint32_t mask = c_fold_mask[item];
+        while (mask != 0u) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += q[k][cg * 16 + j];
+        }
+        // destination image and coordinates of the item
+        int8_t* out;
+        int set, tap, ntaps, nsets, RB;
+        if (item < 36) { out = w_dense; set = item / 9; tap = item - set * 9; ntaps = 9; nsets = 4; RB = RBd; }
+        else if (item < 81) { out = w_rows; set = (item - 36) / 15; tap = (item - 36) - set * 15; ntaps = 15; nsets = 3; RB = 32; }
+        else { out = w_cols; set = (item - 81) / 15; tap = (item - 81) - set * 15; ntaps = 15; nsets = 3; RB = 32; }
+        const int ntile = tile * nsets + set;             // packed "output channel" = (tile * nsets + set) * 32 + r32
+        const int ncb = Cin / RB;
+        const int cb = ch0 / RB, c = ch0 - cb * RB;
+        const size_t buf = (size_t)(ntile * ncb + cb) * ((size_t)ntaps * N * RB);
+        const uint32_t smask = (uint32_t)(RB >> 4) - 1u;
+#pragma unroll
+        for (int pl = planes - 1; pl >= 0; --pl) {
+            uint32_t wd[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                int dgt;
+                if (pl > 0) {
+                    dgt = ((v[j] + 128) & 255) - 128;
+                    v[j] = (v[j] - dgt) >> 8;
+                } else {
+                    dgt = v[j];
+                }
+                wd[j >> 2] |= (uint32_t)(dgt & 255) << (8 * (j & 3));
+            }
+            const uint32_t off = (uint32_t)((tap * N + pl * 32 + r32) * RB + c);
+            *reinterpret_cast<uint4*>(out + buf + (off ^ (((off >> 7) & smask) << 4))) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+    }
+}
+
 // gradient-side correlation: row bytes of the bf16 source patch (Cg channels = 2*Cg bytes per pixel)
 int corr_rowbytes_for(int Cg, int ks) { return (ks <= 3 && (2 * Cg) % 64 == 0) ? 64 : 32; }
 
@@ -1750,6 +1921,50 @@ extern "C" int ss_pack_digits_i8_rect(const float* q_oihw, int32_t Cout, int32_t
 extern "C" int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, const int32_t* zero_exp,
                                  void* w_i8, void* stream) {
     return ss_pack_digits_i8_rect(q_oihw, Cout, Cin, ks, ks, planes, zero_exp, w_i8, stream);
+}
+
+extern "C" int ss_pack_weights_folded(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t planes, void* w_dense, void* w_rows,
+                                      void* w_cols, float* wscale, int32_t* wexp, void* stream) {
+    if (w_oihw == nullptr || w_dense == nullptr || w_rows == nullptr || w_cols == nullptr || wscale == nullptr || Cout <= 0 || Cin <= 0 ||
+        planes < 2 || planes > 3 || Cout % 32 != 0 || Cin % 32 != 0) {
+        set_error("ss_pack_weights_folded: bad argument (5x5 weight, Cout %% 32, Cin %% 32, planes 2 or 3)");
+        return SS_EINVAL;
+    }
+    // item -> taps table of the write kernel (per device, once)
+    static bool table_done[SS_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!table_done[dev]) {
+        uint32_t mask[FOLD_ITEMS];
+        for (int i = 0; i < FOLD_ITEMS; ++i) mask[i] = 0u;
+        for (int ky = 0; ky < 5; ++ky)
+            for (int kx = 0; kx < 5; ++kx) {
+                const uint32_t bit = 1u << (ky * 5 + kx);
+                for (int cy = 0; cy < 2; ++cy)
+                    for (int cx = 0; cx < 2; ++cx) mask[(cy * 2 + cx) * 9 + fold_pat(cy, ky) * 3 + fold_pat(cx, kx)] |= bit;
+                for (int c = 0; c < 3; ++c) {
+                    mask[36 + c * 15 + fold_pat(2 + c, ky) * 5 + kx] |= bit;      // rows: [dy][kx]
+                    mask[81 + c * 15 + fold_pat(2 + c, kx) * 5 + ky] |= bit;      // cols: [dx][ky]
+                }
+            }
+        if (cudaMemcpyToSymbol(c_fold_mask, mask, sizeof(mask)) != cudaSuccess) {
+            set_error("ss_pack_weights_folded: %s", cudaGetErrorString(cudaGetLastError()));
+            return SS_ECUDA;
+        }
+        table_done[dev] = true;
+    }
+    if (wexp == nullptr) {
+        set_error("ss_pack_weights_folded: null wexp workspace");
+        return SS_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    weight_fold_exponent_kernel<<<Cout, 256, 0, st>>>(w_oihw, Cin, planes, wscale, wexp);
+    count_launch();
+    if (check_launch("weight_fold_exponent") != SS_OK) return SS_ECUDA;
+    weight_fold_write_kernel<<<dim3((unsigned)Cout, (unsigned)((Cin + 63) / 64)), 256, 0, st>>>(
+        w_oihw, Cin, planes, rowbytes_for(Cin, 3), wexp, reinterpret_cast<int8_t*>(w_dense), reinterpret_cast<int8_t*>(w_rows),
+        reinterpret_cast<int8_t*>(w_cols));
+    count_launch();
+    return check_launch("weight_fold_pack");
 }
 
 // ------------------------------------------------------------------------------------------------ gradient-side correlation

@@ -287,10 +287,9 @@ class Engine:
             if first and not packed_in and int(x_seq.shape[2]) != g.Cin:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
             use_i8 = impl != SS_IMPL_SIMT
-            # (not while training: the weights change every step and the folded sets are derived on the host side of the C ABI --
-            #  re-deriving them costs more than the taps they save; the 25-tap kernel packs its image in one small launch)
-            fold = use_i8 and self._fold_site(s.name) and not want_h and g.kind == 'upconv' and g.ks == 5 and g.Cin % 32 == 0 and \
-                ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
+            # (also while training: ss_pack_weights_folded re-derives the folded sets from the updated weight in one launch)
+            fold = use_i8 and self._fold_site(s.name) and self.weight_planes <= 3 and g.kind == 'upconv' and g.ks == 5 and \
+                g.Cin % 32 == 0 and ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
             if fold:
                 self.flop_scale[s.name] = ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).taps_per_output / 25.0
             else:

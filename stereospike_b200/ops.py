@@ -244,7 +244,26 @@ def fold_weight_sets(weight, planes):
 
 
 def pack_weights_folded(weight, planes):
-    """Digit-plane images (dense, rows, cols) of fold_weight_sets + wscale fp32 [Cout]."""
+    """Digit-plane images (dense, rows, cols) of a folded NNConvUpsampling block + wscale fp32 [Cout]: one launch of
+    ss_pack_weights_folded (bit-identical to pack_weights_folded_host below, which derives them with torch ops)."""
+    _require_cuda(weight, 'weight')
+    w = weight.detach().contiguous().float()
+    co, ci, kh, kw = (int(v) for v in w.shape)
+    assert kh == 5 and kw == 5 and co % 32 == 0 and ci % 32 == 0
+    dev = w.device
+    dense = torch.empty(4 * co * ci * 9 * planes, dtype=torch.int8, device=dev)
+    rows = torch.empty(3 * co * ci * 15 * planes, dtype=torch.int8, device=dev)
+    cols = torch.empty(3 * co * ci * 15 * planes, dtype=torch.int8, device=dev)
+    wscale = torch.empty(co, dtype=torch.float32, device=dev)
+    wexp = torch.empty(co, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().ss_pack_weights_folded(_ptr(w), co, ci, planes, _ptr(dense), _ptr(rows), _ptr(cols), _ptr(wscale), _ptr(wexp),
+                                                 _stream()), 'ss_pack_weights_folded')
+    return dense, rows, cols, wscale
+
+
+def pack_weights_folded_host(weight, planes):
+    """The same images derived on the host side of the C ABI (fold_weight_sets with torch ops, then ss_pack_digits_i8): the
+    executable specification of ss_pack_weights_folded (tests/test_gpu_parity.py::test_fold_pack_kernel_matches_host_derivation)."""
     _, dense, rows, cols, e = fold_weight_sets(weight, planes)
     co, ci = int(weight.shape[0]), int(weight.shape[1])
 

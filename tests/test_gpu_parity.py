@@ -172,6 +172,25 @@ def test_folded_upsampled_conv_is_bit_identical(Hin, Win, up, Cin, Cout, T, B):
     assert plan.covered > (0.9 if Hin >= 100 else 0.3)
 
 
+@pytest.mark.parametrize('co,ci,planes', [(64, 64, 3), (32, 128, 3), (64, 32, 2)])
+def test_fold_pack_kernel_matches_host_derivation(co, ci, planes):
+    """ss_pack_weights_folded (one launch, used every training step) writes exactly the images of the host-side derivation
+    (ops.fold_weight_sets with torch ops + ss_pack_digits_i8): same exponents, same folded integers, same layout."""
+    from stereospike_b200 import ops
+    g = torch.Generator().manual_seed(co + ci)
+    w = (torch.rand(co, ci, 5, 5, generator=g) * 2 - 1) / 30.0
+    w[1] = 0.0                                   # a dead output channel
+    w[2] = w[2].abs() * 0.999 + 1e-3             # all taps positive and near the maximum: the sums need the extra head-room bits
+    w[3, :, :, :] = 0.03125                      # every tap exactly a power of two
+    w[4] *= torch.logspace(-6, 0, ci).view(ci, 1, 1)
+    w = w.cuda()
+    got = ops.pack_weights_folded(w, planes)
+    want = ops.pack_weights_folded_host(w, planes)
+    for name, a, b in zip(('dense', 'rows', 'cols', 'wscale'), got, want):
+        assert a.shape == b.shape and a.dtype == b.dtype, name
+        assert torch.equal(a, b), (name, int((a != b).sum()))
+
+
 def test_empty_batch_and_bad_arguments():
     from stereospike_b200 import ops, _lib
     geom, x, w = _mk_block(1, 1)

@@ -44,10 +44,16 @@ constexpr int TAPS_NT = 128;
 // one thread per (head, t, b, sy, sx): nine dots over the channels
 __global__ void __launch_bounds__(TAPS_NT) head_taps_kernel(const HeadsParams p) {
     extern __shared__ float wsm[];  // concatenated [9][C_i] weights of the four heads
-    for (int i = 0; i < 4; ++i)
+    // only the heads this block's pixels belong to (pixels are ordered by head, so that is one head for all but three blocks):
+    // loading all four weight sets (17 KB) per 128 pixels cost as much as the dots themselves
+    const long long g_first = (long long)blockIdx.x * TAPS_NT;
+    const long long g_last = min(g_first + TAPS_NT, p.pix_begin[4]) - 1;
+    for (int i = 0; i < 4; ++i) {
+        if (g_last < p.pix_begin[i] || g_first >= p.pix_begin[i + 1]) continue;
         for (int j = threadIdx.x; j < 9 * p.C[i]; j += TAPS_NT) wsm[p.woff[i] + j] = __ldg(p.w[i] + j);
+    }
     __syncthreads();
-    const long long gid = (long long)blockIdx.x * TAPS_NT + threadIdx.x;
+    const long long gid = g_first + threadIdx.x;
     if (gid >= p.pix_begin[4]) return;
     int hd = 0;
 #pragma unroll

@@ -478,15 +478,25 @@ __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, 
                     for (int e = 0; e < 8; ++e) acc[GW ? k : 0][e] = fmaf(b0[k], asum[e], acc[GW ? k : 0][e]);
             }
         }
-        if (GW) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k)
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if (acc[GW ? k : 0][e] != 0.0f) atomicAdd(&gws[k * C + c0 + e], acc[GW ? k : 0][e]);
-        }
     }
     if (GW) {
+        // block reduction of the 9 x 8 partials: lanes that share a channel group (lane % c8n) are folded with shuffles first, so
+        // that one lane per group and warp reaches shared memory -- 256 threads x 72 atomics on 72 * c8n addresses (64-way
+        // conflicts at C = 32) were 0.1 ms per block, most of this kernel
+        const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float v = acc[GW ? k : 0][e];
+                if (pow2) {
+                    for (int o = c8n; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane < c8n && v != 0.0f) atomicAdd(&gws[k * C + c0 + e], v);
+                } else if (pl < lanes && v != 0.0f) {
+                    atomicAdd(&gws[k * C + c0 + e], v);
+                }
+            }
         __syncthreads();
         for (int j = threadIdx.x; j < 9 * C; j += blockDim.x)
             if (gws[j] != 0.0f) atomicAdd(p.g_w[head] + j, gws[j]);
@@ -641,8 +651,10 @@ extern "C" int ss_heads_bwd(const ss_heads_args* a, const float* g_depths, float
             return SS_EUNSUPPORTED;
         }
         const long long S = (long long)p.B * p.Hs[i] * p.Ws[i];
+        // weight-gradient pass: one resident wave (128 registers x 256 threads = 2 blocks per SM) -- every block ends with 9*C
+        // global atomics on the same addresses, so more blocks only add contention (0.1 ms per head at 8 blocks per SM)
         long long blocks = (S + lanes - 1) / lanes;
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > 148 * 2) blocks = 148 * 2;
         const size_t smem = (size_t)18 * p.C[i] * sizeof(float);
         long long blocks_a = (S + lanes - 1) / lanes;
         if (blocks_a > 148 * 32) blocks_a = 148 * 32;

@@ -1,7 +1,11 @@
 export PYTHONPATH=.
-timeout 900 python -m pytest tests -m gpu -x -q -k "gradients or golden or standalone or fold or penal or firing" 2>&1 | tail -6
-timeout 600 python bench.py --mode train --batch 16 --steps 10 --warmup 3 --no-cpu-baseline --no-extras --no-parity > gpurun_out/r2ah_train.json 2> gpurun_out/r2ah_err.log
-tail -2 gpurun_out/r2ah_err.log
-python -c "
+timeout 900 python -m pytest tests -m gpu -x -q -k "bit_identical or first_layer or teacher_forced" 2>&1 | tail -8
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-parity --no-train > gpurun_out/r2ai_bench.json 2> gpurun_out/r2ai_err.log
+SS_EPW16=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-parity --no-train > gpurun_out/r2ai_bench_epw8.json 2>> gpurun_out/r2ai_err.log
+python - <<'P'
 import json
-d=json.loads(open('gpurun_out/r2ah_train.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
+for f in ('gpurun_out/r2ai_bench.json','gpurun_out/r2ai_bench_epw8.json'):
+    d=json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])
+    print(d['roofline']['per_block_ms'])
+P

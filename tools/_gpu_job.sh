@@ -1,11 +1,14 @@
 export PYTHONPATH=.
-timeout 900 python -m pytest tests -m gpu -x -q -k "bit_identical or first_layer or teacher_forced" 2>&1 | tail -8
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-parity --no-train > gpurun_out/r2ai_bench.json 2> gpurun_out/r2ai_err.log
-SS_EPW16=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-parity --no-train > gpurun_out/r2ai_bench_epw8.json 2>> gpurun_out/r2ai_err.log
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2aj_bench.json 2> gpurun_out/r2aj_err.log
+tail -2 gpurun_out/r2aj_err.log
 python - <<'P'
 import json
-for f in ('gpurun_out/r2ai_bench.json','gpurun_out/r2ai_bench_epw8.json'):
-    d=json.loads(open(f).read().strip().splitlines()[-1])
-    print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])
-    print(d['roofline']['per_block_ms'])
+d=json.loads(open('gpurun_out/r2aj_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['traffic'], d['gpu_launches'])
+print(d['roofline']['per_block_ms'])
+print(d['train']['ms_per_step'], d['train']['value'], d['parity']['mde_abs_diff'], d['parity']['teacher_forced'])
+print(d['timestep_sweep']['results'])
+print(d['sj_cupy_proxy']['speedup_vs_fp32'], d['sj_cupy_proxy']['speedup_vs_tf32_allowed'], d['cpu_baseline']['value'], d['clocks'])
 P

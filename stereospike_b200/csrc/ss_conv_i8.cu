@@ -230,13 +230,9 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // tile rows are arbitrary (sample, output row) entries with ROWSTEP private source rows each (patch row = ROWSTEP * tile row + ky).
 // NK: neuron kind fixed at compile time (and v_reset == 0), -1 = run-time switch.  The epilogue is instruction-issue bound on the
 // full-resolution blocks; the generic version executes the other kinds' arithmetic predicated off (~25 % of its instructions).
-// EPW: epilogue warps, 8 (16 output channels per thread) or 16 (8 channels per thread, 768 threads per CTA).  An epilogue warp issues
-// one instruction every ~4.5 cycles (dependent-issue latency: 382 instructions and 1715 cycles per tile-step at EPW = 8, IPC 0.44 per
-// scheduler with its two epilogue warps -- ncu source view of the first layer), so the most epilogue-bound block, the first layer,
-// gets twice the warps with half the channels (and half the registers) each.
 template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false, int KSX = KS, int ROWSTEP = 1,
-          int NK = -1, int EPW = 8>
-__global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid_constant__ I8Params p) {
+          int NK = -1>
+__global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_constant__ I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
     constexpr int cNTAPS = KS * KSX;
@@ -245,8 +241,6 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
     constexpr int cPH = ROWSTEP > 1 ? 16 * ROWSTEP : 15 * STRIDE + KS;
     static_assert(ROWSTEP == 1 || (STRIDE == 1 && ROWSTEP >= KS && !FIRST && !PAIR && MODE == MODE_I8), "row-list pass: stride-1 int8 blocks");
     static_assert(cPH <= 48 && cPWp <= 24, "geometry tables");
-    static_assert(EPW == 8 || (EPW == 16 && MODE == MODE_I8 && !PAIR), "16 epilogue warps: single-CTA int8 forward blocks");
-    constexpr int ECH = 128 / EPW;                           // output channels per epilogue thread
     constexpr int cPPIX = cPH * cPWp;                        // pixels of the patch that carry data
     constexpr int cPLANE = plane_pixels(cPH, cPWhalf);       // stride 2: pixels per parity plane (padded)
     constexpr int cPALLOC = STRIDE == 1 ? cPPIX : 2 * cPLANE;
@@ -302,7 +296,7 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
         }
         for (int s = 0; s < MAX_SLOTS; ++s) {
             mbar_init(bar_full_a + 8 * s, 1);
-            mbar_init(bar_empty_a + 8 * s, PAIR ? 2 * EPW : EPW);      // one arrival per epilogue warp (of both CTAs of a pair)
+            mbar_init(bar_empty_a + 8 * s, PAIR ? 16 : 8);      // one arrival per epilogue warp (of both CTAs of a pair)
         }
         mbar_init(bar_tok, 1);
         mbar_init(bar_tok + 8, 1);
@@ -935,22 +929,7 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
         const uint32_t empty_a_remote = PAIR ? mapa_u32(bar_empty_a, 0u) : 0u;
         SS_DECL();
         int sc_ntile = -1;
-        float sc[ECH];                // wscale * gain (wscale is a power of two, so this product is exact)
-        constexpr int EW = ECH / 4;   // 32-bit words of the thread's output bytes
-        // ECH-byte vector access (16 bytes, or 8 with 16 epilogue warps)
-        auto ld_bytes = [](const uint8_t* q, uint32_t (&w)[EW]) {
-            if constexpr (EW == 4) {
-                const uint4 r = __ldg(reinterpret_cast<const uint4*>(q));
-                w[0] = r.x; w[1] = r.y; w[2] = r.z; w[3] = r.w;
-            } else {
-                const uint2 r = __ldg(reinterpret_cast<const uint2*>(q));
-                w[0] = r.x; w[1] = r.y;
-            }
-        };
-        auto st_bytes = [](uint8_t* q, const uint32_t (&w)[EW]) {
-            if constexpr (EW == 4) *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
-            else *reinterpret_cast<uint2*>(q) = make_uint2(w[0], w[1]);
-        };
+        float sc[16];                 // wscale * gain (wscale is a power of two, so this product is exact)
         // firing statistics (SNN_models.py:194-245, loss.py:96-107) straight from the registers that hold the spikes: per thread
         // {spikes, nonzero outputs, sum out^2} over all steps [0..2] and over the last step [3..5]; one atomic per warp at the end
         uint32_t st[6] = {0u, 0u, 0u, 0u, 0u, 0u};
@@ -984,21 +963,17 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
                 live = live && b < p.B && oy < p.Hout && ox < p.Wout;
                 if (live) pix = (size_t)(b * p.Hout + oy) * p.Wout + ox;
             }
-            const int nb = (wset / p.nclass) * 32 + hf * ECH;
+            const int nb = (wset / p.nclass) * 32 + hf * 16;
             const size_t o0 = pix * p.Cout + nb;                  // element offset inside one timestep
             const bool use_resid = p.resid != nullptr && live;
-            uint32_t rs_next[EW];
-#pragma unroll
-            for (int q = 0; q < EW; ++q) rs_next[q] = 0u;
-            if (use_resid) ld_bytes(p.resid + o0, rs_next);
-            uint32_t ts[EW];                     // running byte-wise sum of the first T-1 output steps (feeds the linear heads)
-#pragma unroll
-            for (int q = 0; q < EW; ++q) ts[q] = 0u;
-            float v[ECH];
+            uint4 rs_next = make_uint4(0u, 0u, 0u, 0u);
+            if (use_resid) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + o0));
+            uint32_t ts[4] = {0u, 0u, 0u, 0u};   // running byte-wise sum of the first T-1 output steps (feeds the linear heads)
+            float v[16];
             if (ntile != sc_ntile) {
                 sc_ntile = ntile;
 #pragma unroll
-                for (int i = 0; i < EW; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     const float4 q = __ldg(reinterpret_cast<const float4*>(p.wscale + nb) + i);
                     sc[4 * i] = q.x * nc.gain; sc[4 * i + 1] = q.y * nc.gain; sc[4 * i + 2] = q.z * nc.gain; sc[4 * i + 3] = q.w * nc.gain;
                 }
@@ -1006,13 +981,13 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
             if (p.v_in != nullptr && live) {
                 const float4* vi = reinterpret_cast<const float4*>(p.v_in + o0);
 #pragma unroll
-                for (int i = 0; i < EW; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     const float4 q = __ldg(vi + i);
                     v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < ECH; ++i) v[i] = NK >= 0 ? 0.0f : p.v_reset;
+                for (int i = 0; i < 16; ++i) v[i] = NK >= 0 ? 0.0f : p.v_reset;
             }
             for (int t0 = 0; t0 < p.T; t0 += cTC) {
                 const int tc = min(cTC, p.T - t0);
@@ -1020,10 +995,8 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
                     const int t = t0 + s0;
                     const int s = (int)((sbase + (uint32_t)s0) % (uint32_t)cTC);
                     // residual of this step was requested one step ago; request the next one before blocking
-                    uint32_t rs_cur[EW];
-#pragma unroll
-                    for (int q = 0; q < EW; ++q) rs_cur[q] = rs_next[q];
-                    if (use_resid && t + 1 < p.T) ld_bytes(p.resid + (size_t)(t + 1) * t_out + o0, rs_next);
+                    const uint4 rs_cur = rs_next;
+                    if (use_resid && t + 1 < p.T) rs_next = __ldg(reinterpret_cast<const uint4*>(p.resid + (size_t)(t + 1) * t_out + o0));
                     {
                         SS_T0();
                         mbar_wait(bar_full_a + 8 * s, (slot_phase >> s) & 1u);
@@ -1031,13 +1004,10 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
                     }
                     slot_phase ^= 1u << s;
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * cN + hf * ECH);
-                    int d[PLANES][ECH];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * cN + hf * 16);
+                    int d[PLANES][16];
 #pragma unroll
-                    for (int pl = 0; pl < PLANES; ++pl) {
-                        if constexpr (ECH == 16) tmem_ld16(taddr + pl * 32, d[pl]);
-                        else tmem_ld8(taddr + pl * 32, d[pl]);
-                    }
+                    for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(taddr + pl * 32, d[pl]);
                     tmem_ld_wait();
                     tc_fence_before();
                     // the slot is in every lane's registers now: one lane hands it back to the MMA threads (rank 0's barrier for a
@@ -1048,9 +1018,9 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
                         else mbar_arrive(bar_empty_a + 8 * s);
                     }
                     if (!live) continue;
-                    float x[ECH];
+                    float x[16];
 #pragma unroll
-                    for (int i = 0; i < ECH; ++i) {
+                    for (int i = 0; i < 16; ++i) {
                         // recombine the base-256 digit planes exactly, round once to fp32, then scale and gain
                         float conv;
                         if (PLANES == 2) {
@@ -1065,56 +1035,54 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
                         }
                         x[i] = __fmul_rn(conv, sc[i]);   // == (conv * wscale) * gain: the first product is exact
                     }
-                    float hbuf[ECH];
-                    uint32_t sb[ECH];      // spike of each channel as 0 / 1
+                    float hbuf[16];
+                    uint32_t sb[16];      // spike of each channel as 0 / 1
                     if constexpr (NK >= 0) {
 #pragma unroll
-                        for (int i = 0; i < ECH; ++i) sb[i] = neuron_step_t<NK, true>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<NK, true>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     } else if (p.neuron == SS_NEURON_IF) {
 #pragma unroll
-                        for (int i = 0; i < ECH; ++i) sb[i] = neuron_step_t<SS_NEURON_IF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<SS_NEURON_IF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     } else if (p.neuron == SS_NEURON_LIF) {
 #pragma unroll
-                        for (int i = 0; i < ECH; ++i) sb[i] = neuron_step_t<SS_NEURON_LIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<SS_NEURON_LIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < ECH; ++i) sb[i] = neuron_step_t<SS_NEURON_PLIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
+                        for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<SS_NEURON_PLIF>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
                     }
-                    // ECH spikes -> ECH bytes (+ residual bytes; sums stay <= 3, no carry between bytes)
-                    uint32_t pk[EW];
+                    // 16 spikes -> 16 bytes (+ residual bytes; sums stay <= 3, no carry between bytes)
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int q = 0; q < EW; ++q)
+                    for (int q = 0; q < 4; ++q)
                         pk[q] = sb[4 * q] | (sb[4 * q + 1] << 8) | (sb[4 * q + 2] << 16) | (sb[4 * q + 3] << 24);
                     const size_t o = (size_t)t * t_out + o0;
                     uint32_t n_spk = 0u;
                     if (p.stats != nullptr) {
 #pragma unroll
-                        for (int q = 0; q < EW; ++q) n_spk = __dp4a(pk[q], 0x01010101u, n_spk);
+                        for (int q = 0; q < 4; ++q) n_spk = __dp4a(pk[q], 0x01010101u, n_spk);
                     }
-#pragma unroll
-                    for (int q = 0; q < EW; ++q) pk[q] += rs_cur[q];
+                    pk[0] += rs_cur.x; pk[1] += rs_cur.y; pk[2] += rs_cur.z; pk[3] += rs_cur.w;
                     if (p.stats != nullptr) {
                         uint32_t n_nz = 0u, n_sq = 0u;
 #pragma unroll
-                        for (int q = 0; q < EW; ++q) {
+                        for (int q = 0; q < 4; ++q) {
                             n_nz = __dp4a((pk[q] | (pk[q] >> 1)) & 0x01010101u, 0x01010101u, n_nz);   // bytes are 0..3
                             n_sq = __dp4a(pk[q], pk[q], n_sq);
                         }
                         st[0] += n_spk; st[1] += n_nz; st[2] += n_sq;
                         if (t + 1 == p.T) { st[3] += n_spk; st[4] += n_nz; st[5] += n_sq; }
                     }
-                    st_bytes(p.out + o, pk);
+                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     if (t + 1 < p.T) {
-#pragma unroll
-                        for (int q = 0; q < EW; ++q) ts[q] += pk[q];
+                        ts[0] += pk[0]; ts[1] += pk[1]; ts[2] += pk[2]; ts[3] += pk[3];
                     }
                     if (p.h_seq != nullptr) {
                         if (p.h_bf16) {
                             // bf16 copy for the surrogate backward: rounded to nearest, then moved one step back across the
                             // threshold if the rounding flipped the side -- the backward reads the spike (reset mask) off h >= v_th
-                            uint32_t hw[ECH / 2];
+                            uint32_t hw[8];
 #pragma unroll
-                            for (int i = 0; i < ECH; ++i) {
+                            for (int i = 0; i < 16; ++i) {
                                 uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hbuf[i]));
                                 const bool side = __uint_as_float(b << 16) >= nc.v_th;
                                 const bool fired = sb[i] != 0u;
@@ -1127,22 +1095,22 @@ __global__ void __launch_bounds__((8 + EPW) * 32, 1) conv_i8_kernel(const __grid
                                 else hw[i >> 1] = b & 0xFFFFu;
                             }
                             uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.h_seq) + o);
-#pragma unroll
-                            for (int i = 0; i < ECH / 8; ++i) hp[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+                            hp[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            hp[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
                         } else {
                             float4* hp = reinterpret_cast<float4*>(p.h_seq + o);
 #pragma unroll
-                            for (int i = 0; i < EW; ++i) hp[i] = make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]);
+                            for (int i = 0; i < 4; ++i) hp[i] = make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]);
                         }
                     }
                 }
                 sbase += (uint32_t)tc;
             }
-            if (p.tsum != nullptr && live) st_bytes(p.tsum + o0, ts);
+            if (p.tsum != nullptr && live) *reinterpret_cast<uint4*>(p.tsum + o0) = make_uint4(ts[0], ts[1], ts[2], ts[3]);
             if (p.v_out != nullptr && live) {
                 float4* vo = reinterpret_cast<float4*>(p.v_out + o0);
 #pragma unroll
-                for (int i = 0; i < EW; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
         }
         if (p.stats != nullptr) {
@@ -1913,29 +1881,6 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>, p);                            \
         launched = true;                                                                                                   \
     }
-    // 16 epilogue warps (768 threads) for the first layer, the most epilogue-bound block (4 MMAs per tile-step): -9 %.  On the other
-    // narrow blocks (<= 64 output channels: deconv1 / deconv2 dense passes, conv1) it measured neutral to +8 %, so they keep 8 --
-    // the epilogue is limited by dependent-issue latency inside each warp (issue slots 60 % busy, no pipe above 40 %), which
-    // more warps only partly hide.  SS_EPW16=0 keeps 8 everywhere.
-    static int epw16_env = -1;
-    if (epw16_env < 0) {
-        const char* e = getenv("SS_EPW16");
-        epw16_env = (e != nullptr && e[0] == '0') ? 0 : 1;
-    }
-    const bool wide = epw16_env != 0 && first && g->planes == 3 && g->v_reset == 0.0f && !pair && !rowlist;
-#define SS_TRY_WIDE(KS_, ST_, RB_, FIRST_, NK_)                                                                              \
-    if (!launched && wide && g->neuron == NK_ && first == FIRST_ && (FIRST_ || (g->ks == KS_ && g->stride == ST_ && p.RB == RB_))) { \
-        SS_ENSURE_SMEM((conv_i8_kernel<3, KS_, ST_, RB_, FIRST_, MODE_I8, false, KS_, 1, NK_, 16>), dev, 227 * 1024);        \
-        cfg.blockDim = dim3(768);                                                                                            \
-        cudaLaunchKernelEx(&cfg, conv_i8_kernel<3, KS_, ST_, RB_, FIRST_, MODE_I8, false, KS_, 1, NK_, 16>, p);              \
-        launched = true;                                                                                                     \
-    }
-#define SS_TRY_WIDE_NK(NK_) SS_TRY_WIDE(1, 1, 128, true, NK_)
-    SS_TRY_WIDE_NK(SS_NEURON_IF)
-    SS_TRY_WIDE_NK(SS_NEURON_LIF)
-    SS_TRY_WIDE_NK(SS_NEURON_PLIF)
-#undef SS_TRY_WIDE_NK
-#undef SS_TRY_WIDE
 #define SS_TRY_PL(PL) SS_TRY_ROWLIST(PL) SS_TRY_FIRST(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
     // default precision (3 planes), v_reset == 0 (every call site of the reference), no CTA pair: neuron kind compiled in
     const bool spec = !pair && !rowlist && !first && g->planes == 3 && g->v_reset == 0.0f;

@@ -172,12 +172,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // one elected lane of a converged warp (the compiler knows exactly one lane is active in the guarded region)
 __device__ __forceinline__ bool elect_one() {

@@ -550,8 +550,7 @@ def test_cta_pair_and_tma_kernels_are_bit_identical():
     """The cta_group::2 variant of the block kernel (two m-tiles per MMA, weights split between the CTAs of a 2-cluster) and the
     TMA-staged halo patches (cp.async.bulk.tensor instead of cp.async gathers) must produce exactly the same results as the
     single-CTA gather kernel.  The choices are made once per process from SS_PAIR / SS_TMA, so each setting runs in its own
-    interpreter: SS_PAIR=2 forces pairs wherever they are possible, SS_PAIR=0 forbids them; SS_TMA=0 forbids tensor maps;
-    SS_EPW16=0 keeps 8 epilogue warps on the blocks that otherwise run 16 (first layer, <= 64 output channels).
+    interpreter: SS_PAIR=2 forces pairs wherever they are possible, SS_PAIR=0 forbids them; SS_TMA=0 forbids tensor maps.
     (Integer accumulation is order-independent, so the forward blocks are bit-reproducible; the bf16 gradient kernels share the
     producer code but accumulate in fp32 and are only reproducible to the last bit or two -- tools/dgrad_determinism.py -- so they
     are checked against float64 autograd in test_gpu_grad_umma.py instead.)"""
@@ -587,7 +586,7 @@ for (kind, Cin, Cout, ks, Hin, Win, stride, pad, up, T, B) in [
     torch.cuda.synchronize()
     dig(name + ':fwd', out, v, hs)
     assert 0.01 < float(out.float().mean()) < 0.9
-# first layer: packed 4-channel event counts, im2col tile, epilogue-bound (16 epilogue warps by default)
+# first layer: packed 4-channel event counts, im2col tile
 g = torch.Generator().manual_seed(4)
 geom = ops.BlockGeom('conv', 4, 32, 5, 21, 27, 21, 27, 1, 2)
 x = torch.poisson(torch.full((3, 2, 21, 27, 4), 0.2), generator=g).clamp(max=255).to(torch.uint8).to(dev)
@@ -610,17 +609,16 @@ torch.cuda.synchronize()
 dig('folded', out, v, hs)
 '''
     results = []
-    # (SS_PAIR, SS_TMA, SS_EPW16): gathers / TMA patches x single CTA / pairs x 8 / 16 epilogue warps on the narrow blocks
-    modes = (('0', '0', '0'), ('2', '0', '0'), ('0', '1', '0'), ('2', '1', '1'), ('0', '0', '1'), ('0', '1', '1'))
-    for pair, tma, epw in modes:
-        env = dict(os.environ, SS_PAIR=pair, SS_TMA=tma, SS_EPW16=epw, PYTHONPATH=ROOT)
+    modes = (('0', '0'), ('2', '0'), ('0', '1'), ('2', '1'))       # (SS_PAIR, SS_TMA): gathers / TMA patches x single CTA / pairs
+    for pair, tma in modes:
+        env = dict(os.environ, SS_PAIR=pair, SS_TMA=tma, PYTHONPATH=ROOT)
         r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         results.append([ln for ln in r.stdout.splitlines() if ln.startswith('DIGEST')])
     assert len(results[0]) == 11
-    for (pair, tma, epw), res in zip(modes[1:], results[1:]):
+    for (pair, tma), res in zip(modes[1:], results[1:]):
         diff = [(a, b) for a, b in zip(results[0], res) if a != b]
-        assert not diff and len(res) == len(results[0]), (f'SS_PAIR={pair} SS_TMA={tma} SS_EPW16={epw}', diff)
+        assert not diff and len(res) == len(results[0]), (f'SS_PAIR={pair} SS_TMA={tma}', diff)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -168,9 +168,6 @@ typedef struct ss_tile_maps {
     uint64_t* stats;       /* any mode, optional: [6] counters this launch ADDS to -- {spikes fired, nonzero outputs (spikes + skip),
                               sum of outputs^2} over all T steps, then the same three over the last step only.  The firing rates of
                               SNN_models.py:194-245 and the spike penalty of loss.py:96-107 without a pass over the spike maps. */
-    int32_t h_bf16;        /* any mode: != 0: h_seq points at bf16 storage (same shape) instead of fp32 -- the copy the surrogate
-                              backward reads (ss_neuron_bwd_h16); rounded to nearest but never across v_th */
-    int32_t reserved;
 } ss_tile_maps;
 int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
                       const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,
@@ -270,11 +267,6 @@ int ss_neuron_bwd_ex(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, fl
                      float v_th, float v_reset, float tau, const float* decay, const float* h_seq,
                      const float* v_init, const float* g_s, const float* g_v_last, float* g_acc, void* g_acc_bf16,
                      float* g_v_init, float* g_decay, void* stream);
-/* Same as ss_neuron_bwd_ex with the saved potentials in bf16 (ss_tile_maps.h_bf16): 8 instead of 10 bytes per neuron step. */
-int ss_neuron_bwd_h16(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain,
-                      float v_th, float v_reset, float tau, const float* decay, const void* h_seq_bf16,
-                      const float* v_init, const float* g_s, const float* g_v_last, float* g_acc, void* g_acc_bf16,
-                      float* g_v_init, float* g_decay, void* stream);
 
 /* Convolution gradients of the fused block (replaces cuDNN dgrad / wgrad and upsample_nearest2d_backward
  * reached through autograd; the (ymap, xmap) tables fold the upsampling into the gather / scatter).

@@ -16,7 +16,7 @@ SS_IMPL_AUTO, SS_IMPL_SIMT, SS_IMPL_UMMA = 0, 1, 2
 
 # every symbol include/stereospike_b200.h declares (tests/test_cabi_symbols.py checks header == this == .so)
 SYMBOLS = ('ss_events_accumulate', 'ss_events_pack', 'ss_conv_i8_fwd', 'ss_conv_i8_fwd_ex', 'ss_pack_digits_i8', 'ss_pack_digits_i8_rect', 'ss_pack_weights_folded', 'ss_conv_i8_rowbytes', 'ss_pack_weights_i8', 'ss_pack_events', 'ss_pack_events_c', 'ss_conv_neuron_fwd',
-           'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_neuron_bwd_ex', 'ss_neuron_bwd_h16', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
+           'ss_heads_fwd', 'ss_neuron_fwd', 'ss_neuron_bwd', 'ss_neuron_bwd_ex', 'ss_conv_dgrad', 'ss_conv_wgrad', 'ss_heads_bwd',
            'ss_pack_weights_bf16', 'ss_corr_bf16', 'ss_conv_wgrad_bf16', 'ss_loss_fwd', 'ss_loss_bwd',
            'ss_abi_version', 'ss_last_error', 'ss_launch_count')
 
@@ -34,8 +34,7 @@ class BlockDesc(ctypes.Structure):
 class TileMaps(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('nclass', ctypes.c_int32), ('rl_n', ctypes.c_int32), ('transposed', ctypes.c_int32),
                 ('ymap_out', ctypes.c_void_p), ('xmap_out', ctypes.c_void_p), ('rl_src', ctypes.c_void_p),
-                ('rl_out', ctypes.c_void_p), ('rl_collive', ctypes.c_void_p), ('stats', ctypes.c_void_p),
-                ('h_bf16', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('rl_out', ctypes.c_void_p), ('rl_collive', ctypes.c_void_p), ('stats', ctypes.c_void_p)]
 
 
 SS_TILES_PLAIN, SS_TILES_FOLDED, SS_TILES_ROW_LIST = 0, 1, 2
@@ -121,8 +120,6 @@ def lib():
     L.ss_neuron_bwd.restype = ctypes.c_int
     L.ss_neuron_bwd_ex.argtypes = [i32, i64, i32, i32, f32, f32, f32, f32, f32] + [vp] * 10
     L.ss_neuron_bwd_ex.restype = ctypes.c_int
-    L.ss_neuron_bwd_h16.argtypes = [i32, i64, i32, i32, f32, f32, f32, f32, f32] + [vp] * 10
-    L.ss_neuron_bwd_h16.restype = ctypes.c_int
     L.ss_pack_weights_bf16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.ss_pack_weights_bf16.restype = ctypes.c_int
     L.ss_corr_bf16.argtypes = [ctypes.POINTER(CorrDesc)] + [vp] * 6

@@ -22,10 +22,10 @@ __device__ __forceinline__ float surrogate_grad(int kind, float alpha, float u) 
 }
 
 // One thread scans VEC consecutive neurons (VEC = 4: 16-byte loads of h and g_s, 8-byte bf16 stores) backwards in time.
-template <int VEC, typename HT = float>
+template <int VEC>
 __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int neuron, int surrogate, float alpha,
                                                          float gain, float v_th, float v_reset, float tau,
-                                                         const float* __restrict__ decay_p, const HT* __restrict__ h_seq,
+                                                         const float* __restrict__ decay_p, const float* __restrict__ h_seq,
                                                          const float* __restrict__ v_init, const float* g_s,
                                                          const float* __restrict__ g_v_last, float* g_acc,
                                                          __nv_bfloat16* __restrict__ g_acc_bf16, float* __restrict__ g_v_init,
@@ -48,25 +48,13 @@ __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int
         };
 #pragma unroll
         for (int i = 0; i < VEC; ++i) g_v[i] = 0.0f;
-        // saved potentials: fp32, or bf16 (8-byte loads of 4)
-        auto load_h = [&](const HT* src, float (&dst)[VEC]) {
-            if constexpr (sizeof(HT) == 4) {
-                load(reinterpret_cast<const float*>(src), dst);
-            } else if constexpr (VEC == 4) {
-                const uint2 q = *reinterpret_cast<const uint2*>(src);
-                dst[0] = __uint_as_float(q.x << 16); dst[1] = __uint_as_float(q.x & 0xFFFF0000u);
-                dst[2] = __uint_as_float(q.y << 16); dst[VEC - 1] = __uint_as_float(q.y & 0xFFFF0000u);
-            } else {
-                dst[0] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src));
-            }
-        };
         if (g_v_last != nullptr) load(g_v_last + n, g_v);
-        load_h(h_seq + (size_t)(T - 1) * N + n, h);
+        load(h_seq + (size_t)(T - 1) * N + n, h);
         for (int t = T - 1; t >= 0; --t) {
             // potential before this step: reset(h_{t-1}) or the initial state
             float v_prev[VEC];
             if (t > 0) {
-                load_h(h_seq + (size_t)(t - 1) * N + n, h_prev);
+                load(h_seq + (size_t)(t - 1) * N + n, h_prev);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) v_prev[i] = (h_prev[i] - v_th >= 0.0f) ? v_reset : h_prev[i];
             } else {
@@ -534,10 +522,10 @@ int fill_params(const ss_conv_geom* g, ConvParams& p) {
 
 using namespace ss;
 
-template <typename HT>
-static int neuron_bwd_launch(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th, float v_reset,
-                             float tau, const float* decay, const HT* h_seq, const float* v_init, const float* g_s,
-                             const float* g_v_last, float* g_acc, void* g_acc_bf16, float* g_v_init, float* g_decay, void* stream) {
+extern "C" int ss_neuron_bwd_ex(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,
+                                float v_reset, float tau, const float* decay, const float* h_seq, const float* v_init,
+                                const float* g_s, const float* g_v_last, float* g_acc, void* g_acc_bf16, float* g_v_init,
+                                float* g_decay, void* stream) {
     if (h_seq == nullptr || g_s == nullptr || (g_acc == nullptr && g_acc_bf16 == nullptr) || T < 0 || N < 0) {
         set_error("ss_neuron_bwd: bad argument");
         return SS_EINVAL;
@@ -551,33 +539,16 @@ static int neuron_bwd_launch(int32_t T, int64_t N, int32_t neuron, int32_t surro
     if (N % 4 == 0 && aligned16(h_seq) && aligned16(g_s) && aligned16(g_acc) && aligned16(g_acc_bf16) && aligned16(v_init) &&
         aligned16(g_v_last) && aligned16(g_v_init)) {
         const long long nt = N / 4;
-        neuron_bwd_kernel<4, HT><<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        neuron_bwd_kernel<4><<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
             T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
             reinterpret_cast<__nv_bfloat16*>(g_acc_bf16), g_v_init, g_decay);
     } else {
-        neuron_bwd_kernel<1, HT><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        neuron_bwd_kernel<1><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
             T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
             reinterpret_cast<__nv_bfloat16*>(g_acc_bf16), g_v_init, g_decay);
     }
     count_launch();
     return check_launch("neuron_bwd");
-}
-
-extern "C" int ss_neuron_bwd_ex(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,
-                                float v_reset, float tau, const float* decay, const float* h_seq, const float* v_init,
-                                const float* g_s, const float* g_v_last, float* g_acc, void* g_acc_bf16, float* g_v_init,
-                                float* g_decay, void* stream) {
-    return neuron_bwd_launch<float>(T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay, h_seq, v_init, g_s, g_v_last, g_acc,
-                                    g_acc_bf16, g_v_init, g_decay, stream);
-}
-
-extern "C" int ss_neuron_bwd_h16(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,
-                                 float v_reset, float tau, const float* decay, const void* h_seq_bf16, const float* v_init,
-                                 const float* g_s, const float* g_v_last, float* g_acc, void* g_acc_bf16, float* g_v_init,
-                                 float* g_decay, void* stream) {
-    return neuron_bwd_launch<__nv_bfloat16>(T, N, neuron, surrogate, alpha, gain, v_th, v_reset, tau, decay,
-                                            reinterpret_cast<const __nv_bfloat16*>(h_seq_bf16), v_init, g_s, g_v_last, g_acc, g_acc_bf16,
-                                            g_v_init, g_decay, stream);
 }
 
 extern "C" int ss_neuron_bwd(int32_t T, int64_t N, int32_t neuron, int32_t surrogate, float alpha, float gain, float v_th,

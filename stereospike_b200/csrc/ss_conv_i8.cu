@@ -98,7 +98,6 @@ struct I8Params {
     const uint8_t* resid;
     uint8_t* out;
     float* h_seq;
-    int h_bf16;            // 1: h_seq points at bf16 storage [T][B][Hout][Wout][Cout] (training: half the write / read traffic)
     uint8_t* tsum;
     unsigned long long* stats;   // optional [6]: {spikes, nonzero outputs, sum of out^2} over all steps, then over the last step
     float* g_dst;          // MODE_BF16 (gradient-side correlation): fp32 NHWC destination [T][B][Hout][Wout][Cout]
@@ -1077,31 +1076,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                         ts[0] += pk[0]; ts[1] += pk[1]; ts[2] += pk[2]; ts[3] += pk[3];
                     }
                     if (p.h_seq != nullptr) {
-                        if (p.h_bf16) {
-                            // bf16 copy for the surrogate backward: rounded to nearest, then moved one step back across the
-                            // threshold if the rounding flipped the side -- the backward reads the spike (reset mask) off h >= v_th
-                            uint32_t hw[8];
+                        float4* hp = reinterpret_cast<float4*>(p.h_seq + o);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hbuf[i]));
-                                const bool side = __uint_as_float(b << 16) >= nc.v_th;
-                                const bool fired = sb[i] != 0u;
-                                if (side != fired) {
-                                    const bool neg = (b & 0x8000u) != 0u;
-                                    // fired: towards +inf, not fired: towards -inf (bit pattern +-1, direction depends on the sign)
-                                    b = (fired != neg) ? b + 1u : (b == 0u ? 0x8001u : b - 1u);
-                                }
-                                if (i & 1) hw[i >> 1] |= b << 16;
-                                else hw[i >> 1] = b & 0xFFFFu;
-                            }
-                            uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.h_seq) + o);
-                            hp[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            hp[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                        } else {
-                            float4* hp = reinterpret_cast<float4*>(p.h_seq + o);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) hp[i] = make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]);
-                        }
+                        for (int i = 0; i < 4; ++i) hp[i] = make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]);
                     }
                 }
                 sbase += (uint32_t)tc;
@@ -1824,7 +1801,6 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.h_seq = h_seq;
     p.tsum = reinterpret_cast<uint8_t*>(tsum);
     p.stats = tm != nullptr ? reinterpret_cast<unsigned long long*>(tm->stats) : nullptr;
-    p.h_bf16 = (tm != nullptr && tm->h_bf16 != 0) ? 1 : 0;
     p.tma = 0;
     if (!first && !up && !rowlist) setup_tma(p, x, (long long)g->T * g->B, g->Hin, g->Win, g->Cin, p.RB, g->stride, g->ks, p.pad);
 

@@ -164,8 +164,6 @@ class Engine:
         #                             less weight precision).  True / False, or a collection of site names ('deconv4', ...)
         self.flop_scale = {}        # site -> executed taps / 25 of the folded blocks of the last forward (bench.py credits these FLOPs)
         self.bwd_impl = 'umma'      # gradients of the convs: 'umma' = bf16 tensor cores (fp32 accumulation), 'simt' = fp32 CUDA cores
-        self.h_bf16 = True          # training on the tensor-core path: the saved pre-reset potentials (read only by the surrogate scan) as
-        #                             bf16, never rounded across the threshold -- 2 instead of 4 bytes per neuron step written and read
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
         #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
 
@@ -320,15 +318,13 @@ class Engine:
                 if s.out in head_srcs and self.heads_time_sum and 1 < T <= 86:
                     tsum = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=ops.ACT_DTYPE, device=dev)
                     tsums[s.out] = tsum
-                hb = bool(want_h and self.h_bf16 and self.bwd_impl == 'umma')
                 if fold:
                     out, v_out, h_seq = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], w_i8[3], planes=self.weight_planes,
-                                                               tsum=tsum, stats=stats[i] if stats is not None else None, h_bf16=hb,
-                                                               **common)
+                                                               tsum=tsum, stats=stats[i] if stats is not None else None, **common)
                 else:
                     out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
                                                         cin=ops.first_layer_channels(g.Cin) if first else g.Cin, tsum=tsum,
-                                                        stats=stats[i] if stats is not None else None, h_bf16=hb, **common)
+                                                        stats=stats[i] if stats is not None else None, **common)
             else:
                 out, v_out, h_seq = ops.conv_neuron_fwd(xin, g, w_kn, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC,
                                                         **common)
@@ -464,8 +460,7 @@ class Engine:
             decay = sv['decay']
             g_decay = torch.zeros((1,), dtype=torch.float32, device=dev) if decay is not None else None
             sf = node.surrogate_function
-            scan = L.ss_neuron_bwd_h16 if sv['h_seq'].dtype == torch.bfloat16 else L.ss_neuron_bwd_ex
-            rc = scan(T, N, node.kind, sf.kind, sf.alpha, s.gain_mod.gain(), node.v_threshold, node.v_reset,
+            rc = L.ss_neuron_bwd_ex(T, N, node.kind, sf.kind, sf.alpha, s.gain_mod.gain(), node.v_threshold, node.v_reset,
                                     node._tau_value(), _ptr(decay), _ptr(sv['h_seq']), _ptr(sv['v_in']), _ptr(g_out), None,
                                     _ptr(g_acc), _ptr(g_b16), None, _ptr(g_decay), _stream())
             _lib.check(rc, 'ss_neuron_bwd')

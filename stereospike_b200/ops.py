@@ -301,22 +301,16 @@ def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
 # ----------------------------------------------------------------------------------------- fused block
 def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau=2.0, decay=None, v_in=None,
                 want_v_out=False, resid=None, want_h=False, planes=3, cin=None, tsum=None, outputs=None, tile_maps=None,
-                desc_override=None, stats=None, h_bf16=False):
+                desc_override=None, stats=None):
     """Tensor-core fused block over all T timesteps (ss_conv_i8_fwd).  x: u8 [T,B,Hin,Win,Cin].
     ``tsum``: optional u8 [B,Hout,Wout,Cout] receiving the sum of the first T-1 output steps (input of the linear heads).
     ``stats``: optional int64 [6] device tensor the launch ADDS its firing statistics to ({spikes, nonzero outputs, sum out^2} over
     all steps, then over the last step).
-    ``h_bf16``: h_seq (the pre-reset potentials the surrogate backward reads) as bf16 instead of fp32.
     Returns (out u8 [T,B,Hout,Wout,Cout], v_out, h_seq)."""
     _require_cuda(x, 'x')
     dev = x.device
     g = geom
     cin = g.Cin if cin is None else cin
-    if h_bf16 and (want_h or outputs is not None):
-        if tile_maps is None:
-            tile_maps = _lib.TileMaps(mode=_lib.SS_TILES_PLAIN, nclass=1, rl_n=0, transposed=0, ymap_out=0, xmap_out=0, rl_src=0,
-                                      rl_out=0, rl_collive=0, stats=0, h_bf16=0, reserved=0)
-        tile_maps.h_bf16 = 1
     if stats is not None:
         assert stats.dtype == torch.int64 and stats.numel() == 6 and stats.is_contiguous() and stats.is_cuda
         if tile_maps is None:
@@ -331,9 +325,7 @@ def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau
     else:
         out = torch.empty(out_shape, dtype=ACT_DTYPE, device=dev)
         v_out = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=torch.float32, device=dev) if want_v_out else None
-        h_seq = torch.empty(out_shape, dtype=torch.bfloat16 if h_bf16 else torch.float32, device=dev) if want_h else None
-    if h_seq is not None:
-        assert h_seq.dtype == (torch.bfloat16 if h_bf16 else torch.float32)
+        h_seq = torch.empty(out_shape, dtype=torch.float32, device=dev) if want_h else None
     _check_block_io(x, g, T, B, resid, v_in, decay, out_shape)
     d = _lib.BlockDesc(T=T, B=B, Hin=g.Hin, Win=g.Win, Cin=cin, Hout=g.Hout, Wout=g.Wout, Cout=g.Cout, ks=g.ks,
                        stride=g.stride, pad=g.pad, upsample=1 if g.kind == 'upconv' else 0, neuron=neuron, planes=planes,

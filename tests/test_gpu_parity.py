@@ -191,28 +191,6 @@ def test_fold_pack_kernel_matches_host_derivation(co, ci, planes):
         assert torch.equal(a, b), (name, int((a != b).sum()))
 
 
-def test_bf16_saved_potentials_never_cross_the_threshold():
-    """h_bf16: the copy of the pre-reset potentials kept for the surrogate backward is the fp32 value rounded to bf16, except
-    that it never lands on the other side of v_th (the backward reads the spike / reset mask off h >= v_th)."""
-    from stereospike_b200 import ops
-    dev = torch.device('cuda')
-    g = torch.Generator().manual_seed(9)
-    geom = ops.BlockGeom('conv', 64, 64, 3, 17, 22, 17, 22, 1, 1)
-    x = (torch.rand(4, 3, 17, 22, 64, generator=g) < 0.2).to(torch.uint8).to(dev)
-    w = ((torch.rand(64, 64, 3, 3, generator=g) * 2 - 1) / 24.0).to(dev)
-    q, sc, _ = ops.pack_weights_i8(w, 3)
-    kw = dict(T=4, B=3, neuron=1, gain=12.0, v_th=1.0, v_reset=0.0, tau=3.0, want_h=True)
-    out32, _, h32 = ops.conv_i8_fwd(x, geom, q, sc, **kw)
-    out16, _, h16 = ops.conv_i8_fwd(x, geom, q, sc, h_bf16=True, **kw)
-    assert h16.dtype == torch.bfloat16 and torch.equal(out32, out16)
-    hf = h16.float()
-    assert torch.equal(hf >= 1.0, h32 >= 1.0)                      # same spikes read back from either copy
-    assert torch.equal(h32 >= 1.0, out32 > 0)
-    rel = (hf - h32).abs() / h32.abs().clamp_min(1e-3)
-    assert float(rel.max()) <= 2.0 ** -7                            # within one bf16 step (half a step unless moved off the threshold)
-    assert float((hf != h32.bfloat16().float()).float().mean()) < 0.01   # ... and plain round-to-nearest almost everywhere
-
-
 def test_empty_batch_and_bad_arguments():
     from stereospike_b200 import ops, _lib
     geom, x, w = _mk_block(1, 1)

@@ -162,6 +162,7 @@ class Engine:
         self.fold_upsample = True   # NNConvUpsampling blocks folded: four 3x3 convs on the source for the regular outputs + two small
         #                             passes for the irregular rows / columns (9 / 15 taps instead of 25, bit-identical integers, 3-4 bits
         #                             less weight precision).  True / False, or a collection of site names ('deconv4', ...)
+        self.fold_min_frames = 16   # ... for calls of at least this many event frames (B * T); smaller calls are launch-latency-bound
         self.flop_scale = {}        # site -> executed taps / 25 of the folded blocks of the last forward (bench.py credits these FLOPs)
         self.bwd_impl = 'umma'      # gradients of the convs: 'umma' = bf16 tensor cores (fp32 accumulation), 'simt' = fp32 CUDA cores
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
@@ -288,8 +289,10 @@ class Engine:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
             use_i8 = impl != SS_IMPL_SIMT
             # (also while training: ss_pack_weights_folded re-derives the folded sets from the updated weight in one launch)
+            # (not for a handful of frames: the two extra row-list launches per block cost more than the taps they save --
+            #  single-frame graph replay 0.28 ms folded vs 0.21 ms unfolded)
             fold = use_i8 and self._fold_site(s.name) and self.weight_planes <= 3 and g.kind == 'upconv' and g.ks == 5 and \
-                g.Cin % 32 == 0 and ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
+                g.Cin % 32 == 0 and B * T >= self.fold_min_frames and ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
             if fold:
                 self.flop_scale[s.name] = ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).taps_per_output / 25.0
             else:

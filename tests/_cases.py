@@ -311,7 +311,7 @@ def parity_summary(variant='lif', gain=15.0, tau=3.0, T=5, B=1, seed=0, planes=3
     from oracle import ref_model as rm, sj_compat as sj
     import stereospike_b200 as sb
     o, n = build_pair(variant, False, gain, tau, seed, planes)
-    n.set_kernel_options(fold_upsample=bool(fold))
+    n.set_kernel_options(fold_upsample=bool(fold), fold_min_frames=1)      # the slice runs the kernels of the benchmarked batch
     x = rm.synthetic_inputs(B, T, 4, seed=x_seed)
     label = rm.synthetic_label(B, seed=x_seed + 1)
     sj.reset_net(o)

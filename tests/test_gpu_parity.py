@@ -390,7 +390,7 @@ def test_folded_decoder_model_matches_unfolded():
         net.set_kernel_options(fold_upsample=False)
         sb.functional.reset_net(net)
         d0, s0 = net.forward_seq(x)
-        net.set_kernel_options(fold_upsample=True)
+        net.set_kernel_options(fold_upsample=True, fold_min_frames=1)
         sb.functional.reset_net(net)
         d1, s1 = net.forward_seq(x)
         assert set(net.engine.flop_scale) == {'deconv4', 'deconv3', 'deconv2', 'deconv1'}

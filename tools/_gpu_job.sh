@@ -1,14 +1,4 @@
 export PYTHONPATH=.
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2aj_bench.json 2> gpurun_out/r2aj_err.log
-tail -2 gpurun_out/r2aj_err.log
-python - <<'P'
-import json
-d=json.loads(open('gpurun_out/r2aj_bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['traffic'], d['gpu_launches'])
-print(d['roofline']['per_block_ms'])
-print(d['train']['ms_per_step'], d['train']['value'], d['parity']['mde_abs_diff'], d['parity']['teacher_forced'])
-print(d['timestep_sweep']['results'])
-print(d['sj_cupy_proxy']['speedup_vs_fp32'], d['sj_cupy_proxy']['speedup_vs_tf32_allowed'], d['cpu_baseline']['value'], d['clocks'])
-P
+timeout 900 python -m pytest tests -m gpu -x -q -k "fold or graphed or benchmark_config or contract" 2>&1 | tail -3
+python tools/bench_latency.py 2>&1 | grep "^{" > gpurun_out/r2ao_latency_graph.jsonl
+cat gpurun_out/r2ao_latency_graph.jsonl

@@ -159,7 +159,10 @@ typedef struct ss_tile_maps {
     int32_t mode;
     int32_t nclass;        /* ROW_LIST: weight sets per output-channel tile */
     int32_t rl_n;          /* ROW_LIST: entries per class (lists padded with -1 to a common length) */
-    int32_t transposed;    /* ROW_LIST: 0 = list of output rows, 1 = list of output columns */
+    int32_t transposed;    /* ROW_LIST: 0 = list of output rows, 1 = list of output columns, 2 = list of output rows with FOLDED
+                              columns: the dense 3x3 sets (w_i8 = w_dense, nclass = 4 = (row class, column class)) evaluated only
+                              on the regular rows of each row class -- rl_src / rl_out [2][rl_n], output column through xmap_out;
+                              replaces the SS_TILES_FOLDED pass where many source rows are irregular (Cin % 64 == 0) */
     const int32_t* ymap_out;
     const int32_t* xmap_out;
     const int32_t* rl_src;

@@ -78,6 +78,8 @@ struct I8Params {
     const int* rl_out;     // [nclass][rl_n] pixel offset of the entry's output row at column 0, or -1
     const uint8_t* rl_collive;   // [c_nout] 1 = this output column belongs to the pass (NULL = all)
     int rl_n;              // entries per class (padded with -1 to a common length)
+    int rl_fold;           // row-list pass with FOLDED columns: tile columns = source positions, classes = (row class, column class),
+                           // output column through xmap_out -- the dense folded pass restricted to the regular rows of each class
     int in_rowstep;        // pixels between the ROWSTEP source rows of an entry (Win; 1 for the transposed pass)
     int in_colpitch;       // pixels between neighbouring source columns (1; Win for the transposed pass)
     int out_colpitch;      // pixels between neighbouring output columns (1; Wout for the transposed pass)
@@ -148,7 +150,7 @@ __device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr, int
         // row list: every tile row has its own ROWSTEP source rows (no sliding window between tile rows)
         const int e = ty * 16 + pr / ROWSTEP;
         if (e >= p.rl_n) return -1;
-        const int s0 = __ldg(p.rl_src + cls * p.rl_n + e);
+        const int s0 = __ldg(p.rl_src + (p.rl_fold ? cls >> 1 : cls) * p.rl_n + e);
         return s0 < 0 ? -1 : s0 + (pr % ROWSTEP) * p.in_rowstep;
     } else {
         const int gi = ty * 16 * STRIDE + pr;
@@ -171,6 +173,7 @@ template <int STRIDE, int PWHALF, int ROWSTEP>
 __device__ __forceinline__ int col_source(const I8Params& p, int tx, int pc) {
     if constexpr (ROWSTEP > 1) {
         const int u = tx * 8 + pc;             // column of the (virtual) upsampled image
+        if (p.rl_fold) return u < p.c_in ? u * p.in_colpitch : -1;      // folded columns: the source column itself
         if (u >= p.c_up) return -1;
         return min((int)floorf((float)u * p.c_scale), p.c_in - 1) * p.in_colpitch;
     } else {
@@ -435,6 +438,63 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
         // patch straddle images, and the box height is a property of the map, so the rows of one image are loaded as the binary
         // decomposition of their count (maps with 1, 2, 4 .. 32 rows).  One elected thread issues everything: ~2-8 instructions
         // per stage instead of 128 threads x 6-18 cp.async.
+        if constexpr (ROWSTEP > 1) {
+            // Row list with folded columns (rl_fold): every tile row owns ROWSTEP consecutive source rows of one image, i.e. one box
+            // of tmap[0] (ROWSTEP rows high); a dead list entry is loaded from an out-of-range image = zeros.
+            // One elected lane per producer warp issues the boxes of 4 tile rows (a single thread issuing all 16 small boxes was
+            // slower than the gather producers); warp 0's lane also posts the stage's transaction count.
+            if (elect_one()) {
+                constexpr uint32_t ROWBYTES = (uint32_t)(cPWp * RB);
+                constexpr uint32_t STAGE_TX = (uint32_t)cPH * ROWBYTES;
+                const int n_oob = p.T * p.B;
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int it = it0; it < nit; it += its) {
+                    const int ntile = fast_div(it, mt_per, m_mt_per);
+                    const int mt = it - ntile * mt_per;
+                    const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
+                    const int rcls = p.rl_fold ? (ntile % p.nclass) >> 1 : ntile % p.nclass;
+                    int ent[4];                       // (image << 16 | source row) of this thread's tile rows, -1 = dead
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = ty * 16 + warp * 4 + k;
+                        const int s0 = e < p.rl_n ? __ldg(p.rl_src + rcls * p.rl_n + e) : -1;
+                        ent[k] = -1;
+                        if (s0 >= 0) {
+                            const int row = s0 / p.Win;           // b * Hin + y
+                            const int b = row / p.Hin;
+                            ent[k] = (b << 16) | (row - b * p.Hin);
+                        }
+                    }
+                    const int x0 = tx * 8;
+                    for (int t0 = 0; t0 < p.T; t0 += cTC) {
+                        const int tc = min(cTC, p.T - t0);
+                        const int n_outer = p.resident ? tc : p.ncb;
+                        const int n_inner = p.resident ? p.ncb : tc;
+                        for (int o = 0; o < n_outer; ++o) {
+                            for (int in = 0; in < n_inner; ++in) {
+                                const int cb = p.resident ? in : o;
+                                const int t = t0 + (p.resident ? o : in);
+                                mbar_wait(bar_empty_p + 8 * stage, phase ^ 1u);
+                                const uint32_t full = bar_full_p + 8 * stage;
+                                if (warp == 0) mbar_arrive_expect_tx(full, STAGE_TX);
+                                const uint32_t dst0 = patch_base + (uint32_t)stage * cPB + (uint32_t)(warp * 4 * ROWSTEP) * ROWBYTES;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int v = ent[k];
+                                    const int n = v >= 0 ? t * p.B + (v >> 16) : n_oob;
+                                    tma_load_4d(dst0 + (uint32_t)(k * ROWSTEP) * ROWBYTES, &p.tmap[0], cb * RB, x0, v >= 0 ? (v & 0xFFFF) : 0, n, full);
+                                }
+                                if (++stage == p.NPS) {
+                                    stage = 0;
+                                    phase ^= 1u;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else
         if (warp == 0 && elect_one()) {
             constexpr int ROWPIX = STRIDE == 1 ? cPWp : cPWhalf;              // pixels per patch row (of one plane)
             constexpr uint32_t ROWBYTES = (uint32_t)(ROWPIX * RB);
@@ -943,9 +1003,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
             if constexpr (ROWSTEP > 1) {
                 // row list: the tile row is an entry of this class's list; columns are plain output columns
                 const int e = ty * 16 + g;
-                const int orow = e < p.rl_n ? __ldg(p.rl_out + cls * p.rl_n + e) : -1;
-                const int oc = tx * 8 + j;
-                live = orow >= 0 && oc < p.c_nout && (p.rl_collive == nullptr || __ldg(p.rl_collive + oc) != 0);
+                const int orow = e < p.rl_n ? __ldg(p.rl_out + (p.rl_fold ? cls >> 1 : cls) * p.rl_n + e) : -1;
+                int oc = tx * 8 + j;
+                if (p.rl_fold) oc = oc < p.Wv ? __ldg(p.xmap_out + (cls & 1) * p.Wv + oc) : -1;   // source position -> output column of the class
+                live = orow >= 0 && oc >= 0 && oc < p.c_nout && (p.rl_collive == nullptr || __ldg(p.rl_collive + oc) != 0);
                 if (live) pix = (size_t)orow + (size_t)oc * p.out_colpitch;
             } else {
                 const int so = ty * 16 + g;
@@ -1301,9 +1362,10 @@ TensorMapEncodeFn tensor_map_encoder() {
 struct TmapKey {
     const void* x;
     long long nimg;
-    int Hin, Win, Cin, RB, stride, ks;
+    int Hin, Win, Cin, RB, stride, ks, fixed_rows;
     bool operator==(const TmapKey& o) const {
-        return x == o.x && nimg == o.nimg && Hin == o.Hin && Win == o.Win && Cin == o.Cin && RB == o.RB && stride == o.stride && ks == o.ks;
+        return x == o.x && nimg == o.nimg && Hin == o.Hin && Win == o.Win && Cin == o.Cin && RB == o.RB && stride == o.stride && ks == o.ks &&
+               fixed_rows == o.fixed_rows;
     }
 };
 struct TmapEntry {
@@ -1316,7 +1378,9 @@ struct TmapEntry {
 // (Cin in BYTES), RB-byte channel blocks, patch rows of PWp pixels (stride 1) or PWhalf pixels per parity plane (stride 2).
 // Encoding a map costs a few microseconds on the host, so the maps of the last calls are kept (the activation buffers of a model
 // come back at the same addresses from the caching allocator; a graph capture bakes them into the launch anyway).
-void setup_tma(I8Params& p, const void* x, long long nimg, int Hin, int Win, int Cin, int RB, int stride, int ks, int pad) {
+void setup_tma(I8Params& p, const void* x, long long nimg, int Hin, int Win, int Cin, int RB, int stride, int ks, int pad,
+               int fixed_rows = 0) {
+    // fixed_rows > 0: a single map (tmap[0]) whose box is that many rows high (row-list pass: one box per tile row)
     p.tma = 0;
     static int tma_env = -1;
     if (tma_env < 0) {
@@ -1337,7 +1401,7 @@ void setup_tma(I8Params& p, const void* x, long long nimg, int Hin, int Win, int
     static TmapEntry cache[64];
     static int next = 0;
     static std::mutex mu;
-    const TmapKey key{x, nimg, Hin, Win, Cin, RB, stride, ks};
+    const TmapKey key{x, nimg, Hin, Win, Cin, RB, stride, ks, fixed_rows};
     std::lock_guard<std::mutex> lock(mu);
     for (int i = 0; i < 64; ++i)
         if (cache[i].valid && cache[i].key == key) {
@@ -1353,7 +1417,7 @@ void setup_tma(I8Params& p, const void* x, long long nimg, int Hin, int Win, int
     const CUtensorMapSwizzle sw = RB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (RB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     for (int lg = 0; lg < TMA_NMAPS; ++lg) {
         // box: RB channel bytes x one patch row (stride 2: every other pixel of 2 * rowpix) x 2^lg rows x one image
-        const cuuint32_t box[4] = {(cuuint32_t)RB, (cuuint32_t)(stride * rowpix), 1u << lg, 1u};
+        const cuuint32_t box[4] = {(cuuint32_t)RB, (cuuint32_t)(stride * rowpix), fixed_rows > 0 ? (cuuint32_t)fixed_rows : 1u << lg, 1u};
         if (enc(&e.maps[lg], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return;
@@ -1658,6 +1722,10 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         set_error("ss_conv_i8_fwd_ex: the folded pass is a 3x3 stride-1 pad-0 conv on the source with output maps");
         return SS_EINVAL;
     }
+    if (rowlist && tm->transposed == 2 && (tm->xmap_out == nullptr || tm->nclass != 4 || g->Cin % 64 != 0 || g->Win < 3)) {
+        set_error("ss_conv_i8_fwd_ex: the row-list pass with folded columns needs xmap_out, 4 classes and Cin %% 64 == 0");
+        return SS_EINVAL;
+    }
     if (rowlist && (!up || g->ks != 5 || first || tm->rl_src == nullptr || tm->rl_out == nullptr || tm->rl_n <= 0 || tm->nclass <= 0 ||
                     tm->nclass > 8)) {
         set_error("ss_conv_i8_fwd_ex: the row-list pass needs a 5x5 upsampled conv, the entry tables and 1..8 classes");
@@ -1682,6 +1750,12 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.N = g->planes * 32;
     if (first) {
         p.RB = 128; p.ncb = 1; p.ntaps = 1; p.PH = 16; p.PWhalf = 8; p.PWp = 8;
+    } else if (rowlist && tm->transposed == 2) {
+        // rows AND columns folded (the dense 3x3 sets), tile rows from the list of regular rows of each row class
+        p.RB = rowbytes_for(g->Cin, 3);
+        p.ncb = g->Cin / p.RB;
+        p.ntaps = 9;
+        p.PH = 48; p.PWhalf = 9; p.PWp = 10;
     } else if (rowlist) {
         // rows folded to 3 taps (class-specific sums of the 5 filter rows), columns still the 5 taps over the upsampled row
         p.RB = 32;
@@ -1708,7 +1782,8 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         p.Hv = g->Hin - 2; p.Wv = g->Win - 2;
         p.ymap_out = tm->ymap_out; p.xmap_out = tm->xmap_out;
     } else if (rowlist) {
-        const bool tr = tm->transposed != 0;      // the list holds output COLUMNS (and the tile columns walk the rows)
+        const bool tr = tm->transposed == 1;      // the list holds output COLUMNS (and the tile columns walk the rows)
+        p.rl_fold = tm->transposed == 2 ? 1 : 0;
         p.rl_src = tm->rl_src; p.rl_out = tm->rl_out; p.rl_collive = tm->rl_collive; p.rl_n = tm->rl_n;
         p.in_rowstep = tr ? 1 : g->Win;
         p.in_colpitch = tr ? g->Win : 1;
@@ -1718,6 +1793,11 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         p.c_up = p.c_nout + g->ks - 1;
         p.c_scale = (float)p.c_in / (float)p.c_up;
         p.Wv = p.c_nout;
+        if (p.rl_fold) {
+            p.Wv = g->Win - 2;                // tile columns walk the source positions of the 3x3 folded conv
+            p.xmap_out = tm->xmap_out;
+            p.nclass = 4;
+        }
     }
     if (mode == SS_TILES_FOLDED) {
         p.HsO = g->Hin;                       // virtual 3x3 pad-0 conv: image b's rows are Hin apart, no shared padding
@@ -1803,6 +1883,8 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.stats = tm != nullptr ? reinterpret_cast<unsigned long long*>(tm->stats) : nullptr;
     p.tma = 0;
     if (!first && !up && !rowlist) setup_tma(p, x, (long long)g->T * g->B, g->Hin, g->Win, g->Cin, p.RB, g->stride, g->ks, p.pad);
+    // row list with folded columns: 3 source rows x 10 source columns per tile row, straight from the source tensor
+    if (rowlist && p.rl_fold && g->Hin < 65536) setup_tma(p, x, (long long)g->T * g->B, g->Hin, g->Win, g->Cin, p.RB, 1, 3, 0, 3);
 
     const size_t smem = 1024 + (size_t)p.nwb * p.WB + (size_t)p.NPS * p.PB + tail_bytes;
     const int num_sms = sms;
@@ -1852,6 +1934,11 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         launched = true;                                                                                                   \
     }
 #define SS_TRY_ROWLIST(PL)                                                                                                 \
+    if (!launched && rowlist && p.rl_fold && g->planes == PL) {                                                            \
+        SS_ENSURE_SMEM((conv_i8_kernel<PL, 3, 1, 64, false, MODE_I8, false, 3, 3>), dev, 227 * 1024);                      \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 3, 1, 64, false, MODE_I8, false, 3, 3>, p);                            \
+        launched = true;                                                                                                   \
+    }                                                                                                                      \
     if (!launched && rowlist && g->planes == PL) {                                                                         \
         SS_ENSURE_SMEM((conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>), dev, 227 * 1024);                      \
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>, p);                            \
@@ -1865,6 +1952,11 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     if (!launched && first && g->planes == 3 && g->v_reset == 0.0f && g->neuron == NK_) {                                  \
         SS_ENSURE_SMEM((conv_i8_kernel<3, 1, 1, 128, true, MODE_I8, false, 1, 1, NK_>), dev, 227 * 1024);                  \
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<3, 1, 1, 128, true, MODE_I8, false, 1, 1, NK_>, p);                        \
+        launched = true;                                                                                                   \
+    }                                                                                                                      \
+    if (!launched && rowlist && p.rl_fold && g->planes == 3 && g->v_reset == 0.0f && g->neuron == NK_) {                   \
+        SS_ENSURE_SMEM((conv_i8_kernel<3, 3, 1, 64, false, MODE_I8, false, 3, 3, NK_>), dev, 227 * 1024);                  \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<3, 3, 1, 64, false, MODE_I8, false, 3, 3, NK_>, p);                        \
         launched = true;                                                                                                   \
     }                                                                                                                      \
     if (!launched && rowlist && g->planes == 3 && g->v_reset == 0.0f && g->neuron == NK_) {                                \

@@ -4,6 +4,7 @@ PyTorch is used here for device memory, streams and autograd plumbing only; all 
 happens inside libstereospike_b200.so.
 """
 import ctypes
+import os
 import functools
 
 import numpy as np
@@ -127,6 +128,8 @@ def pack_events(x_seq, status=None):
 
 
 # ----------------------------------------------------------------------------------------- folded upsampled conv
+FOLD_ROWS_BY_LIST = os.environ.get('SS_FOLD_ROWS_BY_LIST', '1') != '0'    # dense folded pass on listed regular rows (small decoder blocks)
+
 # Replication patterns of the 5 taps of one axis of  UpsamplingNearest2d(n_out + 4) -> valid conv(5)  (source index of tap k
 # relative to the first one): the two regular ones and the three next to a 3-fold replication (include/stereospike_b200.h).
 FOLD_PATTERNS = ((0, 1, 1, 2, 2), (0, 0, 1, 1, 2), (0, 0, 0, 1, 1), (0, 1, 1, 1, 2), (0, 0, 1, 1, 1))     # L, M, A, B, C
@@ -176,13 +179,14 @@ class FoldPlan:
             return m
         self.ymap, self.xmap = t32(dense_map(s0y, py, Hin)), t32(dense_map(s0x, px, Win))
 
-        def lists(s0, pat, src_off, out_off):
-            """[3][n] source / output offsets of the irregular coordinates of every sample, padded with -1."""
-            per = [[o for o in range(len(s0)) if pat[o] == 2 + c] for c in range(3)]
+        def lists(s0, pat, src_off, out_off, classes=(2, 3, 4)):
+            """[len(classes)][n] source / output offsets of the coordinates of every sample whose replication pattern is in
+            ``classes`` (default: the three irregular ones), padded with -1."""
+            per = [[o for o in range(len(s0)) if pat[o] == c] for c in classes]
             n = max(1, B * max(len(v) for v in per))
-            src = np.full((3, n), -1, dtype=np.int64)
-            out = np.full((3, n), -1, dtype=np.int64)
-            for c in range(3):
+            src = np.full((len(classes), n), -1, dtype=np.int64)
+            out = np.full((len(classes), n), -1, dtype=np.int64)
+            for c in range(len(classes)):
                 i = 0
                 for b in range(B):
                     for o in per[c]:
@@ -195,6 +199,13 @@ class FoldPlan:
             s0x, px, lambda b, s: b * Hin * Win + s, lambda b, o: b * Hout * Wout + o)
         self.row_regular = torch.as_tensor((py < 2).astype(np.uint8), device=dev).contiguous()       # rows the column pass owns
         n_reg_r, n_reg_c = int((py < 2).sum()), int((px < 2).sum())
+        # the regular rows of each row class as a list: the dense pass restricted to them (ss_tile_maps.transposed = 2).  The plain
+        # dense pass evaluates every source row for both row classes and discards the irregular ones; worth replacing when a
+        # sizeable part of the rows is irregular (the 17 -> 33 and 33 -> 65 blocks: 45 % / 23 %) -- the list form pays 3 private
+        # source rows per tile row in patch traffic, which the weight-streaming blocks do not notice
+        self.reg_src, self.reg_out, self.reg_n, _ = lists(s0y, py, lambda b, s: (b * Hin + s) * Win, lambda b, o: (b * Hout + o) * Wout,
+                                                          classes=(0, 1))
+        self.rows_by_list = n_reg_r < 0.85 * Hout
         self.covered = n_reg_r * n_reg_c / float(Hout * Wout)                 # fraction of outputs in the dense (9-tap) pass
         # taps executed per output, averaged (25 = unfolded): what bench.py credits a folded block with
         self.taps_per_output = (9.0 * n_reg_r * n_reg_c + 15.0 * self.n_irr_rows * Wout + 15.0 * self.n_irr_cols * n_reg_r) / float(Hout * Wout)
@@ -353,9 +364,16 @@ def conv_i8_fwd_folded(x, geom, w_dense, w_rows, w_cols, wscale, **kw):
     assert g.kind == 'upconv' and g.ks == 5
     plan = fold_plan(g.Hin, g.Win, g.Hout, g.Wout, int(kw['B']), str(x.device))
     assert plan.ok, 'geometry cannot be folded'
-    tm = _lib.TileMaps(mode=_lib.SS_TILES_FOLDED, nclass=4, rl_n=0, transposed=0, ymap_out=plan.ymap.data_ptr(),
-                       xmap_out=plan.xmap.data_ptr(), rl_src=0, rl_out=0, rl_collive=0, stats=0)
-    res = conv_i8_fwd(x, g, w_dense, wscale, tile_maps=tm, desc_override=dict(ks=3, stride=1, pad=0, upsample=0), **kw)
+    if plan.rows_by_list and g.Cin % 64 == 0 and FOLD_ROWS_BY_LIST:
+        # regular rows x regular columns: the dense 3x3 sets on the listed regular rows only
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=4, rl_n=plan.reg_n, transposed=2, ymap_out=0,
+                           xmap_out=plan.xmap.data_ptr(), rl_src=plan.reg_src.data_ptr(), rl_out=plan.reg_out.data_ptr(), rl_collive=0,
+                           stats=0)
+        res = conv_i8_fwd(x, g, w_dense, wscale, tile_maps=tm, **kw)
+    else:
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_FOLDED, nclass=4, rl_n=0, transposed=0, ymap_out=plan.ymap.data_ptr(),
+                           xmap_out=plan.xmap.data_ptr(), rl_src=0, rl_out=0, rl_collive=0, stats=0)
+        res = conv_i8_fwd(x, g, w_dense, wscale, tile_maps=tm, desc_override=dict(ks=3, stride=1, pad=0, upsample=0), **kw)
     kw2 = dict(kw)
     for k in ('want_v_out', 'want_h', 'outputs'):
         kw2.pop(k, None)

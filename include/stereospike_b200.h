@@ -178,6 +178,8 @@ int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void
 
 /* Digit planes of ALREADY QUANTISED integer weights (fp32 holding exact integers, |q| < 2^(8*planes-1)), same layout as
  * ss_pack_weights_i8; zero_exp: device int32 [Cout] of zeros.  Used for the folded weight sets (sums of quantised taps).
+ * More generally the values are quantised as round(q * 2^-zero_exp[n]): with fp32 weights and the exponents ss_pack_weights_folded
+ * returns, this writes the plain 25-tap image of exactly the taps the folded sets are sums of (small calls of a folded block).
  * _rect: filters of ksy rows x ksx columns (OIHW [Cout][Cin][ksy][ksx]); ksy != ksx selects the 32-byte-row image of the
  * row-list pass. */
 int ss_pack_digits_i8(const float* q_oihw, int32_t Cout, int32_t Cin, int32_t ks, int32_t planes, const int32_t* zero_exp,

@@ -37,6 +37,14 @@ class Site:
             self._dgrad = (key, ops.DgradPlan(w, geom, w.device))
         return self._dgrad[1]
 
+    def unfolded_fold_taps(self, planes, wexp):
+        """25-tap image of the taps quantised with the fold's exponents (small calls of a folded block), cached on the weight."""
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version, planes, str(w.device))
+        if getattr(self, '_unfolded', None) is None or self._unfolded[0] != key:
+            self._unfolded = (key, ops.pack_weights_with_exponents(w, planes, wexp))
+        return self._unfolded[1]
+
     def geom(self, Hin, Win):
         c = self.conv
         ks = c.kernel_size[0]
@@ -47,14 +55,15 @@ class Site:
                          conv_out_size(Win, ks, st, pd), st, pd)
 
     def packed(self, planes, need_i8, need_kn=True, fold=False):
-        """(w_kn fp32 [K][Cout] or None, (w_i8, wscale) or (w_fold, w_full, wscale) or None), cached on the weight's version."""
+        """(w_kn fp32 [K][Cout] or None, (w_i8, wscale) or (dense, rows, cols, wscale, wexp) or None), cached on the weight's
+        version."""
         w = self.conv.weight
         key = (w.data_ptr(), w._version, planes, need_i8, need_kn, fold, str(w.device))
         if self._pack is None or self._pack[0] != key:
             w_kn = ops.weight_to_kn(w) if need_kn else None
             w_i8 = None
             if need_i8 and fold:
-                w_i8 = ops.pack_weights_folded(w, planes)          # (dense, rows, cols, wscale)
+                w_i8 = ops.pack_weights_folded(w, planes, with_exp=True)          # (dense, rows, cols, wscale, wexp)
             elif need_i8:
                 cin = w.shape[1]
                 q, sc, _ = ops.pack_weights_i8(w, planes, cin_pad=ops.first_layer_channels(cin) if cin % 32 else cin)
@@ -289,16 +298,20 @@ class Engine:
                 raise ValueError(f'input has {int(x_seq.shape[2])} channels, the model expects {g.Cin}')
             use_i8 = impl != SS_IMPL_SIMT
             # (also while training: ss_pack_weights_folded re-derives the folded sets from the updated weight in one launch)
-            # (not for a handful of frames: the two extra row-list launches per block cost more than the taps they save --
-            #  single-frame graph replay 0.28 ms folded vs 0.21 ms unfolded)
-            fold = use_i8 and self._fold_site(s.name) and self.weight_planes <= 3 and g.kind == 'upconv' and g.ks == 5 and \
-                g.Cin % 32 == 0 and B * T >= self.fold_min_frames and ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
+            fold_w = use_i8 and self._fold_site(s.name) and self.weight_planes <= 3 and g.kind == 'upconv' and g.ks == 5 and \
+                g.Cin % 32 == 0 and ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).ok
+            # (not for a handful of frames: the two extra row-list launches per block cost more than the taps they save -- single-frame
+            #  graph replay 0.28 ms folded vs 0.24 ms unfolded.  Such calls run the 25-tap kernel on the fold's quantised taps, so a
+            #  sample's result is bit-identical whatever the size of the batch it arrives in)
+            fold = fold_w and B * T >= self.fold_min_frames
             if fold:
                 self.flop_scale[s.name] = ops.fold_plan(g.Hin, g.Win, g.Hout, g.Wout, B, str(dev)).taps_per_output / 25.0
             else:
                 self.flop_scale.pop(s.name, None)
             # the fp32 [K][Cout] copy is only read by the CUDA-core kernels (forward impl='simt', backward bwd_impl='simt')
-            w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=(want_h and self.bwd_impl == 'simt') or not use_i8, fold=fold)
+            w_kn, w_i8 = s.packed(self.weight_planes, use_i8, need_kn=(want_h and self.bwd_impl == 'simt') or not use_i8, fold=fold_w)
+            if fold_w and not fold:
+                w_i8 = (s.unfolded_fold_taps(self.weight_planes, w_i8[4]), w_i8[3])     # (25-tap image of the fold's taps, wscale)
             decay = params[2 * i + 1]
             if decay is not None:
                 decay = decay.detach().contiguous()

@@ -254,7 +254,7 @@ def fold_weight_sets(weight, planes):
     return q, dense, rows, cols, e
 
 
-def pack_weights_folded(weight, planes):
+def pack_weights_folded(weight, planes, with_exp=False):
     """Digit-plane images (dense, rows, cols) of a folded NNConvUpsampling block + wscale fp32 [Cout]: one launch of
     ss_pack_weights_folded (bit-identical to pack_weights_folded_host below, which derives them with torch ops)."""
     _require_cuda(weight, 'weight')
@@ -269,7 +269,20 @@ def pack_weights_folded(weight, planes):
     wexp = torch.empty(co, dtype=torch.int32, device=dev)
     _lib.check(_lib.lib().ss_pack_weights_folded(_ptr(w), co, ci, planes, _ptr(dense), _ptr(rows), _ptr(cols), _ptr(wscale), _ptr(wexp),
                                                  _stream()), 'ss_pack_weights_folded')
+    if with_exp:
+        return dense, rows, cols, wscale, wexp
     return dense, rows, cols, wscale
+
+
+def pack_weights_with_exponents(weight, planes, wexp):
+    """Plain (unfolded) digit-plane image of ``weight`` quantised with the given per-output-channel exponents -- with the fold's
+    exponents these are the SAME quantised taps the folded sets are sums of: what a call too small to be worth folding runs, so
+    that a sample's result does not depend on the size of the batch it arrives in."""
+    w = weight.detach().contiguous().float()
+    co, ci, kh, kw = (int(v) for v in w.shape)
+    img = torch.empty(co * ci * kh * kw * planes, dtype=torch.int8, device=w.device)
+    _lib.check(_lib.lib().ss_pack_digits_i8(_ptr(w), co, ci, kh, planes, _ptr(wexp), _ptr(img), _stream()), 'ss_pack_digits_i8')
+    return img
 
 
 def pack_weights_folded_host(weight, planes):

@@ -86,7 +86,8 @@ def block_case(kind, Cin, Cout, ks, Hin, Win, stride, pad, up, neuron, T, B, imp
     return res
 
 
-def model_case(variant, mono, gain, T, B, impl, planes, seed=11, backward=False, tau=3.0, with_fp64=False, bwd_impl=None):
+def model_case(variant, mono, gain, T, B, impl, planes, seed=11, backward=False, tau=3.0, with_fp64=False, bwd_impl=None,
+               fold_min_frames=None):
     import torch
     from oracle import ref_model as rm, sj_compat as sj
     from oracle.make_golden import simple_loss
@@ -101,7 +102,7 @@ def model_case(variant, mono, gain, T, B, impl, planes, seed=11, backward=False,
         n = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=variant == 'plif', tau=tau, multiply_factor=gain)
     n.load_state_dict(o.state_dict())
     n = n.cuda()
-    n.set_kernel_options(impl=impl, weight_planes=planes, bwd_impl=bwd_impl)
+    n.set_kernel_options(impl=impl, weight_planes=planes, bwd_impl=bwd_impl, fold_min_frames=fold_min_frames)
     x = rm.synthetic_inputs(B, T, 2 if mono else 4, seed=seed + 1)
     label = rm.synthetic_label(B, seed=seed + 2)
     sj.reset_net(o)

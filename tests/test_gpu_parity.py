@@ -291,6 +291,15 @@ def test_model_gradients(variant, mono, gain, impl, bwd_impl):
     assert cos >= 0.999, (cos, name, r['grad_rel'])
 
 
+def test_model_gradients_with_folded_decoder():
+    """Training with the folded decoder blocks (what large training batches run: weight sets re-derived by ss_pack_weights_folded,
+    dense pass on listed rows for the small blocks, saved potentials written by all three passes): same gradient bar."""
+    from tests._cases import model_case
+    r = model_case('lif', False, 15.0, 2, 1, 'umma', 3, backward=True, bwd_impl='umma', fold_min_frames=1)
+    cos, name = r['grad_worst_cos']
+    assert cos >= 0.999, (cos, name, r['grad_rel'])
+
+
 @pytest.mark.parametrize('name', ['stereospike_if_T2', 'bino_lif_T2', 'mono_plif_T2'])
 def test_golden_fixture(name, golden_dir):
     """Committed fixtures produced by the reference's own model files (oracle/make_golden.py)."""

@@ -1,11 +1,12 @@
 export PYTHONPATH=.
-timeout 900 python -m pytest tests -m gpu -x -q -k "fold or bit_identical or benchmark_config" 2>&1 | tail -5
-for v in 1 0; do
-SS_FOLD_ROWS_BY_LIST=$v timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-parity --no-train > gpurun_out/r2ap_bench_$v.json 2> gpurun_out/r2ap_err.log
-python - <<P
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2as_bench.json 2> gpurun_out/r2as_err.log
+tail -2 gpurun_out/r2as_err.log
+python - <<'P'
 import json
-d=json.loads(open('gpurun_out/r2ap_bench_$v.json').read().strip().splitlines()[-1])
-print($v, d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])
+d=json.loads(open('gpurun_out/r2as_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['traffic'], d['gpu_launches'])
 print(d['roofline']['per_block_ms'])
+print(d['train']['ms_per_step'], d['train']['value'], d['parity']['mde_abs_diff'], d['parity']['teacher_forced'])
 P
-done

@@ -3,7 +3,7 @@
 //      relative to the box's destination?  -> load the same box at destination offsets 0 / 128 / 384 and dump shared memory
 //  (2) elementStrides = 2 along W (parity-split rows of a stride-2 conv): which pixels arrive, how many
 //  (3) negative / out-of-range coordinates: zero fill, and the full box counts towards the mbarrier's transaction bytes
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tma_probe tma_probe.cu   (driver entry point fetched at run time)
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/probes/tma_probe tools/tma_probe.cu   (driver entry point fetched at run time)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>

@@ -232,8 +232,11 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // tile rows are arbitrary (sample, output row) entries with ROWSTEP private source rows each (patch row = ROWSTEP * tile row + ky).
 // NK: neuron kind fixed at compile time (and v_reset == 0), -1 = run-time switch.  The epilogue is instruction-issue bound on the
 // full-resolution blocks; the generic version executes the other kinds' arithmetic predicated off (~25 % of its instructions).
+// LEAN: stateless inference instantiation -- no saved potentials, no carried / returned membrane state, no firing statistics (the
+// launcher picks it when none of those pointers is given).  The epilogue-bound blocks are limited by dependent-issue latency under
+// a 126-register allocation; without the h_seq / v_out / statistics paths the compiler has 16+ fewer live values to keep.
 template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false, int KSX = KS, int ROWSTEP = 1,
-          int NK = -1>
+          int NK = -1, bool LEAN = false>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_constant__ I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
@@ -1038,7 +1041,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                     sc[4 * i] = q.x * nc.gain; sc[4 * i + 1] = q.y * nc.gain; sc[4 * i + 2] = q.z * nc.gain; sc[4 * i + 3] = q.w * nc.gain;
                 }
             }
-            if (p.v_in != nullptr && live) {
+            if (!LEAN && p.v_in != nullptr && live) {
                 const float4* vi = reinterpret_cast<const float4*>(p.v_in + o0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1117,12 +1120,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                         pk[q] = sb[4 * q] | (sb[4 * q + 1] << 8) | (sb[4 * q + 2] << 16) | (sb[4 * q + 3] << 24);
                     const size_t o = (size_t)t * t_out + o0;
                     uint32_t n_spk = 0u;
-                    if (p.stats != nullptr) {
+                    if (!LEAN && p.stats != nullptr) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) n_spk = __dp4a(pk[q], 0x01010101u, n_spk);
                     }
                     pk[0] += rs_cur.x; pk[1] += rs_cur.y; pk[2] += rs_cur.z; pk[3] += rs_cur.w;
-                    if (p.stats != nullptr) {
+                    if (!LEAN && p.stats != nullptr) {
                         uint32_t n_nz = 0u, n_sq = 0u;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -1136,7 +1139,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                     if (t + 1 < p.T) {
                         ts[0] += pk[0]; ts[1] += pk[1]; ts[2] += pk[2]; ts[3] += pk[3];
                     }
-                    if (p.h_seq != nullptr) {
+                    if (!LEAN && p.h_seq != nullptr) {
                         float4* hp = reinterpret_cast<float4*>(p.h_seq + o);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) hp[i] = make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]);
@@ -1145,13 +1148,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                 sbase += (uint32_t)tc;
             }
             if (p.tsum != nullptr && live) *reinterpret_cast<uint4*>(p.tsum + o0) = make_uint4(ts[0], ts[1], ts[2], ts[3]);
-            if (p.v_out != nullptr && live) {
+            if (!LEAN && p.v_out != nullptr && live) {
                 float4* vo = reinterpret_cast<float4*>(p.v_out + o0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) vo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
         }
-        if (p.stats != nullptr) {
+        if (!LEAN && p.stats != nullptr) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 uint32_t a = st[k];
@@ -1944,6 +1947,28 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>, p);                            \
         launched = true;                                                                                                   \
     }
+    // stateless inference (no h_seq, no membrane state in or out, no statistics): the LEAN instances of the epilogue-bound shapes
+    static int lean_env = -1;
+    if (lean_env < 0) {
+        const char* e = getenv("SS_LEAN");
+        lean_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    // (measured, alternating runs on one box: first layer -5 %, deconv1's dense pass -2.5 %; the wider blocks +1-2 %, so only the
+    //  32-output-channel ones use it)
+    const bool lean = lean_env != 0 && h_seq == nullptr && v_in == nullptr && v_out == nullptr && p.stats == nullptr && !pair && !rowlist &&
+                      g->planes == 3 && g->v_reset == 0.0f && g->Cout <= 32;
+#define SS_TRY_LEAN(KS_, ST_, RB_, FIRST_, NK_)                                                                             \
+    if (!launched && lean && g->neuron == NK_ && first == FIRST_ && (FIRST_ || (g->ks == KS_ && g->stride == ST_ && p.RB == RB_))) { \
+        SS_ENSURE_SMEM((conv_i8_kernel<3, KS_, ST_, RB_, FIRST_, MODE_I8, false, KS_, 1, NK_, true>), dev, 227 * 1024);    \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<3, KS_, ST_, RB_, FIRST_, MODE_I8, false, KS_, 1, NK_, true>, p);          \
+        launched = true;                                                                                                    \
+    }
+#define SS_TRY_LEAN_NK(NK_) SS_TRY_LEAN(1, 1, 128, true, NK_) SS_TRY_LEAN(3, 1, 64, false, NK_)
+    SS_TRY_LEAN_NK(SS_NEURON_IF)
+    SS_TRY_LEAN_NK(SS_NEURON_LIF)
+    SS_TRY_LEAN_NK(SS_NEURON_PLIF)
+#undef SS_TRY_LEAN_NK
+#undef SS_TRY_LEAN
 #define SS_TRY_PL(PL) SS_TRY_ROWLIST(PL) SS_TRY_FIRST(PL) SS_TRY(PL, 5, 1, 32) SS_TRY(PL, 5, 2, 32) SS_TRY(PL, 3, 1, 64) SS_TRY(PL, 3, 1, 32)
     // default precision (3 planes), v_reset == 0 (every call site of the reference), no CTA pair: neuron kind compiled in
     const bool spec = !pair && !rowlist && !first && g->planes == 3 && g->v_reset == 0.0f;

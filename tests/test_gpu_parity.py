@@ -537,7 +537,8 @@ def test_cta_pair_and_tma_kernels_are_bit_identical():
     """The cta_group::2 variant of the block kernel (two m-tiles per MMA, weights split between the CTAs of a 2-cluster) and the
     TMA-staged halo patches (cp.async.bulk.tensor instead of cp.async gathers) must produce exactly the same results as the
     single-CTA gather kernel.  The choices are made once per process from SS_PAIR / SS_TMA, so each setting runs in its own
-    interpreter: SS_PAIR=2 forces pairs wherever they are possible, SS_PAIR=0 forbids them; SS_TMA=0 forbids tensor maps.
+    interpreter: SS_PAIR=2 forces pairs wherever they are possible, SS_PAIR=0 forbids them; SS_TMA=0 forbids tensor maps;
+    SS_LEAN=0 forbids the stateless-inference instances of the 32-channel blocks.
     (Integer accumulation is order-independent, so the forward blocks are bit-reproducible; the bf16 gradient kernels share the
     producer code but accumulate in fp32 and are only reproducible to the last bit or two -- tools/dgrad_determinism.py -- so they
     are checked against float64 autograd in test_gpu_grad_umma.py instead.)"""
@@ -594,18 +595,35 @@ out, v, hs = ops.conv_i8_fwd_folded(x, geom, wd, wr, wc, sc, T=3, B=2, neuron=1,
                                     want_v_out=True, want_h=True)
 torch.cuda.synchronize()
 dig('folded', out, v, hs)
+# stateless inference calls (no h_seq / v_out): the LEAN instances of the first layer and of a 32-channel 3x3 block
+g = torch.Generator().manual_seed(6)
+geom = ops.BlockGeom('conv', 4, 32, 5, 21, 27, 21, 27, 1, 2)
+x = torch.poisson(torch.full((3, 2, 21, 27, 4), 0.2), generator=g).clamp(max=255).to(torch.uint8).to(dev)
+w = ((torch.rand(32, 4, 5, 5, generator=g) * 2 - 1) / 6.0).to(dev)
+q, sc, _ = ops.pack_weights_i8(w, 3, cin_pad=4)
+out1, _, _ = ops.conv_i8_fwd(x, geom, q, sc, T=3, B=2, neuron=1, gain=6.0, v_th=1.0, v_reset=0.0, tau=3.0, cin=4)
+geom = ops.BlockGeom('conv', 64, 32, 3, 19, 23, 19, 23, 1, 1)
+x = (torch.rand(4, 2, 19, 23, 64, generator=g) < 0.2).to(torch.uint8).to(dev)
+w = ((torch.rand(32, 64, 3, 3, generator=g) * 2 - 1) / 24.0).to(dev)
+q, sc, _ = ops.pack_weights_i8(w, 3)
+out2, _, _ = ops.conv_i8_fwd(x, geom, q, sc, T=4, B=2, neuron=1, gain=12.0, v_th=1.0, v_reset=0.0, tau=3.0)
+torch.cuda.synchronize()
+dig('stateless', out1, out2)
+assert 0.01 < float(out1.float().mean()) < 0.9 and 0.01 < float(out2.float().mean()) < 0.9
 '''
     results = []
-    modes = (('0', '0'), ('2', '0'), ('0', '1'), ('2', '1'))       # (SS_PAIR, SS_TMA): gathers / TMA patches x single CTA / pairs
-    for pair, tma in modes:
-        env = dict(os.environ, SS_PAIR=pair, SS_TMA=tma, PYTHONPATH=ROOT)
+    # (SS_PAIR, SS_TMA, SS_LEAN): gathers / TMA patches x single CTA / pairs x general / stateless-inference instances (the cases
+    # below ask for v_out and h_seq, so SS_LEAN only matters for the last, stateless one)
+    modes = (('0', '0', '0'), ('2', '0', '1'), ('0', '1', '1'), ('2', '1', '0'))
+    for pair, tma, lean in modes:
+        env = dict(os.environ, SS_PAIR=pair, SS_TMA=tma, SS_LEAN=lean, PYTHONPATH=ROOT)
         r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         results.append([ln for ln in r.stdout.splitlines() if ln.startswith('DIGEST')])
-    assert len(results[0]) == 11
-    for (pair, tma), res in zip(modes[1:], results[1:]):
+    assert len(results[0]) == 12
+    for (pair, tma, lean), res in zip(modes[1:], results[1:]):
         diff = [(a, b) for a, b in zip(results[0], res) if a != b]
-        assert not diff and len(res) == len(results[0]), (f'SS_PAIR={pair} SS_TMA={tma}', diff)
+        assert not diff and len(res) == len(results[0]), (f'SS_PAIR={pair} SS_TMA={tma} SS_LEAN={lean}', diff)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -171,6 +171,13 @@ typedef struct ss_tile_maps {
     uint64_t* stats;       /* any mode, optional: [6] counters this launch ADDS to -- {spikes fired, nonzero outputs (spikes + skip),
                               sum of outputs^2} over all T steps, then the same three over the last step only.  The firing rates of
                               SNN_models.py:194-245 and the spike penalty of loss.py:96-107 without a pass over the spike maps. */
+    const int32_t* item_tab;   /* ROW_LIST, optional: n_items pairs {weight set = output-channel tile * nclass + class, m-tile = tile row *
+                              tiles_x + tile column}, in execution order (items of one weight set contiguous).  The class lists are then
+                              CONCATENATED in rl_src / rl_out (each class padded to whole 16-row tiles on its own, rl_n = total number of
+                              entries, tile row = index / 16) instead of [nclass][rl_n] padded to a common length, so a class with few
+                              rows costs only the tiles it needs. */
+    int32_t n_items;
+    int32_t reserved;
 } ss_tile_maps;
 int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
                       const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,

@@ -78,6 +78,9 @@ struct I8Params {
     const int* rl_out;     // [nclass][rl_n] pixel offset of the entry's output row at column 0, or -1
     const uint8_t* rl_collive;   // [c_nout] 1 = this output column belongs to the pass (NULL = all)
     int rl_n;              // entries per class (padded with -1 to a common length)
+    const int2* item_tab;  // row-list passes, optional: item -> {weight set, m-tile}.  The class lists are then CONCATENATED (each padded
+                           // to whole 16-row tiles on its own, rl_n = total entries) instead of padded to a common length, and a class
+                           // gets exactly the tiles it needs
     int rl_fold;           // row-list pass with FOLDED columns: tile columns = source positions, classes = (row class, column class),
                            // output column through xmap_out -- the dense folded pass restricted to the regular rows of each class
     int in_rowstep;        // pixels between the ROWSTEP source rows of an entry (Win; 1 for the transposed pass)
@@ -141,6 +144,21 @@ __host__ inline uint32_t div_magic(long long d, long long n_max) {
     return (uint32_t)(((1ULL << 32) + (unsigned long long)d - 1ULL) / (unsigned long long)d);
 }
 
+// item -> (weight set, m-tile): round-robin division, or the table of a row-list pass with per-class tile counts
+template <int ROWSTEP>
+__device__ __forceinline__ void item_decode(const I8Params& p, int it, int mt_per, uint32_t m_mt_per, int& ntile, int& mt) {
+    if constexpr (ROWSTEP > 1) {
+        if (p.item_tab != nullptr) {
+            const int2 e = __ldg(p.item_tab + it);
+            ntile = e.x;
+            mt = e.y;
+            return;
+        }
+    }
+    ntile = fast_div(it, mt_per, m_mt_per);
+    mt = it - ntile * mt_per;
+}
+
 // ------------------------------------------------------------------------------------------------ geometry
 // Pixel offset (inside one timestep) of the source row read by patch row `pr` of tile row `ty`, at column 0, or -1 (zero
 // padding / gap between stacked images / dead list entry).
@@ -150,7 +168,7 @@ __device__ __forceinline__ int row_source(const I8Params& p, int ty, int pr, int
         // row list: every tile row has its own ROWSTEP source rows (no sliding window between tile rows)
         const int e = ty * 16 + pr / ROWSTEP;
         if (e >= p.rl_n) return -1;
-        const int s0 = __ldg(p.rl_src + (p.rl_fold ? cls >> 1 : cls) * p.rl_n + e);
+        const int s0 = __ldg(p.rl_src + (p.item_tab != nullptr ? 0 : (p.rl_fold ? cls >> 1 : cls) * p.rl_n) + e);
         return s0 < 0 ? -1 : s0 + (pr % ROWSTEP) * p.in_rowstep;
     } else {
         const int gi = ty * 16 * STRIDE + pr;
@@ -453,15 +471,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int it = it0; it < nit; it += its) {
-                    const int ntile = fast_div(it, mt_per, m_mt_per);
-                    const int mt = it - ntile * mt_per;
+                    int ntile, mt;
+                    item_decode<ROWSTEP>(p, it, mt_per, m_mt_per, ntile, mt);
                     const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
                     const int rcls = p.rl_fold ? (ntile % p.nclass) >> 1 : ntile % p.nclass;
+                    const int rl_base = p.item_tab != nullptr ? 0 : rcls * p.rl_n;
                     int ent[4];                       // (image << 16 | source row) of this thread's tile rows, -1 = dead
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int e = ty * 16 + warp * 4 + k;
-                        const int s0 = e < p.rl_n ? __ldg(p.rl_src + rcls * p.rl_n + e) : -1;
+                        const int s0 = e < p.rl_n ? __ldg(p.rl_src + rl_base + e) : -1;
                         ent[k] = -1;
                         if (s0 >= 0) {
                             const int row = s0 / p.Win;           // b * Hin + y
@@ -606,8 +625,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
         SS_DECL();
         for (int it = it0; it < nit; it += its, ++itcount) {
             SS_T0();
-            const int ntile = fast_div(it, mt_per, m_mt_per);
-            const int mt = PAIR ? 2 * (it - ntile * mt_per) + (int)crank : it - ntile * mt_per;   // (an odd tail tile is all padding)
+            int ntile, mt;
+            item_decode<ROWSTEP>(p, it, mt_per, m_mt_per, ntile, mt);
+            if constexpr (PAIR) mt = 2 * mt + (int)crank;   // (an odd tail tile is all padding)
             const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
             int* rs = rowsrc + (itcount & 1) * 48;
             int* cs = colsrc + (itcount & 1) * 24;
@@ -784,7 +804,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
             };
 
             for (int it = it0; it < nit; it += its) {
-                const int ntile = fast_div(it, mt_per, m_mt_per);   // weight-set index: (output-channel tile, class)
+                int ntile, mt_unused;                               // weight-set index: (output-channel tile, class)
+                item_decode<ROWSTEP>(p, it, mt_per, m_mt_per, ntile, mt_unused);
                 if (p.resident && ntile != loaded_ntile) {
                     loaded_ntile = ntile;
                     w_pending = (1u << p.ncb) - 1u;
@@ -847,7 +868,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                 if (p.resident) {
                     const int nxt = it + its;
                     // the thread that issued the last stage releases the resident weight buffers before a reload
-                    if (nxt < nit && nxt / mt_per != ntile && ((g - 1u) & 1u) == role)
+                    int nxt_ntile = ntile, nxt_mt;
+                    if (nxt < nit) item_decode<ROWSTEP>(p, nxt, mt_per, m_mt_per, nxt_ntile, nxt_mt);
+                    if (nxt < nit && nxt_ntile != ntile && ((g - 1u) & 1u) == role)
                         for (int cb = 0; cb < p.ncb; ++cb) commit(bar_empty_w + 8 * cb);
                 }
             }
@@ -875,7 +898,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                 }
             };
             for (int it = it0; it < nit; it += its) {
-                const int ntile = fast_div(it, mt_per, m_mt_per);
+                int ntile, mt_unused;
+                item_decode<ROWSTEP>(p, it, mt_per, m_mt_per, ntile, mt_unused);
                 if (p.resident) {
                     if (ntile != loaded_ntile) {
                         for (int cb = 0; cb < p.ncb; ++cb) {
@@ -996,8 +1020,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
         // {spikes, nonzero outputs, sum out^2} over all steps [0..2] and over the last step [3..5]; one atomic per warp at the end
         uint32_t st[6] = {0u, 0u, 0u, 0u, 0u, 0u};
         for (int it = it0; it < nit; it += its) {
-            const int ntile = fast_div(it, mt_per, m_mt_per);
-            const int mt = PAIR ? 2 * (it - ntile * mt_per) + (int)crank : it - ntile * mt_per;
+            int ntile, mt;
+            item_decode<ROWSTEP>(p, it, mt_per, m_mt_per, ntile, mt);
+            if constexpr (PAIR) mt = 2 * mt + (int)crank;
             const int ty = fast_div(mt, p.tiles_x, p.m_tiles_x), tx = mt - ty * p.tiles_x;
             const int wset = ntile;                       // (output-channel tile, class)
             const int cls = wset % p.nclass;
@@ -1006,7 +1031,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
             if constexpr (ROWSTEP > 1) {
                 // row list: the tile row is an entry of this class's list; columns are plain output columns
                 const int e = ty * 16 + g;
-                const int orow = e < p.rl_n ? __ldg(p.rl_out + (p.rl_fold ? cls >> 1 : cls) * p.rl_n + e) : -1;
+                const int orow = e < p.rl_n ? __ldg(p.rl_out + (p.item_tab != nullptr ? 0 : (p.rl_fold ? cls >> 1 : cls) * p.rl_n) + e) : -1;
                 int oc = tx * 8 + j;
                 if (p.rl_fold) oc = oc < p.Wv ? __ldg(p.xmap_out + (cls & 1) * p.Wv + oc) : -1;   // source position -> output column of the class
                 live = orow >= 0 && oc >= 0 && oc < p.c_nout && (p.rl_collive == nullptr || __ldg(p.rl_collive + oc) != 0);
@@ -1829,6 +1854,16 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         return SS_EINVAL;
     }
     p.nitems = (int)nitems;
+    p.item_tab = nullptr;
+    if (rowlist && tm->item_tab != nullptr) {
+        // per-class tile counts: the caller enumerates the items (weight set, m-tile) itself; lists concatenated, rl_n = total
+        if (tm->n_items <= 0) {
+            set_error("ss_conv_i8_fwd_ex: item table without items");
+            return SS_EINVAL;
+        }
+        p.item_tab = reinterpret_cast<const int2*>(tm->item_tab);
+        p.nitems = tm->n_items;
+    }
     p.m_mtiles = div_magic(p.mtiles, nitems);
     p.m_tiles_x = div_magic(p.tiles_x, p.mtiles);
     p.m_per = div_magic((long long)p.stride * p.HsO, (long long)p.stride * (rows + 64));

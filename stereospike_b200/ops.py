@@ -193,6 +193,27 @@ class FoldPlan:
                         src[c, i], out[c, i] = src_off(b, s0[o]), out_off(b, o)
                         i += 1
             return t32(src), t32(out), n, sum(len(v) for v in per)
+
+        def concat_lists(s0, pat, src_off, out_off, classes):
+            """The same lists CONCATENATED, each class padded to whole 16-entry tiles on its own (ss_tile_maps.item_tab):
+            (src, out, total entries, [(first tile row, tile rows)] per class)."""
+            srcs, outs, ranges, ty = [], [], [], 0
+            for c in classes:
+                ent = [(src_off(b, s0[o]), out_off(b, o)) for b in range(B) for o in range(len(s0)) if pat[o] == c]
+                nt = (len(ent) + 15) // 16
+                ent += [(-1, -1)] * (nt * 16 - len(ent))
+                srcs += [e[0] for e in ent]
+                outs += [e[1] for e in ent]
+                ranges.append((ty, nt))
+                ty += nt
+            if ty == 0:
+                srcs, outs = [-1] * 16, [-1] * 16
+            return t32(np.asarray(srcs, dtype=np.int64)), t32(np.asarray(outs, dtype=np.int64)), len(srcs), tuple(ranges)
+        self._t32 = t32
+        self.crow = concat_lists(s0y, py, lambda b, s: (b * Hin + s) * Win, lambda b, o: (b * Hout + o) * Wout, (2, 3, 4))
+        self.ccol = concat_lists(s0x, px, lambda b, s: b * Hin * Win + s, lambda b, o: b * Hout * Wout + o, (2, 3, 4))
+        self.creg = concat_lists(s0y, py, lambda b, s: (b * Hin + s) * Win, lambda b, o: (b * Hout + o) * Wout, (0, 1))
+        self._items = {}
         self.row_src, self.row_out, self.row_n, self.n_irr_rows = lists(
             s0y, py, lambda b, s: (b * Hin + s) * Win, lambda b, o: (b * Hout + o) * Wout)
         self.col_src, self.col_out, self.col_n, self.n_irr_cols = lists(
@@ -209,6 +230,26 @@ class FoldPlan:
         self.covered = n_reg_r * n_reg_c / float(Hout * Wout)                 # fraction of outputs in the dense (9-tap) pass
         # taps executed per output, averaged (25 = unfolded): what bench.py credits a folded block with
         self.taps_per_output = (9.0 * n_reg_r * n_reg_c + 15.0 * self.n_irr_rows * Wout + 15.0 * self.n_irr_cols * n_reg_r) / float(Hout * Wout)
+
+
+    def item_table(self, which, ntiles_out, tiles_x, col_classes=1):
+        """Device int32 [n_items][2] = {weight set, m-tile} of a row-list pass over the concatenated lists ``which`` ('crow', 'ccol',
+        'creg'): per output-channel tile, per (row class, column class), the tiles of that row class -- a class gets exactly the
+        tiles it needs.  Cached."""
+        key = (which, ntiles_out, tiles_x, col_classes)
+        if key not in self._items:
+            ranges = getattr(self, which)[3]
+            nclass = len(ranges) * col_classes
+            items = []
+            for n in range(ntiles_out):
+                for rc, (ty0, nt) in enumerate(ranges):
+                    for cc in range(col_classes):
+                        wset = n * nclass + rc * col_classes + cc
+                        for ty in range(ty0, ty0 + nt):
+                            items += [(wset, ty * tiles_x + tx) for tx in range(tiles_x)]
+            tab = self._t32(np.asarray(items, dtype=np.int64).reshape(-1, 2)) if items else None
+            self._items[key] = (tab, len(items))
+        return self._items[key]
 
 
 @functools.lru_cache(maxsize=None)
@@ -377,11 +418,13 @@ def conv_i8_fwd_folded(x, geom, w_dense, w_rows, w_cols, wscale, **kw):
     assert g.kind == 'upconv' and g.ks == 5
     plan = fold_plan(g.Hin, g.Win, g.Hout, g.Wout, int(kw['B']), str(x.device))
     assert plan.ok, 'geometry cannot be folded'
+    nto = g.Cout // 32
     if plan.rows_by_list and g.Cin % 64 == 0 and FOLD_ROWS_BY_LIST:
         # regular rows x regular columns: the dense 3x3 sets on the listed regular rows only
-        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=4, rl_n=plan.reg_n, transposed=2, ymap_out=0,
-                           xmap_out=plan.xmap.data_ptr(), rl_src=plan.reg_src.data_ptr(), rl_out=plan.reg_out.data_ptr(), rl_collive=0,
-                           stats=0)
+        src, out, n, _ = plan.creg
+        tab, nit = plan.item_table('creg', nto, (g.Win - 2 + 7) // 8, col_classes=2)
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=4, rl_n=n, transposed=2, ymap_out=0, xmap_out=plan.xmap.data_ptr(),
+                           rl_src=src.data_ptr(), rl_out=out.data_ptr(), rl_collive=0, stats=0, item_tab=tab.data_ptr(), n_items=nit)
         res = conv_i8_fwd(x, g, w_dense, wscale, tile_maps=tm, **kw)
     else:
         tm = _lib.TileMaps(mode=_lib.SS_TILES_FOLDED, nclass=4, rl_n=0, transposed=0, ymap_out=plan.ymap.data_ptr(),
@@ -390,14 +433,18 @@ def conv_i8_fwd_folded(x, geom, w_dense, w_rows, w_cols, wscale, **kw):
     kw2 = dict(kw)
     for k in ('want_v_out', 'want_h', 'outputs'):
         kw2.pop(k, None)
+    # the irregular rows / columns: class lists concatenated, every class with its own number of tiles (item table)
     if plan.n_irr_rows:
-        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=plan.row_n, transposed=0, ymap_out=0, xmap_out=0,
-                           rl_src=plan.row_src.data_ptr(), rl_out=plan.row_out.data_ptr(), rl_collive=0, stats=0)
+        src, out, n, _ = plan.crow
+        tab, nit = plan.item_table('crow', nto, (g.Wout + 7) // 8)
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=n, transposed=0, ymap_out=0, xmap_out=0, rl_src=src.data_ptr(),
+                           rl_out=out.data_ptr(), rl_collive=0, stats=0, item_tab=tab.data_ptr(), n_items=nit)
         conv_i8_fwd(x, g, w_rows, wscale, tile_maps=tm, outputs=res, **kw2)
     if plan.n_irr_cols:
-        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=plan.col_n, transposed=1, ymap_out=0, xmap_out=0,
-                           rl_src=plan.col_src.data_ptr(), rl_out=plan.col_out.data_ptr(), rl_collive=plan.row_regular.data_ptr(),
-                           stats=0)
+        src, out, n, _ = plan.ccol
+        tab, nit = plan.item_table('ccol', nto, (g.Hout + 7) // 8)
+        tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=n, transposed=1, ymap_out=0, xmap_out=0, rl_src=src.data_ptr(),
+                           rl_out=out.data_ptr(), rl_collive=plan.row_regular.data_ptr(), stats=0, item_tab=tab.data_ptr(), n_items=nit)
         conv_i8_fwd(x, g, w_cols, wscale, tile_maps=tm, outputs=res, **kw2)
     return res
 

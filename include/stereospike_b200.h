@@ -177,7 +177,10 @@ typedef struct ss_tile_maps {
                               entries, tile row = index / 16) instead of [nclass][rl_n] padded to a common length, so a class with few
                               rows costs only the tiles it needs. */
     int32_t n_items;
-    int32_t reserved;
+    int32_t defer_wait;    /* any mode: != 0 declares that this launch reads nothing the previous launch in the stream writes and writes
+                              nothing it reads or writes (a later pass of the same folded block: same inputs, other output pixels).  Its
+                              CTAs then start on the SMs the previous grid's last round leaves idle (programmatic dependent launch
+                              without the wait at the top) and wait for the previous grid only before exiting. */
 } ss_tile_maps;
 int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
                       const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,

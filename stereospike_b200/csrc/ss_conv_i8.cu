@@ -81,6 +81,8 @@ struct I8Params {
     const int2* item_tab;  // row-list passes, optional: item -> {weight set, m-tile}.  The class lists are then CONCATENATED (each padded
                            // to whole 16-row tiles on its own, rl_n = total entries) instead of padded to a common length, and a class
                            // gets exactly the tiles it needs
+    int defer_wait;        // this launch does not read what the previous launch in the stream writes (2nd / 3rd pass of a folded block):
+                           // it starts as soon as the previous grid leaves SMs free and only waits for it before exiting
     int rl_fold;           // row-list pass with FOLDED columns: tile columns = source positions, classes = (row class, column class),
                            // output column through xmap_out -- the dense folded pass restricted to the regular rows of each class
     int in_rowstep;        // pixels between the ROWSTEP source rows of an entry (Win; 1 for the transposed pass)
@@ -345,7 +347,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the previous
     // kernel in the stream; from here on we read what it wrote.  Let our own dependents start their prologue early as well.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // A later pass of the same folded block reads only what the first pass read (the previous layer's output, complete before the
+    // first pass got past its own wait) and writes other pixels of the same tensors, so it does not wait here: its CTAs take the SMs
+    // the previous pass's last round leaves idle (a pass of 192 items on 148 SMs is two rounds with the second two-thirds empty).
+    // It waits before exiting instead, so that whoever waits for THIS grid still waits for everything before it.
+    if (!p.defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr uint32_t swz_mask = (uint32_t)(RB >> 4) - 1u;  // 32 -> 1, 64 -> 3, 128 -> 7
 
@@ -1200,6 +1206,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
         if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+    if (p.defer_wait && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
@@ -1854,6 +1861,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         return SS_EINVAL;
     }
     p.nitems = (int)nitems;
+    p.defer_wait = (tm != nullptr && tm->defer_wait != 0) ? 1 : 0;
     p.item_tab = nullptr;
     if (rowlist && tm->item_tab != nullptr) {
         // per-class tile counts: the caller enumerates the items (weight set, m-tile) itself; lists concatenated, rl_n = total

@@ -128,6 +128,7 @@ def pack_events(x_seq, status=None):
 
 
 # ----------------------------------------------------------------------------------------- folded upsampled conv
+FOLD_OVERLAP = 0 if os.environ.get('SS_FOLD_OVERLAP', '1') == '0' else 1   # the three passes of a folded block overlap their tails
 FOLD_ROWS_BY_LIST = os.environ.get('SS_FOLD_ROWS_BY_LIST', '1') != '0'    # dense folded pass on listed regular rows (small decoder blocks)
 
 # Replication patterns of the 5 taps of one axis of  UpsamplingNearest2d(n_out + 4) -> valid conv(5)  (source index of tap k
@@ -438,13 +439,14 @@ def conv_i8_fwd_folded(x, geom, w_dense, w_rows, w_cols, wscale, **kw):
         src, out, n, _ = plan.crow
         tab, nit = plan.item_table('crow', nto, (g.Wout + 7) // 8)
         tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=n, transposed=0, ymap_out=0, xmap_out=0, rl_src=src.data_ptr(),
-                           rl_out=out.data_ptr(), rl_collive=0, stats=0, item_tab=tab.data_ptr(), n_items=nit)
+                           rl_out=out.data_ptr(), rl_collive=0, stats=0, item_tab=tab.data_ptr(), n_items=nit, defer_wait=FOLD_OVERLAP)
         conv_i8_fwd(x, g, w_rows, wscale, tile_maps=tm, outputs=res, **kw2)
     if plan.n_irr_cols:
         src, out, n, _ = plan.ccol
         tab, nit = plan.item_table('ccol', nto, (g.Hout + 7) // 8)
         tm = _lib.TileMaps(mode=_lib.SS_TILES_ROW_LIST, nclass=3, rl_n=n, transposed=1, ymap_out=0, xmap_out=0, rl_src=src.data_ptr(),
-                           rl_out=out.data_ptr(), rl_collive=plan.row_regular.data_ptr(), stats=0, item_tab=tab.data_ptr(), n_items=nit)
+                           rl_out=out.data_ptr(), rl_collive=plan.row_regular.data_ptr(), stats=0, item_tab=tab.data_ptr(), n_items=nit,
+                           defer_wait=FOLD_OVERLAP)
         conv_i8_fwd(x, g, w_cols, wscale, tile_maps=tm, outputs=res, **kw2)
     return res
 

@@ -545,7 +545,7 @@ def run_ours(args):
     if not train and not args.no_train:
         del xs, pipe
         torch.cuda.empty_cache()
-        tsteps, twarm = max(5, min(args.steps, 20)), 5
+        tsteps, twarm = max(5, min(args.steps, 20)), 10
         ms_sync, ms_nosync, ncoll, tl = time_training(args, dev, world, rank, args.train_batch, tsteps, twarm, barrier)
         tt = torch.tensor([ms_sync, ms_nosync], dtype=torch.float64, device=dev)
         if world > 1:

@@ -174,6 +174,9 @@ class Engine:
         self.fold_min_frames = 16   # ... for calls of at least this many event frames (B * T); smaller calls are launch-latency-bound
         self.flop_scale = {}        # site -> executed taps / 25 of the folded blocks of the last forward (bench.py credits these FLOPs)
         self.bwd_impl = 'umma'      # gradients of the convs: 'umma' = bf16 tensor cores (fp32 accumulation), 'simt' = fp32 CUDA cores
+        import os
+        self.wgrad_stream = os.environ.get('SS_WGRAD_STREAM', '1') != '0'    # tensor-core weight gradients on a second stream, overlapping the rest of the backward
+        self._side = None
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
         #                             False = per-timestep accumulation in the reference's order (bit-identical to T single steps)
 
@@ -457,6 +460,13 @@ class Engine:
             buf[T - 1] += gs.permute(0, 2, 3, 1).to(torch.float32)
 
         # ---- spiking blocks, reverse order
+        main = torch.cuda.current_stream(dev)
+        side = None
+        if self.wgrad_stream and self.bwd_impl == 'umma' and not torch.cuda.is_current_stream_capturing():
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+        side_keep = []
         for i in range(len(self.sites) - 1, -1, -1):
             s, sv = self.sites[i], saved['sites'][i]
             gm = sv['geom']
@@ -489,21 +499,42 @@ class Engine:
                                ks=gm.ks, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC, neuron=node.kind,
                                reserved0=0, gain=1.0, v_th=1.0, v_reset=0.0, tau=2.0, reserved1=0, reserved2=0)
             ym, xm = gm.maps(dev)
-            if tc_w:
-                cin_dev = int(x_in.shape[-1])
-                g_wkn = ops.conv_wgrad_bf16(x_in, g_b16, gm, T, B, cin=cin_dev, x_full_range=first)   # event counts may exceed 127
-                if cin_dev != gm.Cin:       # packed first layer: drop the padding channels
-                    g_wkn = g_wkn.view(gm.ks * gm.ks, cin_dev, gm.Cout)[:, :gm.Cin].reshape(gm.K, gm.Cout)
+            if tc_w and side is not None:
+                # The weight gradient hangs off the critical path (scan -> data gradient -> next block's scan): it runs on a second
+                # stream, so that its CTAs and the data-gradient / scan kernels of the following blocks fill each other's partly empty
+                # rounds (a weight-gradient grid is one wave of 128-148 CTAs of unequal length; both kinds of CTA take a whole SM).
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    cin_dev = int(x_in.shape[-1])
+                    g_wkn = ops.conv_wgrad_bf16(x_in, g_b16, gm, T, B, cin=cin_dev, x_full_range=first)
+                    if cin_dev != gm.Cin:       # packed first layer: drop the padding channels
+                        g_wkn = g_wkn.view(gm.ks * gm.ks, cin_dev, gm.Cout)[:, :gm.Cin].reshape(gm.K, gm.Cout)
+                    grads[2 * i] = ops.kn_to_weight(g_wkn, gm.Cout, gm.Cin, gm.ks)
+                    if hook is not None:
+                        hook.ready(grads[2 * i])
+                # (no record_stream: it defers the allocator's reuse of these blocks and the step time then takes ~10 steps to settle;
+                #  the operands are simply kept alive until the main stream has waited for the side stream below, and the gradient's
+                #  block is only ever re-used by the side stream, which is ordered after everything the main stream did with it)
+                side_keep.append((x_in, g_b16))
             else:
-                g_wkn = torch.zeros((gm.K, gm.Cout), dtype=torch.float32, device=dev)
-                rc = L.ss_conv_wgrad(ctypes.byref(cg), _ptr(acts[s.src]), _ptr(ym), _ptr(xm), _ptr(g_acc), _ptr(g_wkn), _stream())
-                _lib.check(rc, 'ss_conv_wgrad')
-            grads[2 * i] = ops.kn_to_weight(g_wkn, gm.Cout, gm.Cin, gm.ks)
+                if tc_w:
+                    cin_dev = int(x_in.shape[-1])
+                    g_wkn = ops.conv_wgrad_bf16(x_in, g_b16, gm, T, B, cin=cin_dev, x_full_range=first)   # event counts may exceed 127
+                    if cin_dev != gm.Cin:       # packed first layer: drop the padding channels
+                        g_wkn = g_wkn.view(gm.ks * gm.ks, cin_dev, gm.Cout)[:, :gm.Cin].reshape(gm.K, gm.Cout)
+                else:
+                    g_wkn = torch.zeros((gm.K, gm.Cout), dtype=torch.float32, device=dev)
+                    rc = L.ss_conv_wgrad(ctypes.byref(cg), _ptr(acts[s.src]), _ptr(ym), _ptr(xm), _ptr(g_acc), _ptr(g_wkn), _stream())
+                    _lib.check(rc, 'ss_conv_wgrad')
+                grads[2 * i] = ops.kn_to_weight(g_wkn, gm.Cout, gm.Cin, gm.ks)
+                if hook is not None:
+                    # all-reduce this block's gradient now, on NCCL's stream, while the earlier layers' gradients are computed
+                    hook.ready(grads[2 * i])
             if g_decay is not None:
                 grads[2 * i + 1] = g_decay.reshape(params[2 * i + 1].shape)
             if hook is not None:
-                # all-reduce this block's gradient now, on NCCL's stream, while the earlier layers' gradients are computed
-                hook.ready(grads[2 * i])
                 hook.ready(grads[2 * i + 1])
             if not first:
                 gx = gbuf(s.src)
@@ -514,6 +545,9 @@ class Engine:
                     rc = L.ss_conv_dgrad(ctypes.byref(cg), _ptr(ym), _ptr(xm), _ptr(w_kn), _ptr(g_acc), _ptr(gx), _stream())
                     _lib.check(rc, 'ss_conv_dgrad')
             del g_acc, g_b16, g_out
+        if side is not None:
+            main.wait_stream(side)          # every weight gradient is complete before autograd hands them on
+            side_keep.clear()
         if hook is not None:
             hook.finish()
         if input_grad_of is not None:

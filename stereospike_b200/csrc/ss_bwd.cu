@@ -22,8 +22,9 @@ __device__ __forceinline__ float surrogate_grad(int kind, float alpha, float u) 
 }
 
 // One thread scans VEC consecutive neurons (VEC = 4: 16-byte loads of h and g_s, 8-byte bf16 stores) backwards in time.
+constexpr int SCAN_TC = 5;   // timesteps of the reverse scan whose loads are in flight together
 template <int VEC>
-__global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int neuron, int surrogate, float alpha,
+__global__ void __launch_bounds__(256, 3) neuron_bwd_kernel(int T, long long N, int neuron, int surrogate, float alpha,
                                                          float gain, float v_th, float v_reset, float tau,
                                                          const float* __restrict__ decay_p, const float* __restrict__ h_seq,
                                                          const float* __restrict__ v_init, const float* g_s,
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int
         if (neuron == SS_NEURON_LIF) r = 1.0f / tau;
         if (neuron == SS_NEURON_PLIF) r = __ldg(decay_p);
         const float keep = (neuron == SS_NEURON_IF) ? 1.0f : 1.0f - r;
-        float g_v[VEC], h[VEC], h_prev[VEC], gs[VEC];
+        float g_v[VEC], h[VEC], h_prev[VEC];
         auto load = [&](const float* src, float (&dst)[VEC]) {
             if constexpr (VEC == 4) {
                 const float4 q = *reinterpret_cast<const float4*>(src);
@@ -50,46 +51,61 @@ __global__ void __launch_bounds__(256) neuron_bwd_kernel(int T, long long N, int
         for (int i = 0; i < VEC; ++i) g_v[i] = 0.0f;
         if (g_v_last != nullptr) load(g_v_last + n, g_v);
         load(h_seq + (size_t)(T - 1) * N + n, h);
-        for (int t = T - 1; t >= 0; --t) {
-            // potential before this step: reset(h_{t-1}) or the initial state
-            float v_prev[VEC];
-            if (t > 0) {
-                load(h_seq + (size_t)(t - 1) * N + n, h_prev);
+        // The recurrence runs backwards in time, but its inputs do not depend on it: the loads of SCAN_TC timesteps are issued
+        // together (one load pair per step left the kernel waiting on HBM latency with 32 bytes in flight per thread).
+        for (int t1 = T - 1; t1 >= 0; t1 -= SCAN_TC) {
+            float hp[SCAN_TC][VEC], gsv[SCAN_TC][VEC];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) v_prev[i] = (h_prev[i] - v_th >= 0.0f) ? v_reset : h_prev[i];
-            } else {
+            for (int j = 0; j < SCAN_TC; ++j) {
+                const int t = t1 - j;
+                if (t > 0) load(h_seq + (size_t)(t - 1) * N + n, hp[j]);
+                if (t >= 0) load(g_s + (size_t)t * N + n, gsv[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < SCAN_TC; ++j) {
+                const int t = t1 - j;
+                if (t < 0) break;
+                // potential before this step: reset(h_{t-1}) or the initial state
+                float v_prev[VEC];
+                if (t > 0) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        h_prev[i] = hp[j][i];
+                        v_prev[i] = (h_prev[i] - v_th >= 0.0f) ? v_reset : h_prev[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        h_prev[i] = 0.0f;
+                        v_prev[i] = v_reset;
+                    }
+                    if (v_init != nullptr) load(v_init + n, v_prev);
+                }
+                float gx[VEC];
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    h_prev[i] = 0.0f;
-                    v_prev[i] = v_reset;
+                    const float u = h[i] - v_th;
+                    const float sp = (u >= 0.0f) ? 1.0f : 0.0f;
+                    const float g_h = gsv[j][i] * surrogate_grad(surrogate, alpha, u) + g_v[i] * (1.0f - sp);
+                    gx[i] = ((neuron == SS_NEURON_IF) ? g_h : g_h * r) * gain;
+                    if (neuron == SS_NEURON_PLIF) gd_local += g_h * ((h[i] - v_prev[i]) / r);  // d h / d r = x - (v - v_reset)
+                    g_v[i] = g_h * keep;
+                    h[i] = h_prev[i];
                 }
-                if (v_init != nullptr) load(v_init + n, v_prev);
-            }
-            load(g_s + (size_t)t * N + n, gs);
-            float gx[VEC];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float u = h[i] - v_th;
-                const float sp = (u >= 0.0f) ? 1.0f : 0.0f;
-                const float g_h = gs[i] * surrogate_grad(surrogate, alpha, u) + g_v[i] * (1.0f - sp);
-                gx[i] = ((neuron == SS_NEURON_IF) ? g_h : g_h * r) * gain;
-                if (neuron == SS_NEURON_PLIF) gd_local += g_h * ((h[i] - v_prev[i]) / r);  // d h / d r = x - (v - v_reset)
-                g_v[i] = g_h * keep;
-                h[i] = h_prev[i];
-            }
-            if constexpr (VEC == 4) {
-                if (g_acc != nullptr) *reinterpret_cast<float4*>(g_acc + (size_t)t * N + n) = make_float4(gx[0], gx[1], gx[2], gx[VEC - 1]);
-                if (g_acc_bf16 != nullptr) {
-                    const __nv_bfloat162 lo = __floats2bfloat162_rn(gx[0], gx[1]);
-                    const __nv_bfloat162 hi = __floats2bfloat162_rn(gx[2], gx[VEC - 1]);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                    *reinterpret_cast<uint2*>(g_acc_bf16 + (size_t)t * N + n) = pk;
+                if constexpr (VEC == 4) {
+                    if (g_acc != nullptr) *reinterpret_cast<float4*>(g_acc + (size_t)t * N + n) = make_float4(gx[0], gx[1], gx[2], gx[VEC - 1]);
+                    if (g_acc_bf16 != nullptr) {
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(gx[0], gx[1]);
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(gx[2], gx[VEC - 1]);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                        *reinterpret_cast<uint2*>(g_acc_bf16 + (size_t)t * N + n) = pk;
+                    }
+                } else {
+                    if (g_acc != nullptr) g_acc[(size_t)t * N + n] = gx[0];
+                    if (g_acc_bf16 != nullptr) g_acc_bf16[(size_t)t * N + n] = __float2bfloat16_rn(gx[0]);
                 }
-            } else {
-                if (g_acc != nullptr) g_acc[(size_t)t * N + n] = gx[0];
-                if (g_acc_bf16 != nullptr) g_acc_bf16[(size_t)t * N + n] = __float2bfloat16_rn(gx[0]);
             }
         }
         if (g_v_init != nullptr) {
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__(256) heads_bias_kernel(const HeadsBwdParams p)
 // weight-gradient one keeps 9 x 8 partials per thread in registers (they meet in shared memory once per block and reach
 // HBM with 9*C atomics per block) and only reads the u8 activations.
 template <bool GACT, bool GW>
-__global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, int head) {
+__global__ void __launch_bounds__(256, GW ? 2 : 4) heads_src_kernel(const HeadsBwdParams p, int head) {
     extern __shared__ float sh[];  // w [9][C] then g_w accumulators [9][C]
     const int C = p.C[head];
     float* wsm = sh;
@@ -453,29 +469,38 @@ __global__ void __launch_bounds__(256) heads_src_kernel(const HeadsBwdParams p, 
                 }
             }
             if (GW) {
-                float asum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int t = 0; t < T; ++t) {
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + ((size_t)t * S + s) * C + c0));
-                    float a[8];
+                // sum of the first T-1 steps (small integers: exact in fp32) and the last step; TU timesteps are loaded together: the
+                // block count is capped for the reduction below, so one 8-byte load in flight per thread left the kernel latency-bound
+                float asum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, alast[8];
+                constexpr int TU = 5;
+                for (int t0 = 0; t0 < T; t0 += TU) {
+                    uint2 raws[TU];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        a[e] = (float)((raw.x >> (8 * e)) & 0xFFu);
-                        a[4 + e] = (float)((raw.y >> (8 * e)) & 0xFFu);
-                    }
-                    if (t != T - 1) {
+                    for (int j = 0; j < TU; ++j)
+                        if (t0 + j < T)
+                            raws[j] = __ldg(reinterpret_cast<const uint2*>(p.acts[head] + ((size_t)(t0 + j) * S + s) * C + c0));
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) asum[e] += a[e];      // small integers: exact
-                    } else {
+                    for (int j = 0; j < TU; ++j) {
+                        if (t0 + j >= T) break;
+                        const bool last = t0 + j == T - 1;
 #pragma unroll
-                        for (int k = 0; k < 9; ++k)
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) acc[GW ? k : 0][e] = fmaf(b1[k], a[e], acc[GW ? k : 0][e]);
+                        for (int e = 0; e < 4; ++e) {
+                            const float lo = (float)((raws[j].x >> (8 * e)) & 0xFFu), hi = (float)((raws[j].y >> (8 * e)) & 0xFFu);
+                            if (last) {
+                                alast[e] = lo;
+                                alast[4 + e] = hi;
+                            } else {
+                                asum[e] += lo;
+                                asum[4 + e] += hi;
+                            }
+                        }
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < 9; ++k)
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[GW ? k : 0][e] = fmaf(b0[k], asum[e], acc[GW ? k : 0][e]);
+                    for (int e = 0; e < 8; ++e)
+                        acc[GW ? k : 0][e] = fmaf(b0[k], asum[e], fmaf(b1[k], alast[e], acc[GW ? k : 0][e]));
             }
         }
     }

@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(TAPS_NT) head_taps_kernel(const HeadsParams p)
         const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (wds[q] == 0u) continue;                       // four silent channels
             const float a0 = (float)(wds[q] & 0xFFu), a1 = (float)((wds[q] >> 8) & 0xFFu);
             const float a2 = (float)((wds[q] >> 16) & 0xFFu), a3 = (float)(wds[q] >> 24);
             const float* wc = wt + c16 * 16 + q * 4;
@@ -98,6 +97,10 @@ __global__ void __launch_bounds__(TAPS_NT) head_taps_kernel(const HeadsParams p)
 
 constexpr int GATHER_NT = 128;
 
+// NE_T = 2: the summed mode (two pseudo-timesteps), fully unrolled; NE_T = 0: any number of timesteps, one at a time.
+// All tap loads of a timestep (of both pseudo-timesteps when NE_T = 2) are issued before the first add: written as
+// `if (off >= 0) acc += load` every add waited for its own load and the kernel ran at one L2 round trip per tap.
+template <int NE_T>
 __global__ void __launch_bounds__(GATHER_NT) heads_gather_kernel(const HeadsParams p) {
     const int HW = p.H * p.W;
     const long long pix = (long long)blockIdx.x * GATHER_NT + threadIdx.x;
@@ -123,18 +126,30 @@ __global__ void __launch_bounds__(GATHER_NT) heads_gather_kernel(const HeadsPara
         }
     }
     float v = p.v_io[pix];
-    for (int e = 0; e < p.NE; ++e) {
-        const float bm = p.summed ? p.bias_mul[e] : 1.0f;
+    constexpr int EU = NE_T > 0 ? NE_T : 1;          // timesteps whose loads are in flight together
+    for (int e0 = 0; e0 < p.NE; e0 += EU) {
+        float tv[EU][4][9];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float* base = p.taps[i] + ((size_t)e * p.B + b) * 9 * p.Hs[i] * p.Ws[i];
-            float acc = 0.0f;
+        for (int eu = 0; eu < EU; ++eu)
 #pragma unroll
-            for (int k = 0; k < 9; ++k)
-                if (off[i][k] >= 0) acc += __ldg(base + off[i][k]);
-            // (conv + bias) * gain, then IF charge with v_threshold = inf: v = v + x, never fires
-            v = __fadd_rn(v, __fmul_rn(fmaf(bm, bias[i], acc), p.gain));
-            if (e == p.NE - 1) p.depths[(size_t)i * p.B * HW + pix] = v;
+            for (int i = 0; i < 4; ++i) {
+                const float* base = p.taps[i] + ((size_t)(e0 + eu) * p.B + b) * 9 * p.Hs[i] * p.Ws[i];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) tv[eu][i][k] = off[i][k] >= 0 ? __ldg(base + off[i][k]) : 0.0f;
+            }
+#pragma unroll
+        for (int eu = 0; eu < EU; ++eu) {
+            const int e = e0 + eu;
+            const float bm = p.summed ? p.bias_mul[e] : 1.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc += tv[eu][i][k];      // a padding tap adds +0: same sum as skipping it
+                // (conv + bias) * gain, then IF charge with v_threshold = inf: v = v + x, never fires
+                v = __fadd_rn(v, __fmul_rn(fmaf(bm, bias[i], acc), p.gain));
+                if (e == p.NE - 1) p.depths[(size_t)i * p.B * HW + pix] = v;
+            }
         }
     }
     p.v_io[pix] = v;
@@ -192,7 +207,9 @@ extern "C" int ss_heads_fwd(const ss_heads_args* a, float* v_io, float* depths, 
     head_taps_kernel<<<(unsigned)((p.pix_begin[4] + TAPS_NT - 1) / TAPS_NT), TAPS_NT, smem, st>>>(p);
     count_launch();
     if (check_launch("head_taps") != SS_OK) return SS_ECUDA;
-    heads_gather_kernel<<<(unsigned)((npix + GATHER_NT - 1) / GATHER_NT), GATHER_NT, 0, st>>>(p);
+    const unsigned gblocks = (unsigned)((npix + GATHER_NT - 1) / GATHER_NT);
+    if (p.NE == 2) heads_gather_kernel<2><<<gblocks, GATHER_NT, 0, st>>>(p);
+    else heads_gather_kernel<0><<<gblocks, GATHER_NT, 0, st>>>(p);
     count_launch();
     return check_launch("heads_gather");
 }

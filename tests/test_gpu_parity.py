@@ -191,6 +191,53 @@ def test_fold_pack_kernel_matches_host_derivation(co, ci, planes):
         assert torch.equal(a, b), (name, int((a != b).sum()))
 
 
+@pytest.mark.parametrize('chans,summed', [((128, 64, 32, 16), True), ((128, 64, 32, 16), False), ((64, 256, 32, 32), True),
+                                          ((48, 64, 32, 16), True)])
+def test_heads_readout_matches_float64(chans, summed):
+    """ss_heads_fwd (tap dots on the tensor cores with exactly split fp32 weights + gather; the CUDA-core taps kernel when a
+    head has a channel count the MMA tiling does not cover: 48) against nearest-upsample -> 3x3 conv -> gain -> I-neuron
+    accumulation in float64 (network/SNN_models.py:133-150,172-188), activations and time sums over the whole u8 range."""
+    import torch.nn.functional as F
+    from stereospike_b200 import ops
+    T, B, H, W, gain = 3, 2, 20, 26, 7.0
+    srcs = [(3, 4), (5, 7), (10, 13), (20, 26)]
+    g = torch.Generator().manual_seed(sum(chans) + summed)
+    geoms, acts, sums, ws, bs = [], [], [], [], []
+    for (hs, wsz), c in zip(srcs, chans):
+        geoms.append(ops.BlockGeom('upconv', c, 1, 3, hs, wsz, H, W))
+        a = torch.randint(0, 256, (T, B, hs, wsz, c), generator=g, dtype=torch.uint8)
+        a[torch.rand(a.shape, generator=g) < 0.6] = 0
+        acts.append(a.cuda())
+        sums.append(torch.randint(0, 256, (B, hs, wsz, c), generator=g, dtype=torch.uint8).cuda())
+        ws.append(((torch.rand(9, c, generator=g) * 2 - 1) * torch.logspace(-3, 0, c)).cuda())
+        bs.append((torch.rand(1, generator=g) - 0.5).cuda())
+    v0 = torch.randn(B, H, W, generator=g).cuda()
+    v_io = v0.clone()
+    depths = ops.heads_fwd(acts, geoms, ws, bs, T=T, B=B, H=H, W=W, gain=gain, v_io=v_io, acts_sum=sums if summed else None)
+
+    def head(i, x_bhwc):                                  # one head on one (pseudo-)timestep, float64
+        x = x_bhwc.permute(0, 3, 1, 2).double()
+        x = F.interpolate(x, size=(H + 2, W + 2), mode='nearest')
+        w = ws[i].double().reshape(3, 3, chans[i]).permute(2, 0, 1).unsqueeze(0)
+        return F.conv2d(x, w)[:, 0]
+    v = v0.double()
+    want = []
+    if summed:
+        for i in range(4):
+            v = v + (head(i, sums[i]) + (T - 1) * bs[i].double()) * gain
+    else:
+        for t in range(T - 1):
+            for i in range(4):
+                v = v + (head(i, acts[i][t]) + bs[i].double()) * gain
+    for i in range(4):
+        v = v + (head(i, acts[i][T - 1]) + bs[i].double()) * gain
+        want.append(v.clone())
+    want = torch.stack(want)
+    scale = float(want.abs().max())
+    assert float((depths.double() - want).abs().max()) < 5e-6 * scale, float((depths.double() - want).abs().max()) / scale
+    assert float((v_io.double() - want[3]).abs().max()) < 5e-6 * scale
+
+
 def test_empty_batch_and_bad_arguments():
     from stereospike_b200 import ops, _lib
     geom, x, w = _mk_block(1, 1)

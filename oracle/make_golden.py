@@ -49,6 +49,11 @@ def weights_match(model, stored):
     return bool(np.array_equal(got[1:], stored[1:]) and abs(got[0] - stored[0]) <= 1e-9 * abs(stored[0]))
 
 
+def weights_match_arrays(got, stored):
+    got, stored = np.asarray(got, dtype=np.float64), np.asarray(stored, dtype=np.float64)
+    return bool(np.array_equal(got[1:], stored[1:]) and abs(got[0] - stored[0]) <= 1e-9 * abs(stored[0]))
+
+
 def simple_loss(depths, label):
     """Sum over the 4 scales of the NaN-masked mean absolute error (metrics.py:83-95 per scale).
     Used instead of network/loss.py::Total_Loss, whose Sobel filters are moved to CUDA whenever
@@ -111,8 +116,50 @@ def run_case(name, build=None):
     return res
 
 
+ANN_SEED = 2024
+
+
+def run_ann_case(build=None):
+    """The analog comparison model (network/ANN_models.py, Sigmoid): one eval-mode forward (B = 1, BatchNorm on seeded running
+    statistics) and one train-mode forward + backward (B = 2, batch statistics, running statistics updated)."""
+    from . import ann_ref
+    torch.manual_seed(ANN_SEED)
+    net = (build or rr.build_reference_ann)()
+    ann_ref.randomize_batchnorm(net, seed=ANN_SEED + 1)
+    x = rm.synthetic_inputs(2, 1, 4, lam=0.05, seed=ANN_SEED + 100)
+    label = rm.synthetic_label(2, seed=ANN_SEED + 200)
+    res = dict(x=x.numpy().astype(np.uint8), weight_checksum=weight_checksum(net))      # the label is regenerated from its seed
+    net.eval()
+    sj.reset_net(net)
+    if hasattr(net, 'reset'):
+        net.reset()
+    with torch.no_grad():
+        d = net(x[:1])
+    res['eval_depth1_sub'] = d[0][0, 0, ::4, ::4].numpy().copy()          # every 4th pixel of the finest depth map
+    res['eval_depth_sums'] = np.array([float(t.double().sum()) for t in d])
+    res['eval_mde'] = np.array(float(rm.mean_depth_error(d[0], label[:1])))
+    net.train()
+    sj.reset_net(net)
+    if hasattr(net, 'reset'):
+        net.reset()
+    d = net(x)
+    loss = simple_loss(d, label)
+    loss.backward()
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    res['train_depth_sums'] = np.array([float(t.detach().double().sum()) for t in d])
+    res['train_loss'] = np.array(float(loss.detach()))
+    res['grad_names'] = np.array(sorted(grads))
+    res['grad_l2'] = np.array([float(grads[k].double().norm()) for k in sorted(grads)])
+    res['running_mean_sum'] = np.array(sum(float(b.double().sum()) for k, b in net.named_buffers() if k.endswith('running_mean')))
+    return res
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    res = run_ann_case()
+    path = os.path.join(GOLDEN_DIR, 'ann_sigmoid.npz')
+    np.savez_compressed(path, **res)
+    print('ann_sigmoid eval mde', float(res['eval_mde']), 'train loss', float(res['train_loss']), os.path.getsize(path), 'bytes')
     for name in CASES:
         res = run_case(name)
         path = os.path.join(GOLDEN_DIR, name + '.npz')

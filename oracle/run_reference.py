@@ -45,3 +45,11 @@ def build_reference(variant='if', monocular=False, multiply_factor=5.0, tau=3.0)
     cls = (m.fromZero_feedforward_multiscale_tempo_monocular_SpikeFlowNetLike if monocular
            else m.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike)
     return cls(use_plif=(variant == 'plif'), tau=tau, multiply_factor=multiply_factor)
+
+
+def build_reference_ann(activation_function=None):
+    """The reference's StereoSpike_equivalentANN (network/ANN_models.py), executed from its own source."""
+    load_reference_models()                       # installs the spikingjelly shim and the `network` package stub
+    m = importlib.import_module('network.ANN_models')
+    import torch.nn as nn
+    return m.StereoSpike_equivalentANN(activation_function if activation_function is not None else nn.Sigmoid())

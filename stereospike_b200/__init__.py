@@ -2,10 +2,10 @@
 
 Public surface mirrors the reference (urancon/StereoSpike ``network`` package + the SpikingJelly pieces it uses):
 ``stereospike_b200.models`` (StereoSpike, fromZero_* classes), ``.blocks`` (MultiplyBy, NNConvUpsampling,
-SEWResBlock), ``.neuron`` / ``.surrogate`` / ``.functional`` (SpikingJelly replacements), ``.loss`` (network/loss.py +
+SEWResBlock), ``.ann`` (the analog comparison model of network/ANN_models.py), ``.neuron`` / ``.surrogate`` / ``.functional`` (SpikingJelly replacements), ``.loss`` (network/loss.py +
 MeanDepthError), ``.events`` (event stream -> input frames).
 """
-from . import blocks, events, functional, loss, models, neuron, parallel, pipeline, surrogate  # noqa: F401
+from . import ann, blocks, events, functional, loss, models, neuron, parallel, pipeline, surrogate  # noqa: F401
 from .blocks import MultiplyBy, NNConvUpsampling, SEWResBlock  # noqa: F401
 from .models import (NeuromorphicNet, StereoSpike,  # noqa: F401
                      fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike,

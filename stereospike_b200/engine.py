@@ -622,11 +622,16 @@ class _LinearBlockFunction(torch.autograd.Function):
     ss_conv_wgrad.  The 1-channel 3x3 heads inside the models go through the dedicated heads kernels instead."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, up_size):
+    def forward(ctx, x, weight, bias, up_size, conv=None):
         B, C, Hs, Ws = x.shape
         co, ci, ks, _ = weight.shape
         cp = (co + 31) // 32 * 32                               # the kernel tiles 32 output channels
-        g = BlockGeom('upconv', C, cp, ks, Hs, Ws, up_size[0], up_size[1])
+        if conv is None:
+            g = BlockGeom('upconv', C, cp, ks, Hs, Ws, up_size[0], up_size[1])
+        else:                                                   # plain Conv2d (stride, padding): the analog comparison model
+            stride, pad = conv
+            g = BlockGeom('conv', C, cp, ks, Hs, Ws, conv_out_size(Hs, ks, stride, pad), conv_out_size(Ws, ks, stride, pad),
+                          stride, pad)
         w_kn = torch.zeros((ks * ks * C, cp), dtype=torch.float32, device=x.device)
         w_kn[:, :co] = ops.weight_to_kn(weight.detach().float())
         x5 = x.detach().float().contiguous().view(B, 1, C, Hs, Ws)
@@ -663,17 +668,29 @@ class _LinearBlockFunction(torch.autograd.Function):
             gw = ops.kn_to_weight(g_wkn, g.Cout, g.Cin, g.ks)[:co].contiguous()
         if ctx.needs_input_grad[2]:
             gb = g_y.float().sum(dim=(0, 2, 3))
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
+
+
+def run_dense_conv(conv, x):
+    """nn.Conv2d.forward (square kernel, one stride / padding for both axes, groups = dilation = 1) on arbitrary fp32 input through
+    the fp32 CUDA-core kernel, with gradients: the convolutions of the analog comparison model (network/ANN_models.py:39-72)."""
+    ops._require_cuda(x, 'x')
+    ks, st, pd = conv.kernel_size, conv.stride, conv.padding
+    if ks[0] != ks[1] or st[0] != st[1] or pd[0] != pd[1] or conv.groups != 1 or tuple(conv.dilation) != (1, 1) or \
+            conv.padding_mode != 'zeros':
+        raise NotImplementedError('run_dense_conv: square kernels, equal strides / zero paddings, groups = dilation = 1')
+    return _LinearBlockFunction.apply(x, conv.weight, conv.bias, None, (int(st[0]), int(pd[0])))
 
 
 def run_linear_block(up, x):
     """NNConvUpsampling.forward for a stand-alone call (no neuron; reference network/blocks.py:130-132).  The 1-channel 3x3 heads
-    (the only stand-alone use in the reference, predict_depthK) run on the heads kernel when no gradient is needed; every other
-    shape, and any grad-enabled call, runs the general fp32 kernel with gradients w.r.t. input, weight and bias."""
+    (the only stand-alone use in the reference, predict_depthK) run on the heads kernels when the input is a uint8 spike-count
+    tensor and no gradient is needed; every other call -- any fp32 input, whose values may be arbitrary reals as in the analog
+    comparison model -- runs the general fp32 kernel with gradients w.r.t. input, weight and bias."""
     conv = up.up[1]
     ops._require_cuda(x, 'x')
     need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in conv.parameters()))
-    spikes_like = x.dtype == torch.float32 and conv.in_channels % 8 == 0
+    spikes_like = x.dtype == torch.uint8 and conv.in_channels % 16 == 0
     if need_grad or conv.out_channels != 1 or conv.kernel_size[0] != 3 or not spikes_like:
         return _LinearBlockFunction.apply(x, conv.weight, conv.bias, up.up_size)
     B, C, Hs, Ws = x.shape

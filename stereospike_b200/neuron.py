@@ -30,23 +30,26 @@ class _NeuronStep(torch.autograd.Function):
         _lib.check(rc, 'ss_neuron_fwd')
         ctx.node = node
         ctx.save_for_backward(h, v0.detach().contiguous().float(), decay if decay is not None else torch.empty(0))
-        ctx.mark_non_differentiable(v)
         return s, v
 
     @staticmethod
-    def backward(ctx, g_s, _g_v):
+    def backward(ctx, g_s, g_v):
+        # Both outputs are differentiable, like upstream: the potential of a non-firing pool IS the prediction (Ineurons.v,
+        # network/SNN_models.py:150, ANN_models.py:99) and the state carried to the next call keeps its graph until detach().
         node = ctx.node
         h, v0, decay = ctx.saved_tensors
         decay = decay if decay.numel() else None
         g_s = g_s.contiguous().float()
+        g_v = g_v.contiguous().float() if g_v is not None else None
         g_x = torch.empty_like(h)
+        g_v0 = torch.empty_like(h) if ctx.needs_input_grad[1] else None
         g_decay = torch.zeros((1,), dtype=torch.float32, device=h.device) if decay is not None else None     # decay_tensor() is [1]
         sf = node.surrogate_function
         rc = _lib.lib().ss_neuron_bwd(1, h.numel(), node.kind, sf.kind, sf.alpha, 1.0, node.v_threshold,
                                       node._v_reset_value(), node._tau_value(), _ptr(decay), _ptr(h), _ptr(v0),
-                                      _ptr(g_s), None, _ptr(g_x), None, _ptr(g_decay), _stream())
+                                      _ptr(g_s), _ptr(g_v), _ptr(g_x), _ptr(g_v0), _ptr(g_decay), _stream())
         _lib.check(rc, 'ss_neuron_bwd')
-        return g_x, None, g_decay, None
+        return g_x, g_v0, g_decay, None
 
 
 class BaseNode(nn.Module):

@@ -174,3 +174,21 @@ def test_fold_plan_and_weight_sets_reproduce_upsampled_conv(Hin, Win, Hout, Wout
     got = of.reshape(B, Hout, Wout, Cout).permute(0, 3, 1, 2)
     assert torch.equal(got, ref)
     assert 9.0 <= plan.taps_per_output < 25.0
+
+
+def test_analog_comparison_model_surface():
+    """stereospike_b200.ann mirrors network/ANN_models.py + the ANN blocks: same state-dict keys and parameter count as the
+    oracle restatement (which tests/test_oracle_vs_reference.py pins against the reference's own file), no CPU fallback."""
+    import pytest
+    import torch
+    import stereospike_b200 as sb
+    from oracle import ann_ref
+    net, o = sb.ann.StereoSpike_equivalentANN(), ann_ref.AnalogUNet()
+    assert sorted(net.state_dict()) == sorted(o.state_dict())
+    assert net.count_trainable_params() == sum(p.numel() for p in o.parameters()) == 18158788
+    assert isinstance(net.Ineurons, sb.neuron.IFNode) and net.Ineurons.v_threshold == float('inf')
+    assert sb.ann.SteroSpike_equivalentANN is sb.ann.StereoSpike_equivalentANN
+    net.increment_epoch()
+    assert net.epoch == 1 and net.get_max_accuracy() == float('inf')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        net(torch.zeros(1, 1, 4, 260, 346))

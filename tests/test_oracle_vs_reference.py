@@ -46,3 +46,31 @@ def test_bit_identical_forward_backward(variant, mono, gain):
 
 def test_binocular_param_count():
     assert sum(p.numel() for p in rm.SpikingUNet('if').parameters()) == 18148708
+
+
+@pytest.mark.parametrize('train', [False, True])
+def test_analog_comparison_model_bit_identical(train):
+    """oracle/ann_ref.py against network/ANN_models.py executed by path: same keys, same depths, same gradients."""
+    from oracle import ann_ref
+    torch.manual_seed(11)
+    ref = rr.build_reference_ann()
+    mine = ann_ref.AnalogUNet()
+    assert sorted(ref.state_dict()) == sorted(mine.state_dict())
+    ann_ref.randomize_batchnorm(ref, seed=5)
+    mine.load_state_dict(ref.state_dict())
+    ref.train(train)
+    mine.train(train)
+    x = rm.synthetic_inputs(2 if train else 1, 1, 4, seed=3)
+    label = rm.synthetic_label(2 if train else 1, seed=4)
+    sj.reset_net(ref)
+    d_ref, d_me = ref(x), mine(x)
+    for a, b in zip(d_ref, d_me):
+        assert torch.equal(a, b)
+    simple_loss(d_ref, label).backward()
+    simple_loss(d_me, label).backward()
+    g_ref = dict(ref.named_parameters())
+    for k, p in mine.named_parameters():
+        assert torch.equal(p.grad, g_ref[k].grad), k
+    if train:
+        for (k, a), (_, b) in zip(ref.named_buffers(), mine.named_buffers()):
+            assert torch.equal(a, b), k

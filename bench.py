@@ -385,6 +385,68 @@ def timestep_sweep(args, dev, B=16, Ts=(1, 5, 10, 20), steps=10, warmup=3):
     return {'batch': B, 'steps': steps, 'warmup': warmup, 'results': res}
 
 
+def analog_model_record(dev, B=8, steps=5, warmup=3):
+    """The analog comparison model (network/ANN_models.py, one frame per depth map): eval-mode forward on the library's fp32
+    convolution kernels, beside the same model in PyTorch eager on the same GPU (cuDNN: true fp32 and TF32 allowed) and the CPU
+    oracle.  It is the paper's Table-4 baseline, not the spiking hot path: the convolutions run on CUDA cores in exact fp32."""
+    import time
+    import torch
+    import stereospike_b200 as sb
+    from oracle import ann_ref, ref_model as rm
+    torch.manual_seed(5)
+    oracle = ann_ref.AnalogUNet().eval()
+    ann_ref.randomize_batchnorm(oracle, seed=6)
+    net = sb.ann.StereoSpike_equivalentANN()
+    net.load_state_dict(oracle.state_dict())
+    net = net.to(dev).eval()
+    x = rm.synthetic_inputs(B, 1, 4, seed=31)
+    xd = x.to(dev)
+
+    def timed(fn):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def ours():
+        sb.functional.reset_net(net)
+        return net(xd)
+
+    ms = timed(ours)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        want = oracle(x[:1])
+        cpu_s = time.perf_counter() - t0
+        oracle.reset()
+        sb.functional.reset_net(net)
+        got = net(xd[:1])
+    diff = max(float((g.cpu() - w).abs().max()) for g, w in zip(got, want)) / max(float(w.abs().max()) for w in want)
+    eager = oracle.to(dev)
+    rec = {'value': B / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms, 'batch': B, 'mode': 'eval forward',
+           'max_depth_diff_vs_oracle_rel': diff, 'cpu_oracle_frames_per_s': 1.0 / cpu_s}
+
+    def eager_fn():
+        eager.reset()
+        return eager(xd)
+
+    before = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    for name, tf32 in (('torch_eager_fp32_frames_per_s', False), ('torch_eager_tf32_frames_per_s', True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        rec[name] = B / (timed(eager_fn) / 1e3)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = before
+    del net, eager, oracle
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -623,6 +685,7 @@ def run_ours(args):
                                      'what': 'PROXY (spikingjelly / cupy are not installable here): cuDNN convs over the flattened [T*B] batch '
                                              '+ one unfused per-neuron T-loop CUDA kernel per layer + elementwise gain / skip adds, fp32 NCHW, '
                                              f'forward, B={B}, T={T}, same GPU, same run'}
+            line['analog_model'] = analog_model_record(dev)
         if world == 1 and not args.no_parity and not train:
             from tests._cases import parity_summary          # the oracle as the checker, outside every timed region
             line['parity'] = parity_summary(args.neuron, args.gain, args.tau, T=T, B=1, seed=0, planes=args.planes,

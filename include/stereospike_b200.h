@@ -181,6 +181,12 @@ typedef struct ss_tile_maps {
                               nothing it reads or writes (a later pass of the same folded block: same inputs, other output pixels).  Its
                               CTAs then start on the SMs the previous grid's last round leaves idle (programmatic dependent launch
                               without the wait at the top) and wait for the previous grid only before exiting. */
+    int32_t independent_steps; /* any mode: != 0 declares that the T steps of this call are INDEPENDENT samples, not a time sequence: the
+                              membrane potential restarts from rest at every step (stateless inference only: h_seq, v_in, v_out, tsum
+                              and stats must be NULL, 3 planes, v_reset 0).  A single-step call on a batch of k*B' samples -- the
+                              reference's calling convention, one forward(x) per frame (SNN_models.py:152-192) -- is then issued as
+                              T = k, B = B' on the same [k*B'][H][W][C] tensors: identical results, but a tile streams its weights
+                              once for k patches instead of once per patch. */
 } ss_tile_maps;
 int ss_conv_i8_fwd_ex(const ss_block_desc* g, const ss_tile_maps* tm, const void* x, const void* w_i8, const float* wscale,
                       const float* decay, const float* v_in, float* v_out, const void* resid, void* out, float* h_seq,

@@ -35,7 +35,8 @@ class TileMaps(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('nclass', ctypes.c_int32), ('rl_n', ctypes.c_int32), ('transposed', ctypes.c_int32),
                 ('ymap_out', ctypes.c_void_p), ('xmap_out', ctypes.c_void_p), ('rl_src', ctypes.c_void_p),
                 ('rl_out', ctypes.c_void_p), ('rl_collive', ctypes.c_void_p), ('stats', ctypes.c_void_p),
-                ('item_tab', ctypes.c_void_p), ('n_items', ctypes.c_int32), ('defer_wait', ctypes.c_int32)]
+                ('item_tab', ctypes.c_void_p), ('n_items', ctypes.c_int32), ('defer_wait', ctypes.c_int32),
+                ('independent_steps', ctypes.c_int32)]
 
 
 SS_TILES_PLAIN, SS_TILES_FOLDED, SS_TILES_ROW_LIST = 0, 1, 2

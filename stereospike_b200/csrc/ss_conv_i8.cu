@@ -255,8 +255,12 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint64_t a0, uint64_t b0,
 // LEAN: stateless inference instantiation -- no saved potentials, no carried / returned membrane state, no firing statistics (the
 // launcher picks it when none of those pointers is given).  The epilogue-bound blocks are limited by dependent-issue latency under
 // a 126-register allocation; without the h_seq / v_out / statistics paths the compiler has 16+ fewer live values to keep.
+// LEAN = 2: the T "timesteps" of an item are INDEPENDENT samples (ss_tile_maps.independent_steps): the potential restarts from
+// rest at every step.  A single-step call on a batch -- the reference's calling convention, forward(x) once per frame -- then
+// runs as T' = k steps of B / k samples: one weight stream per tile serves k patches instead of one (the deep blocks of a T = 1
+// call are bound by re-streaming their weights from L2 for every tile).
 template <int PLANES, int KS, int STRIDE, int RB, bool FIRST = false, int MODE = MODE_I8, bool PAIR = false, int KSX = KS, int ROWSTEP = 1,
-          int NK = -1, bool LEAN = false>
+          int NK = -1, int LEAN = 0>
 __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_constant__ I8Params p) {
     // compile-time geometry: every descriptor offset of the MMA issue loop folds to an immediate
     constexpr int cN = PLANES * 32;
@@ -1131,6 +1135,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_i8_kernel(const __grid_consta
                     }
                     float hbuf[16];
                     uint32_t sb[16];      // spike of each channel as 0 / 1
+                    if constexpr (LEAN == 2) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.0f;      // independent steps: every step starts from rest (v_reset == 0)
+                    }
                     if constexpr (NK >= 0) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) sb[i] = neuron_step_t<NK, true>(x[i], v[i], nc, hbuf[i]) != 0.0f ? 1u : 0u;
@@ -1752,6 +1760,12 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         return SS_EINVAL;
     }
     const bool rowlist = mode == SS_TILES_ROW_LIST;
+    const bool indep = tm != nullptr && tm->independent_steps != 0;
+    if (indep && (h_seq != nullptr || v_in != nullptr || v_out != nullptr || tsum != nullptr || tm->stats != nullptr || g->planes != 3 ||
+                  g->v_reset != 0.0f)) {
+        set_error("ss_conv_i8_fwd_ex: independent steps are for stateless inference (no h_seq / v_in / v_out / tsum / stats, 3 planes, v_reset 0)");
+        return SS_EINVAL;
+    }
     if (mode == SS_TILES_FOLDED && (tm->ymap_out == nullptr || tm->xmap_out == nullptr || g->ks != 3 || g->stride != 1 || g->pad != 0 ||
                                     up || g->Hin < 3 || g->Win < 3)) {
         set_error("ss_conv_i8_fwd_ex: the folded pass is a 3x3 stride-1 pad-0 conv on the source with output maps");
@@ -1890,7 +1904,7 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
     p.m_mtiles2 = div_magic(p.mtiles2, p.nitems2);
     const int dev = current_device();
     const int sms = device_sm_count(dev);
-    bool pair = pair_env != 0 && !first && mode == SS_TILES_PLAIN && (g->planes * 32) % 16 == 0 && p.mtiles >= 2 && sms >= 2;
+    bool pair = pair_env != 0 && !indep && !first && mode == SS_TILES_PLAIN && (g->planes * 32) % 16 == 0 && p.mtiles >= 2 && sms >= 2;
     if (pair && pair_env == 1) {
         const long long rounds1 = (nitems + sms - 1) / sms;
         const long long rounds2 = ((long long)p.nitems2 + sms / 2 - 1) / (sms / 2);
@@ -1989,6 +2003,32 @@ static int conv_i8_launch(const ss_block_desc* g, const ss_tile_maps* tm, const 
         SS_ENSURE_SMEM((conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>), dev, 227 * 1024);                      \
         cudaLaunchKernelEx(&cfg, conv_i8_kernel<PL, 3, 1, 32, false, MODE_I8, false, 5, 3>, p);                            \
         launched = true;                                                                                                   \
+    }
+    // independent steps (LEAN = 2): one instance per shape and neuron kind
+#define SS_TRY_INDEP(COND, KS_, ST_, RB_, FIRST_, KSX_, RS_, NK_)                                                            \
+    if (!launched && indep && g->neuron == NK_ && (COND)) {                                                                 \
+        SS_ENSURE_SMEM((conv_i8_kernel<3, KS_, ST_, RB_, FIRST_, MODE_I8, false, KSX_, RS_, NK_, 2>), dev, 227 * 1024);      \
+        cudaLaunchKernelEx(&cfg, conv_i8_kernel<3, KS_, ST_, RB_, FIRST_, MODE_I8, false, KSX_, RS_, NK_, 2>, p);            \
+        launched = true;                                                                                                    \
+    }
+#define SS_PLAIN_IS(KS_, ST_, RB_) (!first && !rowlist && g->ks == KS_ && g->stride == ST_ && p.RB == RB_)
+#define SS_TRY_INDEP_NK(NK_)                                                                                                \
+    SS_TRY_INDEP(first, 1, 1, 128, true, 1, 1, NK_)                                                                         \
+    SS_TRY_INDEP(rowlist && p.rl_fold, 3, 1, 64, false, 3, 3, NK_)                                                          \
+    SS_TRY_INDEP(rowlist && !p.rl_fold, 3, 1, 32, false, 5, 3, NK_)                                                         \
+    SS_TRY_INDEP(SS_PLAIN_IS(5, 1, 32), 5, 1, 32, false, 5, 1, NK_)                                                         \
+    SS_TRY_INDEP(SS_PLAIN_IS(5, 2, 32), 5, 2, 32, false, 5, 1, NK_)                                                         \
+    SS_TRY_INDEP(SS_PLAIN_IS(3, 1, 64), 3, 1, 64, false, 3, 1, NK_)                                                         \
+    SS_TRY_INDEP(SS_PLAIN_IS(3, 1, 32), 3, 1, 32, false, 3, 1, NK_)
+    SS_TRY_INDEP_NK(SS_NEURON_IF)
+    SS_TRY_INDEP_NK(SS_NEURON_LIF)
+    SS_TRY_INDEP_NK(SS_NEURON_PLIF)
+#undef SS_TRY_INDEP_NK
+#undef SS_PLAIN_IS
+#undef SS_TRY_INDEP
+    if (indep && !launched) {
+        set_error("ss_conv_i8_fwd_ex: no independent-steps instance for ks %d stride %d rowbytes %d", g->ks, g->stride, p.RB);
+        return SS_EUNSUPPORTED;
     }
     // stateless inference (no h_seq, no membrane state in or out, no statistics): the LEAN instances of the epilogue-bound shapes
     static int lean_env = -1;

@@ -10,6 +10,7 @@ Backward: ss_heads_bwd, then per block in reverse order ss_neuron_bwd_ex (surrog
           (SURVEY.md section 3(C)).
 """
 import ctypes
+import os
 
 import torch
 
@@ -172,9 +173,12 @@ class Engine:
         #                             passes for the irregular rows / columns (9 / 15 taps instead of 25, bit-identical integers, 3-4 bits
         #                             less weight precision).  True / False, or a collection of site names ('deconv4', ...)
         self.fold_min_frames = 16   # ... for calls of at least this many event frames (B * T); smaller calls are launch-latency-bound
+        self.batch_as_steps = os.environ.get('SS_BATCH_AS_STEPS', '1') != '0'   # stateless single-step calls on a batch: k independent
+        #                             "steps" of B / k samples per launch (one weight stream per tile serves k patches), bit-identical
+        self.bas_min_batch = int(os.environ.get('SS_BAS_MIN_BATCH', '4'))
+        self.bas_min_cin = int(os.environ.get('SS_BAS_MIN_CIN', '128'))
         self.flop_scale = {}        # site -> executed taps / 25 of the folded blocks of the last forward (bench.py credits these FLOPs)
         self.bwd_impl = 'umma'      # gradients of the convs: 'umma' = bf16 tensor cores (fp32 accumulation), 'simt' = fp32 CUDA cores
-        import os
         self.wgrad_stream = os.environ.get('SS_WGRAD_STREAM', '1') != '0'    # tensor-core weight gradients on a second stream, overlapping the rest of the backward
         self._side = None
         self.heads_time_sum = True  # fold the time loop of the (linear, non-firing) readout: 2 head passes instead of T;
@@ -292,6 +296,17 @@ class Engine:
         if (self.collect_stats or (want_h and side.get('spike_outputs'))) and impl != SS_IMPL_SIMT:
             stats = torch.zeros((len(self.sites), 6), dtype=torch.int64, device=dev)
         side['stats'] = stats
+        # A single-step call on a batch (the reference's calling convention: one forward(x) per frame) is issued as k independent
+        # "steps" of B / k samples: every tile then streams its weights once for k patches instead of once per patch -- the deep
+        # blocks of a T = 1 call are bound by re-streaming their weights from L2.  Stateless inference only; bit-identical.
+        k_steps = 1
+        if self.batch_as_steps and T == 1 and B > 1 and not want_h and not self.keep_state and impl != SS_IMPL_SIMT and \
+                self.weight_planes == 3 and stats is None and not side.get('seed_acts') and \
+                all(not isinstance(s.node.v, torch.Tensor) and float(s.node.v) == 0.0 and s.node.v_reset == 0.0 for s in self.sites):
+            # at least 3 steps of at least 4 samples (measured, T = 1: B = 16 as 4 x 4 +16 %, B = 32 as 4 x 8 +37 %; B = 8 as 2 x 4
+            # -2 %, B = 5 as 5 x 1 -13 %: too few items per launch for the 148 SMs)
+            k_steps = next((c for c in (5, 4, 3) if B % c == 0 and B // c >= self.bas_min_batch), 1)
+        k_all = self.last_batch_steps = k_steps       # (read by the tests)
         for i, s in enumerate(self.sites):
             xin = acts[s.src]
             first = s.src == 'x'
@@ -326,6 +341,12 @@ class Engine:
                 ev0.record()
             common = dict(T=T, B=B, neuron=node.kind, gain=s.gain_mod.gain(), v_th=node.v_threshold, v_reset=node.v_reset,
                           tau=node._tau_value(), decay=decay, v_in=v_in, want_v_out=self.keep_state, resid=resid, want_h=want_h)
+            # per block: the [k, B / k] view is the same memory as [1, B], so only the blocks that stream many weight channel
+            # blocks per tile take it (the full-resolution blocks have nothing to amortise and lose tile-level parallelism)
+            k_steps = k_all if g.Cin >= (self.bas_min_cin if B // k_all < 8 else min(self.bas_min_cin, 64)) else 1
+            as_steps = (lambda a, k=k_steps: a.view(k, B // k, *a.shape[2:])) if k_steps > 1 else (lambda a: a)
+            if k_steps > 1:
+                common.update(T=k_steps, B=B // k_steps, independent_steps=True, resid=as_steps(resid) if resid is not None else None)
             if use_i8:
                 if first and not packed_in:
                     status = self._status_word(dev) if self.check_input else None
@@ -338,12 +359,15 @@ class Engine:
                     tsum = torch.empty((B, g.Hout, g.Wout, g.Cout), dtype=ops.ACT_DTYPE, device=dev)
                     tsums[s.out] = tsum
                 if fold:
-                    out, v_out, h_seq = ops.conv_i8_fwd_folded(xin, g, w_i8[0], w_i8[1], w_i8[2], w_i8[3], planes=self.weight_planes,
-                                                               tsum=tsum, stats=stats[i] if stats is not None else None, **common)
+                    out, v_out, h_seq = ops.conv_i8_fwd_folded(as_steps(xin), g, w_i8[0], w_i8[1], w_i8[2], w_i8[3],
+                                                               planes=self.weight_planes, tsum=tsum,
+                                                               stats=stats[i] if stats is not None else None, **common)
                 else:
-                    out, v_out, h_seq = ops.conv_i8_fwd(xin, g, w_i8[0], w_i8[1], planes=self.weight_planes,
+                    out, v_out, h_seq = ops.conv_i8_fwd(as_steps(xin), g, w_i8[0], w_i8[1], planes=self.weight_planes,
                                                         cin=ops.first_layer_channels(g.Cin) if first else g.Cin, tsum=tsum,
                                                         stats=stats[i] if stats is not None else None, **common)
+                if k_steps > 1:
+                    out = out.view(T, B, *out.shape[2:])
             else:
                 out, v_out, h_seq = ops.conv_neuron_fwd(xin, g, w_kn, in_layout=SS_IN_F32_BTCHW if first else SS_IN_U8_TBHWC,
                                                         **common)

@@ -134,13 +134,14 @@ class _SpikingUNet(NeuromorphicNet):
         return self._engine
 
     def set_kernel_options(self, impl=None, weight_planes=None, keep_state=None, heads_time_sum=None, fold_upsample=None,
-                           bwd_impl=None, fold_min_frames=None):
+                           bwd_impl=None, fold_min_frames=None, batch_as_steps=None):
         """impl: 'umma' (tcgen05 int8 tensor-core kernel; default) or 'simt' (exact-fp32 CUDA cores).
         weight_planes: int8 digit planes per weight -- 3 = 24-bit fixed point, fp32-class (default);
         2 = 16-bit (the reduced-precision training configuration); 4 = 32-bit.
         bwd_impl: 'umma' (conv gradients on the bf16 tensor cores, fp32 accumulation; default) or 'simt' (fp32 CUDA cores).
         fold_upsample / fold_min_frames: NNConvUpsampling blocks as folded 3x3 convs (default on) for calls of at least
-        fold_min_frames event frames (B * T, default 16; smaller calls are launch-latency-bound and keep the single 25-tap launch)."""
+        fold_min_frames event frames (B * T, default 16; smaller calls are launch-latency-bound and keep the single 25-tap launch).
+        batch_as_steps: stateless single-step calls on a batch run as k independent steps of B / k samples per launch (default on)."""
         e = self.engine
         if impl is not None:
             assert impl in ('auto', 'umma', 'simt')
@@ -159,6 +160,8 @@ class _SpikingUNet(NeuromorphicNet):
             e.bwd_impl = bwd_impl
         if fold_min_frames is not None:
             e.fold_min_frames = int(fold_min_frames)
+        if batch_as_steps is not None:
+            e.batch_as_steps = bool(batch_as_steps)
         return self
 
     # ---- forward

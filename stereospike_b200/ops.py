@@ -367,8 +367,9 @@ def _check_block_io(x, g, T, B, resid, v_in, decay, out_shape):
 # ----------------------------------------------------------------------------------------- fused block
 def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau=2.0, decay=None, v_in=None,
                 want_v_out=False, resid=None, want_h=False, planes=3, cin=None, tsum=None, outputs=None, tile_maps=None,
-                desc_override=None, stats=None):
+                desc_override=None, stats=None, independent_steps=False):
     """Tensor-core fused block over all T timesteps (ss_conv_i8_fwd).  x: u8 [T,B,Hin,Win,Cin].
+    ``independent_steps``: the T steps are independent samples (stateless inference; ss_tile_maps.independent_steps).
     ``tsum``: optional u8 [B,Hout,Wout,Cout] receiving the sum of the first T-1 output steps (input of the linear heads).
     ``stats``: optional int64 [6] device tensor the launch ADDS its firing statistics to ({spikes, nonzero outputs, sum out^2} over
     all steps, then over the last step).
@@ -383,6 +384,11 @@ def conv_i8_fwd(x, geom, w_i8, wscale, *, T, B, neuron, gain, v_th, v_reset, tau
             tile_maps = _lib.TileMaps(mode=_lib.SS_TILES_PLAIN, nclass=1, rl_n=0, transposed=0, ymap_out=0, xmap_out=0, rl_src=0,
                                       rl_out=0, rl_collive=0, stats=0)
         tile_maps.stats = stats.data_ptr()
+    if independent_steps:
+        if tile_maps is None:
+            tile_maps = _lib.TileMaps(mode=_lib.SS_TILES_PLAIN, nclass=1, rl_n=0, transposed=0, ymap_out=0, xmap_out=0, rl_src=0,
+                                      rl_out=0, rl_collive=0, stats=0)
+        tile_maps.independent_steps = 1
     assert x.dtype == ACT_DTYPE and x.is_contiguous() and tuple(x.shape) == (T, B, g.Hin, g.Win, cin), \
         (x.dtype, tuple(x.shape), (T, B, g.Hin, g.Win, cin))
     out_shape = (T, B, g.Hout, g.Wout, g.Cout)

@@ -238,6 +238,42 @@ def test_heads_readout_matches_float64(chans, summed):
     assert float((v_io.double() - want[3]).abs().max()) < 5e-6 * scale
 
 
+@pytest.mark.parametrize('variant,B', [('lif', 16), ('if', 12), ('plif', 20)])
+def test_single_step_batch_as_independent_steps_is_bit_identical(variant, B):
+    """A stateless single-step call on a batch runs as k independent steps of B / k samples per launch (one weight stream per tile
+    for k patches; ss_tile_maps.independent_steps): depths and spike maps identical, bit for bit, to the plain T = 1 launch."""
+    import stereospike_b200 as sb
+    from oracle import ref_model as rm
+    torch.manual_seed(31)
+    if variant == 'if':
+        net = sb.StereoSpike(surrogate_function=sb.surrogate.ATan(), multiply_factor=5.0).cuda()
+    else:
+        net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=variant == 'plif', tau=3.0,
+                                                                             multiply_factor=15.0).cuda()
+    x = rm.synthetic_inputs(B, 1, 4, seed=32).cuda()
+    res = []
+    with torch.no_grad():
+        for on in (False, True):
+            net.set_kernel_options(batch_as_steps=on, keep_state=False, fold_min_frames=4)
+            sb.functional.reset_net(net)
+            res.append(net(x))
+            assert net.engine.last_batch_steps == ({16: 4, 12: 3, 20: 5}[B] if on else 1)
+    (d0, s0), (d1, s1) = res
+    assert all(torch.equal(a, b) for a, b in zip(d0, d1)) and all(torch.equal(a, b) for a, b in zip(s0, s1))
+    assert 0.01 < float((s1[-1] != 0).float().mean()) < 0.9
+    # a stateful call (the potentials are carried to the next forward) keeps the time semantics
+    with torch.no_grad():
+        net.set_kernel_options(batch_as_steps=True, keep_state=True)
+        sb.functional.reset_net(net)
+        net(x)
+        d2, _ = net(x)
+        net.set_kernel_options(batch_as_steps=False)
+        sb.functional.reset_net(net)
+        net(x)
+        d3, _ = net(x)
+    assert all(torch.equal(a, b) for a, b in zip(d2, d3)) and not torch.equal(d2[0], d0[0])
+
+
 def test_empty_batch_and_bad_arguments():
     from stereospike_b200 import ops, _lib
     geom, x, w = _mk_block(1, 1)

@@ -561,6 +561,7 @@ def run_ours(args):
         e2.record()
         for i in range(args.steps):
             depth_host = pipe.step(xs_host[i % len(xs_host)])
+        pipe.join()              # the depth maps return on their own stream: the closing event waits for the last one
         e3.record()
         barrier()
         d2h_bytes = depth_host.numel() * 4
@@ -651,7 +652,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': ms_e2e / args.steps,
                     'host_frames': str(xs_host[0].dtype).replace('torch.', '') + ' ' + 'x'.join(str(int(v)) for v in xs_host[0].shape),
                     'api': ('forward_seq + backward + Adam on frames copied from pinned host memory on a second stream, loss scalar back to pinned memory' if train else
-                            'stereospike_b200.pipeline.HostPipeline.step (pinned host frames -> H2D on a copy stream -> forward_seq -> pinned depth map)')},
+                            'stereospike_b200.pipeline.HostPipeline.step (pinned host frames -> H2D on a copy stream -> forward_seq -> pinned depth map on a copy-out stream)')},
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_burst'], 'unit': 'TFLOP/s',

@@ -6,7 +6,7 @@ finest depth map is copied back asynchronously, so that the PCIe transfer is hid
 
     pipe = HostPipeline(net, batch_shape=(8, 5, 4, 260, 346))
     for depth in pipe.run(batches):          # batches: iterable of pinned fp32 host tensors [B,T,C,H,W]
-        ...                                   # depth: pinned host tensor [B,1,H,W], valid after pipe.sync()
+        ...                                   # depth: pinned host tensor [B,1,H,W], valid after pipe.sync() (or pipe.done[k])
 """
 import torch
 
@@ -42,6 +42,12 @@ class HostPipeline:
         else:
             B, _, _, H, W = batch_shape
         self.depth_host = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        # the depth map goes back on a stream of its own: on the compute stream its 2.9 MB (B = 8) would hold back the next
+        # batch's kernels for the 50 us PCIe takes
+        self.out_stream = torch.cuda.Stream(self.device)
+        self.computed = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self._keep = [None] * depth             # the device depth map of the slot's batch, alive until its copy has finished
         self.stateless = bool(stateless)
         self._i = 0
 
@@ -67,8 +73,19 @@ class HostPipeline:
             eng.keep_state = keep
         self.free[k].record(main)
         depths = out if not isinstance(out, tuple) else out[0]
-        self.depth_host[k].copy_(depths[0], non_blocking=True)
+        if self._keep[k] is not None:
+            main.wait_event(self.done[k])       # the slot's previous copy-out (long finished) before its tensor may be reused
+        self._keep[k] = depths[0]
+        self.computed[k].record(main)
+        self.out_stream.wait_event(self.computed[k])
+        with torch.cuda.stream(self.out_stream):
+            self.depth_host[k].copy_(depths[0], non_blocking=True)
+            self.done[k].record(self.out_stream)
         return self.depth_host[k]
+
+    def join(self):
+        """The current stream waits (on the device, no host synchronisation) for every depth map enqueued so far."""
+        torch.cuda.current_stream(self.device).wait_stream(self.out_stream)
 
     def run(self, batches):
         for x in batches:

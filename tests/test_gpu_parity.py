@@ -274,6 +274,36 @@ def test_single_step_batch_as_independent_steps_is_bit_identical(variant, B):
     assert all(torch.equal(a, b) for a, b in zip(d2, d3)) and not torch.equal(d2[0], d0[0])
 
 
+@pytest.mark.parametrize('packed', [False, True])
+def test_host_pipeline_matches_direct_calls(packed):
+    """pipeline.HostPipeline (H2D on a copy stream, forward, depth map back on a copy-out stream, two-slot rings) returns, for every
+    batch of a stream of batches, exactly what reset_net + forward_seq gives on the same frames."""
+    import stereospike_b200 as sb
+    from stereospike_b200.pipeline import HostPipeline, pack_events_host
+    from oracle import ref_model as rm
+    torch.manual_seed(2)
+    net = sb.fromZero_feedforward_multiscale_tempo_Matt_SpikeFlowNetLike(use_plif=False, tau=3.0, multiply_factor=15.0).cuda()
+    batches = [rm.synthetic_inputs(2, 3, 4, seed=50 + i) for i in range(5)]
+    want = []
+    with torch.no_grad():
+        net.set_kernel_options(keep_state=False)
+        for x in batches:
+            sb.functional.reset_net(net)
+            want.append(net.forward_seq(x.cuda())[0][0].cpu())
+        net.set_kernel_options(keep_state=True)
+    host = [(pack_events_host(x) if packed else x).pin_memory() for x in batches]
+    pipe = HostPipeline(net, tuple(host[0].shape), dtype=host[0].dtype)
+    got = []
+    for i, x in enumerate(host):
+        d = pipe.step(x)
+        pipe.done[i % 2].synchronize()           # this batch's depth map has landed; the next step reuses the other slot
+        got.append(d.clone())
+    pipe.sync()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert net.engine.keep_state is True         # the pipeline's stateless switch is scoped to its own calls
+
+
 def test_empty_batch_and_bad_arguments():
     from stereospike_b200 import ops, _lib
     geom, x, w = _mk_block(1, 1)

@@ -30,6 +30,11 @@ import sys
 import tempfile
 import time
 
+# The training step allocates ~9 GB of transient tensors per step on two streams; with the default caching allocator a fragmented
+# pool occasionally grows by a cudaMalloc -- a device synchronisation that costs 3-17 ms on that step (tools/train_step_trace.py:
+# 1-2 such steps in 40).  Expandable segments grow the pool without it.  Must be set before torch initialises CUDA.
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

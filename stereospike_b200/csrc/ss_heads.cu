@@ -11,10 +11,12 @@
 // When the producing blocks hand over  acts_sum = sum_{t < T-1} act_t  (u8, accumulated for free in their epilogues) the
 // heads are evaluated on two pseudo-timesteps only -- the summed past (bias counted T-1 times) and the last step, which
 // the four running-sum outputs need separately -- instead of T.  Again the same math up to fp32 reassociation.
-//   kernel 1  head_taps_kernel   : u8 NHWC spikes -> fp32 taps[e][b][tap][sy][sx]      (one launch, all heads)
+//   kernel 1  head_taps_mma_kernel: u8 NHWC spikes -> fp32 taps[e][b][tap][sy][sx]     (one launch, all heads) as warp-level
+//                                  bf16 MMAs with the fp32 weights split exactly into three bf16 pieces; head_taps_kernel is
+//                                  the CUDA-core version for channel counts the MMA tiling does not cover
 //   kernel 2  heads_gather_kernel: one thread per output pixel, potential in a register across heads and
-//                                  timesteps, 36 coalesced gathers per timestep, depth planes written at the
-//                                  last timestep.  HBM/L2-bound.
+//                                  timesteps, 36 coalesced gathers per timestep (all issued before the first add), depth
+//                                  planes written at the last timestep.  HBM/L2-bound.
 #include <cuda_bf16.h>
 
 #include <algorithm>

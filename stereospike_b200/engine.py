@@ -716,7 +716,7 @@ def run_linear_block(up, x):
     need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in conv.parameters()))
     spikes_like = x.dtype == torch.uint8 and conv.in_channels % 16 == 0
     if need_grad or conv.out_channels != 1 or conv.kernel_size[0] != 3 or not spikes_like:
-        return _LinearBlockFunction.apply(x, conv.weight, conv.bias, up.up_size)
+        return _LinearBlockFunction.apply(x, conv.weight, conv.bias, up.up_size, None)
     B, C, Hs, Ws = x.shape
     xb = _nchw_to_tbhwc(x)
     g = BlockGeom('upconv', C, 1, 3, Hs, Ws, up.up_size[0], up.up_size[1])

@@ -116,7 +116,8 @@ def test_engine_wiring():
     assert [h.src for h in e.heads] == ['out_add4', 'out_add3', 'out_add2', 'out_add1']
 
 
-@pytest.mark.parametrize('Hin,Win,Hout,Wout', [(17, 22, 33, 44), (9, 11, 17, 21), (33, 44, 65, 87), (20, 27, 40, 53)])
+@pytest.mark.parametrize('Hin,Win,Hout,Wout', [(17, 22, 33, 44), (33, 44, 65, 87), (65, 87, 130, 173), (130, 173, 260, 346),      # deconv4..1
+                                                (9, 11, 17, 21), (20, 27, 40, 53), (37, 13, 75, 26), (5, 10, 7, 18)])
 def test_fold_plan_and_weight_sets_reproduce_upsampled_conv(Hin, Win, Hout, Wout):
     """Host logic of the folded NNConvUpsampling block, emulated in float64 on CPU: the dense 3x3 pass on the source (4 class
     pairs, output maps), the irregular-row pass (row lists, rows folded to 3 taps, 5 taps over the upsampled columns) and the

@@ -193,3 +193,57 @@ def test_analog_comparison_model_surface():
     assert net.epoch == 1 and net.get_max_accuracy() == float('inf')
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         net(torch.zeros(1, 1, 4, 260, 346))
+
+
+def _emulate_corr(plan, src, Cdst):
+    """float64 emulation of ss_corr_bf16 as include/stereospike_b200.h specifies it: stride-1 correlation of the zero-padded source
+    with every weight set on the virtual grid, result channel (tile, class, c) routed to destination channel tile * ntile + c at
+    (ymap[row class][i], xmap[col class][j]); -1 = no destination; destinations accumulate."""
+    g = plan.geom
+    w = plan.w_img.double()                                   # (the test keeps the OIHW sets instead of the bf16 image)
+    nt, nc = plan.ntile, plan.nclass
+    r = F.conv2d(F.pad(src, (plan.pad,) * 4), w)              # [B, nsets * nt, Hv, Wv]
+    B = src.shape[0]
+    assert tuple(r.shape[2:]) == (plan.Hv, plan.Wv) and r.shape[1] == (Cdst // nt) * nc * nt
+    r = r.view(B, Cdst // nt, nc, nt, plan.Hv, plan.Wv)
+    dst = torch.zeros(B, Cdst, g.Hin, g.Win, dtype=torch.float64)
+    if plan.ymap is None:
+        assert nc == 1 and (plan.Hv, plan.Wv) == (g.Hin, g.Win)
+        return r[:, :, 0].reshape(B, Cdst, g.Hin, g.Win)
+    ym, xm = plan.ymap.view(-1, plan.Hv).long(), plan.xmap.view(-1, plan.Wv).long()
+    for cls in range(nc):
+        yy, xx = ym[cls // 2 if nc > 1 else 0], xm[cls % 2 if nc > 1 else 0]
+        iy, ix = (yy >= 0).nonzero().flatten(), (xx >= 0).nonzero().flatten()
+        part = r[:, :, cls].reshape(B, Cdst, plan.Hv, plan.Wv)[:, :, iy][:, :, :, ix]
+        flat = (yy[iy][:, None] * g.Win + xx[ix][None, :]).reshape(-1)
+        dst.view(B, Cdst, -1).index_add_(2, flat, part.reshape(B, Cdst, -1))
+    return dst
+
+
+@pytest.mark.parametrize('kind,Cin,Cout,ks,stride,pad,Hin,Win,up', [
+    ('conv', 64, 32, 3, 1, 1, 17, 22, None),           # bottleneck convs
+    ('conv', 32, 32, 5, 2, 2, 33, 44, None),           # conv4-type (odd height, even width)
+    ('conv', 64, 16, 5, 2, 2, 26, 35, None),           # conv2-type sizes (even height, odd width), 64-channel weight sets
+    ('upconv', 32, 16, 5, 1, 0, 17, 22, (33, 44)),     # deconv4
+    ('upconv', 64, 32, 5, 1, 0, 13, 9, (27, 17)),
+])
+def test_data_gradient_plan_equals_autograd(monkeypatch, kind, Cin, Cout, ks, stride, pad, Hin, Win, up):
+    """Host logic of ops.DgradPlan (correlation weights, parity classes of the stride-2 blocks, virtual grid and output maps of the
+    upsampled blocks) run through a float64 emulation of the ss_corr_bf16 contract: equals autograd's input gradient of the
+    reference block (Conv2d / UpsamplingNearest2d -> Conv2d, network/blocks.py:124-127)."""
+    monkeypatch.setattr(ops, '_pack_bf16', lambda w_eff, k, ntile: w_eff.contiguous())      # keep the OIHW sets (no CUDA library call)
+    gen = torch.Generator().manual_seed(Hin * 100 + Win)
+    w = (torch.randn(Cout, Cin, ks, ks, generator=gen) / 8).double()                       # fp32-representable: the plan's .float() is lossless
+    x = torch.randn(2, Cin, Hin, Win, generator=gen, dtype=torch.float64, requires_grad=True)
+    if kind == 'conv':
+        y = F.conv2d(x, w, stride=stride, padding=pad)
+    else:
+        y = F.conv2d(F.interpolate(x, size=(up[0] + ks - 1, up[1] + ks - 1), mode='nearest'), w)
+        assert tuple(y.shape[2:]) == up
+    gy = torch.randn(y.shape, generator=gen, dtype=torch.float64)
+    want, = torch.autograd.grad(y, x, gy)
+    geom = ops.BlockGeom(kind, Cin, Cout, ks, Hin, Win, int(y.shape[2]), int(y.shape[3]), stride, pad)
+    plan = ops.DgradPlan(w, geom, 'cpu')
+    assert plan.ntile == (64 if Cin % 64 == 0 else 32)
+    got = _emulate_corr(plan, gy, Cin)
+    assert float((got - want).abs().max()) < 1e-10

@@ -247,3 +247,54 @@ def test_data_gradient_plan_equals_autograd(monkeypatch, kind, Cin, Cout, ks, st
     assert plan.ntile == (64 if Cin % 64 == 0 else 32)
     got = _emulate_corr(plan, gy, Cin)
     assert float((got - want).abs().max()) < 1e-10
+
+
+@pytest.mark.parametrize('Hin,Win,Hout,Wout', [(17, 22, 33, 44), (33, 44, 65, 87), (65, 87, 130, 173), (130, 173, 260, 346), (9, 11, 17, 21)])
+def test_fold_plan_concatenated_lists_and_item_tables(Hin, Win, Hout, Wout):
+    """The row-list passes read the CONCATENATED class lists (each class padded to whole 16-entry tiles on its own) through an item
+    table {weight set, m-tile}: same entries per class as the padded lists the emulation above walks, every (weight set, tile) of a
+    class exactly once, no tile of another class."""
+    B = 3
+    plan = ops.FoldPlan(Hin, Win, Hout, Wout, B, 'cpu')
+    assert plan.ok
+    for conc, src_pad, out_pad in ((plan.crow, plan.row_src, plan.row_out), (plan.ccol, plan.col_src, plan.col_out),
+                                   (plan.creg, plan.reg_src, plan.reg_out)):
+        src, out, n, ranges = conc
+        assert n == src.numel() == out.numel() and n % 16 == 0
+        assert len(ranges) == src_pad.shape[0]
+        ty = 0
+        for c, (ty0, nt) in enumerate(ranges):
+            assert ty0 == ty
+            ty += nt
+            seg_s, seg_o = src[ty0 * 16:(ty0 + nt) * 16], out[ty0 * 16:(ty0 + nt) * 16]
+            live = seg_s >= 0
+            assert torch.equal(live, seg_o >= 0)
+            assert bool(live[:int(live.sum())].all()), 'padding only at the end of a class'
+            want = src_pad[c] >= 0
+            assert torch.equal(seg_s[live], src_pad[c][want]) and torch.equal(seg_o[live], out_pad[c][want])
+            assert nt == (int(live.sum()) + 15) // 16
+        assert ty * 16 == n or (ty == 0 and n == 16)
+    # every output row appears exactly once over the regular + irregular row lists, every column once over (dense map, column lists)
+    rows = torch.cat([plan.crow[1][plan.crow[1] >= 0], plan.creg[1][plan.creg[1] >= 0]]).sort().values
+    assert torch.equal(rows, (torch.arange(B * Hout) * Wout).int())
+    cols0 = plan.ccol[1][plan.ccol[1] >= 0]
+    dense_cols = plan.xmap[plan.xmap >= 0]
+    assert torch.equal(torch.cat([cols0[cols0 < Wout], dense_cols]).sort().values, torch.arange(Wout).int())
+    for which, col_classes in (('crow', 1), ('ccol', 1), ('creg', 2)):
+        ranges = getattr(plan, which)[3]
+        for ntiles_out, tiles_x in ((1, 1), (2, 3)):
+            tab, n_items = plan.item_table(which, ntiles_out, tiles_x, col_classes)
+            total_ty = sum(nt for _, nt in ranges)
+            assert n_items == ntiles_out * col_classes * total_ty * tiles_x
+            if n_items == 0:
+                assert tab is None
+                continue
+            assert tuple(tab.shape) == (n_items, 2)
+            seen = set()
+            nclass = len(ranges) * col_classes
+            for wset, mt in tab.tolist():
+                assert (wset, mt) not in seen
+                seen.add((wset, mt))
+                rc = (wset % nclass) // col_classes
+                ty0, nt = ranges[rc]
+                assert 0 <= wset < ntiles_out * nclass and ty0 <= mt // tiles_x < ty0 + nt

@@ -93,6 +93,31 @@ def test_bptt_lif_tau2_T2():
         assert float(x.grad[0]) == pytest.approx(gh0 / 2, rel=1e-5)
 
 
+def test_bptt_plif_tau3_T2_with_decay_gradient():
+    """Row 6, PLIF: r = sigmoid(w) = 1/3; g_h(1) = b d1, g_v(0) = g_h(1) (1 - r) (1 - s0), g_h(0) = a d0 + g_v(0), g_x(t) = g_h(t) r,
+    g_w = r (1 - r) sum_t g_h(t) (x_t - v_{t-1}); Sigmoid(alpha = 4) surrogate: d(h) = 4 sig(4 (h - 1)) (1 - sig(4 (h - 1)))."""
+    a, b = 0.7, -1.3
+    sig = lambda z: 1.0 / (1.0 + math.exp(-z))
+    d = lambda h: 4.0 * sig(4.0 * (h - 1.0)) * (1.0 - sig(4.0 * (h - 1.0)))
+    for x0 in (0.9, 3.6):                       # no spike at t=0 (h0 = 0.3) / spike at t=0 (h0 = 1.2)
+        n = sj.ParametricLIFNode(init_tau=3.0, surrogate_function=sj.Sigmoid(), detach_reset=True)
+        x = torch.tensor([x0, 0.9], requires_grad=True)
+        s0 = n(x[0:1])
+        s1 = n(x[1:2])
+        r = 1.0 / 3.0
+        h0 = x0 * r
+        v0 = 0.0 if h0 >= 1 else h0
+        h1 = v0 + (0.9 - v0) * r
+        assert float(s0) == (1.0 if h0 >= 1 else 0.0) and float(s1) == 0.0
+        (a * s0 + b * s1).sum().backward()
+        gh1 = b * d(h1)
+        gv0 = gh1 * (1 - r) * (1 - float(s0))
+        gh0 = a * d(h0) + gv0
+        assert float(x.grad[1]) == pytest.approx(gh1 * r, rel=1e-5)
+        assert float(x.grad[0]) == pytest.approx(gh0 * r, rel=1e-5)
+        assert float(n.w.grad) == pytest.approx(r * (1 - r) * (gh1 * (0.9 - v0) + gh0 * x0), rel=1e-5)
+
+
 def test_reset_net_and_shim():
     sj.install_shim()
     from spikingjelly.clock_driven import neuron, functional, surrogate  # noqa: F401

@@ -86,7 +86,12 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()][getattr(self, 'skip', 0):]
+        allrows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+        skip = getattr(self, 'skip', 0)
+        rows, window = allrows[skip:], 'timed region'
+        if not rows and allrows:
+            # a timed region shorter than one 20 ms poll: fall back to the last samples of the warm-up (same kernels, same load)
+            rows, window = allrows[max(0, skip - 3):], 'end of warm-up (timed region shorter than one poll)'
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -101,7 +106,7 @@ class ClockSampler:
                     reasons.add(n)
         busy = sorted(sm)[len(sm) // 2:] if sm else []
         return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 def build_oracle(neuron, gain, tau):
